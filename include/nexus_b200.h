@@ -1,0 +1,202 @@
+/* nexus_b200 — C ABI of the B200-native (sm_100a) wavefront path-tracing hot path.
+ *
+ * Drop-in boundary for three C++ surfaces of StokastX/Nexus (reference paths relative to /root/reference/Nexus):
+ *   builder  : NXB::BuildBVH2 / BuildBVH8 / ToHost / FreeDeviceBVH / BenchmarkBuild
+ *              vendor/NexusBVH/NexusBVH/include/NXB/BVHBuilder.h:19-55, BVHBuildMetrics.h:7-108, BuildConfig.h:6-12
+ *   scene    : Scene / AssetManager / Mesh / MeshInstance / Material / Light / Camera / RenderSettings
+ *              src/Scene/Scene.h:19-49, src/Assets/AssetManager.h:18-44, src/Scene/MeshInstance.h:22-66,
+ *              src/Assets/Material.h:6-26, src/Scene/Light.h:10-54, src/Scene/Camera.h:9-52, src/Renderer/RenderSettings.h:5-17
+ *   renderer : PathTracer::{Reset, ResetFrameNumber, Render, OnResize, UpdateDeviceScene, GetFrameNumber}
+ *              src/Renderer/PathTracer.h:12-29 (+ the six kernels of src/Cuda/PathTracer/PathTracer.cuh:69-74)
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative nx_status and records a
+ * message retrievable with nx_last_error() (the reference prints and exit(99)s: src/Utils/Utils.cpp:3-12).  One host
+ * thread per context.  All device work of a context is issued on the context's own streams; there is no process-global
+ * device state, so one process can drive several GPUs (the reference keeps its state in __constant__ symbols,
+ * src/Cuda/PathTracer/PathTracer.cu:21-37, which limits it to one renderer per process).
+ */
+#ifndef NEXUS_B200_H
+#define NEXUS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NX_ABI_VERSION 1
+
+typedef enum nx_status {
+    NX_OK = 0,
+    NX_ERR_CUDA = -1,
+    NX_ERR_INVALID = -2,
+    NX_ERR_OOM = -3,
+    NX_ERR_STATE = -4
+} nx_status;
+
+typedef struct nx_ctx nx_ctx;
+typedef struct nx_scene nx_scene;
+typedef struct nx_renderer nx_renderer;
+
+/* ---------------------------------------------------------------- PODs (layouts are part of the contract) ---- */
+typedef struct nx_aabb { float bmin[3]; float bmax[3]; } nx_aabb;                      /* NXB::AABB, 24 B            */
+typedef struct nx_triangle { float v0[3], v1[3], v2[3]; } nx_triangle;                 /* NXB::Triangle, 36 B        */
+typedef struct nx_triangle_data {                                                       /* D_TriangleData, 96 B       */
+    float normal0[3], normal1[3], normal2[3];
+    float tangent0[3], tangent1[3], tangent2[3];
+    float uv0[2], uv1[2], uv2[2];
+} nx_triangle_data;
+
+/* NXB::BVH2::Node (32 B): leaf <=> left == 0xffffffff, then right = primitive id.  Leaves are [0,n), root = 2n-2. */
+typedef struct nx_bvh2_node { nx_aabb bounds; uint32_t left, right; } nx_bvh2_node;
+/* NXB::BVH8::NodeExplicit (80 B, 16-byte aligned on the device). */
+typedef struct nx_bvh8_node {
+    float p[3]; uint8_t e[3]; uint8_t imask;
+    uint32_t child_base, prim_base;
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
+} nx_bvh8_node;
+
+/* Handles returned by value like NXB::BVH2 / NXB::BVH8 (BVH.h:18-96); pointers are DEVICE pointers owned by the library. */
+typedef struct nx_bvh2 { nx_bvh2_node* nodes; uint32_t node_count; uint32_t prim_count; nx_aabb bounds; } nx_bvh2;
+typedef struct nx_bvh8 { nx_bvh8_node* nodes; uint32_t node_count; uint32_t* prim_idx; uint32_t prim_count; nx_aabb bounds; } nx_bvh8;
+
+typedef struct nx_build_config { int prioritize_speed; } nx_build_config;             /* NXB::BuildConfig           */
+typedef struct nx_build_metrics {                                                       /* NXB::BVHBuildMetrics       */
+    float scene_bounds_ms, morton_ms, sort_ms, bvh2_ms, bvh8_ms, total_ms;
+    float bvh2_cost, bvh8_cost, avg_children_per_node;
+} nx_build_metrics;
+
+typedef struct nx_material {                                                            /* Material / D_Material, 92 B */
+    float base_color[3]; float metalness; float roughness; float anisotropy; float specular_weight;
+    float specular_color[3]; float ior; float transmission;
+    float emission_color[3]; float intensity; float opacity;
+    int32_t base_color_map, emissive_map, normal_map, roughness_map, metalness_map, metallic_roughness_map;
+} nx_material;
+
+typedef enum nx_light_type { NX_LIGHT_POINT = 0, NX_LIGHT_SPOT = 1, NX_LIGHT_DIRECTIONAL = 2, NX_LIGHT_MESH = 3 } nx_light_type;
+typedef struct nx_light {                 /* flattened Light union (src/Scene/Light.h:10-54) */
+    int32_t type;
+    float position[3]; float direction[3]; float color[3]; float intensity;
+    float falloff_start, falloff_end;
+    uint32_t instance;                    /* NX_LIGHT_MESH: emissive instance index (Light::mesh.meshId) */
+} nx_light;
+
+typedef struct nx_camera {                /* Camera ctor arguments, src/Scene/Camera.cpp:24-30 */
+    float position[3]; float forward[3]; float right[3];   /* right = {0,0,0} => cross(forward, +Y) as the ctor does */
+    float horizontal_fov_deg; float focus_distance; float defocus_angle_deg;
+} nx_camera;
+
+typedef struct nx_render_settings {       /* RenderSettings, src/Renderer/RenderSettings.h:5-17 */
+    int32_t use_mis; int32_t path_length;
+    float background_color[3]; float background_intensity;
+    int32_t tone_mapping; float exposure; /* display transform only; the accumulation buffer stays linear */
+} nx_render_settings;
+
+typedef struct nx_ray { float origin[3]; float tmax; float direction[3]; uint32_t pad; } nx_ray;     /* 32 B */
+typedef struct nx_hit { float t, u, v; uint32_t prim; uint32_t instance; } nx_hit;                    /* D_Intersection */
+
+typedef struct nx_frame_stats {           /* queue totals of the frames rendered by the last nx_render_frames call */
+    uint64_t extension_rays; uint64_t shadow_rays; uint64_t shaded_hits; uint64_t frames;
+    float device_ms;                      /* CUDA-event time of that call on the context's stream */
+    uint32_t kernel_launches;
+} nx_frame_stats;
+
+/* ------------------------------------------------------------------------------------------------ context ---- */
+int nx_abi_version(void);
+int nx_ctx_create(int device, nx_ctx** out);
+void nx_ctx_destroy(nx_ctx* ctx);
+const char* nx_last_error(const nx_ctx* ctx);
+int nx_ctx_synchronize(nx_ctx* ctx);
+int nx_ctx_sm_count(const nx_ctx* ctx);
+void* nx_ctx_stream(nx_ctx* ctx);                                   /* cudaStream_t all work is issued on */
+
+/* device memory helpers so a C / ctypes host needs no CUDA runtime of its own (replace N/Device/CudaMemory.h) */
+int nx_malloc(nx_ctx* ctx, size_t bytes, void** out_dev);
+int nx_free(nx_ctx* ctx, void* dev);
+int nx_memcpy_h2d(nx_ctx* ctx, void* dev, const void* host, size_t bytes);
+int nx_memcpy_d2h(nx_ctx* ctx, void* host, const void* dev, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------ builder ---- */
+/* d_prims: DEVICE pointer, caller-owned, not modified (as NXB::BuildBVH*).  metrics may be NULL; when non-NULL every
+ * stage is bracketed by CUDA events like the reference (BVHBuilder.cpp:35-46).  Blocking like the reference. */
+int nx_bvh2_build_tri(nx_ctx* ctx, const nx_triangle* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh2* out);
+int nx_bvh2_build_aabb(nx_ctx* ctx, const nx_aabb* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh2* out);
+int nx_bvh8_build_tri(nx_ctx* ctx, const nx_triangle* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out);
+int nx_bvh8_build_aabb(nx_ctx* ctx, const nx_aabb* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out);
+int nx_bvh2_to_host(nx_ctx* ctx, const nx_bvh2* bvh, nx_bvh2_node* host_nodes);                       /* NXB::ToHost */
+int nx_bvh8_to_host(nx_ctx* ctx, const nx_bvh8* bvh, nx_bvh8_node* host_nodes, uint32_t* host_prim_idx);
+int nx_bvh2_free(nx_ctx* ctx, nx_bvh2* bvh);                                                           /* FreeDeviceBVH */
+int nx_bvh8_free(nx_ctx* ctx, nx_bvh8* bvh);
+/* NXB::BenchmarkBuild: averaged per-stage times over `iters` builds after `warmup` builds (prim_type 0 = AABB, 1 = triangle). */
+int nx_bvh8_benchmark(nx_ctx* ctx, const void* d_prims, uint32_t n, int prim_type, const nx_build_config* cfg,
+                      int warmup, int iters, nx_build_metrics* metrics, uint32_t* out_node_count);
+/* Parity hook: the sorted Morton keys / primitive order the last *_build call of this context used (uint64 per key). */
+int nx_bvh_debug_morton(nx_ctx* ctx, const void* d_prims, uint32_t n, int prim_type, int bits64, uint64_t* host_codes /* n, primitive order */);
+
+/* -------------------------------------------------------------------------------------------------- scene ---- */
+int nx_scene_create(nx_ctx* ctx, uint32_t width, uint32_t height, nx_scene** out);    /* Scene(uint2 resolution) */
+void nx_scene_destroy(nx_scene* scene);
+int nx_scene_add_material(nx_scene* scene, const nx_material* m);                       /* returns index >= 0  */
+int nx_scene_set_material(nx_scene* scene, uint32_t idx, const nx_material* m);         /* InvalidateMaterial  */
+/* AssetManager::AddMesh: host triangles + per-triangle shading data (may be NULL => geometric normals); builds the BLAS
+ * with prioritizeSpeed = true exactly like Mesh::Mesh (src/Assets/Mesh.h:15-46).  Returns mesh index >= 0. */
+int nx_scene_add_mesh(nx_scene* scene, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t material_idx);
+int nx_scene_mesh_bounds(nx_scene* scene, uint32_t mesh_idx, nx_aabb* out);
+int nx_scene_mesh_bvh(nx_scene* scene, uint32_t mesh_idx, nx_bvh8* out);                /* borrowed handle */
+/* Scene::CreateMeshInstance + MeshInstance::SetTransform (T * Rz * Ry * Rx * S, Euler degrees). Returns instance index. */
+int nx_scene_add_instance(nx_scene* scene, uint32_t mesh_idx, int32_t material_idx /* <0: mesh default */,
+                          const float position[3], const float rotation_deg[3], const float scale[3]);
+/* Same, with an explicit row-major 4x4 (used by parity tests so both arms see identical matrices). */
+int nx_scene_add_instance_matrix(nx_scene* scene, uint32_t mesh_idx, int32_t material_idx, const float m[16]);
+int nx_scene_set_instance_transform(nx_scene* scene, uint32_t inst, const float position[3], const float rotation_deg[3], const float scale[3]);
+int nx_scene_add_light(nx_scene* scene, const nx_light* light);                         /* Scene::AddLight */
+int nx_scene_set_camera(nx_scene* scene, const nx_camera* cam);
+int nx_scene_set_render_settings(nx_scene* scene, const nx_render_settings* rs);
+int nx_scene_set_hdr_map(nx_scene* scene, const float* rgba, uint32_t w, uint32_t h);   /* Scene::AddHDRMap (RGBA32F equirect) */
+/* Scene::Update: uploads dirty instances/materials, rebuilds the TLAS (BuildBVH8<AABB>, default config) and maintains the
+ * emissive-mesh light list (Scene::UpdateSceneLighting, src/Scene/Scene.cpp:157-219). */
+int nx_scene_update(nx_scene* scene);
+/* Device-layout mirrors for parity with the reference arm (160-byte D_MeshInstance, 88-byte D_Camera, 52-byte D_Light). */
+int nx_scene_export_instances(nx_scene* scene, void* out160 /* n*160 */, uint32_t* out_count);
+int nx_scene_export_camera(nx_scene* scene, void* out88);
+int nx_scene_export_lights(nx_scene* scene, void* out52 /* n*52 */, uint32_t* out_count);
+int nx_scene_tlas(nx_scene* scene, nx_bvh8* out);                                       /* borrowed handle */
+
+/* Parity hook: closest hits of a ray batch through the product traversal kernel (HOST buffers). */
+int nx_trace_closest(nx_scene* scene, const nx_ray* rays, uint32_t n, nx_hit* hits, float* out_device_ms);
+/* Any-hit (shadow) variant: out_occluded[i] = 1 if anything lies in (0, tmax). */
+int nx_trace_any(nx_scene* scene, const nx_ray* rays, uint32_t n, uint8_t* out_occluded, float* out_device_ms);
+/* Same on DEVICE buffers (rays/hits already resident), used by bench.py for the kernel-only number. */
+int nx_trace_closest_device(nx_scene* scene, const nx_ray* d_rays, uint32_t n, nx_hit* d_hits, float* out_device_ms);
+
+/* Traversal work counters over a DEVICE ray batch: out4 = {nodes visited, triangles tested, instances entered, rays}.  These are
+ * the per-scene averages SURVEY.md 8(d)'s algorithmic-byte formula needs. */
+int nx_trace_stats(nx_scene* scene, const nx_ray* d_rays, uint32_t n, nx_hit* d_hits, uint64_t out4[4]);
+
+/* ----------------------------------------------------------------------------------------------- renderer ---- */
+int nx_renderer_create(nx_ctx* ctx, uint32_t width, uint32_t height, nx_renderer** out);   /* PathTracer(uint2) + Reset  */
+void nx_renderer_destroy(nx_renderer* r);
+int nx_renderer_resize(nx_renderer* r, uint32_t width, uint32_t height);                   /* PathTracer::OnResize       */
+int nx_renderer_reset_accumulation(nx_renderer* r);                                        /* ResetFrameNumber           */
+/* Renders frames first_frame .. first_frame + n - 1 (frame numbers start at 1 and seed the RNG, N/Cuda/Random.cuh:67-78)
+ * and adds them to the accumulation.  Asynchronous like PathTracer::Render; nx_renderer_stats() synchronises. */
+int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t first_frame, uint32_t n_frames);
+int nx_renderer_frame_count(const nx_renderer* r);                                         /* GetFrameNumber             */
+int nx_renderer_stats(nx_renderer* r, nx_frame_stats* out);
+/* Linear radiance mean, float RGB, row-major, HOST buffer of w*h*3 floats. */
+int nx_renderer_read_accum(nx_renderer* r, float* host_rgb);
+/* DEVICE pointer to the running float3 SUM (w*h*3 floats) and the number of frames in it — what the NCCL reduce consumes. */
+int nx_renderer_accum_device(nx_renderer* r, float** out_dev_sum, uint32_t* out_frames);
+int nx_renderer_set_accum_frames(nx_renderer* r, uint32_t frames);                         /* after an external all-reduce */
+/* Tone-mapped RGBA8 (AccumulateKernel's display transform, PathTracer.cu:527-548), HOST buffer of w*h uint32. */
+int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* host_rgba);
+/* Headless output (north_star): PFM (little-endian float RGB) and EXR (uncompressed scanline, float RGB). */
+int nx_write_pfm(const char* path, const float* rgb, uint32_t w, uint32_t h);
+int nx_write_exr(const char* path, const float* rgb, uint32_t w, uint32_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXUS_B200_H */

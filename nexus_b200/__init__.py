@@ -1,0 +1,488 @@
+"""nexus_b200 — B200-native (sm_100a) implementation of the StokastX/Nexus wavefront path-tracing hot path.
+
+Python mirror of the reference's host API (same class and method names, reference file:line in each docstring), a thin
+layer over the C ABI in include/nexus_b200.h.  All computation happens in libnexus_b200.so on the GPU; nothing here has
+a CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._capi import (Aabb, BuildConfig, BuildMetrics, Bvh2, Bvh8, CameraPod, FrameStats, LightPod, MaterialPod, NexusError,
+                    RenderSettingsPod, check, lib)
+
+__all__ = ["Context", "Scene", "AssetManager", "Material", "Light", "Camera", "RenderSettings", "PathTracer", "MeshInstance",
+           "BuildBVH2", "BuildBVH8", "BenchmarkBuild", "BVH2", "BVH8", "NexusError", "write_pfm", "write_exr"]
+
+RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("tmax", np.float32), ("direction", np.float32, 3), ("pad", np.uint32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.uint32), ("instance", np.uint32)])
+MISS_T = np.float32(1.0e30)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU.  Replaces the reference's process-global device state (src/Cuda/PathTracer/PathTracer.cu:21-37)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().nx_ctx_create(int(device), C.byref(self._h))
+        if rc < 0:
+            raise NexusError(f"nx_ctx_create(device={device}) failed with status {rc}: no usable CUDA device (no CPU fallback exists)")
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            lib().nx_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self._h, lib().nx_ctx_synchronize(self._h), "synchronize")
+
+    @property
+    def sm_count(self):
+        return lib().nx_ctx_sm_count(self._h)
+
+    # device memory (N/Device/CudaMemory.h)
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        check(self._h, lib().nx_malloc(self._h, C.c_size_t(nbytes), C.byref(p)), "nx_malloc")
+        return p.value
+
+    def free(self, dev):
+        check(self._h, lib().nx_free(self._h, C.c_void_p(dev)), "nx_free")
+
+    def upload(self, array):
+        array = np.ascontiguousarray(array)
+        dev = self.malloc(array.nbytes)
+        check(self._h, lib().nx_memcpy_h2d(self._h, C.c_void_p(dev), _ptr(array), C.c_size_t(array.nbytes)), "h2d")
+        return dev
+
+    def download(self, dev, shape, dtype):
+        out = np.empty(shape, dtype)
+        check(self._h, lib().nx_memcpy_d2h(self._h, _ptr(out), C.c_void_p(dev), C.c_size_t(out.nbytes)), "d2h")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ builder ----
+class BVH2:
+    """NXB::BVH2 (vendor/NexusBVH/NexusBVH/include/NXB/BVH.h:18-37): device handle + ToHost."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    def ToHost(self):
+        """NXB::ToHost (BVHBuilder.h:40): (2n-1, 8) uint32 view of the 32-byte nodes."""
+        nodes = np.empty((self.h.node_count, 8), np.uint32)
+        check(self.ctx._h, lib().nx_bvh2_to_host(self.ctx._h, C.byref(self.h), _ptr(nodes)), "nx_bvh2_to_host")
+        return nodes
+
+    @property
+    def bounds(self):
+        return np.array(list(self.h.bounds.bmin) + list(self.h.bounds.bmax), np.float32)
+
+    def Free(self):
+        lib().nx_bvh2_free(self.ctx._h, C.byref(self.h))
+
+
+class BVH8:
+    """NXB::BVH8 (BVH.h:39-96)."""
+
+    def __init__(self, ctx, handle, owned=True):
+        self.ctx, self.h, self.owned = ctx, handle, owned
+
+    @property
+    def nodeCount(self):
+        return self.h.node_count
+
+    @property
+    def primCount(self):
+        return self.h.prim_count
+
+    @property
+    def bounds(self):
+        return np.array(list(self.h.bounds.bmin) + list(self.h.bounds.bmax), np.float32)
+
+    def ToHost(self):
+        nodes = np.empty((self.h.node_count, 20), np.uint32)
+        prim = np.empty(self.h.prim_count, np.uint32)
+        check(self.ctx._h, lib().nx_bvh8_to_host(self.ctx._h, C.byref(self.h), _ptr(nodes), _ptr(prim)), "nx_bvh8_to_host")
+        return nodes, prim
+
+    def Free(self):
+        if self.owned:
+            lib().nx_bvh8_free(self.ctx._h, C.byref(self.h))
+
+
+def _prims_to_device(ctx, prims):
+    prims = np.ascontiguousarray(prims, np.float32)
+    if prims.ndim != 2 or prims.shape[1] not in (6, 9):
+        raise ValueError("primitives must be (n, 9) triangles or (n, 6) AABBs")
+    return prims, ctx.upload(prims), 1 if prims.shape[1] == 9 else 0
+
+
+def BuildBVH2(ctx, prims, prioritizeSpeed=False, metrics=False):
+    """NXB::BuildBVH2<PrimT> (BVHBuilder.h:19).  prims: host (n,9) triangles or (n,6) AABBs (uploaded here)."""
+    prims, dev, tri = _prims_to_device(ctx, prims)
+    cfg, m, out = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), Bvh2()
+    fn = lib().nx_bvh2_build_tri if tri else lib().nx_bvh2_build_aabb
+    try:
+        check(ctx._h, fn(ctx._h, C.c_void_p(dev), C.c_uint32(prims.shape[0]), C.byref(cfg), C.byref(m) if metrics else None, C.byref(out)), "BuildBVH2")
+    finally:
+        ctx.free(dev)
+    bvh = BVH2(ctx, out)
+    return (bvh, m.as_dict()) if metrics else bvh
+
+
+def BuildBVH8(ctx, prims, prioritizeSpeed=False, metrics=False):
+    """NXB::BuildBVH8<PrimT> (BVHBuilder.h:31)."""
+    prims, dev, tri = _prims_to_device(ctx, prims)
+    cfg, m, out = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), Bvh8()
+    fn = lib().nx_bvh8_build_tri if tri else lib().nx_bvh8_build_aabb
+    try:
+        check(ctx._h, fn(ctx._h, C.c_void_p(dev), C.c_uint32(prims.shape[0]), C.byref(cfg), C.byref(m) if metrics else None, C.byref(out)), "BuildBVH8")
+    finally:
+        ctx.free(dev)
+    bvh = BVH8(ctx, out)
+    return (bvh, m.as_dict()) if metrics else bvh
+
+
+def BenchmarkBuild(ctx, prims_dev, n, prim_type, prioritizeSpeed, warmup, iters):
+    """NXB::BenchmarkBuild (BVHBuildMetrics.h:63-108) on primitives already resident on the device."""
+    cfg, m, nodes = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), C.c_uint32(0)
+    check(ctx._h, lib().nx_bvh8_benchmark(ctx._h, C.c_void_p(prims_dev), C.c_uint32(n), C.c_int(prim_type), C.byref(cfg), C.c_int(warmup),
+                                          C.c_int(iters), C.byref(m), C.byref(nodes)), "BenchmarkBuild")
+    d = m.as_dict()
+    d["node_count"] = nodes.value
+    return d
+
+
+def debug_morton(ctx, prims, bits64):
+    """Parity hook: Morton codes (primitive order) exactly as the device computes them."""
+    prims, dev, tri = _prims_to_device(ctx, prims)
+    out = np.empty(prims.shape[0], np.uint64)
+    try:
+        check(ctx._h, lib().nx_bvh_debug_morton(ctx._h, C.c_void_p(dev), C.c_uint32(prims.shape[0]), C.c_int(tri), C.c_int(int(bits64)), _ptr(out)), "debug_morton")
+    finally:
+        ctx.free(dev)
+    return out
+
+
+# -------------------------------------------------------------------------------------------------- scene ----
+class Material:
+    """Material (src/Assets/Material.h:6-26), same defaults."""
+
+    def __init__(self, **kw):
+        self.baseColor = (0.8, 0.8, 0.8)
+        self.metalness = 0.0
+        self.roughness = 0.3
+        self.anisotropy = 0.0
+        self.specularWeight = 1.0
+        self.specularColor = (1.0, 1.0, 1.0)
+        self.ior = 1.5
+        self.transmission = 0.0
+        self.emissionColor = (1.0, 1.0, 1.0)
+        self.intensity = 0.0
+        self.opacity = 1.0
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+    def pod(self):
+        p = MaterialPod()
+        p.base_color[:] = self.baseColor
+        p.metalness, p.roughness, p.anisotropy, p.specular_weight = self.metalness, self.roughness, self.anisotropy, self.specularWeight
+        p.specular_color[:] = self.specularColor
+        p.ior, p.transmission = self.ior, self.transmission
+        p.emission_color[:] = self.emissionColor
+        p.intensity, p.opacity = self.intensity, self.opacity
+        p.base_color_map = p.emissive_map = p.normal_map = p.roughness_map = p.metalness_map = p.metallic_roughness_map = -1
+        return p
+
+
+class Light:
+    """Light (src/Scene/Light.h:10-54)."""
+    POINT, SPOT, DIRECTIONAL, MESH = 0, 1, 2, 3
+
+    def __init__(self, type, position=(0, 0, 0), direction=(0, -1, 0), color=(1, 1, 1), intensity=1.0, instance=0):
+        self.type, self.position, self.direction, self.color, self.intensity, self.instance = type, position, direction, color, intensity, instance
+
+    def pod(self):
+        p = LightPod()
+        p.type = self.type
+        p.position[:] = self.position
+        p.direction[:] = self.direction
+        p.color[:] = self.color
+        p.intensity = self.intensity
+        p.instance = self.instance
+        return p
+
+
+class Camera:
+    """Camera (src/Scene/Camera.h:9-52): position, forward, horizontal FOV (degrees), focus distance, defocus angle."""
+
+    def __init__(self, position=(0.0, 4.0, 14.0), forward=(0.0, 0.0, -1.0), horizontalFOV=45.0, focusDistance=5.0, defocusAngle=0.0, right=(0.0, 0.0, 0.0)):
+        self.position, self.forward, self.right = position, forward, right
+        self.horizontalFOV, self.focusDistance, self.defocusAngle = horizontalFOV, focusDistance, defocusAngle
+
+    def pod(self):
+        p = CameraPod()
+        p.position[:] = self.position
+        p.forward[:] = self.forward
+        p.right[:] = self.right
+        p.horizontal_fov_deg, p.focus_distance, p.defocus_angle_deg = self.horizontalFOV, self.focusDistance, self.defocusAngle
+        return p
+
+
+class RenderSettings:
+    """RenderSettings (src/Renderer/RenderSettings.h:5-17)."""
+
+    def __init__(self, useMIS=True, pathLength=10, backgroundColor=(0.0, 0.0, 0.0), backgroundIntensity=1.0, toneMapping=3, exposure=0.0):
+        self.useMIS, self.pathLength, self.backgroundColor = useMIS, pathLength, backgroundColor
+        self.backgroundIntensity, self.toneMapping, self.exposure = backgroundIntensity, toneMapping, exposure
+
+    def pod(self):
+        p = RenderSettingsPod()
+        p.use_mis, p.path_length = int(self.useMIS), int(self.pathLength)
+        p.background_color[:] = self.backgroundColor
+        p.background_intensity, p.tone_mapping, p.exposure = self.backgroundIntensity, self.toneMapping, self.exposure
+        return p
+
+
+class MeshInstance:
+    """MeshInstance (src/Scene/MeshInstance.h:9-77): handle returned by Scene.CreateMeshInstance."""
+
+    def __init__(self, scene, index, meshIdx):
+        self.scene, self.index, self.meshIdx = scene, index, meshIdx
+
+    def SetTransform(self, position, rotation, scale):
+        p, r, s = (np.asarray(v, np.float32) for v in (position, rotation, scale))
+        check(self.scene.ctx._h, lib().nx_scene_set_instance_transform(self.scene._h, C.c_uint32(self.index), _ptr(p), _ptr(r), _ptr(s)), "SetTransform")
+
+
+class AssetManager:
+    """AssetManager (src/Assets/AssetManager.h:13-57): meshes and materials of a scene."""
+
+    def __init__(self, scene):
+        self.scene = scene
+
+    def AddMaterial(self, material):
+        p = material.pod()
+        return check(self.scene.ctx._h, lib().nx_scene_add_material(self.scene._h, C.byref(p)), "AddMaterial")
+
+    def AddMesh(self, name, materialIdx, triangles, triangleData=None):
+        """AddMesh(name, materialIdx, triangles, triangleData) (AssetManager.cpp:24-33): builds the BLAS immediately."""
+        tris = np.ascontiguousarray(triangles, np.float32).reshape(-1, 9)
+        td = None if triangleData is None else np.ascontiguousarray(triangleData, np.float32).reshape(-1, 24)
+        if td is not None and td.shape[0] != tris.shape[0]:
+            raise ValueError("triangleData must have one row per triangle")
+        return check(self.scene.ctx._h, lib().nx_scene_add_mesh(self.scene._h, _ptr(tris), _ptr(td) if td is not None else None,
+                                                                 C.c_uint32(tris.shape[0]), C.c_uint32(materialIdx)), f"AddMesh({name})")
+
+    def InvalidateMaterial(self, index, material):
+        p = material.pod()
+        check(self.scene.ctx._h, lib().nx_scene_set_material(self.scene._h, C.c_uint32(index), C.byref(p)), "InvalidateMaterial")
+
+
+class Scene:
+    """Scene (src/Scene/Scene.h:16-77)."""
+
+    def __init__(self, ctx, resolution):
+        self.ctx = ctx
+        self.resolution = (int(resolution[0]), int(resolution[1]))
+        self._h = C.c_void_p()
+        check(ctx._h, lib().nx_scene_create(ctx._h, C.c_uint32(self.resolution[0]), C.c_uint32(self.resolution[1]), C.byref(self._h)), "Scene")
+        self._assets = AssetManager(self)
+
+    def close(self):
+        if self._h:
+            lib().nx_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def GetAssetManager(self):
+        return self._assets
+
+    def AddMaterial(self, material):
+        return self._assets.AddMaterial(material)
+
+    def CreateMeshInstance(self, meshId, materialIdx=-1, position=(0, 0, 0), rotation=(0, 0, 0), scale=(1, 1, 1)):
+        p, r, s = (np.asarray(v, np.float32) for v in (position, rotation, scale))
+        idx = check(self.ctx._h, lib().nx_scene_add_instance(self._h, C.c_uint32(meshId), C.c_int32(materialIdx), _ptr(p), _ptr(r), _ptr(s)), "CreateMeshInstance")
+        return MeshInstance(self, idx, meshId)
+
+    def CreateMeshInstanceMatrix(self, meshId, matrix, materialIdx=-1):
+        m = np.ascontiguousarray(matrix, np.float32).reshape(16)
+        idx = check(self.ctx._h, lib().nx_scene_add_instance_matrix(self._h, C.c_uint32(meshId), C.c_int32(materialIdx), _ptr(m)), "CreateMeshInstance")
+        return MeshInstance(self, idx, meshId)
+
+    def AddLight(self, light):
+        p = light.pod()
+        return check(self.ctx._h, lib().nx_scene_add_light(self._h, C.byref(p)), "AddLight")
+
+    def SetCamera(self, camera):
+        p = camera.pod()
+        check(self.ctx._h, lib().nx_scene_set_camera(self._h, C.byref(p)), "SetCamera")
+
+    def SetRenderSettings(self, rs):
+        p = rs.pod()
+        check(self.ctx._h, lib().nx_scene_set_render_settings(self._h, C.byref(p)), "SetRenderSettings")
+
+    def AddHDRMap(self, rgba):
+        """Scene::AddHDRMap with pixels instead of a file: (h, w, 4) float32 equirect."""
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        check(self.ctx._h, lib().nx_scene_set_hdr_map(self._h, _ptr(rgba), C.c_uint32(rgba.shape[1]), C.c_uint32(rgba.shape[0])), "AddHDRMap")
+
+    def Update(self):
+        check(self.ctx._h, lib().nx_scene_update(self._h), "Scene::Update")
+
+    def MeshBounds(self, meshId):
+        b = Aabb()
+        check(self.ctx._h, lib().nx_scene_mesh_bounds(self._h, C.c_uint32(meshId), C.byref(b)), "MeshBounds")
+        return np.array(list(b.bmin) + list(b.bmax), np.float32)
+
+    def MeshBVH(self, meshId):
+        h = Bvh8()
+        check(self.ctx._h, lib().nx_scene_mesh_bvh(self._h, C.c_uint32(meshId), C.byref(h)), "MeshBVH")
+        return BVH8(self.ctx, h, owned=False)
+
+    def TLAS(self):
+        h = Bvh8()
+        check(self.ctx._h, lib().nx_scene_tlas(self._h, C.byref(h)), "TLAS")
+        return BVH8(self.ctx, h, owned=False)
+
+    # reference device layouts, for the reference arm of parity tests
+    def ExportInstances(self):
+        n = C.c_uint32(0)
+        check(self.ctx._h, lib().nx_scene_export_instances(self._h, None, C.byref(n)), "ExportInstances")
+        out = np.zeros((n.value, 160), np.uint8)
+        check(self.ctx._h, lib().nx_scene_export_instances(self._h, _ptr(out), C.byref(n)), "ExportInstances")
+        return out
+
+    def ExportCamera(self):
+        out = np.zeros(88, np.uint8)
+        check(self.ctx._h, lib().nx_scene_export_camera(self._h, _ptr(out)), "ExportCamera")
+        return out
+
+    def ExportLights(self):
+        n = C.c_uint32(0)
+        check(self.ctx._h, lib().nx_scene_export_lights(self._h, None, C.byref(n)), "ExportLights")
+        out = np.zeros((max(n.value, 1), 52), np.uint8)
+        check(self.ctx._h, lib().nx_scene_export_lights(self._h, _ptr(out), C.byref(n)), "ExportLights")
+        return out[:n.value]
+
+    # traversal parity hooks
+    def TraceClosest(self, rays, timed=False):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        ms = C.c_float(0)
+        check(self.ctx._h, lib().nx_trace_closest(self._h, _ptr(rays), C.c_uint32(rays.shape[0]), _ptr(hits), C.byref(ms) if timed else None), "TraceClosest")
+        return (hits, ms.value) if timed else hits
+
+    def TraceAny(self, rays):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        occ = np.empty(rays.shape[0], np.uint8)
+        check(self.ctx._h, lib().nx_trace_any(self._h, _ptr(rays), C.c_uint32(rays.shape[0]), _ptr(occ), None), "TraceAny")
+        return occ
+
+    def TraceClosestDevice(self, rays_dev, n, hits_dev):
+        ms = C.c_float(0)
+        check(self.ctx._h, lib().nx_trace_closest_device(self._h, C.c_void_p(rays_dev), C.c_uint32(n), C.c_void_p(hits_dev), C.byref(ms)), "TraceClosestDevice")
+        return ms.value
+
+    def TraceStats(self, rays_dev, n, hits_dev):
+        out = (C.c_uint64 * 4)()
+        check(self.ctx._h, lib().nx_trace_stats(self._h, C.c_void_p(rays_dev), C.c_uint32(n), C.c_void_p(hits_dev), out), "TraceStats")
+        return {"nodes": out[0], "tris": out[1], "insts": out[2], "rays": out[3]}
+
+
+def make_rays(origins, directions, tmax=1.0e30):
+    rays = np.zeros(len(origins), RAY_DTYPE)
+    rays["origin"] = origins
+    rays["direction"] = directions
+    rays["tmax"] = tmax
+    return rays
+
+
+# ----------------------------------------------------------------------------------------------- renderer ----
+class PathTracer:
+    """PathTracer (src/Renderer/PathTracer.h:9-66): owns the wavefront queues and the accumulation buffer."""
+
+    def __init__(self, ctx, resolution):
+        self.ctx = ctx
+        self.resolution = (int(resolution[0]), int(resolution[1]))
+        self._h = C.c_void_p()
+        check(ctx._h, lib().nx_renderer_create(ctx._h, C.c_uint32(self.resolution[0]), C.c_uint32(self.resolution[1]), C.byref(self._h)), "PathTracer")
+        self._frame = 0
+
+    def close(self):
+        if self._h:
+            lib().nx_renderer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def ResetFrameNumber(self):
+        check(self.ctx._h, lib().nx_renderer_reset_accumulation(self._h), "ResetFrameNumber")
+        self._frame = 0
+
+    def OnResize(self, resolution):
+        self.resolution = (int(resolution[0]), int(resolution[1]))
+        check(self.ctx._h, lib().nx_renderer_resize(self._h, C.c_uint32(self.resolution[0]), C.c_uint32(self.resolution[1])), "OnResize")
+        self._frame = 0
+
+    def Render(self, scene, frames=1, firstFrame=None):
+        """PathTracer::Render (PathTracer.cpp:166-200): one call renders `frames` consecutive frame numbers (1 spp each)."""
+        first = self._frame + 1 if firstFrame is None else int(firstFrame)
+        check(self.ctx._h, lib().nx_renderer_render(self._h, scene._h, C.c_uint32(first), C.c_uint32(frames)), "Render")
+        self._frame = first + frames - 1
+
+    def GetFrameNumber(self):
+        return lib().nx_renderer_frame_count(self._h)
+
+    def Stats(self):
+        st = FrameStats()
+        check(self.ctx._h, lib().nx_renderer_stats(self._h, C.byref(st)), "Stats")
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+    def ReadAccumulation(self, out=None):
+        """Linear radiance mean, (h, w, 3) float32, row 0 = bottom row (the reference's pixel order)."""
+        w, h = self.resolution
+        if out is None:
+            out = np.empty((h, w, 3), np.float32)
+        check(self.ctx._h, lib().nx_renderer_read_accum(self._h, _ptr(out)), "ReadAccumulation")
+        return out
+
+    def AccumulationDevice(self):
+        p, n = C.c_void_p(), C.c_uint32(0)
+        check(self.ctx._h, lib().nx_renderer_accum_device(self._h, C.byref(p), C.byref(n)), "AccumulationDevice")
+        return p.value, n.value
+
+    def SetAccumulatedFrames(self, frames):
+        check(self.ctx._h, lib().nx_renderer_set_accum_frames(self._h, C.c_uint32(frames)), "SetAccumulatedFrames")
+
+    def ReadRGBA8(self, scene):
+        w, h = self.resolution
+        out = np.empty((h, w), np.uint32)
+        check(self.ctx._h, lib().nx_renderer_read_rgba8(self._h, scene._h, _ptr(out)), "ReadRGBA8")
+        return out
+
+
+def write_pfm(path, rgb):
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    rc = lib().nx_write_pfm(str(path).encode(), _ptr(rgb), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]))
+    if rc < 0:
+        raise NexusError(f"nx_write_pfm({path}) failed")
+
+
+def write_exr(path, rgb):
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    rc = lib().nx_write_exr(str(path).encode(), _ptr(rgb), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]))
+    if rc < 0:
+        raise NexusError(f"nx_write_exr({path}) failed")

@@ -1,0 +1,796 @@
+// H-PLOC BVH2 builder + BVH2 -> CWBVH8 collapse/compression for sm_100a.
+//
+// Replaces NXB::BuildBVH2 / BuildBVH8 (vendor/NexusBVH/NexusBVH/src/BVHBuilder.cpp:115-267) and its kernels
+// (src/Cuda/Setup.cu, BinaryBuilder.cu, WideConverter.cu, Eval.cu).  The produced trees are the reference's trees bit for
+// bit (same Morton keys, same PLOC merges, same collapse decisions, same quantisation); only the node numbering, which
+// in the reference depends on the GPU schedule, is ours (BVH8 nodes come out level by level).
+//
+// Design deltas against the reference, all HBM/latency motivated:
+//   * primitives are staged through shared memory with 16-byte loads instead of nine 4-byte loads at a 36-byte stride;
+//   * scene bounds use order-preserving integer atomics (one RED per block and component) instead of CAS loops per warp;
+//   * PLOC nearest-neighbour search sends each candidate once (shfl_up) instead of a three-shuffle round trip;
+//   * the collapse is a persistent cooperative kernel that walks the BVH8 level by level: leaf-ness and the primitive id
+//     of a BVH2 child are read off its index (< n), allocation is one atomic per warp and counter, and there is no
+//     spin-waiting work queue.
+#include "nx_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr uint32_t kSearchRadius = 8;     // H-PLOC search radius (BinaryBuilder.cu:9)
+constexpr uint32_t kMergeThreshold = 16;  // clusters kept per LBVH range (BinaryBuilder.cu:10)
+constexpr int kSetupBlock = 256;
+constexpr int kPlocBlock = 128;
+constexpr int kCollapseBlock = 256;
+
+struct SceneKeys { uint32_t lo[3], hi[3]; };  // order-preserving uint encoding of the scene AABB
+
+// ------------------------------------------------------------------------------------------ leaf bounds ----
+// One leaf node per primitive: {bounds, left = INVALID, right = i}; scene bounds by min/max reduction.
+template <int FLOATS>  // 9 = triangle, 6 = AABB
+__global__ void __launch_bounds__(kSetupBlock) leaf_bounds_kernel(const float* __restrict__ prims, uint32_t n, float4* __restrict__ nodes, SceneKeys* scene)
+{
+    __shared__ float tile[kSetupBlock * FLOATS];
+    __shared__ float red[6][kSetupBlock / 32];
+    Box acc; acc.lo = v3(3.402823466e38f, 3.402823466e38f, 3.402823466e38f); acc.hi = v3(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
+
+    const uint32_t tiles = (n + kSetupBlock - 1) / kSetupBlock;
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x)
+    {
+        const uint32_t first = t * kSetupBlock;
+        const uint32_t count = min((uint32_t)kSetupBlock, n - first);
+        const size_t base = (size_t)first * FLOATS;             // kSetupBlock*FLOATS*4 is a multiple of 16 bytes
+        const uint32_t floats = count * FLOATS;
+        const uint32_t vec = ((reinterpret_cast<uintptr_t>(prims) & 15u) == 0) ? floats / 4 : 0;   // 16-byte path needs an aligned base
+        const float4* src4 = reinterpret_cast<const float4*>(prims + base);
+        float4* dst4 = reinterpret_cast<float4*>(tile);
+        for (uint32_t i = threadIdx.x; i < vec; i += kSetupBlock) dst4[i] = __ldg(src4 + i);
+        for (uint32_t i = vec * 4 + threadIdx.x; i < floats; i += kSetupBlock) tile[i] = __ldg(prims + base + i);
+        __syncthreads();
+        if (threadIdx.x < count)
+        {
+            const float* p = tile + threadIdx.x * FLOATS;
+            Box b;
+            if (FLOATS == 9) {
+                V3 a = v3(p[0], p[1], p[2]), c = v3(p[3], p[4], p[5]), d = v3(p[6], p[7], p[8]);
+                b.lo = vmin3(a, vmin3(c, d)); b.hi = vmax3(a, vmax3(c, d));
+            } else {
+                b.lo = v3(p[0], p[1], p[2]); b.hi = v3(p[3], p[4], p[5]);
+            }
+            const uint32_t i = first + threadIdx.x;
+            nodes[2 * (size_t)i] = make_float4(b.lo.x, b.lo.y, b.lo.z, b.hi.x);
+            nodes[2 * (size_t)i + 1] = make_float4(b.hi.y, b.hi.z, __uint_as_float(NX_INVALID), __uint_as_float(i));
+            box_grow(acc, b);
+        }
+        __syncthreads();
+    }
+    float v[6] = {acc.lo.x, acc.lo.y, acc.lo.z, acc.hi.x, acc.hi.y, acc.hi.z};
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { float w = __shfl_xor_sync(NX_FULL, v[k], o); v[k] = k < 3 ? fminf(v[k], w) : fmaxf(v[k], w); }
+        if (lane_id() == 0) red[k][threadIdx.x / 32] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6)
+    {
+        const int k = threadIdx.x;
+        float r = red[k][0];
+        for (int w = 1; w < kSetupBlock / 32; w++) r = k < 3 ? fminf(r, red[k][w]) : fmaxf(r, red[k][w]);
+        if (k < 3) atomicMin(&scene->lo[k], f2ord(r)); else atomicMax(&scene->hi[k - 3], f2ord(r));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ Morton keys ----
+// Bit-identical to the reference's fast-math Morton normalisation: add/mul/sub/div.approx with flush-to-zero, truncating
+// conversion (checked against the PTX nvcc emits for Setup.cu:43-59 with --use_fast_math).
+__device__ __forceinline__ uint32_t morton_axis(float lo, float hi, float smin, float smax, float scale)
+{
+    float c, num, den, q, m; uint32_t r;
+    asm("add.ftz.f32 %0, %1, %2;" : "=f"(c) : "f"(lo), "f"(hi));
+    asm("mul.ftz.f32 %0, %1, 0f3F000000;" : "=f"(c) : "f"(c));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(num) : "f"(c), "f"(smin));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(den) : "f"(smax), "f"(smin));
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(num), "f"(den));
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(m) : "f"(q), "f"(scale));
+    asm("cvt.rzi.ftz.u32.f32 %0, %1;" : "=r"(r) : "f"(m));
+    return r;
+}
+__device__ __forceinline__ uint32_t spread10(uint32_t x)
+{
+    x = (x | (x << 16)) & 0x030000ffu; x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;  x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__device__ __forceinline__ uint64_t spread21(uint64_t x)
+{
+    x = (x | (x << 32)) & 0x001f00000000ffffull; x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSetupBlock) morton_kernel(const float4* __restrict__ nodes, uint32_t n, const SceneKeys* __restrict__ scene,
+                                                             KeyT* __restrict__ keys, uint32_t* __restrict__ order, float* __restrict__ sceneOut)
+{
+    const float sx0 = ord2f(scene->lo[0]), sy0 = ord2f(scene->lo[1]), sz0 = ord2f(scene->lo[2]);
+    const float sx1 = ord2f(scene->hi[0]), sy1 = ord2f(scene->hi[1]), sz1 = ord2f(scene->hi[2]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sceneOut[0] = sx0; sceneOut[1] = sy0; sceneOut[2] = sz0; sceneOut[3] = sx1; sceneOut[4] = sy1; sceneOut[5] = sz1; }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 a = __ldg(nodes + 2 * (size_t)i), b = __ldg(nodes + 2 * (size_t)i + 1);
+        if (sizeof(KeyT) == 4) {
+            const float s = 1023.0f;
+            uint32_t x = morton_axis(a.x, a.w, sx0, sx1, s), y = morton_axis(a.y, b.x, sy0, sy1, s), z = morton_axis(a.z, b.y, sz0, sz1, s);
+            keys[i] = (KeyT)(spread10(x) | (spread10(y) << 1) | (spread10(z) << 2));
+        } else {
+            const float s = 2097151.0f;
+            uint32_t x = morton_axis(a.x, a.w, sx0, sx1, s), y = morton_axis(a.y, b.x, sy0, sy1, s), z = morton_axis(a.z, b.y, sz0, sz1, s);
+            keys[i] = (KeyT)(spread21(x) | (spread21(y) << 1) | (spread21(z) << 2));
+        }
+        order[i] = i;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- H-PLOC ----
+struct PlocArgs {
+    float4* nodes;        // BVH2 nodes, 2 x float4 each: (lo.xyz, hi.x) (hi.y, hi.z, left, right)
+    uint32_t* cluster;    // cluster ids, sorted-primitive order; rewritten in place as ranges merge
+    uint32_t* parent;     // LBVH "other boundary" slots, 0xffffffff until the first child arrives
+    uint32_t* allocated;  // number of BVH2 nodes handed out so far (starts at n)
+    uint32_t n;
+};
+
+// Highest differing bit between neighbouring keys, with the position as tie-break (Apetrei 2014; the 32-bit flavour
+// concatenates key and position, the 64-bit one falls back to the position only on equal keys - BinaryBuilder.cu:16-28).
+__device__ __forceinline__ uint64_t key_delta(const uint32_t* keys, uint32_t a, uint32_t b)
+{
+    return (((uint64_t)__ldg(keys + a) << 32) | a) ^ (((uint64_t)__ldg(keys + b) << 32) | b);
+}
+__device__ __forceinline__ uint64_t key_delta(const uint64_t* keys, uint32_t a, uint32_t b)
+{
+    const uint64_t d = __ldg(keys + a) ^ __ldg(keys + b);
+    return d ? d : (uint64_t)(a ^ b);
+}
+
+__device__ __forceinline__ Box shfl_box(const Box& b, uint32_t src)
+{
+    Box r;
+    r.lo.x = __shfl_sync(NX_FULL, b.lo.x, src); r.lo.y = __shfl_sync(NX_FULL, b.lo.y, src); r.lo.z = __shfl_sync(NX_FULL, b.lo.z, src);
+    r.hi.x = __shfl_sync(NX_FULL, b.hi.x, src); r.hi.y = __shfl_sync(NX_FULL, b.hi.y, src); r.hi.z = __shfl_sync(NX_FULL, b.hi.z, src);
+    return r;
+}
+
+// Warp-cooperative PLOC over the clusters of one LBVH range [lo, hiEnd) split at mid.  Every lane holds at most one cluster.
+__device__ void ploc_merge_range(const PlocArgs& a, uint32_t lo, uint32_t mid, uint32_t hiEnd, bool isRoot)
+{
+    const uint32_t lane = lane_id();
+    uint32_t id = NX_INVALID;
+
+    // gather: up to kMergeThreshold ids from the left range into lanes [0..), then from the right range behind them
+    const uint32_t takeL = min(mid - lo, kMergeThreshold);
+    if (lane < takeL) id = __ldcg(a.cluster + lo + lane);
+    const uint32_t numL = __popc(__ballot_sync(NX_FULL, lane < takeL && id != NX_INVALID));
+    const uint32_t takeR = min(hiEnd - mid, kMergeThreshold);
+    const uint32_t offR = lane - numL;  // wraps for lanes below numL
+    if (offR < takeR) id = __ldcg(a.cluster + mid + offR);
+    const uint32_t numR = __popc(__ballot_sync(NX_FULL, offR < takeR && id != NX_INVALID));
+    const uint32_t loaded = numL + numR;
+    uint32_t num = loaded;
+
+    Box box; box.lo = v3(0.f, 0.f, 0.f); box.hi = v3(0.f, 0.f, 0.f);
+    if (lane < num) {
+        const float4 p = ld_cg4(a.nodes + 2 * (size_t)id), q = ld_cg4(a.nodes + 2 * (size_t)id + 1);
+        box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y);
+    }
+
+    const uint32_t keep = isRoot ? 1u : kMergeThreshold;
+    while (num > keep)
+    {
+        // nearest neighbour within +-kSearchRadius by merged half-area, compared on the float bits; ties keep the
+        // candidate seen first (+1, -1, +2, -2, ...)
+        uint32_t bestArea = NX_INVALID, bestLane = NX_INVALID;
+#pragma unroll
+        for (uint32_t r = 1; r <= kSearchRadius; r++)
+        {
+            Box other;
+            other.lo.x = __shfl_down_sync(NX_FULL, box.lo.x, r); other.lo.y = __shfl_down_sync(NX_FULL, box.lo.y, r); other.lo.z = __shfl_down_sync(NX_FULL, box.lo.z, r);
+            other.hi.x = __shfl_down_sync(NX_FULL, box.hi.x, r); other.hi.y = __shfl_down_sync(NX_FULL, box.hi.y, r); other.hi.z = __shfl_down_sync(NX_FULL, box.hi.z, r);
+            uint32_t fwd = NX_INVALID;
+            if (lane + r < num) {
+                box_grow(other, box);
+                fwd = __float_as_uint(half_area_ref(other));
+                if (fwd < bestArea) { bestArea = fwd; bestLane = lane + r; }
+            }
+            const uint32_t bwd = __shfl_up_sync(NX_FULL, fwd, r);   // the same pair seen from the other side
+            if (lane >= r && bwd < bestArea) { bestArea = bwd; bestLane = lane - r; }
+        }
+
+        const bool alive = lane < num;
+        const uint32_t theirs = __shfl_sync(NX_FULL, bestLane, bestLane);
+        const bool mutual = alive && theirs == lane;
+        const bool owner = mutual && lane < bestLane;          // the lower lane of a mutual pair creates the node
+        const uint32_t ownerMask = __ballot_sync(NX_FULL, owner);
+        const uint32_t created = __popc(ownerMask);
+        uint32_t base = 0;
+        if (lane == 0 && created) base = atomicAdd(a.allocated, created);
+        base = __shfl_sync(NX_FULL, base, 0);
+
+        const uint32_t partnerId = __shfl_sync(NX_FULL, id, bestLane);
+        const Box partnerBox = shfl_box(box, bestLane);
+        if (owner) {
+            box_grow(box, partnerBox);
+            const uint32_t node = base + __popc(ownerMask & ((1u << lane) - 1u));
+            st_cg4(a.nodes + 2 * (size_t)node, make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x));
+            st_cg4(a.nodes + 2 * (size_t)node + 1, make_float4(box.hi.y, box.hi.z, __uint_as_float(id), __uint_as_float(partnerId)));
+            id = node;
+        }
+        // compact: survivors are the pair owners and every cluster without a mutual partner, order preserved
+        const uint32_t keepMask = __ballot_sync(NX_FULL, alive && (owner || !mutual));
+        const uint32_t src = __fns(keepMask, 0, lane + 1);
+        const uint32_t movedId = __shfl_sync(NX_FULL, id, src);
+        box = shfl_box(box, src);
+        num -= created;
+        id = lane < num ? movedId : NX_INVALID;
+    }
+
+    if (lane < loaded) __stcg(a.cluster + lo + lane, id);
+    __threadfence();
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kPlocBlock) hploc_kernel(PlocArgs a, const KeyT* __restrict__ keys)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lo = i, hi = i, mid = 0;
+    bool climbing = i < a.n;
+
+    while (__ballot_sync(NX_FULL, climbing))
+    {
+        if (climbing)
+        {
+            // Apetrei's bottom-up step: the parent is on the side with the smaller key delta
+            const bool parentAtHi = lo == 0 || (hi != a.n - 1 && key_delta(keys, hi, hi + 1) < key_delta(keys, lo - 1, lo));
+            uint32_t other;
+            if (parentAtHi) { other = atomicExch(a.parent + hi, lo); if (other != NX_INVALID) { mid = hi + 1; hi = other; } }
+            else            { other = atomicExch(a.parent + lo - 1, hi); if (other != NX_INVALID) { mid = lo; lo = other; } }
+            if (other == NX_INVALID) climbing = false;   // first to arrive: the sibling's thread continues
+            else __threadfence();                        // second to arrive: acquire the sibling's cluster list
+        }
+        const uint32_t size = hi - lo + 1;
+        const bool isRoot = climbing && size == a.n;
+        uint32_t todo = __ballot_sync(NX_FULL, (climbing && size > kMergeThreshold) || isRoot);
+        while (todo)
+        {
+            const uint32_t src = __ffs(todo) - 1;
+            ploc_merge_range(a, __shfl_sync(NX_FULL, lo, src), __shfl_sync(NX_FULL, mid, src), __shfl_sync(NX_FULL, hi, src) + 1,
+                             __shfl_sync(NX_FULL, (int)isRoot, src) != 0);
+            todo &= todo - 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- collapse ----
+struct CollapseArgs {
+    const float4* n2;      // BVH2 nodes
+    float4* n8;            // CWBVH8 nodes, 5 x float4 each
+    uint32_t* primIdx;     // leaf slot -> primitive id
+    uint32_t* bvh2Of;      // work map: BVH8 node index -> BVH2 node it collapses
+    uint32_t* counters;    // [0] nodes allocated, [1] leaf slots allocated
+    uint32_t n;
+};
+
+__device__ __forceinline__ Box load_box2(const float4* n2, uint32_t i)
+{
+    const float4 p = __ldg(n2 + 2 * (size_t)i), q = __ldg(n2 + 2 * (size_t)i + 1);
+    Box b; b.lo = v3(p.x, p.y, p.z); b.hi = v3(p.w, q.x, q.y);
+    return b;
+}
+__device__ __forceinline__ uint32_t ceil_log2_biased(float x)   // biased exponent of the smallest power of two >= x
+{
+    const uint32_t u = __float_as_uint(x);
+    return ((u >> 23) & 0xffu) + ((u & 0x7fffffu) ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t quant(float c, float p, float inv, bool up)
+{
+    float d, m, r; uint32_t q;
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(c), "f"(p));
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(m) : "f"(d), "f"(inv));
+    if (up) asm("cvt.rpi.ftz.f32.f32 %0, %1;" : "=f"(r) : "f"(m)); else asm("cvt.rmi.ftz.f32.f32 %0, %1;" : "=f"(r) : "f"(m));
+    asm("cvt.rzi.ftz.u32.f32 %0, %1;" : "=r"(q) : "f"(r));
+    return q & 0xffu;
+}
+
+// Collapses BVH2 node `root2` into BVH8 node `self`.
+__device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root2)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t n = a.n;
+    uint32_t child[8];
+    uint32_t innerMask = 0, count = 0;
+    const bool live = root2 != NX_INVALID;
+    Box parent; parent.lo = v3(0, 0, 0); parent.hi = v3(0, 0, 0);
+    uint32_t slotOf = 0;   // 4 bits per slot: child index or 0xf
+
+    if (live)
+    {
+        const float4 p = __ldg(a.n2 + 2 * (size_t)root2), q = __ldg(a.n2 + 2 * (size_t)root2 + 1);
+        parent.lo = v3(p.x, p.y, p.z); parent.hi = v3(p.w, q.x, q.y);
+        uint32_t l = __float_as_uint(q.z), r = __float_as_uint(q.w);
+        int open = 0;
+        // Open inner children (highest array position first) until eight children or only leaves remain.  Of each opened
+        // pair the smaller-area child takes the vacated position, the other is appended (WideConverter.cu:291-324).
+        while (true)
+        {
+            const float al = half_area_ref(load_box2(a.n2, l)), ar = half_area_ref(load_box2(a.n2, r));
+            const uint32_t first = al < ar ? l : r, second = al < ar ? r : l;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {   // register-resident "child[open] = first; child[count] = second"
+                if (k == open) child[k] = first;
+            }
+            if (first >= n) innerMask |= 1u << open;
+            count++;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k == (int)count) child[k] = second;
+            if (second >= n) innerMask |= 1u << count;
+            count++;
+            open = 31 - __clz(innerMask);
+            if (open < 0 || count == 8) break;
+            innerMask &= ~(1u << open);
+            count--;
+            uint32_t o = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k == open) o = child[k];
+            const float4 oq = __ldg(a.n2 + 2 * (size_t)o + 1);
+            l = __float_as_uint(oq.z); r = __float_as_uint(oq.w);
+        }
+
+        // Greedy octant-slot assignment (Ylitie et al. 2017 §4.2 as WideConverter.cu:106-153 implements it): children in
+        // array order, each takes the free slot maximising (parentCentroid - childCentroid) . signs(slot); first max wins.
+        const V3 pc = parent.lo + parent.hi;
+        slotOf = 0xffffffffu;
+        uint32_t freeSlots = 0xffu;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+        {
+            if (c < (int)count)
+            {
+                const Box cb = load_box2(a.n2, child[c]);
+                const V3 off = pc - (cb.hi + cb.lo);
+                float best = -3.402823466e38f; uint32_t bestSlot = 0xf;
+#pragma unroll
+                for (uint32_t s = 0; s < 8; s++)
+                {
+                    const float cost = __fadd_rn(__fadd_rn((s & 4) ? -off.x : off.x, (s & 2) ? -off.y : off.y), (s & 1) ? -off.z : off.z);
+                    if (((freeSlots >> s) & 1u) && cost > best) { best = cost; bestSlot = s; }
+                }
+                freeSlots &= ~(1u << bestSlot);
+                slotOf = (slotOf & ~(0xfu << (4 * bestSlot))) | ((uint32_t)c << (4 * bestSlot));
+            }
+        }
+    }
+
+    // slot-ordered masks
+    uint32_t slotInner = 0, slotLeaf = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 8; s++) {
+        const uint32_t c = (slotOf >> (4 * s)) & 0xfu;
+        if (live && c != 0xfu) { if ((innerMask >> c) & 1u) slotInner |= 1u << s; else slotLeaf |= 1u << s; }
+    }
+    const uint32_t nInner = __popc(slotInner), nLeaf = __popc(slotLeaf);
+
+    // one atomic per warp and counter: inclusive scan of (inner | leaf << 16)
+    uint32_t packed = nInner | (nLeaf << 16), scan = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NX_FULL, scan, o); if (lane >= (uint32_t)o) scan += t; }
+    const uint32_t total = __shfl_sync(NX_FULL, scan, 31);
+    uint32_t baseNode = 0, baseLeaf = 0;
+    if (lane == 31) {
+        if (total & 0xffffu) baseNode = atomicAdd(a.counters + 0, total & 0xffffu);
+        if (total >> 16) baseLeaf = atomicAdd(a.counters + 1, total >> 16);
+    }
+    baseNode = __shfl_sync(NX_FULL, baseNode, 31) + ((scan - packed) & 0xffffu);
+    baseLeaf = __shfl_sync(NX_FULL, baseLeaf, 31) + ((scan - packed) >> 16);
+    if (!live) return;
+
+    const uint32_t childBase = nInner ? baseNode : 0u, primBase = nLeaf ? baseLeaf : 0u;
+
+    // quantisation frame: origin = parent min, per-axis power-of-two cell >= extent / 255 (WideConverter.cu:160-171)
+    float ext[3];
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext[0]) : "f"(parent.hi.x), "f"(parent.lo.x));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext[1]) : "f"(parent.hi.y), "f"(parent.lo.y));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext[2]) : "f"(parent.hi.z), "f"(parent.lo.z));
+    uint32_t e[3]; float inv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float s; asm("mul.ftz.f32 %0, %1, 0f3B808081;" : "=f"(s) : "f"(ext[k]));   // * (1.0f / 255.0f)
+        e[k] = ceil_log2_biased(s) & 0xffu;
+        inv[k] = __uint_as_float((254u - e[k]) << 23);
+    }
+
+    uint32_t meta[2] = {0, 0}, qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+    for (uint32_t s = 0; s < 8; s++)
+    {
+        const uint32_t c = (slotOf >> (4 * s)) & 0xfu;
+        if (c == 0xfu) continue;
+        uint32_t id = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k == (int)c) id = child[k];
+        uint32_t m;
+        if ((slotInner >> s) & 1u) {
+            m = 0x20u | (24u + s);
+            a.bvh2Of[childBase + bits_below(slotInner, s)] = id;
+        } else {
+            const uint32_t off = bits_below(slotLeaf, s);
+            m = 0x20u | off;
+            a.primIdx[primBase + off] = id;   // a BVH2 leaf's index is its primitive id
+        }
+        const Box cb = load_box2(a.n2, id);
+        const uint32_t w = s >> 2, sh = (s & 3u) * 8u;
+        meta[w] |= m << sh;
+        qlo[0][w] |= quant(cb.lo.x, parent.lo.x, inv[0], false) << sh;
+        qlo[1][w] |= quant(cb.lo.y, parent.lo.y, inv[1], false) << sh;
+        qlo[2][w] |= quant(cb.lo.z, parent.lo.z, inv[2], false) << sh;
+        qhi[0][w] |= quant(cb.hi.x, parent.lo.x, inv[0], true) << sh;
+        qhi[1][w] |= quant(cb.hi.y, parent.lo.y, inv[1], true) << sh;
+        qhi[2][w] |= quant(cb.hi.z, parent.lo.z, inv[2], true) << sh;
+    }
+    float4* out = a.n8 + 5 * (size_t)self;
+    out[0] = make_float4(parent.lo.x, parent.lo.y, parent.lo.z, __uint_as_float(e[0] | (e[1] << 8) | (e[2] << 16) | (slotInner << 24)));
+    out[1] = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float(meta[0]), __uint_as_float(meta[1]));
+    out[2] = make_float4(__uint_as_float(qlo[0][0]), __uint_as_float(qlo[0][1]), __uint_as_float(qlo[1][0]), __uint_as_float(qlo[1][1]));
+    out[3] = make_float4(__uint_as_float(qlo[2][0]), __uint_as_float(qlo[2][1]), __uint_as_float(qhi[0][0]), __uint_as_float(qhi[0][1]));
+    out[4] = make_float4(__uint_as_float(qhi[1][0]), __uint_as_float(qhi[1][1]), __uint_as_float(qhi[2][0]), __uint_as_float(qhi[2][1]));
+}
+
+// Persistent cooperative kernel: BVH8 level L is exactly the node index range allocated while level L-1 was processed.
+__global__ void __launch_bounds__(kCollapseBlock) collapse_kernel(CollapseArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    uint32_t begin = 0, end = 1;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    while (begin < end)
+    {
+        const uint32_t span = end - begin;
+        const uint32_t rounds = (span + stride - 1) / stride;
+        for (uint32_t r = 0; r < rounds; r++)
+        {
+            const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+            const uint32_t node = begin + k;
+            collapse_one(a, node, k < span ? __ldcg(a.bvh2Of + node) : NX_INVALID);   // whole warps call in, idle lanes pass INVALID
+        }
+        __threadfence();
+        grid.sync();
+        begin = end;
+        end = __ldcg(a.counters);
+    }
+}
+
+// Single-primitive BVH: one node with one leaf child in slot 0 (WideConverter.cu:209-222).
+__global__ void single_leaf_kernel(CollapseArgs a)
+{
+    const float4 p = a.n2[0], q = a.n2[1];
+    float ext[3];
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext[0]) : "f"(p.w), "f"(p.x));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext[1]) : "f"(q.x), "f"(p.y));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext[2]) : "f"(q.y), "f"(p.z));
+    uint32_t e[3]; float inv[3];
+    for (int k = 0; k < 3; k++) { float s; asm("mul.ftz.f32 %0, %1, 0f3B808081;" : "=f"(s) : "f"(ext[k])); e[k] = ceil_log2_biased(s) & 0xffu; inv[k] = __uint_as_float((254u - e[k]) << 23); }
+    a.n8[0] = make_float4(p.x, p.y, p.z, __uint_as_float(e[0] | (e[1] << 8) | (e[2] << 16)));
+    a.n8[1] = make_float4(__uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0x20u), __uint_as_float(0u));
+    a.n8[2] = make_float4(__uint_as_float(quant(p.x, p.x, inv[0], false)), 0.f, __uint_as_float(quant(p.y, p.y, inv[1], false)), 0.f);
+    a.n8[3] = make_float4(__uint_as_float(quant(p.z, p.z, inv[2], false)), 0.f, __uint_as_float(quant(p.w, p.x, inv[0], true)), 0.f);
+    a.n8[4] = make_float4(__uint_as_float(quant(q.x, p.y, inv[1], true)), 0.f, __uint_as_float(quant(q.y, p.z, inv[2], true)), 0.f);
+    a.primIdx[0] = 0;
+    a.counters[0] = 1; a.counters[1] = 1;
+}
+
+// -------------------------------------------------------------------------------------------------- SAH ----
+// Cost metrics as Eval.cu:12-80 defines them (BVH2: 3 per inner, 2 per leaf; BVH8: 2 per inner child, 3 per leaf child).
+__global__ void bvh2_cost_kernel(const float4* __restrict__ n2, uint32_t nodeCount, Box scene, double* out)
+{
+    const float rootArea = half_area_ref(scene);
+    double v = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nodeCount; i += gridDim.x * blockDim.x) {
+        const float4 q = __ldg(n2 + 2 * (size_t)i + 1);
+        v += (double)((__float_as_uint(q.z) != NX_INVALID ? 3.0f : 2.0f) * __fdividef(half_area_ref(load_box2(n2, i)), rootArea));
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NX_FULL, v, o);
+    if (lane_id() == 0) atomicAdd(out, v);
+}
+__global__ void bvh8_cost_kernel(const float4* __restrict__ n8, uint32_t nodeCount, Box scene, double* out)
+{
+    const float rootArea = half_area_ref(scene);
+    double v = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nodeCount; i += gridDim.x * blockDim.x) {
+        const float4 h0 = __ldg(n8 + 5 * (size_t)i), h1 = __ldg(n8 + 5 * (size_t)i + 1), h2 = __ldg(n8 + 5 * (size_t)i + 2),
+                     h3 = __ldg(n8 + 5 * (size_t)i + 3), h4 = __ldg(n8 + 5 * (size_t)i + 4);
+        const uint32_t eim = __float_as_uint(h0.w);
+        const float ex = __uint_as_float((eim & 0xffu) << 23), ey = __uint_as_float(((eim >> 8) & 0xffu) << 23), ez = __uint_as_float(((eim >> 16) & 0xffu) << 23);
+        const uint32_t meta[2] = {__float_as_uint(h1.z), __float_as_uint(h1.w)};
+        const uint32_t lox[2] = {__float_as_uint(h2.x), __float_as_uint(h2.y)}, loy[2] = {__float_as_uint(h2.z), __float_as_uint(h2.w)};
+        const uint32_t loz[2] = {__float_as_uint(h3.x), __float_as_uint(h3.y)}, hix[2] = {__float_as_uint(h3.z), __float_as_uint(h3.w)};
+        const uint32_t hiy[2] = {__float_as_uint(h4.x), __float_as_uint(h4.y)}, hiz[2] = {__float_as_uint(h4.z), __float_as_uint(h4.w)};
+        for (uint32_t s = 0; s < 8; s++) {
+            const uint32_t w = s >> 2, sh = (s & 3u) * 8u;
+            const uint32_t m = (meta[w] >> sh) & 0xffu;
+            if (!m) continue;
+            Box b;
+            b.lo = v3(__fmaf_rn(ex, (float)((lox[w] >> sh) & 0xffu), h0.x), __fmaf_rn(ey, (float)((loy[w] >> sh) & 0xffu), h0.y), __fmaf_rn(ez, (float)((loz[w] >> sh) & 0xffu), h0.z));
+            b.hi = v3(__fmaf_rn(ex, (float)((hix[w] >> sh) & 0xffu), h0.x), __fmaf_rn(ey, (float)((hiy[w] >> sh) & 0xffu), h0.y), __fmaf_rn(ez, (float)((hiz[w] >> sh) & 0xffu), h0.z));
+            v += (double)(((m & 0x1fu) >= 24u ? 2.0f : 3.0f) * __fdividef(half_area_ref(b), rootArea));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NX_FULL, v, o);
+    if (lane_id() == 0) atomicAdd(out, v);
+}
+
+// ------------------------------------------------------------------------------------------ host driver ----
+struct StageTimer {
+    cudaStream_t s; bool on; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(cudaStream_t s_, bool on_) : s(s_), on(on_) { if (on) { cudaEventCreate(&a); cudaEventCreate(&b); } }
+    ~StageTimer() { if (on) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+    void begin() { if (on) cudaEventRecord(a, s); }
+    float end() { if (!on) return 0.f; cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+template <typename T> cudaError_t allocAsync(T** p, size_t count, cudaStream_t s) { return cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), s); }
+
+struct Bvh2Result { float4* nodes = nullptr; nx_aabb bounds{}; };
+
+template <typename KeyT>
+int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, float* dSceneOut, nx_build_metrics* metrics, StageTimer& timer,
+                    std::vector<uint64_t>* dbgCodes)
+{
+    cudaStream_t s = ctx->stream;
+    KeyT *keys = nullptr, *keysAlt = nullptr; uint32_t *order = nullptr, *orderAlt = nullptr, *parent = nullptr, *allocated = nullptr;
+    NX_CUDA(ctx, allocAsync(&keys, n, s)); NX_CUDA(ctx, allocAsync(&keysAlt, n, s));
+    NX_CUDA(ctx, allocAsync(&order, n, s)); NX_CUDA(ctx, allocAsync(&orderAlt, n, s));
+    NX_CUDA(ctx, allocAsync(&parent, n, s)); NX_CUDA(ctx, allocAsync(&allocated, 1, s));
+    NX_CUDA(ctx, cudaMemsetAsync(parent, 0xff, sizeof(uint32_t) * (size_t)n, s));
+    NX_CUDA(ctx, cudaMemcpyAsync(allocated, &n, 4, cudaMemcpyHostToDevice, s));
+
+    const int grid = (int)std::min<uint32_t>(div_up(n, kSetupBlock), (uint32_t)ctx->sm_count * 8u);
+    timer.begin();
+    morton_kernel<KeyT><<<grid, kSetupBlock, 0, s>>>(nodes, n, dScene, keys, order, dSceneOut);
+    if (metrics) metrics->morton_ms = timer.end();
+    if (dbgCodes) {
+        dbgCodes->assign(n, 0);
+        std::vector<KeyT> tmp(n);
+        NX_CUDA(ctx, cudaMemcpyAsync(tmp.data(), keys, sizeof(KeyT) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        NX_CUDA(ctx, cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < n; i++) (*dbgCodes)[i] = (uint64_t)tmp[i];
+    }
+
+    // stable LSD radix sort over the same bit window as the reference (Setup.cu:74-78): [2,32) or [1,64)
+    cub::DoubleBuffer<KeyT> kb(keys, keysAlt); cub::DoubleBuffer<uint32_t> vb(order, orderAlt);
+    const int beginBit = sizeof(KeyT) == 4 ? 2 : 1, endBit = sizeof(KeyT) * 8;
+    size_t tempBytes = 0; void* temp = nullptr;
+    NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
+    NX_CUDA(ctx, cudaMallocAsync(&temp, tempBytes ? tempBytes : 1, s));
+    timer.begin();
+    NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(temp, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
+    if (metrics) metrics->sort_ms = timer.end();
+
+    PlocArgs pa; pa.nodes = nodes; pa.cluster = vb.Current(); pa.parent = parent; pa.allocated = allocated; pa.n = n;
+    timer.begin();
+    hploc_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, kb.Current());
+    if (metrics) metrics->bvh2_ms = timer.end();
+    NX_CUDA(ctx, cudaGetLastError());
+
+    cudaFreeAsync(temp, s); cudaFreeAsync(keys, s); cudaFreeAsync(keysAlt, s); cudaFreeAsync(order, s); cudaFreeAsync(orderAlt, s);
+    cudaFreeAsync(parent, s); cudaFreeAsync(allocated, s);
+    return NX_OK;
+}
+
+int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics,
+               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1)
+{
+    if (!dPrims || n == 0) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: empty primitive list");
+    if (n > 0x7fffffffu / 2) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: primitive count %u exceeds 2^30", n);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    if (metrics) std::memset(metrics, 0, sizeof(*metrics));
+    StageTimer timer(s, metrics != nullptr);
+
+    float4* nodes = nullptr; SceneKeys* dScene = nullptr; float* dSceneOut = nullptr;
+    NX_CUDA(ctx, allocAsync(&nodes, 2 * (size_t)(2 * (size_t)n - 1), s));
+    NX_CUDA(ctx, allocAsync(&dScene, 1, s)); NX_CUDA(ctx, allocAsync(&dSceneOut, 6, s));
+    SceneKeys init; for (int k = 0; k < 3; k++) { init.lo[k] = 0xffffffffu; init.hi[k] = 0u; }
+    NX_CUDA(ctx, cudaMemcpyAsync(dScene, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+
+    const int grid = (int)std::min<uint32_t>(div_up(n, kSetupBlock), (uint32_t)ctx->sm_count * 8u);
+    timer.begin();
+    if (primType) leaf_bounds_kernel<9><<<grid, kSetupBlock, 0, s>>>((const float*)dPrims, n, nodes, dScene);
+    else leaf_bounds_kernel<6><<<grid, kSetupBlock, 0, s>>>((const float*)dPrims, n, nodes, dScene);
+    if (metrics) metrics->scene_bounds_ms = timer.end();
+
+    const bool bits64 = forceBits64 >= 0 ? forceBits64 != 0 : !(cfg && cfg->prioritize_speed);
+    int rc = bits64 ? build_bvh2_keys<uint64_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes)
+                    : build_bvh2_keys<uint32_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes);
+    if (rc) return rc;
+    NX_CUDA(ctx, cudaMemcpyAsync(&out->bounds, dSceneOut, 24, cudaMemcpyDeviceToHost, s));
+    if (metrics)
+    {
+        metrics->total_ms = metrics->scene_bounds_ms + metrics->morton_ms + metrics->sort_ms + metrics->bvh2_ms;
+        NX_CUDA(ctx, cudaStreamSynchronize(s));
+        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(&dCost, 1, s));
+        NX_CUDA(ctx, cudaMemsetAsync(dCost, 0, 8, s));
+        Box sb; sb.lo = v3(out->bounds.bmin[0], out->bounds.bmin[1], out->bounds.bmin[2]); sb.hi = v3(out->bounds.bmax[0], out->bounds.bmax[1], out->bounds.bmax[2]);
+        bvh2_cost_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(nodes, 2 * n - 1, sb, dCost);
+        double cost = 0; NX_CUDA(ctx, cudaMemcpyAsync(&cost, dCost, 8, cudaMemcpyDeviceToHost, s));
+        NX_CUDA(ctx, cudaStreamSynchronize(s));
+        metrics->bvh2_cost = (float)cost;
+        cudaFreeAsync(dCost, s);
+    }
+    cudaFreeAsync(dScene, s); cudaFreeAsync(dSceneOut, s);
+    NX_CUDA(ctx, cudaStreamSynchronize(s));
+    NX_CUDA(ctx, cudaGetLastError());
+    out->nodes = nodes;
+    return NX_OK;
+}
+
+int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out)
+{
+    Bvh2Result b2;
+    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2);
+    if (rc) return rc;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    StageTimer timer(s, metrics != nullptr);
+
+    const size_t cap = ((size_t)4 * n - 1 + 6) / 7;   // worst case node count (BVHBuilder.cpp:184-186)
+    CollapseArgs ca; ca.n2 = b2.nodes; ca.n = n;
+    NX_CUDA(ctx, allocAsync(&ca.n8, 5 * cap, s));
+    NX_CUDA(ctx, allocAsync(&ca.primIdx, n, s));
+    NX_CUDA(ctx, allocAsync(&ca.bvh2Of, cap, s));
+    NX_CUDA(ctx, allocAsync(&ca.counters, 2, s));
+    const uint32_t initCounters[2] = {1u, 0u}, root2 = 2 * n - 2;
+    NX_CUDA(ctx, cudaMemcpyAsync(ca.counters, initCounters, 8, cudaMemcpyHostToDevice, s));
+    NX_CUDA(ctx, cudaMemcpyAsync(ca.bvh2Of, &root2, 4, cudaMemcpyHostToDevice, s));
+
+    timer.begin();
+    if (n == 1) single_leaf_kernel<<<1, 1, 0, s>>>(ca);
+    else {
+        int perSm = 0;
+        NX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, collapse_kernel, kCollapseBlock, 0));
+        uint32_t grid = std::min<uint32_t>((uint32_t)(perSm * ctx->sm_count), std::max<uint32_t>(1u, div_up((uint32_t)cap, kCollapseBlock)));
+        void* args[] = {&ca};
+        NX_CUDA(ctx, cudaLaunchCooperativeKernel((void*)collapse_kernel, dim3(grid), dim3(kCollapseBlock), args, 0, s));
+    }
+    if (metrics) { metrics->bvh8_ms = timer.end(); metrics->total_ms += metrics->bvh8_ms; }
+    uint32_t counters[2] = {0, 0};
+    NX_CUDA(ctx, cudaMemcpyAsync(counters, ca.counters, 8, cudaMemcpyDeviceToHost, s));
+    NX_CUDA(ctx, cudaStreamSynchronize(s));
+    NX_CUDA(ctx, cudaGetLastError());
+    if (counters[1] != n) NX_FAIL(ctx, NX_ERR_STATE, "BuildBVH8: collapse placed %u of %u primitives", counters[1], n);
+
+    out->nodes = (nx_bvh8_node*)ca.n8; out->node_count = counters[0]; out->prim_idx = ca.primIdx; out->prim_count = n; out->bounds = b2.bounds;
+    if (metrics)
+    {
+        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(&dCost, 1, s));
+        NX_CUDA(ctx, cudaMemsetAsync(dCost, 0, 8, s));
+        Box sb; sb.lo = v3(b2.bounds.bmin[0], b2.bounds.bmin[1], b2.bounds.bmin[2]); sb.hi = v3(b2.bounds.bmax[0], b2.bounds.bmax[1], b2.bounds.bmax[2]);
+        bvh8_cost_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(ca.n8, counters[0], sb, dCost);
+        double cost = 0; NX_CUDA(ctx, cudaMemcpyAsync(&cost, dCost, 8, cudaMemcpyDeviceToHost, s));
+        NX_CUDA(ctx, cudaStreamSynchronize(s));
+        metrics->bvh8_cost = (float)cost;
+        metrics->avg_children_per_node = (float)(n + counters[0] - 1) / (float)counters[0];
+        cudaFreeAsync(dCost, s);
+    }
+    cudaFreeAsync(b2.nodes, s); cudaFreeAsync(ca.bvh2Of, s); cudaFreeAsync(ca.counters, s);
+    NX_CUDA(ctx, cudaStreamSynchronize(s));
+    return NX_OK;
+}
+
+} // namespace
+
+// Internal entry used by the scene code (same translation-unit-free interface as the public C ABI).
+int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out)
+{
+    nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed;
+    return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out);
+}
+
+extern "C" {
+
+int nx_bvh2_build_tri(nx_ctx* ctx, const nx_triangle* p, uint32_t n, const nx_build_config* cfg, nx_build_metrics* m, nx_bvh2* out)
+{
+    if (!ctx || !out) return NX_ERR_INVALID;
+    Bvh2Result r; int rc = build_bvh2(ctx, p, n, 1, cfg, m, &r); if (rc) return rc;
+    out->nodes = (nx_bvh2_node*)r.nodes; out->node_count = 2 * n - 1; out->prim_count = n; out->bounds = r.bounds; return NX_OK;
+}
+int nx_bvh2_build_aabb(nx_ctx* ctx, const nx_aabb* p, uint32_t n, const nx_build_config* cfg, nx_build_metrics* m, nx_bvh2* out)
+{
+    if (!ctx || !out) return NX_ERR_INVALID;
+    Bvh2Result r; int rc = build_bvh2(ctx, p, n, 0, cfg, m, &r); if (rc) return rc;
+    out->nodes = (nx_bvh2_node*)r.nodes; out->node_count = 2 * n - 1; out->prim_count = n; out->bounds = r.bounds; return NX_OK;
+}
+int nx_bvh8_build_tri(nx_ctx* ctx, const nx_triangle* p, uint32_t n, const nx_build_config* cfg, nx_build_metrics* m, nx_bvh8* out)
+{
+    if (!ctx || !out) return NX_ERR_INVALID;
+    return build_bvh8(ctx, p, n, 1, cfg, m, out);
+}
+int nx_bvh8_build_aabb(nx_ctx* ctx, const nx_aabb* p, uint32_t n, const nx_build_config* cfg, nx_build_metrics* m, nx_bvh8* out)
+{
+    if (!ctx || !out) return NX_ERR_INVALID;
+    return build_bvh8(ctx, p, n, 0, cfg, m, out);
+}
+
+int nx_bvh2_to_host(nx_ctx* ctx, const nx_bvh2* b, nx_bvh2_node* host)
+{
+    if (!ctx || !b || !host) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaMemcpyAsync(host, b->nodes, sizeof(nx_bvh2_node) * (size_t)b->node_count, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NX_OK;
+}
+int nx_bvh8_to_host(nx_ctx* ctx, const nx_bvh8* b, nx_bvh8_node* hostNodes, uint32_t* hostPrim)
+{
+    if (!ctx || !b) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    if (hostNodes) NX_CUDA(ctx, cudaMemcpyAsync(hostNodes, b->nodes, sizeof(nx_bvh8_node) * (size_t)b->node_count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hostPrim) NX_CUDA(ctx, cudaMemcpyAsync(hostPrim, b->prim_idx, 4 * (size_t)b->prim_count, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NX_OK;
+}
+int nx_bvh2_free(nx_ctx* ctx, nx_bvh2* b)
+{
+    if (!ctx || !b) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    if (b->nodes) cudaFreeAsync(b->nodes, ctx->stream);
+    b->nodes = nullptr; b->node_count = 0;
+    return NX_OK;
+}
+int nx_bvh8_free(nx_ctx* ctx, nx_bvh8* b)
+{
+    if (!ctx || !b) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    if (b->nodes) cudaFreeAsync(b->nodes, ctx->stream);
+    if (b->prim_idx) cudaFreeAsync(b->prim_idx, ctx->stream);
+    b->nodes = nullptr; b->prim_idx = nullptr; b->node_count = 0;
+    return NX_OK;
+}
+
+int nx_bvh8_benchmark(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, int warmup, int iters,
+                      nx_build_metrics* metrics, uint32_t* outNodeCount)
+{
+    if (!ctx || !metrics || iters <= 0) return NX_ERR_INVALID;
+    nx_build_metrics agg; std::memset(&agg, 0, sizeof(agg));
+    uint32_t nodes = 0;
+    for (int i = 0; i < warmup + iters; i++)
+    {
+        nx_build_metrics m; nx_bvh8 b;
+        int rc = build_bvh8(ctx, dPrims, n, primType, cfg, &m, &b); if (rc) return rc;
+        nodes = b.node_count;
+        nx_bvh8_free(ctx, &b);
+        if (i >= warmup) {
+            float* d = (float*)&agg; const float* sre = (const float*)&m;
+            for (size_t k = 0; k < sizeof(agg) / sizeof(float); k++) d[k] += sre[k];
+        }
+    }
+    float* d = (float*)&agg;
+    for (size_t k = 0; k < sizeof(agg) / sizeof(float); k++) d[k] /= (float)iters;
+    *metrics = agg;
+    if (outNodeCount) *outNodeCount = nodes;
+    return NX_OK;
+}
+
+int nx_bvh_debug_morton(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int bits64, uint64_t* hostCodes)
+{
+    if (!ctx || !hostCodes) return NX_ERR_INVALID;
+    Bvh2Result r; std::vector<uint64_t> codes;
+    int rc = build_bvh2(ctx, dPrims, n, primType, nullptr, nullptr, &r, &codes, bits64);
+    if (rc) return rc;
+    std::memcpy(hostCodes, codes.data(), 8 * (size_t)n);
+    cudaFreeAsync(r.nodes, ctx->stream);
+    return NX_OK;
+}
+
+} // extern "C"

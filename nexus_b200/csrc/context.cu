@@ -1,0 +1,140 @@
+// Context, device-memory helpers and headless image output of the nexus_b200 C ABI.
+#include "nx_common.cuh"
+#include <fstream>
+
+extern "C" {
+
+int nx_abi_version(void) { return NX_ABI_VERSION; }
+
+int nx_ctx_create(int device, nx_ctx** out)
+{
+    if (!out) return NX_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return NX_ERR_CUDA;   // no silent CPU fallback: there is none
+    if (device < 0 || device >= count) return NX_ERR_INVALID;
+    nx_ctx* ctx = new nx_ctx();
+    ctx->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return NX_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NX_ERR_CUDA; }
+    // keep freed blocks in the stream-ordered pool: builds and per-frame scratch reuse them without going to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    *out = ctx;
+    return NX_OK;
+}
+
+void nx_ctx_destroy(nx_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream_aux);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream_aux);
+    delete ctx;
+}
+
+const char* nx_last_error(const nx_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+int nx_ctx_sm_count(const nx_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+void* nx_ctx_stream(nx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int nx_ctx_synchronize(nx_ctx* ctx)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
+    NX_CUDA(ctx, cudaGetLastError());
+    return NX_OK;
+}
+
+int nx_malloc(nx_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return NX_OK;
+}
+int nx_free(nx_ctx* ctx, void* dev)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    NX_CUDA(ctx, cudaFree(dev));
+    return NX_OK;
+}
+int nx_memcpy_h2d(nx_ctx* ctx, void* dev, const void* host, size_t bytes)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NX_OK;
+}
+int nx_memcpy_d2h(nx_ctx* ctx, void* host, const void* dev, size_t bytes)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NX_OK;
+}
+
+// ------------------------------------------------------------------------------------------ image output ----
+// PFM: "PF\nW H\n-1.0\n" then bottom-to-top rows of little-endian float RGB.
+int nx_write_pfm(const char* path, const float* rgb, uint32_t w, uint32_t h)
+{
+    if (!path || !rgb) return NX_ERR_INVALID;
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return NX_ERR_INVALID;
+    f << "PF\n" << w << " " << h << "\n-1.0\n";
+    for (uint32_t y = 0; y < h; y++) f.write((const char*)(rgb + 3 * (size_t)(h - 1 - y) * w), 12 * (size_t)w);
+    return f ? NX_OK : NX_ERR_INVALID;
+}
+
+// Minimal OpenEXR 2.0 writer: single-part scanline image, three FLOAT channels (B, G, R in file order), no compression.
+int nx_write_exr(const char* path, const float* rgb, uint32_t w, uint32_t h)
+{
+    if (!path || !rgb || !w || !h) return NX_ERR_INVALID;
+    std::vector<uint8_t> hd;
+    auto put = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; hd.insert(hd.end(), b, b + n); };
+    auto str = [&](const char* s) { put(s, std::strlen(s) + 1); };
+    auto i32 = [&](int32_t v) { put(&v, 4); };
+    auto f32 = [&](float v) { put(&v, 4); };
+    i32(20000630); i32(2);
+    str("channels"); str("chlist"); i32(3 * 18 + 1);
+    for (const char* c : {"B", "G", "R"}) { str(c); i32(2 /* FLOAT */); uint8_t lin[4] = {0, 0, 0, 0}; put(lin, 4); i32(1); i32(1); }
+    hd.push_back(0);
+    str("compression"); str("compression"); i32(1); hd.push_back(0);
+    str("dataWindow"); str("box2i"); i32(16); i32(0); i32(0); i32((int32_t)w - 1); i32((int32_t)h - 1);
+    str("displayWindow"); str("box2i"); i32(16); i32(0); i32(0); i32((int32_t)w - 1); i32((int32_t)h - 1);
+    str("lineOrder"); str("lineOrder"); i32(1); hd.push_back(0);
+    str("pixelAspectRatio"); str("float"); i32(4); f32(1.0f);
+    str("screenWindowCenter"); str("v2f"); i32(8); f32(0.0f); f32(0.0f);
+    str("screenWindowWidth"); str("float"); i32(4); f32(1.0f);
+    hd.push_back(0);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return NX_ERR_INVALID;
+    f.write((const char*)hd.data(), hd.size());
+    const uint64_t rowBytes = 12ull * w, chunk = 8 + rowBytes;
+    uint64_t off = hd.size() + 8ull * h;
+    for (uint32_t y = 0; y < h; y++) { f.write((const char*)&off, 8); off += chunk; }
+    std::vector<float> row(3 * (size_t)w);
+    for (uint32_t y = 0; y < h; y++) {
+        const float* src = rgb + 3 * (size_t)y * w;
+        for (uint32_t x = 0; x < w; x++) { row[x] = src[3 * x + 2]; row[w + x] = src[3 * x + 1]; row[2 * (size_t)w + x] = src[3 * x]; }
+        int32_t yy = (int32_t)y, sz = (int32_t)rowBytes;
+        f.write((const char*)&yy, 4); f.write((const char*)&sz, 4); f.write((const char*)row.data(), rowBytes);
+    }
+    return f ? NX_OK : NX_ERR_INVALID;
+}
+
+} // extern "C"

@@ -1,0 +1,98 @@
+// Shared device/host helpers for the nexus_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/nexus_b200.h"
+
+#define NX_WARP 32u
+#define NX_FULL 0xffffffffu
+#define NX_INVALID 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------- context ----
+struct nx_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;      // main stream: build, generate, closest-hit trace, shade
+    cudaStream_t stream_aux = nullptr;  // shadow rays overlap the next extension trace
+    std::string error;
+    // scratch reused by the builder's parity hook
+    std::vector<uint64_t> dbg_codes;
+};
+
+#define NX_FAIL(ctx, code, ...) do { char b_[512]; std::snprintf(b_, sizeof(b_), __VA_ARGS__); (ctx)->error = b_; return (code); } while (0)
+#define NX_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    char b_[512]; std::snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    (ctx)->error = b_; return NX_ERR_CUDA; } } while (0)
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------- float math ----
+// All geometry arithmetic that decides topology or hit ids is written with explicit-rounding intrinsics so the compiler
+// can neither contract nor reorder it; the CPU oracle restates the same operation sequence with fmaf().
+struct V3 { float x, y, z; };
+__host__ __device__ __forceinline__ V3 v3(float x, float y, float z) { return {x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }
+__device__ __forceinline__ V3 vmin3(V3 a, V3 b) { return {fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}; }
+__device__ __forceinline__ V3 vmax3(V3 a, V3 b) { return {fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
+// dot(a,b) = fma(a.x,b.x, fma(a.y,b.y, a.z*b.z))
+__device__ __forceinline__ float xdot(V3 a, V3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, __fmul_rn(a.z, b.z))); }
+// cross(a,b).x = fma(a.y,b.z, -(a.z*b.y)) ...
+__device__ __forceinline__ V3 xcross(V3 a, V3 b)
+{
+    return {__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x))};
+}
+
+struct Box { V3 lo, hi; };
+// Half surface area in the operation order the reference compiles to for sm_100a (mul dy*dz; fma dx*dy; fma dx*dz) with
+// flush-to-zero, because H-PLOC compares these values bit for bit (B/include/NXB/AABB.h:43-47, BinaryBuilder.cu:143-148).
+__device__ __forceinline__ float half_area_ref(const Box& b)
+{
+    float dx, dy, dz, t;
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(dx) : "f"(b.hi.x), "f"(b.lo.x));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(dy) : "f"(b.hi.y), "f"(b.lo.y));
+    asm("sub.ftz.f32 %0, %1, %2;" : "=f"(dz) : "f"(b.hi.z), "f"(b.lo.z));
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(dy), "f"(dz));
+    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(dx), "f"(dy), "f"(t));
+    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(dx), "f"(dz), "f"(t));
+    return t;
+}
+__device__ __forceinline__ void box_grow(Box& a, const Box& b) { a.lo = vmin3(a.lo, b.lo); a.hi = vmax3(a.hi, b.hi); }
+
+// order-preserving float <-> uint mapping for atomicMin/atomicMax on floats
+__host__ __device__ __forceinline__ uint32_t f2ord(float f)
+{
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(f);
+#else
+    std::memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t k)
+{
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; std::memcpy(&f, &u, 4); return f;
+#endif
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t bits_below(uint32_t x, uint32_t i) { return __popc(x & ((1u << i) - 1u)); }
+
+// 16-byte cache-global (L2) loads/stores for data produced by other SMs within the same kernel
+__device__ __forceinline__ float4 ld_cg4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg4(float4* p, float4 v) { __stcg(p, v); }
+
+static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }

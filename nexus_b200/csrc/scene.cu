@@ -1,0 +1,446 @@
+// Host scene logic behind the C ABI: materials, meshes (+BLAS), instances (+TLAS), lights, camera, device mirrors.
+// Mirrors Scene / AssetManager / Mesh / MeshInstance / Camera of the reference (src/Scene/*.cpp, src/Assets/*.h); the
+// reference's DeviceVector/DeviceInstance plumbing is replaced by plain uploads in nx_scene_update().
+#include "scene.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace {
+
+// ---------------------------------------------------------------------------------- row-major 4x4 helpers ----
+struct M4 { float c[16]; };
+M4 m4_identity() { M4 r; for (int i = 0; i < 16; i++) r.c[i] = (i % 5 == 0) ? 1.f : 0.f; return r; }
+M4 m4_mul(const M4& a, const M4& b)
+{
+    M4 r;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++)
+        r.c[4 * i + j] = a.c[4 * i] * b.c[j] + a.c[4 * i + 1] * b.c[4 + j] + a.c[4 * i + 2] * b.c[8 + j] + a.c[4 * i + 3] * b.c[12 + j];
+    return r;
+}
+float to_radians(float deg) { return (float)((double)deg * 3.14159265358979323846 / 180.0); }   // Utils::ToRadians (double PI)
+M4 m4_translate(const float p[3]) { M4 r = m4_identity(); r.c[3] = p[0]; r.c[7] = p[1]; r.c[11] = p[2]; return r; }
+M4 m4_scale(const float s[3]) { M4 r = m4_identity(); r.c[0] = s[0]; r.c[5] = s[1]; r.c[10] = s[2]; return r; }
+M4 m4_rotx(float a) { M4 r = m4_identity(); r.c[5] = cosf(a); r.c[6] = -sinf(a); r.c[9] = sinf(a); r.c[10] = cosf(a); return r; }
+M4 m4_roty(float a) { M4 r = m4_identity(); r.c[0] = cosf(a); r.c[2] = sinf(a); r.c[8] = -sinf(a); r.c[10] = cosf(a); return r; }
+M4 m4_rotz(float a) { M4 r = m4_identity(); r.c[0] = cosf(a); r.c[1] = -sinf(a); r.c[4] = sinf(a); r.c[5] = cosf(a); return r; }
+
+// General inverse by cofactors (the instance matrices are affine, but user matrices need not be).
+bool m4_inverse(const M4& m, M4& out)
+{
+    const float* a = m.c;
+    float s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+    float s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+    float c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+    float c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+    float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    if (det == 0.f) { out = m4_identity(); return false; }
+    float id = 1.0f / det;
+    float* b = out.c;
+    b[0] = (a[5] * c5 - a[6] * c4 + a[7] * c3) * id;   b[1] = (-a[1] * c5 + a[2] * c4 - a[3] * c3) * id;
+    b[2] = (a[13] * s5 - a[14] * s4 + a[15] * s3) * id; b[3] = (-a[9] * s5 + a[10] * s4 - a[11] * s3) * id;
+    b[4] = (-a[4] * c5 + a[6] * c2 - a[7] * c1) * id;  b[5] = (a[0] * c5 - a[2] * c2 + a[3] * c1) * id;
+    b[6] = (-a[12] * s5 + a[14] * s2 - a[15] * s1) * id; b[7] = (a[8] * s5 - a[10] * s2 + a[11] * s1) * id;
+    b[8] = (a[4] * c4 - a[5] * c2 + a[7] * c0) * id;   b[9] = (-a[0] * c4 + a[1] * c2 - a[3] * c0) * id;
+    b[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * id; b[11] = (-a[8] * s4 + a[9] * s2 - a[11] * s0) * id;
+    b[12] = (-a[4] * c3 + a[5] * c1 - a[6] * c0) * id; b[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * id;
+    b[14] = (-a[12] * s3 + a[13] * s1 - a[14] * s0) * id; b[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * id;
+    return true;
+}
+void m4_point(const float* m, const float p[3], float out[3])
+{
+    for (int r = 0; r < 3; r++) out[r] = m[4 * r] * p[0] + m[4 * r + 1] * p[1] + m[4 * r + 2] * p[2] + m[4 * r + 3];
+}
+
+// MeshInstance::GetTransfromationMatrix: T * Rz * Ry * Rx * S (src/Scene/MeshInstance.h:36-40)
+M4 compose_trs(const float pos[3], const float rotDeg[3], const float scale[3])
+{
+    return m4_mul(m4_mul(m4_mul(m4_mul(m4_translate(pos), m4_rotz(to_radians(rotDeg[2]))), m4_roty(to_radians(rotDeg[1]))), m4_rotx(to_radians(rotDeg[0]))),
+                  m4_scale(scale));
+}
+// MeshInstance::GetBounds: AABB of the eight transformed corners (MeshInstance.h:42-53)
+nx_aabb transformed_bounds(const float* m, const nx_aabb& b)
+{
+    nx_aabb r; for (int k = 0; k < 3; k++) { r.bmin[k] = 3.402823466e38f; r.bmax[k] = -3.402823466e38f; }
+    for (int i = 0; i < 8; i++) {
+        float p[3] = {(i & 1) ? b.bmax[0] : b.bmin[0], (i & 2) ? b.bmax[1] : b.bmin[1], (i & 4) ? b.bmax[2] : b.bmin[2]}, q[3];
+        m4_point(m, p, q);
+        for (int k = 0; k < 3; k++) { r.bmin[k] = fminf(r.bmin[k], q[k]); r.bmax[k] = fmaxf(r.bmax[k], q[k]); }
+    }
+    return r;
+}
+
+bool material_emits(const nx_material& m)   // Scene::UpdateSceneLighting's test (Scene.cpp:162-185)
+{
+    float mx = fmaxf(m.emission_color[0], fmaxf(m.emission_color[1], m.emission_color[2]));
+    return (m.emissive_map != -1 || mx > 0.0f) && m.intensity > 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------- device prep ----
+// Leaf-ordered triangle stream: slot k of the BLAS gets {v0, primId}, {v1 - v0, 0}, {v2 - v0, 0}.
+__global__ void leaf_triangles_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ primIdx, uint32_t n, float4* __restrict__ out)
+{
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(primIdx + k);
+        const float* t = tris + 9 * (size_t)p;
+        const V3 a = v3(__ldg(t), __ldg(t + 1), __ldg(t + 2)), b = v3(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)), c = v3(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
+        const V3 e0 = b - a, e1 = c - a;
+        out[3 * (size_t)k] = make_float4(a.x, a.y, a.z, __uint_as_float(p));
+        out[3 * (size_t)k + 1] = make_float4(e0.x, e0.y, e0.z, 0.f);
+        out[3 * (size_t)k + 2] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    }
+}
+
+// Default shading data when the caller passes none: flat geometric normal, zero tangents and texture coordinates.
+__global__ void default_tridata_kernel(const float* __restrict__ tris, uint32_t n, float* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* t = tris + 9 * (size_t)i;
+        const float ax = t[3] - t[0], ay = t[4] - t[1], az = t[5] - t[2], bx = t[6] - t[0], by = t[7] - t[1], bz = t[8] - t[2];
+        float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+        const float l = sqrtf(nx * nx + ny * ny + nz * nz), il = l > 0.f ? 1.0f / l : 0.f;
+        nx *= il; ny *= il; nz *= il;
+        float* o = out + 24 * (size_t)i;
+        for (int v = 0; v < 3; v++) { o[3 * v] = nx; o[3 * v + 1] = ny; o[3 * v + 2] = nz; }
+        for (int k = 9; k < 24; k++) o[k] = 0.f;
+    }
+}
+
+template <typename T> int upload_vec(nx_ctx* ctx, T** dst, const std::vector<T>& src)
+{
+    if (*dst) { cudaFreeAsync(*dst, ctx->stream); *dst = nullptr; }
+    NX_CUDA(ctx, cudaMallocAsync((void**)dst, sizeof(T) * std::max<size_t>(src.size(), 1), ctx->stream));
+    if (!src.empty()) NX_CUDA(ctx, cudaMemcpyAsync(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return NX_OK;
+}
+
+} // namespace
+
+// Camera::ToDevice (src/Scene/Camera.cpp:130-156)
+DCamera nxi_camera_to_device(const nx_camera& c, uint32_t w, uint32_t h)
+{
+    DCamera d{};
+    float f[3] = {c.forward[0], c.forward[1], c.forward[2]};
+    float r[3] = {c.right[0], c.right[1], c.right[2]};
+    if (r[0] == 0.f && r[1] == 0.f && r[2] == 0.f) { r[0] = f[1] * 0.f - f[2] * 1.f; r[1] = f[2] * 0.f - f[0] * 0.f; r[2] = f[0] * 1.f - f[1] * 0.f; }  // cross(forward, +Y)
+    float up[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};                                                 // cross(right, forward)
+    const float aspect = (float)w / (float)h;
+    const float halfW = c.focus_distance * tanf((float)((double)(c.horizontal_fov_deg / 2.0f) * 3.14159265358979323846 / 180.0));
+    const float halfH = halfW / aspect;
+    const float lens = c.focus_distance * tanf((float)((double)(c.defocus_angle_deg / 2.0f) * 3.14159265358979323846 / 180.0));
+    for (int k = 0; k < 3; k++) {
+        d.position[k] = c.position[k]; d.right[k] = r[k]; d.up[k] = up[k];
+        d.viewportX[k] = 2 * halfW * r[k]; d.viewportY[k] = 2 * halfH * up[k];
+        d.lowerLeft[k] = c.position[k] - d.viewportX[k] / 2.0f - d.viewportY[k] / 2.0f + f[k] * c.focus_distance;
+    }
+    d.lensRadius = lens; d.resX = w; d.resY = h;
+    return d;
+}
+
+int nxi_scene_view(nx_scene* s, DSceneView* v)
+{
+    if (s->dirtyInstances || s->dirtyMaterials || s->dirtyLights) { int rc = nx_scene_update(s); if (rc) return rc; }
+    std::memset(v, 0, sizeof(*v));
+    v->trace.tlasNodes = (const float4*)s->tlas.nodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst;
+    v->shadeInst = s->dShadeInst; v->meshes = s->dMeshes; v->materials = s->dMaterials; v->lights = s->dLights;
+    v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr;
+    v->camera = nxi_camera_to_device(s->camera, s->width, s->height);
+    v->useMIS = s->settings.use_mis ? 1u : 0u; v->pathLength = (uint32_t)s->settings.path_length;
+    for (int k = 0; k < 3; k++) v->bg[k] = s->settings.background_color[k];
+    v->bgIntensity = s->settings.background_intensity;
+    return NX_OK;
+}
+
+extern "C" {
+
+int nx_scene_create(nx_ctx* ctx, uint32_t width, uint32_t height, nx_scene** out)
+{
+    if (!ctx || !out || !width || !height) return NX_ERR_INVALID;
+    nx_scene* s = new nx_scene();
+    s->ctx = ctx; s->width = width; s->height = height;
+    // Scene::Scene default camera (src/Scene/Scene.cpp:8-12) and RenderSettings defaults (RenderSettings.h:5-17)
+    s->camera = nx_camera{{0.f, 4.f, 14.f}, {0.f, 0.f, -1.f}, {0.f, 0.f, 0.f}, 45.f, 5.f, 0.f};
+    s->settings = nx_render_settings{1, 10, {0.f, 0.f, 0.f}, 1.0f, 3, 0.0f};
+    *out = s;
+    return NX_OK;
+}
+
+void nx_scene_destroy(nx_scene* s)
+{
+    if (!s) return;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
+    for (auto& m : s->meshes) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); nx_bvh8_free(ctx, &m.bvh); }
+    if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
+    cudaFree(s->dTravInst); cudaFree(s->dShadeInst); cudaFree(s->dMeshes); cudaFree(s->dMaterials); cudaFree(s->dLights);
+    if (s->hasHdr) { cudaDestroyTextureObject(s->hdr); cudaFreeArray(s->hdrArray); }
+    cudaStreamSynchronize(ctx->stream);
+    delete s;
+}
+
+int nx_scene_add_material(nx_scene* s, const nx_material* m)
+{
+    if (!s || !m) return NX_ERR_INVALID;
+    s->materials.push_back(*m); s->dirtyMaterials = true; s->dirtyLights = true;
+    return (int)s->materials.size() - 1;
+}
+int nx_scene_set_material(nx_scene* s, uint32_t idx, const nx_material* m)
+{
+    if (!s || !m || idx >= s->materials.size()) return NX_ERR_INVALID;
+    s->materials[idx] = *m; s->dirtyMaterials = true; s->dirtyLights = true;
+    return NX_OK;
+}
+
+int nx_scene_add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx)
+{
+    if (!s || !tris || !n) return NX_ERR_INVALID;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    HostMesh m; m.materialIdx = materialIdx;
+    NX_CUDA(ctx, cudaMalloc((void**)&m.dTris, 36 * (size_t)n));
+    NX_CUDA(ctx, cudaMalloc((void**)&m.dTriData, 96 * (size_t)n));
+    NX_CUDA(ctx, cudaMalloc((void**)&m.dLeafTris, 48 * (size_t)n));
+    NX_CUDA(ctx, cudaMemcpyAsync(m.dTris, tris, 36 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
+    if (data) NX_CUDA(ctx, cudaMemcpyAsync(m.dTriData, data, 96 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    else default_tridata_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, n, m.dTriData);
+    int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, 1 /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
+    if (rc) return rc;
+    leaf_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris);
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NX_CUDA(ctx, cudaGetLastError());
+    s->meshes.push_back(m);
+    return (int)s->meshes.size() - 1;
+}
+
+int nx_scene_mesh_bounds(nx_scene* s, uint32_t meshIdx, nx_aabb* out)
+{
+    if (!s || !out || meshIdx >= s->meshes.size()) return NX_ERR_INVALID;
+    *out = s->meshes[meshIdx].bvh.bounds; return NX_OK;
+}
+int nx_scene_mesh_bvh(nx_scene* s, uint32_t meshIdx, nx_bvh8* out)
+{
+    if (!s || !out || meshIdx >= s->meshes.size()) return NX_ERR_INVALID;
+    *out = s->meshes[meshIdx].bvh; return NX_OK;
+}
+
+int nx_scene_add_instance_matrix(nx_scene* s, uint32_t meshIdx, int32_t materialIdx, const float mtx[16])
+{
+    if (!s || !mtx || meshIdx >= s->meshes.size()) return NX_ERR_INVALID;
+    HostInstance inst; inst.meshIdx = meshIdx;
+    inst.materialIdx = materialIdx >= 0 ? (uint32_t)materialIdx : s->meshes[meshIdx].materialIdx;
+    M4 m, inv; std::memcpy(m.c, mtx, 64);
+    m4_inverse(m, inv);
+    std::memcpy(inst.m, m.c, 64); std::memcpy(inst.inv, inv.c, 64);
+    inst.bounds = transformed_bounds(inst.m, s->meshes[meshIdx].bvh.bounds);
+    s->instances.push_back(inst); s->dirtyInstances = true; s->dirtyLights = true;
+    return (int)s->instances.size() - 1;
+}
+int nx_scene_add_instance(nx_scene* s, uint32_t meshIdx, int32_t materialIdx, const float pos[3], const float rot[3], const float scale[3])
+{
+    if (!s || !pos || !rot || !scale) return NX_ERR_INVALID;
+    M4 m = compose_trs(pos, rot, scale);
+    return nx_scene_add_instance_matrix(s, meshIdx, materialIdx, m.c);
+}
+int nx_scene_set_instance_transform(nx_scene* s, uint32_t idx, const float pos[3], const float rot[3], const float scale[3])
+{
+    if (!s || idx >= s->instances.size()) return NX_ERR_INVALID;
+    HostInstance& inst = s->instances[idx];
+    M4 m = compose_trs(pos, rot, scale), inv; m4_inverse(m, inv);
+    std::memcpy(inst.m, m.c, 64); std::memcpy(inst.inv, inv.c, 64);
+    inst.bounds = transformed_bounds(inst.m, s->meshes[inst.meshIdx].bvh.bounds);
+    s->dirtyInstances = true;
+    return NX_OK;
+}
+
+int nx_scene_add_light(nx_scene* s, const nx_light* l)
+{
+    if (!s || !l) return NX_ERR_INVALID;
+    s->userLights.push_back(*l); s->dirtyLights = true;
+    return (int)s->userLights.size() - 1;
+}
+int nx_scene_set_camera(nx_scene* s, const nx_camera* c) { if (!s || !c) return NX_ERR_INVALID; s->camera = *c; return NX_OK; }
+int nx_scene_set_render_settings(nx_scene* s, const nx_render_settings* r)
+{
+    if (!s || !r || r->path_length < 1 || r->path_length > 255) return NX_ERR_INVALID;
+    s->settings = *r; return NX_OK;
+}
+
+// Texture::ToDevice for the HDR environment (src/Assets/Texture.cpp:12-46): RGBA32F array, wrap, linear, normalised coords.
+int nx_scene_set_hdr_map(nx_scene* s, const float* rgba, uint32_t w, uint32_t h)
+{
+    if (!s || !rgba || !w || !h) return NX_ERR_INVALID;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    if (s->hasHdr) { cudaStreamSynchronize(ctx->stream); cudaDestroyTextureObject(s->hdr); cudaFreeArray(s->hdrArray); s->hasHdr = false; }
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+    NX_CUDA(ctx, cudaMallocArray(&s->hdrArray, &desc, w, h));
+    NX_CUDA(ctx, cudaMemcpy2DToArray(s->hdrArray, 0, 0, rgba, 16 * (size_t)w, 16 * (size_t)w, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc res; std::memset(&res, 0, sizeof(res)); res.resType = cudaResourceTypeArray; res.res.array.array = s->hdrArray;
+    cudaTextureDesc tex; std::memset(&tex, 0, sizeof(tex));
+    tex.addressMode[0] = tex.addressMode[1] = cudaAddressModeWrap; tex.filterMode = cudaFilterModeLinear;
+    tex.readMode = cudaReadModeElementType; tex.normalizedCoords = 1; tex.sRGB = 0;
+    NX_CUDA(ctx, cudaCreateTextureObject(&s->hdr, &res, &tex, nullptr));
+    s->hasHdr = true;
+    return NX_OK;
+}
+
+int nx_scene_update(nx_scene* s)
+{
+    if (!s) return NX_ERR_INVALID;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    if (s->instances.empty()) NX_FAIL(ctx, NX_ERR_STATE, "Scene::Update: the scene has no mesh instances");
+    if (s->materials.empty()) NX_FAIL(ctx, NX_ERR_STATE, "Scene::Update: the scene has no materials");
+    for (const auto& i : s->instances) if (i.materialIdx >= s->materials.size()) NX_FAIL(ctx, NX_ERR_INVALID, "instance refers to material %u of %zu", i.materialIdx, s->materials.size());
+
+    if (s->dirtyMaterials) { int rc = upload_vec(ctx, &s->dMaterials, s->materials); if (rc) return rc; }
+
+    if (s->dirtyInstances)
+    {
+        // device mesh table
+        std::vector<DMesh> dm(s->meshes.size());
+        for (size_t i = 0; i < dm.size(); i++) { dm[i].tris = s->meshes[i].dTris; dm[i].tridata = s->meshes[i].dTriData; dm[i].primCount = s->meshes[i].bvh.prim_count; dm[i].pad = 0; }
+        int rc = upload_vec(ctx, &s->dMeshes, dm); if (rc) return rc;
+
+        // shading records in instance order
+        std::vector<DShadeInst> si(s->instances.size());
+        std::vector<nx_aabb> bounds(s->instances.size());
+        for (size_t i = 0; i < si.size(); i++) {
+            const HostInstance& h = s->instances[i];
+            std::memcpy(&si[i].m0, h.m, 48); std::memcpy(&si[i].i0, h.inv, 48);
+            si[i].meshIdx = h.meshIdx; si[i].materialIdx = h.materialIdx; si[i].pad0 = si[i].pad1 = 0;
+            bounds[i] = h.bounds;
+        }
+        rc = upload_vec(ctx, &s->dShadeInst, si); if (rc) return rc;
+
+        // Scene::BuildTLAS (src/Scene/Scene.cpp:65-78): BuildBVH8<AABB> over the instance bounds, default config (64-bit keys)
+        nx_aabb* dBounds = nullptr;
+        rc = upload_vec(ctx, &dBounds, bounds); if (rc) return rc;
+        if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
+        rc = nxi_build_bvh8(ctx, dBounds, (uint32_t)bounds.size(), 0, 0, &s->tlas);
+        cudaFreeAsync(dBounds, ctx->stream);
+        if (rc) return rc;
+
+        // traversal records in TLAS leaf order
+        std::vector<uint32_t> order(bounds.size());
+        NX_CUDA(ctx, cudaMemcpyAsync(order.data(), s->tlas.prim_idx, 4 * order.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<DTravInst> ti(order.size());
+        for (size_t k = 0; k < order.size(); k++) {
+            const HostInstance& h = s->instances[order[k]];
+            std::memcpy(&ti[k].r0, h.inv, 48);
+            ti[k].nodes = (const float4*)s->meshes[h.meshIdx].bvh.nodes; ti[k].ltris = s->meshes[h.meshIdx].dLeafTris;
+        }
+        rc = upload_vec(ctx, &s->dTravInst, ti); if (rc) return rc;
+    }
+
+    if (s->dirtyLights || s->dirtyInstances || s->dirtyMaterials)
+    {
+        // punctual lights first, then one MESH light per emissive instance (Scene::UpdateSceneLighting, Scene.cpp:157-219)
+        s->lights.clear();
+        for (const nx_light& l : s->userLights) {
+            DLight d{}; d.type = l.type;
+            d.px = l.position[0]; d.py = l.position[1]; d.pz = l.position[2];
+            d.dx = l.direction[0]; d.dy = l.direction[1]; d.dz = l.direction[2];
+            d.cr = l.color[0]; d.cg = l.color[1]; d.cb = l.color[2]; d.intensity = l.intensity; d.instance = l.instance;
+            s->lights.push_back(d);
+        }
+        for (uint32_t mat = 0; mat < s->materials.size(); mat++) {
+            if (!material_emits(s->materials[mat])) continue;
+            for (uint32_t j = 0; j < s->instances.size(); j++)
+                if (s->instances[j].materialIdx == mat) { DLight d{}; d.type = NX_LIGHT_MESH; d.instance = j; s->lights.push_back(d); }
+        }
+        int rc = upload_vec(ctx, &s->dLights, s->lights); if (rc) return rc;
+    }
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s->dirtyInstances = s->dirtyMaterials = s->dirtyLights = false;
+    return NX_OK;
+}
+
+// ---- exports in the reference's device layouts (parity with the reference arm) ----
+int nx_scene_export_instances(nx_scene* s, void* out160, uint32_t* outCount)
+{
+    if (!s || !outCount) return NX_ERR_INVALID;
+    *outCount = (uint32_t)s->instances.size();
+    if (!out160) return NX_OK;
+    uint8_t* o = (uint8_t*)out160;
+    for (size_t i = 0; i < s->instances.size(); i++, o += 160) {
+        const HostInstance& h = s->instances[i];
+        std::memcpy(o, &h.meshIdx, 4); std::memcpy(o + 4, &h.materialIdx, 4);
+        std::memcpy(o + 8, h.m, 64); std::memcpy(o + 72, h.inv, 64); std::memcpy(o + 136, &h.bounds, 24);
+    }
+    return NX_OK;
+}
+int nx_scene_export_camera(nx_scene* s, void* out88)
+{
+    if (!s || !out88) return NX_ERR_INVALID;
+    DCamera c = nxi_camera_to_device(s->camera, s->width, s->height);
+    std::memcpy(out88, &c, 88);
+    return NX_OK;
+}
+int nx_scene_export_lights(nx_scene* s, void* out52, uint32_t* outCount)
+{
+    if (!s || !outCount) return NX_ERR_INVALID;
+    if (s->dirtyLights || s->dirtyInstances || s->dirtyMaterials) { int rc = nx_scene_update(s); if (rc) return rc; }
+    *outCount = (uint32_t)s->lights.size();
+    if (!out52) return NX_OK;
+    uint8_t* o = (uint8_t*)out52;
+    for (const DLight& l : s->lights) {   // D_Light: 48-byte union + type byte at offset 48
+        std::memset(o, 0, 52);
+        if (l.type == NX_LIGHT_MESH) std::memcpy(o, &l.instance, 4);
+        else if (l.type == NX_LIGHT_POINT) { float v[7] = {l.px, l.py, l.pz, l.cr, l.cg, l.cb, l.intensity}; std::memcpy(o, v, 28); }
+        else if (l.type == NX_LIGHT_DIRECTIONAL) { float v[7] = {l.cr, l.cg, l.cb, l.dx, l.dy, l.dz, l.intensity}; std::memcpy(o, v, 28); }
+        o[48] = (uint8_t)l.type;
+        o += 52;
+    }
+    return NX_OK;
+}
+int nx_scene_tlas(nx_scene* s, nx_bvh8* out)
+{
+    if (!s || !out) return NX_ERR_INVALID;
+    if (s->dirtyInstances) { int rc = nx_scene_update(s); if (rc) return rc; }
+    *out = s->tlas; return NX_OK;
+}
+
+// ---- parity hooks ----
+int nx_trace_closest_device(nx_scene* s, const nx_ray* dRays, uint32_t n, nx_hit* dHits, float* outMs)
+{
+    if (!s || !dRays || !dHits) return NX_ERR_INVALID;
+    DSceneView v; int rc = nxi_scene_view(s, &v); if (rc) return rc;
+    return nxi_trace_closest(s->ctx, v.trace, dRays, n, dHits, outMs);
+}
+int nx_trace_closest(nx_scene* s, const nx_ray* rays, uint32_t n, nx_hit* hits, float* outMs)
+{
+    if (!s || !rays || !hits) return NX_ERR_INVALID;
+    if (n == 0) return NX_OK;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    DSceneView v; int rc = nxi_scene_view(s, &v); if (rc) return rc;
+    nx_ray* dRays = nullptr; nx_hit* dHits = nullptr;
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dRays, sizeof(nx_ray) * (size_t)n, ctx->stream));
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dHits, sizeof(nx_hit) * (size_t)n, ctx->stream));
+    NX_CUDA(ctx, cudaMemcpyAsync(dRays, rays, sizeof(nx_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = nxi_trace_closest(ctx, v.trace, dRays, n, dHits, outMs);
+    if (!rc) { NX_CUDA(ctx, cudaMemcpyAsync(hits, dHits, sizeof(nx_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream)); NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    cudaFreeAsync(dRays, ctx->stream); cudaFreeAsync(dHits, ctx->stream);
+    return rc;
+}
+int nx_trace_any(nx_scene* s, const nx_ray* rays, uint32_t n, uint8_t* occluded, float* outMs)
+{
+    if (!s || !rays || !occluded) return NX_ERR_INVALID;
+    if (n == 0) return NX_OK;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    DSceneView v; int rc = nxi_scene_view(s, &v); if (rc) return rc;
+    nx_ray* dRays = nullptr; uint8_t* dOcc = nullptr;
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dRays, sizeof(nx_ray) * (size_t)n, ctx->stream));
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dOcc, n, ctx->stream));
+    NX_CUDA(ctx, cudaMemcpyAsync(dRays, rays, sizeof(nx_ray) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = nxi_trace_any(ctx, v.trace, dRays, n, dOcc, outMs);
+    if (!rc) { NX_CUDA(ctx, cudaMemcpyAsync(occluded, dOcc, n, cudaMemcpyDeviceToHost, ctx->stream)); NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    cudaFreeAsync(dRays, ctx->stream); cudaFreeAsync(dOcc, ctx->stream);
+    return rc;
+}
+
+} // extern "C"

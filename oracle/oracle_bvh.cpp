@@ -440,6 +440,9 @@ int orc_canon_bvh8(const void* nodesIn, const uint32_t* primIdxIn, uint32_t node
         }
         leafCounter += leafPrims;
         nd.childBaseIdx = childBase; nd.primBaseIdx = primBase;
+        // the reference never initialises the quantised boxes of empty slots (NodeExplicit is a stack temporary,
+        // WideConverter.cu:160); they carry no information, so the canonical form zeroes them
+        for (int i = 0; i < 8; i++) if (!nd.meta[i]) nd.qlox[i] = nd.qloy[i] = nd.qloz[i] = nd.qhix[i] = nd.qhiy[i] = nd.qhiz[i] = 0;
         if (nw >= nodeCount) return -3;
         out[nw] = nd;
     }

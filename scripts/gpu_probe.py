@@ -1,0 +1,153 @@
+"""First-contact GPU probe: runs every parity check once and prints diagnostics instead of stopping at the first failure."""
+import os, sys, time, traceback
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import nexus_b200 as nx
+from nexus_b200 import scenes
+import oracle_lib as O
+
+ctx = nx.Context(0)
+print("SMs", ctx.sm_count, "ref available", O.have_ref())
+rng = np.random.default_rng(3)
+
+
+def section(name):
+    print("\n==== " + name, flush=True)
+
+
+def rand_tris(n, spread=5.0, size=0.1):
+    c = rng.uniform(-spread, spread, (n, 1, 3)).astype(np.float32)
+    return (c + rng.uniform(-size, size, (n, 3, 3)).astype(np.float32)).reshape(n, 9)
+
+
+def builder_check(prims, speed, label):
+    n = prims.shape[0]
+    tri = 1 if prims.shape[1] == 9 else 0
+    bits64 = 0 if speed else 1
+    bounds, sceneb = O.prim_bounds(prims, tri)
+    codes = nx.debug_morton(ctx, prims, bits64)
+    ocodes = O.morton(bounds, sceneb, bits64)
+    mism = int((codes != ocodes).sum())
+    b2 = nx.BuildBVH2(ctx, prims, prioritizeSpeed=speed)
+    n2 = b2.ToHost(); b2.Free()
+    o2 = O.build_bvh2(bounds, codes, bits64)
+    ok2 = n == 1 or bool((O.canon_bvh2(n2, n) == O.canon_bvh2(o2, n)).all())
+    b8, met = nx.BuildBVH8(ctx, prims, prioritizeSpeed=speed, metrics=True)
+    n8, p8 = b8.ToHost(); b8.Free()
+    o8, op8 = O.build_bvh8(o2, n)
+    c8, cp8 = O.canon_bvh8(n8, p8)
+    ok8 = c8.shape == o8.shape and bool((c8 == O.canon_bvh8(o8, op8)[0]).all()) and bool((cp8 == op8).all())
+    inv = O.check_bvh8(n8, p8, bounds)
+    msg = f"{label}: n={n} morton_mismatch_vs_ieee={mism} bvh2_vs_oracle={ok2} bvh8_vs_oracle={ok8} invariants={inv} nodes8={len(n8)} cost8 dev={met['bvh8_cost']:.4f} orc={O.bvh8_cost(n8, sceneb):.4f}"
+    if O.have_ref():
+        r8, rp8, rb = O.ref_build_bvh8(prims, speed)
+        rc8, rcp8 = O.canon_bvh8(r8, rp8)
+        okr = rc8.shape == c8.shape and bool((rc8 == c8).all()) and bool((rcp8 == cp8).all())
+        r2, _ = O.ref_build_bvh2(prims, speed)
+        okr2 = n == 1 or bool((O.canon_bvh2(r2, n) == O.canon_bvh2(n2, n)).all())
+        msg += f" | vs REFERENCE bvh2={okr2} bvh8={okr} (ref nodes {len(r8)})"
+        if not okr and rc8.shape == c8.shape:
+            bad = np.nonzero((rc8 != c8).any(1))[0]
+            msg += f" first_bad_node={bad[:5]} nbad={len(bad)}"
+    print(msg, flush=True)
+
+
+try:
+    section("builder parity")
+    for n in (1, 2, 3, 16, 17, 33, 100, 1000, 20000, 300000):
+        for speed in (True, False):
+            builder_check(rand_tris(n), speed, f"tri speed={speed}")
+    builder_check(np.concatenate([rand_tris(50)[:, :3] - 0.2, rand_tris(50)[:, :3] + 0.2], 1)[:50].astype(np.float32), False, "aabb 64-bit")
+    same = np.tile(rand_tris(1), (40, 1)); builder_check(same, True, "40 identical tris")
+    flat = rand_tris(500); flat[:, 2::3] = 0.0; builder_check(flat, True, "flat z=0")
+    builder_check(scenes.uv_sphere(64, 64), True, "sphere 8192")
+except Exception:
+    traceback.print_exc()
+
+try:
+    section("builder timing 1M/10M (our metrics vs reference)")
+    for n in (1_000_000, 10_000_000):
+        tris = scenes.test_triangles(n)
+        dev = ctx.upload(tris)
+        for speed in (True, False):
+            m = nx.BenchmarkBuild(ctx, dev, n, 1, speed, 2, 5)
+            print(f"ours n={n} speed={speed}: " + " ".join(f"{k}={v:.3f}" for k, v in m.items()), flush=True)
+            if O.have_ref():
+                import ctypes as C
+                mm = np.zeros(9, np.float32); cnt = C.c_uint32(0)
+                O.ref().nxref_bench_build8(tris.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, int(speed), 2, 5, mm.ctypes.data_as(C.c_void_p), C.byref(cnt))
+                print(f"REF  n={n} speed={speed}: bounds={mm[0]:.3f} morton={mm[1]:.3f} sort={mm[2]:.3f} bvh2={mm[3]:.3f} bvh8={mm[4]:.3f} total={mm[5]:.3f} cost2={mm[6]:.3f} cost8={mm[7]:.3f} nodes={cnt.value}", flush=True)
+        ctx.free(dev)
+except Exception:
+    traceback.print_exc()
+
+try:
+    section("traversal parity: cornell")
+    desc = scenes.with_triangle_data(scenes.cornell_box())
+    res = (640, 360)
+    scene = scenes.build(ctx, desc, res)
+    o, d = scenes.camera_rays(desc["camera"], res)
+    ro = rng.uniform(-0.9, 0.9, (100000, 3)).astype(np.float32) + np.array([0, 1, 0], np.float32)
+    rd = rng.normal(size=(100000, 3)).astype(np.float32); rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    rays = nx.make_rays(np.concatenate([o, ro]), np.concatenate([d, rd]))
+    hits, ms = scene.TraceClosest(rays, timed=True)
+    ora = O.oracle_scene_from_product(desc, scene)
+    want = ora.trace_closest(rays)
+    print("ours vs oracle:", O.compare_hits(ora, rays, hits, want), "bit-exact t:", int((hits["t"] == want["t"]).sum()), f"{len(rays)/ms/1e3:.1f} Mrays/s")
+    brute = ora.trace_brute(rays[:20000])
+    print("oracle vs brute:", O.compare_hits(ora, rays[:20000], want[:20000], brute))
+    occ = scene.TraceAny(nx.make_rays(rays["origin"], rays["direction"], 1.5))
+    print("any-hit equal:", int((occ == ora.trace_any(nx.make_rays(rays["origin"], rays["direction"], 1.5))).sum()), "of", len(occ))
+    if O.have_ref():
+        O.ref_load_scene(desc, scene, (1024, 1024))
+        rh, rms = O.ref_trace(rays)
+        print("ours vs REFERENCE kernel:", O.compare_hits(ora, rays, hits, rh), f"ref {len(rays)/rms/1e3:.1f} Mrays/s")
+    section("render: cornell 256x256")
+    res2 = (256, 256)
+    scene2 = scenes.build(ctx, desc, res2)
+    pt = nx.PathTracer(ctx, res2)
+    pt.Render(scene2, frames=64)
+    st = pt.Stats(); img = pt.ReadAccumulation()
+    print("ours:", st, "mean", img.mean(axis=(0, 1)))
+    nx.write_pfm(os.path.join(ROOT, "gpurun_out", "cornell_ours.pfm"), img)
+    if O.have_ref():
+        O.ref_load_scene(desc, scene2, res2)
+        rms, re, rs = O.ref_render(1, 64)
+        rimg = O.ref_read_accum(res2)
+        print(f"REF: {rms:.2f} ms ext={re} shadow={rs} mean", rimg.mean(axis=(0, 1)))
+        rmse = float(np.sqrt(((img - rimg) ** 2).mean())); print("rmse ours-vs-ref", rmse, "rel", rmse / float(rimg.mean()))
+        rms2, _, _ = O.ref_render(65, 64)   # accumulates frames 65..128 on top? (reference running mean) -> compare noise floor separately
+        nx.write_pfm(os.path.join(ROOT, "gpurun_out", "cornell_ref.pfm"), rimg)
+except Exception:
+    traceback.print_exc()
+
+try:
+    section("traversal parity + render: small instanced scene")
+    desc = scenes.with_triangle_data(scenes.instanced_scene(n_blas=16, n_instances=64, nu=24, nv=24))
+    res = (320, 180)
+    scene = scenes.build(ctx, desc, res)
+    o, d = scenes.camera_rays(desc["camera"], res)
+    rays = nx.make_rays(o, d)
+    hits, ms = scene.TraceClosest(rays, timed=True)
+    ora = O.oracle_scene_from_product(desc, scene)
+    want = ora.trace_closest(rays)
+    print("ours vs oracle:", O.compare_hits(ora, rays, hits, want), "bit-exact t:", int((hits["t"] == want["t"]).sum()))
+    brute = ora.trace_brute(rays[::7])
+    print("oracle vs brute:", O.compare_hits(ora, rays[::7], want[::7], brute))
+    if O.have_ref():
+        O.ref_load_scene(desc, scene, res)
+        rh, rms = O.ref_trace(rays)
+        print("ours vs REFERENCE kernel:", O.compare_hits(ora, rays, hits, rh))
+    pt = nx.PathTracer(ctx, res)
+    pt.Render(scene, frames=32)
+    st = pt.Stats(); img = pt.ReadAccumulation()
+    print("ours:", st, "mean", img.mean(axis=(0, 1)))
+    if O.have_ref():
+        rms, re, rs = O.ref_render(1, 32)
+        rimg = O.ref_read_accum(res)
+        print(f"REF: {rms:.2f} ms ext={re} shadow={rs} mean", rimg.mean(axis=(0, 1)))
+        rmse = float(np.sqrt(((img - rimg) ** 2).mean())); print("rmse", rmse, "rel", rmse / float(rimg.mean()))
+except Exception:
+    traceback.print_exc()
+print("probe done")

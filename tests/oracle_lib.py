@@ -117,3 +117,192 @@ def check_bvh8(nodes, prim_idx, bounds):
     nodes = np.ascontiguousarray(nodes)
     return oracle().orc_check_bvh8(_p(nodes), _p(np.ascontiguousarray(prim_idx, np.uint32)), C.c_uint32(nodes.shape[0]),
                                    C.c_uint32(prim_idx.shape[0]), _p(np.ascontiguousarray(bounds, np.float32)))
+
+
+# ------------------------------------------------------------------ oracle: traversal ----
+RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("tmax", np.float32), ("direction", np.float32, 3), ("pad", np.uint32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.uint32), ("instance", np.uint32)])
+
+
+class OracleScene:
+    """Two-level scene for the CPU traversal oracle (oracle/oracle_trace.cpp)."""
+
+    def __init__(self):
+        L = oracle()
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_triangle_t.restype = C.c_float
+        self._h = C.c_void_p(L.orc_scene_create())
+        self.n_instances = 0
+
+    def __del__(self):
+        try:
+            oracle().orc_scene_destroy(self._h)
+        except Exception:
+            pass
+
+    def add_mesh(self, tris, nodes8, prim_idx):
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        nodes8 = np.ascontiguousarray(nodes8).view(np.uint32).reshape(-1, 20)
+        prim_idx = np.ascontiguousarray(prim_idx, np.uint32)
+        return oracle().orc_scene_add_mesh(self._h, _p(tris), C.c_uint32(tris.shape[0]), _p(nodes8), C.c_uint32(nodes8.shape[0]), _p(prim_idx))
+
+    def set_instances(self, mesh_idx, inv12, tlas_nodes, tlas_prim_idx):
+        mesh_idx = np.ascontiguousarray(mesh_idx, np.uint32)
+        inv12 = np.ascontiguousarray(inv12, np.float32).reshape(-1, 12)
+        tlas_nodes = np.ascontiguousarray(tlas_nodes).view(np.uint32).reshape(-1, 20)
+        tlas_prim_idx = np.ascontiguousarray(tlas_prim_idx, np.uint32)
+        self.n_instances = mesh_idx.shape[0]
+        oracle().orc_scene_set_instances(self._h, _p(mesh_idx), _p(inv12), C.c_uint32(mesh_idx.shape[0]), _p(tlas_nodes),
+                                         C.c_uint32(tlas_nodes.shape[0]), _p(tlas_prim_idx))
+
+    def trace_closest(self, rays, threads=8, stats=False):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        st = np.zeros(3, np.uint64)
+        oracle().orc_trace_closest(self._h, _p(rays), C.c_uint32(rays.shape[0]), _p(hits), C.c_int(threads), _p(st))
+        return (hits, {"nodes": int(st[0]), "tris": int(st[1]), "insts": int(st[2])}) if stats else hits
+
+    def trace_any(self, rays, threads=8):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        occ = np.empty(rays.shape[0], np.uint8)
+        oracle().orc_trace_any(self._h, _p(rays), C.c_uint32(rays.shape[0]), _p(occ), C.c_int(threads))
+        return occ
+
+    def trace_brute(self, rays, threads=8):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        oracle().orc_trace_brute(self._h, _p(rays), C.c_uint32(rays.shape[0]), _p(hits), C.c_int(threads))
+        return hits
+
+    def triangle_t(self, ray, inst, prim):
+        ray = np.ascontiguousarray(ray, RAY_DTYPE)
+        return float(oracle().orc_triangle_t(self._h, _p(ray), C.c_uint32(int(inst)), C.c_uint32(int(prim))))
+
+
+def cpu_build_bvh8(prims, prim_type, bits64):
+    """Whole CPU pipeline: bounds -> Morton (IEEE division) -> H-PLOC -> collapse.  Returns nodes8, primIdx, scene bounds."""
+    bounds, scene = prim_bounds(prims, prim_type)
+    codes = morton(bounds, scene, bits64)
+    n2 = build_bvh2(bounds, codes, bits64)
+    n8, pidx = build_bvh8(n2, bounds.shape[0])
+    return n8, pidx, scene
+
+
+def compare_hits(ora, rays, got, want, rel=1e-5):
+    """Classifies differences between two closest-hit arrays.  Returns dict(exact, id_mismatch_tie, id_mismatch_hard, t_bad).
+    A 'tie' is an id mismatch where the other side's triangle, evaluated by the oracle for the same ray, lies within `rel`
+    of the reported distance (coincident or abutting geometry; the reference itself is order-dependent there)."""
+    same_id = (got["prim"] == want["prim"]) & (got["instance"] == want["instance"])
+    miss_both = (got["t"] == np.float32(1e30)) & (want["t"] == np.float32(1e30))
+    denom = np.maximum(np.abs(want["t"].astype(np.float64)), 1e-30)
+    t_ok = (np.abs(got["t"].astype(np.float64) - want["t"].astype(np.float64)) / denom <= rel) | miss_both
+    res = {"n": int(len(got)), "exact_id": int(same_id.sum()), "t_bad": int((same_id & ~t_ok).sum()), "tie": 0, "hard": 0, "hard_idx": []}
+    for i in np.nonzero(~same_id)[0]:
+        tg, tw = float(got["t"][i]), float(want["t"][i])
+        alt = ora.triangle_t(rays[i:i + 1], want["instance"][i], want["prim"][i]) if want["prim"][i] != 0xffffffff else 1e30
+        alt2 = ora.triangle_t(rays[i:i + 1], got["instance"][i], got["prim"][i]) if got["prim"][i] != 0xffffffff else 1e30
+        close = lambda a, b: abs(a - b) <= rel * max(abs(a), abs(b), 1e-30)  # noqa: E731
+        if close(tg, tw) or close(alt, tg) or close(alt2, tw):
+            res["tie"] += 1
+        else:
+            res["hard"] += 1
+            res["hard_idx"].append(int(i))
+    return res
+
+
+# ------------------------------------------------------------------ reference arm helpers (GPU only) ----
+def ref_build_bvh8(prims, prioritize_speed, metrics=False):
+    prims = np.ascontiguousarray(prims, np.float32)
+    n, tri = prims.shape[0], 1 if prims.shape[1] == 9 else 0
+    cap = (4 * n - 1 + 6) // 7
+    nodes = np.zeros((cap, 20), np.uint32)
+    pidx = np.zeros(n, np.uint32)
+    cnt = C.c_uint32(0)
+    bounds = np.zeros(6, np.float32)
+    m = np.zeros(9, np.float32)
+    rc = ref().nxref_build_bvh8(_p(prims), C.c_uint32(n), C.c_int(tri), C.c_int(int(prioritize_speed)), _p(nodes), _p(pidx), C.byref(cnt),
+                                _p(bounds), _p(m) if metrics else None)
+    assert rc == 0
+    out = (nodes[:cnt.value].copy(), pidx, bounds)
+    return out + (m,) if metrics else out
+
+
+def ref_build_bvh2(prims, prioritize_speed):
+    prims = np.ascontiguousarray(prims, np.float32)
+    n, tri = prims.shape[0], 1 if prims.shape[1] == 9 else 0
+    nodes = np.zeros((2 * n - 1, 8), np.uint32)
+    bounds = np.zeros(6, np.float32)
+    rc = ref().nxref_build_bvh2(_p(prims), C.c_uint32(n), C.c_int(tri), C.c_int(int(prioritize_speed)), _p(nodes), _p(bounds), None)
+    assert rc == 0
+    return nodes, bounds
+
+
+def ref_load_scene(desc, scene, resolution):
+    """Feeds the reference harness the same scene the product got: identical triangles, shading data, materials, and the
+    instance matrices / camera / light list exported by the product's host layer in the reference's device layouts."""
+    R = ref()
+    R.nxref_scene_reset()
+    for m in desc["meshes"]:
+        tris = np.ascontiguousarray(m["triangles"], np.float32)
+        td = np.ascontiguousarray(m["triangle_data"], np.float32)
+        assert R.nxref_add_mesh(_p(tris), _p(td), C.c_uint32(tris.shape[0])) >= 0
+    inst = scene.ExportInstances()
+    assert R.nxref_set_instances(_p(inst), C.c_uint32(inst.shape[0])) == 0
+    mats = np.frombuffer(b"".join(bytes(m.pod()) for m in desc["materials"]), np.uint8).copy()
+    assert R.nxref_set_materials(_p(mats), C.c_uint32(len(desc["materials"]))) == 0
+    lights = scene.ExportLights()
+    assert R.nxref_set_lights(_p(lights) if len(lights) else None, C.c_uint32(len(lights))) == 0
+    cam = scene.ExportCamera()
+    assert R.nxref_set_camera(_p(cam)) == 0
+    st = desc["settings"]
+    bg = np.asarray(st.backgroundColor, np.float32)
+    assert R.nxref_set_settings(C.c_int(int(st.useMIS)), C.c_int(int(st.pathLength)), _p(bg), C.c_float(st.backgroundIntensity)) == 0
+    if desc.get("hdr") is not None:
+        hdr = np.ascontiguousarray(desc["hdr"], np.float32)
+        assert R.nxref_set_hdr(_p(hdr), C.c_uint32(hdr.shape[1]), C.c_uint32(hdr.shape[0])) == 0
+    assert R.nxref_render_init(C.c_uint32(resolution[0]), C.c_uint32(resolution[1])) == 0
+
+
+def ref_render(first_frame, n_frames):
+    ms = C.c_float(0)
+    rays = (C.c_ulonglong * 2)()
+    assert ref().nxref_render(C.c_uint32(first_frame), C.c_uint32(n_frames), C.byref(ms), rays) == 0
+    return ms.value, int(rays[0]), int(rays[1])
+
+
+def ref_read_accum(resolution):
+    out = np.empty((resolution[1], resolution[0], 3), np.float32)
+    assert ref().nxref_read_accum(_p(out)) == 0
+    return out
+
+
+def ref_trace(rays):
+    rays = np.ascontiguousarray(rays, RAY_DTYPE)
+    n = rays.shape[0]
+    o = np.ascontiguousarray(rays["origin"])
+    d = np.ascontiguousarray(rays["direction"])
+    t, u, v = (np.empty(n, np.float32) for _ in range(3))
+    tri, inst = np.empty(n, np.uint32), np.empty(n, np.uint32)
+    ms = C.c_float(0)
+    rc = ref().nxref_trace(_p(o), _p(d), C.c_uint32(n), _p(t), _p(u), _p(v), _p(tri), _p(inst), C.byref(ms))
+    assert rc == 0, rc
+    hits = np.empty(n, HIT_DTYPE)
+    hits["t"], hits["u"], hits["v"], hits["prim"], hits["instance"] = t, u, v, tri, inst
+    miss = hits["t"] == np.float32(1e30)
+    hits["prim"][miss] = 0xffffffff
+    hits["instance"][miss] = 0xffffffff
+    return hits, ms.value
+
+
+def oracle_scene_from_product(desc, scene):
+    """CPU oracle scene that uses the BVHs the product built on the GPU (so traversal, not building, is under test)."""
+    S = OracleScene()
+    for i, m in enumerate(desc["meshes"]):
+        nodes, pidx = scene.MeshBVH(i).ToHost()
+        S.add_mesh(m["triangles"], nodes, pidx)
+    inst = scene.ExportInstances()
+    mesh_idx = inst[:, 0:4].copy().view(np.uint32).ravel()
+    inv = inst[:, 72:136].copy().view(np.float32).reshape(-1, 16)[:, :12]
+    tn, tp = scene.TLAS().ToHost()
+    S.set_instances(mesh_idx, inv, tn, tp)
+    return S
