@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the wavefront path-tracing hot path (BASELINE.json / SURVEY.md §8d).
+
+  python bench.py --gpus N --steps K --warmup W [--workload instanced10m_4k|cornell_1080p] [--impl reference]
+
+A step is one frame (1 sample per pixel) of the wavefront pipeline: generate -> closest-hit trace -> shade (+NEE) ->
+{closest-hit trace, any-hit shadow trace} per bounce -> accumulate.  Metric: Mrays/s = (extension + shadow rays traced) /
+device time / 1e6, as SURVEY.md §8(d) defines it; spp/s (frames/s) rides along in `spp_per_s`.
+
+N > 1 (launched by torchrun, one rank per GPU): the scene is replicated, rank g renders its own block of K frame indices
+(sample partition, weak scaling) and the float accumulation buffers are summed with one NCCL all-reduce inside the timed
+region.  Timing is CUDA events on the stream the kernels run on; the reported time is the max over ranks.
+
+--impl reference runs the UNMODIFIED reference CUDA kernels (oracle/_ref/libnexus_ref.so, compiled from /root/reference by
+oracle/Makefile with the reference's own flags) through a headless replay of PathTracer::Render on the same GPU, same scene,
+same metric: the reference has no CPU implementation of this path, its implementation IS CUDA, and north_star names "the
+reference's own CUDA renderer on the same B200" as the baseline.  No product code (libnexus_b200.so) is loaded on that arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration north_star's target is quoted on; fits one GPU (about 2.5 GB resident)
+    "instanced10m_4k": dict(res=(3840, 2160), desc="10M-triangle instanced scene (1024 BLAS x 9798 tris, 1026 instances, TLAS), OpenPBR "
+                            "dielectric/metal/translucent, NEE+MIS, pathLength 8, 3840x2160, 1 spp/step"),
+    # BASELINE.json configs[1]
+    "cornell_1080p": dict(res=(1920, 1080), desc="Cornell box (32 triangles, 8 instances, diffuse + 35x area light), NEE+MIS, pathLength 10, 1920x1080, 1 spp/step"),
+    # reduced variant for quick functional checks (not a bench line)
+    "instanced_small": dict(res=(640, 360), desc="64-BLAS reduced instanced scene, 640x360 (functional check only)"),
+}
+
+
+def make_desc(workload):
+    from nexus_b200 import scenes
+    if workload == "instanced10m_4k":
+        d = scenes.instanced_scene(n_blas=1024, n_instances=1024, path_length=8)
+    elif workload == "cornell_1080p":
+        d = scenes.cornell_box(path_length=10)
+    elif workload == "instanced_small":
+        d = scenes.instanced_scene(n_blas=64, n_instances=64, nu=24, nv=24, path_length=8)
+    else:
+        raise SystemExit(f"unknown workload {workload}")
+    return scenes.with_triangle_data(d)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, reasons, mx, power = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            # under load = samples at or above the median power of the upper half
+            out.update(sm_mhz=float(np.median(sm[len(sm) // 4:])), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power) if power else None)
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(work, kind):
+    """closest hit 24 + 20 B/ray, shadow 44 B/ray; 80 B per node visited, 4 + 36 B per triangle tested,
+    144 B per instance entered."""
+    per_ray = 44
+    return per_ray * work["rays"] + 80 * work["nodes"] + 40 * work["tris"] + 144 * work["insts"]
+
+
+# ----------------------------------------------------------------------------------------------- our arm ----
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nexus_b200 as nx
+    from nexus_b200 import scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    res = wl["res"]
+
+    ctx = nx.Context(local)          # raises when the CUDA library or a GPU is missing: there is no fallback
+    desc = make_desc(args.workload)
+    t_scene = time.time()
+    scene = scenes.build(ctx, desc, res)
+    ctx.synchronize()
+    t_scene = time.time() - t_scene
+    pt = nx.PathTracer(ctx, res)
+    stream = torch.cuda.ExternalStream(int(nx.lib().nx_ctx_stream(ctx._h)), device=torch.device("cuda", local))
+    from nexus_b200.multigpu import accumulation_tensor, frame_block, reduce_accumulation
+    acc_t = accumulation_tensor(pt, torch.device("cuda", local)) if world > 1 else None   # zero-copy view for NCCL
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up: W untimed steps (also warms NCCL)
+    pt.Render(scene, frames=max(W, 1), firstFrame=1)
+    if world > 1:
+        with torch.cuda.stream(stream):
+            reduce_accumulation(acc_t, max(W, 1))
+    barrier()
+    pt.ResetFrameNumber()
+
+    # ---- timed region: exactly K steps per rank, kernel events on, + the NCCL reduce for N > 1
+    first = frame_block(rank, world, K)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    pt.SetProfiling(events=True, work=False)
+    barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    wall0 = time.time()
+    e0.record(stream)
+    pt.Render(scene, frames=K, firstFrame=first)
+    e1.record(stream)
+    if world > 1:
+        with torch.cuda.stream(stream):
+            pt.SetAccumulatedFrames(reduce_accumulation(acc_t, K))
+    e2.record(stream)
+    barrier()
+    wall = time.time() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total, ms_reduce = e0.elapsed_time(e2), e1.elapsed_time(e2)
+    st = pt.Stats()
+    prof = pt.Profile()
+    rays_local = st["extension_rays"] + st["shadow_rays"]
+    agg = torch.tensor([ms_total, ms_reduce], device="cuda", dtype=torch.float64)
+    cnt = torch.tensor([rays_local, st["extension_rays"], st["shadow_rays"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total, ms_reduce = float(agg[0]), float(agg[1])
+    rays_all = float(cnt[0])
+    value = rays_all / (ms_total * 1e-3) / 1e6
+    mean_radiance = float(pt.ReadAccumulation().mean()) if rank == 0 else 0.0
+
+    # ---- roofline of the dominant kernel (closest-hit traversal): algorithmic bytes from a counted, untimed replay of the same frames
+    pt.SetProfiling(events=False, work=True)
+    pt.ResetFrameNumber()
+    pt.Render(scene, frames=K, firstFrame=first)
+    ctx.synchronize()
+    workp = pt.Profile()
+    pt.SetProfiling(events=False, work=False)
+    tc = prof["trace_closest"]
+    cw, aw = workp["closest_work"], workp["any_work"]
+    bytes_closest = algorithmic_bytes(cw, "closest")
+    hbm, hbm_src = peaks()
+    avg_launch_ms = tc["ms"] / max(tc["launches"], 1)
+    achieved = bytes_closest / max(tc["launches"], 1) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload, {}).get("trace_closest_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "trace_closest_kernel", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": hbm_src,
+                "avg_launch_ms": round(avg_launch_ms, 4), "launches": tc["launches"],
+                "algorithmic_bytes_per_launch": int(bytes_closest / max(tc["launches"], 1)),
+                "per_ray": {"nodes": round(cw["nodes"] / max(cw["rays"], 1), 2), "tris": round(cw["tris"] / max(cw["rays"], 1), 2),
+                            "insts": round(cw["insts"] / max(cw["rays"], 1), 3)},
+                "shadow_per_ray": {"nodes": round(aw["nodes"] / max(aw["rays"], 1), 2), "tris": round(aw["tris"] / max(aw["rays"], 1), 2),
+                                   "insts": round(aw["insts"] / max(aw["rays"], 1), 3)},
+                "kernel_ms_per_step": {k: round(prof[k]["ms"] / K, 4) for k in pt.KERNELS}}
+
+    # ---- e2e: the call a host application makes per frame, HOST buffers on both sides, copies inside the timed region:
+    # camera + render settings from host structs (H2D: the kernel parameter block), one frame, tone-mapped RGBA8 frame read
+    # back into pinned host memory (what Renderer::Render + UnpackToTexture move per frame in the reference).
+    pt.ResetFrameNumber()
+    host_rgba = torch.empty((res[1], res[0]), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    cam = desc["camera"]
+    barrier()
+    t0 = time.time()
+    e2e_rays = 0
+    for i in range(K):
+        scene.SetCamera(cam)
+        scene.SetRenderSettings(desc["settings"])
+        pt.Render(scene, frames=1, firstFrame=first + i)
+        pt.ReadRGBA8(scene, out=host_rgba)
+        s1 = pt.Stats()
+        e2e_rays += s1["extension_rays"] + s1["shadow_rays"]
+    barrier()
+    e2e_s = time.time() - t0
+    e2e_t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    e2e_c = torch.tensor([float(e2e_rays)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_c, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_c[0]) / float(e2e_t[0]) / 1e6
+    # H2D per step: nx_camera (48 B) + nx_render_settings (32 B), marshalled into the kernels' parameter block
+    e2e = {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": 48 + 32, "d2h_bytes_per_step": 4 * res[0] * res[1],
+           "ms_per_step": round(float(e2e_t[0]) * 1e3 / K, 3), "what": "SetCamera+SetRenderSettings (host structs) -> Render(1 frame) -> ReadRGBA8 into pinned host memory"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the CPU oracle's closest-hit traversal on a bounded sample of this workload's primary rays
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(desc, scene, res)
+
+    if rank == 0:
+        line = {"metric": "Mrays/s", "value": round(value, 1), "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": wl["desc"], "resolution": list(res), "path_length": desc["settings"].pathLength,
+                           "partition": f"sample partition: rank g renders frames [1+g*K, (g+1)*K]; NCCL all-reduce(sum) of float[3*W*H] accumulation ({'%.1f' % (12e-6 * res[0] * res[1])} MB)" if world > 1 else "single GPU",
+                           "l2": "per-step working set (ray/hit/state queues %.0f MB at this resolution + BVH/triangles) exceeds the 126 MB L2; no flush needed" % (164e-6 * res[0] * res[1])},
+                "spp_per_s": round(world * K / (ms_total * 1e-3), 2),
+                "rays_per_step": int(rays_all / (K * world)), "extension_rays": int(cnt[1]), "shadow_rays": int(cnt[2]),
+                "primary_Mrays_per_s": round(world * K * res[0] * res[1] / (ms_total * 1e-3) / 1e6, 1),
+                "reduce_ms": round(ms_reduce, 3), "wall_s": round(wall, 3), "scene_setup_s": round(t_scene, 2),
+                "mean_radiance": round(mean_radiance, 5),
+                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    pt.close(); scene.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(desc, scene, res, budget_s=15.0):
+    """CPU port (oracle/oracle_trace.cpp) of the closest-hit traversal, all host cores, on a bounded sample of the workload's
+    primary rays.  The oracle is used here as the thing being timed on the CPU, never on the product path."""
+    import oracle_lib as O
+    from nexus_b200 import scenes
+    import nexus_b200 as nx
+    cores = os.cpu_count() or 1
+    ora = O.oracle_scene_from_product(desc, scene)
+    n = 20000
+    o, d = scenes.camera_rays(desc["camera"], res, n=n, seed=1)
+    rays = nx.make_rays(o, d)
+    t0 = time.time(); ora.trace_closest(rays, threads=cores); dt = time.time() - t0
+    n2 = int(min(4_000_000, max(n, n * budget_s / max(dt, 1e-4))))
+    o, d = scenes.camera_rays(desc["camera"], res, n=n2, seed=2)
+    rays = nx.make_rays(o, d)
+    t0 = time.time(); ora.trace_closest(rays, threads=cores); dt = time.time() - t0
+    return {"value": round(len(rays) / dt / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": f"{len(rays)} primary (camera) rays of this workload, closest-hit traversal only, {dt:.1f} s"}
+
+
+# ----------------------------------------------------------------------------------------- reference arm ----
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    res = wl["res"]
+    if not O.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnexus_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    desc = make_desc(args.workload)
+    O.ref_load_scene_standalone(desc, res)
+    O.ref_render(1, max(W, 1))
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start(); time.sleep(0.3)
+    # the reference's running mean restarts at frame 1; its RNG is keyed on the frame number, so use the same indices as our arm
+    ms, ext, sh = O.ref_render(1, K)
+    clocks = sampler.stop()
+    value = (ext + sh) / (ms * 1e-3) / 1e6
+    img = O.ref_read_accum(res)
+    line = {"impl": "reference", "metric": "Mrays/s", "value": round(value, 1), "unit": "Mrays/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": wl["desc"], "resolution": list(res), "path_length": desc["settings"].pathLength},
+            "spp_per_s": round(K / (ms * 1e-3), 2), "rays_per_step": int((ext + sh) / K), "extension_rays": ext, "shadow_rays": sh,
+            "primary_Mrays_per_s": round(K * res[0] * res[1] / (ms * 1e-3) / 1e6, 1), "mean_radiance": round(float(img.mean()), 5),
+            "clocks": clocks,
+            "cpu_baseline": {"value": round(value, 1), "unit": "Mrays/s", "cores": 0, "kind": "reference",
+                             "sample": f"{K} full frames of this workload through the unmodified reference CUDA kernels (compiled -arch=sm_100a --use_fast_math "
+                                       "from /root/reference) on the same B200; the reference has no CPU implementation of this path"},
+            "e2e": {"value": round(value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="instanced10m_4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,14 @@ typedef struct nx_frame_stats {           /* queue totals of the frames rendered
     uint32_t kernel_launches;
 } nx_frame_stats;
 
+/* Per-kernel device times and traversal work of the last nx_renderer_render call (see nx_renderer_set_profiling).
+ * Kernel classes: 0 generate, 1 closest-hit trace, 2 shade, 3 any-hit (shadow) trace. */
+typedef struct nx_kernel_profile {
+    float ms[4]; uint32_t launches[4];
+    uint64_t closest_work[4];             /* nodes visited, triangles tested, instances entered, rays (flags & 2) */
+    uint64_t any_work[4];
+} nx_kernel_profile;
+
 /* ------------------------------------------------------------------------------------------------ context ---- */
 int nx_abi_version(void);
 int nx_ctx_create(int device, nx_ctx** out);
@@ -185,6 +193,11 @@ int nx_renderer_reset_accumulation(nx_renderer* r);                             
 int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t first_frame, uint32_t n_frames);
 int nx_renderer_frame_count(const nx_renderer* r);                                         /* GetFrameNumber             */
 int nx_renderer_stats(nx_renderer* r, nx_frame_stats* out);
+/* Measurement hooks (the reference's only instrumentation is BVHBuildMetrics; MetricsPanel.cpp:22-40 counts primary rays).
+ * flags & 1: bracket every kernel launch of nx_renderer_render with CUDA events on its stream; flags & 2: run the counting
+ * variants of the two traversal kernels (nodes / triangles / instances per ray for SURVEY.md 8(d)'s byte formula). */
+int nx_renderer_set_profiling(nx_renderer* r, int flags);
+int nx_renderer_profile(nx_renderer* r, nx_kernel_profile* out);
 /* Linear radiance mean, float RGB, row-major, HOST buffer of w*h*3 floats. */
 int nx_renderer_read_accum(nx_renderer* r, float* host_rgb);
 /* DEVICE pointer to the running float3 SUM (w*h*3 floats) and the number of frames in it — what the NCCL reduce consumes. */

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import (Aabb, BuildConfig, BuildMetrics, Bvh2, Bvh8, CameraPod, FrameStats, LightPod, MaterialPod, NexusError,
+from ._capi import (Aabb, BuildConfig, BuildMetrics, Bvh2, Bvh8, CameraPod, FrameStats, KernelProfile, LightPod, MaterialPod, NexusError,
                     RenderSettingsPod, check, lib)
 
 __all__ = ["Context", "Scene", "AssetManager", "Material", "Light", "Camera", "RenderSettings", "PathTracer", "MeshInstance",
@@ -451,6 +451,20 @@ class PathTracer:
         check(self.ctx._h, lib().nx_renderer_stats(self._h, C.byref(st)), "Stats")
         return {n: getattr(st, n) for n, _ in st._fields_}
 
+    KERNELS = ("generate", "trace_closest", "shade", "trace_any")
+
+    def SetProfiling(self, events=True, work=False):
+        """Measurement hook: per-kernel CUDA-event times (events) and traversal work counters (work) for the next Render calls."""
+        check(self.ctx._h, lib().nx_renderer_set_profiling(self._h, C.c_int(int(events) | (int(work) << 1))), "SetProfiling")
+
+    def Profile(self):
+        p = KernelProfile()
+        check(self.ctx._h, lib().nx_renderer_profile(self._h, C.byref(p)), "Profile")
+        out = {k: {"ms": p.ms[i], "launches": p.launches[i]} for i, k in enumerate(self.KERNELS)}
+        for name, arr in (("closest_work", p.closest_work), ("any_work", p.any_work)):
+            out[name] = {"nodes": arr[0], "tris": arr[1], "insts": arr[2], "rays": arr[3]}
+        return out
+
     def ReadAccumulation(self, out=None):
         """Linear radiance mean, (h, w, 3) float32, row 0 = bottom row (the reference's pixel order)."""
         w, h = self.resolution
@@ -467,9 +481,11 @@ class PathTracer:
     def SetAccumulatedFrames(self, frames):
         check(self.ctx._h, lib().nx_renderer_set_accum_frames(self._h, C.c_uint32(frames)), "SetAccumulatedFrames")
 
-    def ReadRGBA8(self, scene):
+    def ReadRGBA8(self, scene, out=None):
+        """Display transform of AccumulateKernel (PathTracer.cu:527-548) on the running mean, (h, w) packed RGBA8."""
         w, h = self.resolution
-        out = np.empty((h, w), np.uint32)
+        if out is None:
+            out = np.empty((h, w), np.uint32)
         check(self.ctx._h, lib().nx_renderer_read_rgba8(self._h, scene._h, _ptr(out)), "ReadRGBA8")
         return out
 

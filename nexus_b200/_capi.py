@@ -63,6 +63,10 @@ class FrameStats(C.Structure):
                 ("device_ms", C.c_float), ("kernel_launches", C.c_uint32)]
 
 
+class KernelProfile(C.Structure):
+    _fields_ = [("ms", C.c_float * 4), ("launches", C.c_uint32 * 4), ("closest_work", C.c_uint64 * 4), ("any_work", C.c_uint64 * 4)]
+
+
 assert C.sizeof(MaterialPod) == 92 and C.sizeof(Aabb) == 24
 
 _lib = None

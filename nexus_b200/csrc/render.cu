@@ -120,15 +120,18 @@ __global__ void __launch_bounds__(NX_TRACE_BLOCK) trace_closest_kernel(TraceScen
 
 // Any-hit.  mode 0: write occlusion flags (parity hook); mode 1: add the queued radiance to the pixel when unoccluded
 // (TraceShadowKernel's fused accumulate, PathTracer.cu:115-122 / BVH8Traversal.cuh:517-519).
+template <bool STATS>
 __global__ void __launch_bounds__(NX_TRACE_BLOCK) trace_any_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
-                                                                     uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum)
+                                                                     uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum,
+                                                                     TraceStats* stats)
 {
     __shared__ uint2 sstack[NX_STACK_SHARED * NX_TRACE_BLOCK];
     const uint32_t n = nPtr ? __ldg(nPtr) : nImm;
-    Traverser<true, false> tr; tr.st.sh = sstack + threadIdx.x;
+    Traverser<true, STATS> tr; tr.st.sh = sstack + threadIdx.x;
     WarpFetcher fetch;
     bool need = true, dead = false;
     uint32_t rayIdx = 0, pixel = 0;
+    unsigned long long sN = 0, sT = 0, sI = 0, sR = 0;
     while (true)
     {
         const uint32_t got = fetch.take(cursor, need && !dead);
@@ -145,9 +148,11 @@ __global__ void __launch_bounds__(NX_TRACE_BLOCK) trace_any_kernel(TraceScene sc
         if (!dead && tr.step(sc)) {
             if (occluded) occluded[rayIdx] = tr.occluded ? 1 : 0;
             else if (!tr.occluded) { const float4 L = __ldg(radiance + rayIdx); add_radiance(accum, pixel, f3(L.x, L.y, L.z)); }
+            if (STATS) { sN += tr.cNodes; sT += tr.cTris; sI += tr.cInsts; sR++; }
             need = true;
         }
     }
+    if (STATS) { atomicAdd(&stats->nodes, sN); atomicAdd(&stats->tris, sT); atomicAdd(&stats->insts, sI); atomicAdd(&stats->rays, sR); }
 }
 
 // --------------------------------------------------------------------------------------------- generate ----
@@ -409,7 +414,7 @@ int persistent_grid(nx_ctx* ctx, const void* fn, int block, int* cache)
     *cache = perSm * ctx->sm_count;
     return *cache;
 }
-int g_gridClosest = 0, g_gridClosestStats = 0, g_gridAny = 0, g_gridShade = 0;
+int g_gridClosest = 0, g_gridClosestStats = 0, g_gridAny = 0, g_gridAnyStats = 0, g_gridShade = 0;
 
 } // namespace
 
@@ -422,6 +427,15 @@ struct nx_renderer {
     bool timed = false;
     uint32_t launches = 0;
     uint32_t pathLengthLast = 0;
+    // optional per-kernel profiling (nx_renderer_set_profiling): event pairs per launch, grouped by kernel
+    int profFlags = 0;
+    std::vector<cudaEvent_t> evPool; size_t evUsed = 0;
+    std::vector<std::pair<int, size_t>> evLaunches;   // (kernel class, index of the start event; stop = index + 1)
+    TraceStats* dWork = nullptr;                      // [0] closest-hit traversal work, [1] any-hit traversal work
+
+    cudaEvent_t next_event() { if (evUsed == evPool.size()) { cudaEvent_t e; cudaEventCreate(&e); evPool.push_back(e); } return evPool[evUsed++]; }
+    void prof_begin(int cls, cudaStream_t st) { if (profFlags & 1) { evLaunches.push_back({cls, evUsed}); cudaEventRecord(next_event(), st); next_event(); } }
+    void prof_end(cudaStream_t st) { if (profFlags & 1) cudaEventRecord(evPool[evLaunches.back().second + 1], st); }
 };
 
 int nxi_trace_closest(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32_t n, nx_hit* dHits, float* outMs)
@@ -447,10 +461,10 @@ int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32
     uint32_t* cursor = nullptr;
     NX_CUDA(ctx, cudaMallocAsync((void**)&cursor, 4, ctx->stream));
     NX_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
-    const int grid = persistent_grid(ctx, (const void*)trace_any_kernel, NX_TRACE_BLOCK, &g_gridAny);
+    const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<false>, NX_TRACE_BLOCK, &g_gridAny);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    trace_any_kernel<<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr);
+    trace_any_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr);
     if (outMs) { cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1); cudaEventElapsedTime(outMs, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     cudaFreeAsync(cursor, ctx->stream);
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -522,6 +536,9 @@ int nx_renderer_create(nx_ctx* ctx, uint32_t width, uint32_t height, nx_renderer
     if (rc) { delete r; return rc; }
     cudaEventCreate(&r->evStart); cudaEventCreate(&r->evStop);
     cudaEventCreateWithFlags(&r->evShade, cudaEventDisableTiming); cudaEventCreateWithFlags(&r->evShadow, cudaEventDisableTiming);
+    if (cudaMalloc((void**)&r->dWork, 2 * sizeof(TraceStats)) != cudaSuccess || cudaMemset(r->dWork, 0, 2 * sizeof(TraceStats)) != cudaSuccess) {
+        ctx->error = "nx_renderer_create: cudaMalloc failed"; nx_renderer_destroy(r); return NX_ERR_CUDA;
+    }
     *out = r;
     return NX_OK;
 }
@@ -532,6 +549,8 @@ void nx_renderer_destroy(nx_renderer* r)
     DeviceGuard guard(r->ctx->device);
     free_buffers(r);
     cudaEventDestroy(r->evStart); cudaEventDestroy(r->evStop); cudaEventDestroy(r->evShade); cudaEventDestroy(r->evShadow);
+    for (cudaEvent_t e : r->evPool) cudaEventDestroy(e);
+    cudaFree(r->dWork);
     delete r;
 }
 
@@ -564,11 +583,24 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
     DSceneView sv; int rc = nxi_scene_view(scene, &sv); if (rc) return rc;
     cudaStream_t s = ctx->stream, sa = ctx->stream_aux;
     const uint32_t L = sv.pathLength;
-    const int gClosest = persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
-    const int gAny = persistent_grid(ctx, (const void*)trace_any_kernel, NX_TRACE_BLOCK, &g_gridAny);
+    const bool work = (r->profFlags & 2) != 0;
+    const int gClosest = work ? persistent_grid(ctx, (const void*)trace_closest_kernel<true>, NX_TRACE_BLOCK, &g_gridClosestStats)
+                              : persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
+    const int gAny = work ? persistent_grid(ctx, (const void*)trace_any_kernel<true>, NX_TRACE_BLOCK, &g_gridAnyStats)
+                          : persistent_grid(ctx, (const void*)trace_any_kernel<false>, NX_TRACE_BLOCK, &g_gridAny);
     const int gShade = persistent_grid(ctx, (const void*)shade_kernel, kShadeBlock, &g_gridShade);
     const int gGen = ctx->sm_count * 8;
     WaveBuffers& wb = r->wb;
+    r->evUsed = 0; r->evLaunches.clear();
+    if (work) NX_CUDA(ctx, cudaMemsetAsync(r->dWork, 0, 2 * sizeof(TraceStats), s));
+
+    auto closest = [&](const nx_ray* q, uint32_t b) {
+        r->prof_begin(1, s);
+        if (work) trace_closest_kernel<true><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, r->dWork);
+        else trace_closest_kernel<false><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, nullptr);
+        r->prof_end(s);
+        r->launches++;
+    };
 
     NX_CUDA(ctx, cudaMemsetAsync(wb.totals, 0, sizeof(WaveTotals), s));
     NX_CUDA(ctx, cudaEventRecord(r->evStart, s));
@@ -577,28 +609,33 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
     {
         const uint32_t frame = firstFrame + f;
         NX_CUDA(ctx, cudaMemsetAsync(wb.counters, 0, sizeof(WaveCounters), s));
+        r->prof_begin(0, s);
         generate_kernel<<<gGen, 256, 0, s>>>(sv, wb, frame);
-        trace_closest_kernel<false><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, wb.ext[0], 0, &wb.counters->extCount[0], &wb.counters->extFetch[0], wb.hits, nullptr);
-        r->launches += 2;
+        r->prof_end(s);
+        r->launches++;
+        closest(wb.ext[0], 0);
         for (uint32_t b = 1; b <= L; b++)
         {
             // the shadow rays of bounce b-1 must have been consumed before shade(b) refills the shadow queue
             if (b > 1) NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evShadow, 0));
+            r->prof_begin(2, s);
             shade_kernel<<<gShade, kShadeBlock, 0, s>>>(sv, wb, b, frame);
+            r->prof_end(s);
             r->launches++;
             NX_CUDA(ctx, cudaEventRecord(r->evShade, s));
             // shadow rays on the auxiliary stream overlap the extension trace (the reference's graph runs them as siblings)
             NX_CUDA(ctx, cudaStreamWaitEvent(sa, r->evShade, 0));
-            trace_any_kernel<<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum);
+            r->prof_begin(3, sa);
+            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, r->dWork + 1);
+            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, nullptr);
+            r->prof_end(sa);
             NX_CUDA(ctx, cudaEventRecord(r->evShadow, sa));
             r->launches++;
-            if (b < L) {
-                trace_closest_kernel<false><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, wb.ext[b & 1u], 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, nullptr);
-                r->launches++;
-            }
+            if (b < L) closest(wb.ext[b & 1u], b);
         }
         NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evShadow, 0));
         frame_totals_kernel<<<1, 32, 0, s>>>(wb, L);
+        r->launches++;
     }
     NX_CUDA(ctx, cudaEventRecord(r->evStop, s));
     NX_CUDA(ctx, cudaGetLastError());
@@ -621,6 +658,34 @@ int nx_renderer_stats(nx_renderer* r, nx_frame_stats* out)
     out->extension_rays = t.ext; out->shadow_rays = t.shadow; out->shaded_hits = t.shaded; out->frames = t.frames;
     if (r->timed) NX_CUDA(ctx, cudaEventElapsedTime(&out->device_ms, r->evStart, r->evStop));
     out->kernel_launches = r->launches;
+    return NX_OK;
+}
+
+int nx_renderer_set_profiling(nx_renderer* r, int flags)
+{
+    if (!r) return NX_ERR_INVALID;
+    r->profFlags = flags;
+    return NX_OK;
+}
+
+int nx_renderer_profile(nx_renderer* r, nx_kernel_profile* out)
+{
+    if (!r || !out) return NX_ERR_INVALID;
+    nx_ctx* ctx = r->ctx;
+    DeviceGuard guard(ctx->device);
+    std::memset(out, 0, sizeof(*out));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
+    for (const auto& l : r->evLaunches) {
+        float ms = 0.f;
+        NX_CUDA(ctx, cudaEventElapsedTime(&ms, r->evPool[l.second], r->evPool[l.second + 1]));
+        out->ms[l.first] += ms; out->launches[l.first]++;
+    }
+    if (r->profFlags & 2) {
+        TraceStats h[2];
+        NX_CUDA(ctx, cudaMemcpy(h, r->dWork, sizeof(h), cudaMemcpyDeviceToHost));
+        out->closest_work[0] = h[0].nodes; out->closest_work[1] = h[0].tris; out->closest_work[2] = h[0].insts; out->closest_work[3] = h[0].rays;
+        out->any_work[0] = h[1].nodes; out->any_work[1] = h[1].tris; out->any_work[2] = h[1].insts; out->any_work[3] = h[1].rays;
+    }
     return NX_OK;
 }
 

@@ -24,6 +24,7 @@
 #include "Cuda/Scene/MeshInstance.cuh"
 #include "NXB/BVHBuilder.h"
 #include "NXB/BVHBuildMetrics.h"
+#include "Cuda/Setup.h"          // B/src/Cuda/Setup.h: the reference's bounds / Morton kernels (explicitly instantiated in Setup.cu:114-118)
 
 #define REF_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     std::fprintf(stderr, "[nxref] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while (0)
@@ -147,6 +148,42 @@ int nxref_build_bvh8(const void* hostPrims, uint32_t n, int primType, int priori
     NXB::FreeDeviceBVH(bvh);
     cudaFree(dPrims);
     return 0;
+}
+
+// The reference's own Morton keys: ComputeSceneBoundsKernel + ComputeMortonCodesKernel launched as BuildBVH2 /
+// BuildBVH2Impl launch them (B/src/BVHBuilder.cpp:119-153, 17-49).  outCodes: n x uint64 in primitive order.
+} // extern "C"
+template <typename PrimT, typename McT>
+static int refMorton(const void* hostPrims, uint32_t n, uint64_t* outCodes, float* outBounds6)
+{
+    PrimT* dPrims = nullptr; McT* dCodes = nullptr;
+    NXB::BVH2BuildState st{};
+    st.primCount = n;
+    REF_CHECK(cudaMalloc((void**)&dPrims, sizeof(PrimT) * n));
+    REF_CHECK(cudaMemcpy(dPrims, hostPrims, sizeof(PrimT) * n, cudaMemcpyHostToDevice));
+    REF_CHECK(cudaMalloc((void**)&st.sceneBounds, sizeof(NXB::AABB)));
+    REF_CHECK(cudaMalloc((void**)&st.nodes, sizeof(NXB::BVH2::Node) * (2 * (size_t)n - 1)));
+    REF_CHECK(cudaMalloc((void**)&st.clusterIdx, 4 * (size_t)n));
+    REF_CHECK(cudaMalloc((void**)&dCodes, sizeof(McT) * n));
+    NXB::AABB sb; sb.Clear();
+    REF_CHECK(cudaMemcpy(st.sceneBounds, &sb, sizeof(sb), cudaMemcpyHostToDevice));
+    void* a1[2] = {&st, &dPrims};
+    REF_CHECK(cudaLaunchKernel((void*)NXB::ComputeSceneBoundsKernel<PrimT>, dim3(occupancyGrid((const void*)NXB::ComputeSceneBoundsKernel<PrimT>, 64)), dim3(64), a1, 0, 0));
+    void* a2[2] = {&st, &dCodes};
+    REF_CHECK(cudaLaunchKernel((void*)NXB::ComputeMortonCodesKernel<McT>, dim3(occupancyGrid((const void*)NXB::ComputeMortonCodesKernel<McT>, 64)), dim3(64), a2, 0, 0));
+    REF_CHECK(cudaDeviceSynchronize());
+    std::vector<McT> h(n);
+    REF_CHECK(cudaMemcpy(h.data(), dCodes, sizeof(McT) * n, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) outCodes[i] = (uint64_t)h[i];
+    if (outBounds6) REF_CHECK(cudaMemcpy(outBounds6, st.sceneBounds, 24, cudaMemcpyDeviceToHost));
+    cudaFree(dPrims); cudaFree(dCodes); cudaFree(st.sceneBounds); cudaFree(st.nodes); cudaFree(st.clusterIdx);
+    return 0;
+}
+extern "C" {
+int nxref_morton(const void* hostPrims, uint32_t n, int primType, int bits64, uint64_t* outCodes, float* outBounds6)
+{
+    if (primType) return bits64 ? refMorton<NXB::Triangle, uint64_t>(hostPrims, n, outCodes, outBounds6) : refMorton<NXB::Triangle, uint32_t>(hostPrims, n, outCodes, outBounds6);
+    return bits64 ? refMorton<NXB::AABB, uint64_t>(hostPrims, n, outCodes, outBounds6) : refMorton<NXB::AABB, uint32_t>(hostPrims, n, outCodes, outBounds6);
 }
 
 // NXB::BenchmarkBuild (B/include/NXB/BVHBuildMetrics.h:63-108) without the printing:

@@ -1,0 +1,70 @@
+"""Deterministic inputs shared by scripts/make_golden.py (which runs the reference on them) and the parity tests."""
+import numpy as np
+
+
+def _rand_tris(rng, n, spread=5.0, size=0.1):
+    c = rng.uniform(-spread, spread, (n, 1, 3)).astype(np.float32)
+    return (c + rng.uniform(-size, size, (n, 3, 3)).astype(np.float32)).reshape(n, 9)
+
+
+def builder_cases():
+    """(name, prims (n,9) triangles or (n,6) AABBs, prioritizeSpeed).  Covers single/tiny inputs, the PLOC merge threshold
+    (16/17/33), duplicates (equal Morton keys and equal areas), a degenerate flat cloud, AABB primitives, a closed mesh."""
+    from nexus_b200 import scenes
+    rng = np.random.default_rng(20261017)
+    cases = []
+    for n in (1, 2, 3, 16, 17, 33, 100, 1000, 5000):
+        t = _rand_tris(rng, n)
+        cases.append((f"tri{n}_m32", t, True))
+        cases.append((f"tri{n}_m64", t, False))
+    lo = rng.uniform(-3, 3, (50, 3)).astype(np.float32)
+    cases.append(("aabb50_m64", np.concatenate([lo, lo + rng.uniform(0.01, 0.5, (50, 3)).astype(np.float32)], 1), False))
+    cases.append(("aabb50_m32", cases[-1][1], True))
+    cases.append(("dup40_m32", np.tile(_rand_tris(rng, 1), (40, 1)), True))
+    flat = _rand_tris(rng, 500); flat[:, 2::3] = 0.0
+    cases.append(("flat500_m32", flat, True))
+    cases.append(("sphere2048_m32", scenes.uv_sphere(32, 32), True))
+    cases.append(("sphere8192_m32", scenes.uv_sphere(64, 64), True))
+    # lattice with a power-of-two extent: Morton normalisation is exact in both IEEE and approximate division
+    g = rng.integers(0, 256, (3000, 1, 3)).astype(np.float32) / 8.0
+    lat = (g + rng.integers(0, 5, (3000, 3, 3)).astype(np.float32) / 16.0).reshape(3000, 9)
+    lat[0, :3] = 0.0; lat[1, :3] = 32.0
+    cases.append(("lattice3000_m32", lat, True))
+    cases.append(("lattice3000_m64", lat, False))
+    return cases
+
+
+def trace_scenes():
+    from nexus_b200 import scenes
+    return [
+        ("cornell", scenes.with_triangle_data(scenes.cornell_box()), (128, 128)),
+        ("instanced", scenes.with_triangle_data(scenes.instanced_scene(n_blas=6, n_instances=20, nu=16, nv=14)), (128, 128)),
+    ]
+
+
+def trace_rays(name, desc, res):
+    """Camera rays + rays from random points in random directions (inside the scene's bounding region)."""
+    import nexus_b200 as nx
+    from nexus_b200 import scenes
+    rng = np.random.default_rng(7 + len(name))
+    o, d = scenes.camera_rays(desc["camera"], res, n=6000, seed=3)
+    lo, hi = np.array([1e30] * 3), np.array([-1e30] * 3)
+    for m in desc["meshes"][:2] if name == "instanced" else desc["meshes"]:
+        v = m["triangles"].reshape(-1, 3)
+        lo, hi = np.minimum(lo, v.min(0)), np.maximum(hi, v.max(0))
+    if name == "instanced":
+        lo, hi = np.array([-8.0, 0.1, -8.0]), np.array([8.0, 4.0, 8.0])
+    ro = rng.uniform(lo, hi, (6000, 3)).astype(np.float32)
+    rd = rng.normal(size=(6000, 3)).astype(np.float32)
+    rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    return nx.make_rays(np.concatenate([o, ro]), np.concatenate([d, rd]))
+
+
+def render_cases():
+    """(name, desc, resolution, spp, block): converged block means are compared, not pixels (the reference's RNG is keyed
+    on racing queue slots, so its frames are not reproducible run to run — SURVEY.md §3.1)."""
+    from nexus_b200 import scenes
+    return [
+        ("cornell", scenes.with_triangle_data(scenes.cornell_box(path_length=6)), (128, 128), 2048, 8),
+        ("instanced", scenes.with_triangle_data(scenes.instanced_scene(n_blas=6, n_instances=20, nu=16, nv=14, path_length=6)), (128, 72), 2048, 8),
+    ]

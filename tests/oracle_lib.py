@@ -227,6 +227,16 @@ def ref_build_bvh8(prims, prioritize_speed, metrics=False):
     return out + (m,) if metrics else out
 
 
+def ref_morton(prims, bits64):
+    """The reference's own (fast-math) Morton keys, primitive order."""
+    prims = np.ascontiguousarray(prims, np.float32)
+    n, tri = prims.shape[0], 1 if prims.shape[1] == 9 else 0
+    out = np.zeros(n, np.uint64)
+    bounds = np.zeros(6, np.float32)
+    assert ref().nxref_morton(_p(prims), C.c_uint32(n), C.c_int(tri), C.c_int(int(bits64)), _p(out), _p(bounds)) == 0
+    return out, bounds
+
+
 def ref_build_bvh2(prims, prioritize_speed):
     prims = np.ascontiguousarray(prims, np.float32)
     n, tri = prims.shape[0], 1 if prims.shape[1] == 9 else 0
@@ -306,3 +316,91 @@ def oracle_scene_from_product(desc, scene):
     tn, tp = scene.TLAS().ToHost()
     S.set_instances(mesh_idx, inv, tn, tp)
     return S
+
+
+# ------------------------------------------------------------------ reference arm, standalone host side ----
+# bench.py's `--impl reference` must not run any product code, so the host-side scene assembly the reference does in
+# MeshInstance::GetTransfromationMatrix / GetBounds / ToDevice (N/Scene/MeshInstance.h:36-66), Camera::ToDevice
+# (N/Scene/Camera.cpp:130-156) and Scene::UpdateSceneLighting (N/Scene/Scene.cpp:157-219) is restated here in numpy.
+def _trs(position, rotation_deg, scale):
+    rx, ry, rz = (np.radians(np.float64(a)) for a in rotation_deg)
+    T = np.eye(4); T[:3, 3] = position
+    S = np.diag([scale[0], scale[1], scale[2], 1.0])
+    Rx = np.eye(4); Rx[1, 1], Rx[1, 2], Rx[2, 1], Rx[2, 2] = np.cos(rx), -np.sin(rx), np.sin(rx), np.cos(rx)
+    Ry = np.eye(4); Ry[0, 0], Ry[0, 2], Ry[2, 0], Ry[2, 2] = np.cos(ry), np.sin(ry), -np.sin(ry), np.cos(ry)
+    Rz = np.eye(4); Rz[0, 0], Rz[0, 1], Rz[1, 0], Rz[1, 1] = np.cos(rz), -np.sin(rz), np.sin(rz), np.cos(rz)
+    return T @ Rz @ Ry @ Rx @ S
+
+
+def camera_record(cam, resolution):
+    """D_Camera (88 B) from Camera ctor arguments."""
+    w, h = resolution
+    f = np.asarray(cam.forward, np.float64)
+    r = np.asarray(cam.right, np.float64)
+    if not r.any():
+        r = np.cross(f, [0.0, 1.0, 0.0])
+    up = np.cross(r, f)
+    half_w = cam.focusDistance * np.tan(np.radians(cam.horizontalFOV / 2.0))
+    half_h = half_w / (w / h)
+    lens = cam.focusDistance * np.tan(np.radians(cam.defocusAngle / 2.0))
+    pos = np.asarray(cam.position, np.float64)
+    vx, vy = 2 * half_w * r, 2 * half_h * up
+    ll = pos - vx / 2 - vy / 2 + f * cam.focusDistance
+    rec = np.zeros(22, np.float32)
+    rec[0:3], rec[3:6], rec[6:9], rec[9] = pos, r, up, lens
+    rec[10:13], rec[13:16], rec[16:19] = ll, vx, vy
+    out = rec.view(np.uint8).copy()
+    out[80:88] = np.array([w, h], np.uint32).view(np.uint8)
+    return out
+
+
+def ref_load_scene_standalone(desc, resolution):
+    """Loads a scene description into the reference harness without touching the product library."""
+    R = ref()
+    R.nxref_scene_reset()
+    mesh_bounds = []
+    for m in desc["meshes"]:
+        tris = np.ascontiguousarray(m["triangles"], np.float32)
+        td = np.ascontiguousarray(m["triangle_data"], np.float32)
+        idx = R.nxref_add_mesh(_p(tris), _p(td), C.c_uint32(tris.shape[0]))
+        assert idx >= 0
+        b = np.zeros(6, np.float32)
+        R.nxref_mesh_bounds(C.c_int(idx), _p(b))
+        mesh_bounds.append(b)
+    inst = np.zeros((len(desc["instances"]), 160), np.uint8)
+    mats_of = []
+    for k, i in enumerate(desc["instances"]):
+        M = _trs(i["position"], i["rotation"], i["scale"])
+        Mi = np.linalg.inv(M)
+        b = mesh_bounds[i["mesh"]]
+        corners = np.array([[b[0 + 3 * (c & 1)], b[1 + 3 * ((c >> 1) & 1)], b[2 + 3 * ((c >> 2) & 1)], 1.0] for c in range(8)])
+        wc = (M.astype(np.float32).astype(np.float64) @ corners.T).T[:, :3]
+        mat = i.get("material", -1)
+        mat = desc["meshes"][i["mesh"]]["material"] if mat < 0 else mat
+        mats_of.append(mat)
+        inst[k, 0:8] = np.array([i["mesh"], mat], np.uint32).view(np.uint8)
+        inst[k, 8:72] = M.astype(np.float32).ravel().view(np.uint8)
+        inst[k, 72:136] = Mi.astype(np.float32).ravel().view(np.uint8)
+        inst[k, 136:160] = np.concatenate([wc.min(0), wc.max(0)]).astype(np.float32).view(np.uint8)
+    assert R.nxref_set_instances(_p(inst), C.c_uint32(inst.shape[0])) == 0
+    mats = np.frombuffer(b"".join(bytes(m.pod()) for m in desc["materials"]), np.uint8).copy()
+    assert R.nxref_set_materials(_p(mats), C.c_uint32(len(desc["materials"]))) == 0
+    lights = []
+    for mi, m in enumerate(desc["materials"]):
+        if max(m.emissionColor) > 0.0 and m.intensity > 0.0:
+            for k, mo in enumerate(mats_of):
+                if mo == mi:
+                    rec = np.zeros(52, np.uint8)
+                    rec[0:4] = np.array([k], np.uint32).view(np.uint8)
+                    rec[48] = 3
+                    lights.append(rec)
+    lights = np.stack(lights) if lights else np.zeros((0, 52), np.uint8)
+    assert R.nxref_set_lights(_p(lights) if len(lights) else None, C.c_uint32(len(lights))) == 0
+    assert R.nxref_set_camera(_p(camera_record(desc["camera"], resolution))) == 0
+    st = desc["settings"]
+    bg = np.asarray(st.backgroundColor, np.float32)
+    assert R.nxref_set_settings(C.c_int(int(st.useMIS)), C.c_int(int(st.pathLength)), _p(bg), C.c_float(st.backgroundIntensity)) == 0
+    if desc.get("hdr") is not None:
+        hdr = np.ascontiguousarray(desc["hdr"], np.float32)
+        assert R.nxref_set_hdr(_p(hdr), C.c_uint32(hdr.shape[1]), C.c_uint32(hdr.shape[0])) == 0
+    assert R.nxref_render_init(C.c_uint32(resolution[0]), C.c_uint32(resolution[1])) == 0

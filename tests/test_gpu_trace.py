@@ -1,0 +1,150 @@
+"""GPU parity of the two-level CWBVH8 traversal kernels through the C ABI.
+
+Bar (north_star): closest-hit primitive and instance ids bit-exact on fixed ray batches, hit t within 1e-5 relative.
+ * vs the CPU oracle (same IEEE operation sequence): ids AND t/u/v bit for bit;
+ * vs the committed reference golden hits and, when present, the live reference kernel: ids exact except exact-distance
+   ties (coincident/abutting triangles, where the reference itself is order-dependent), t within 1e-5 relative
+   for all but a counted handful of grazing hits where the reference's --use_fast_math reciprocal loses accuracy — for those
+   the product must be at least as close to the float64 ground truth as the reference is.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import nexus_b200 as nx
+import oracle_lib as O
+from golden_cases import trace_rays, trace_scenes
+from nexus_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz")
+REL = 1e-5   # north_star's tolerance on hit distance
+
+
+def exact_t(desc, scene, rays, hits):
+    """float64 Moeller-Trumbore distance of the reported (instance, prim) for each ray."""
+    inst = scene.ExportInstances()
+    inv = inst[:, 72:136].copy().view(np.float32).reshape(-1, 4, 4).astype(np.float64)
+    mesh_of = inst[:, 0:4].copy().view(np.uint32).ravel()
+    out = np.full(len(rays), 1e30)
+    for i in np.nonzero(hits["prim"] != 0xffffffff)[0]:
+        k = hits["instance"][i]
+        tri = desc["meshes"][mesh_of[k]]["triangles"][hits["prim"][i]].astype(np.float64)
+        o = inv[k][:3, :3] @ rays["origin"][i].astype(np.float64) + inv[k][:3, 3]
+        d = inv[k][:3, :3] @ rays["direction"][i].astype(np.float64)
+        e0, e1 = tri[3:6] - tri[0:3], tri[6:9] - tri[0:3]
+        pv = np.cross(d, e1); det = e0 @ pv
+        qv = np.cross(o - tri[0:3], e0)
+        out[i] = (e1 @ qv) / det
+    return out
+
+
+def check_against_reference(desc, scene, ora, rays, got, ref_hits):
+    cmp = O.compare_hits(ora, rays, got, ref_hits, rel=REL)
+    assert cmp["hard"] == 0, cmp
+    assert cmp["tie"] <= 0.001 * cmp["n"], cmp
+    same = (got["prim"] == ref_hits["prim"]) & (got["instance"] == ref_hits["instance"]) & (got["prim"] != 0xffffffff)
+    rel = np.abs(got["t"].astype(np.float64) - ref_hits["t"]) / np.maximum(np.abs(ref_hits["t"].astype(np.float64)), 1e-30)
+    bad = np.nonzero(same & (rel > REL))[0]
+    assert len(bad) <= 1e-4 * len(rays), f"{len(bad)} hits differ from the reference by more than {REL}"
+    if len(bad):
+        truth = exact_t(desc, scene, rays[bad], got[bad])
+        ours = np.abs(got["t"][bad] - truth)
+        theirs = np.abs(ref_hits["t"][bad] - truth)
+        assert (ours <= theirs + 1e-7 * np.abs(truth)).all(), "product is further from the float64 distance than the reference"
+    return cmp, len(bad)
+
+
+@pytest.mark.parametrize("case", trace_scenes(), ids=lambda c: c[0])
+def test_closest_hit_parity(ctx, have_ref, case):
+    name, desc, res = case
+    scene = scenes.build(ctx, desc, res)
+    rays = trace_rays(name, desc, res)
+    got = scene.TraceClosest(rays)
+    ora = O.oracle_scene_from_product(desc, scene)
+    # (1) CPU oracle on the BVHs the product built: everything bit for bit
+    want = ora.trace_closest(rays)
+    for f in ("prim", "instance"):
+        assert (got[f] == want[f]).all(), f
+    for f in ("t", "u", "v"):
+        assert (got[f].view(np.uint32) == want[f].view(np.uint32)).all(), f
+    # (2) brute force over every instance x triangle (independent of any BVH)
+    sub = slice(0, 3000)
+    brute = ora.trace_brute(rays[sub])
+    cmp = O.compare_hits(ora, rays[sub], got[sub], brute, rel=REL)
+    assert cmp["hard"] == 0 and cmp["t_bad"] == 0, cmp
+    # (3) the reference's TraceKernel: golden file, and live when oracle/_ref is on the box
+    gold = np.load(GOLD)[name + "/hits"]
+    check_against_reference(desc, scene, ora, rays, got, gold)
+    if have_ref:
+        O.ref_load_scene(desc, scene, res)
+        live, _ = O.ref_trace(rays)
+        check_against_reference(desc, scene, ora, rays, got, live)
+    scene.close()
+
+
+@pytest.mark.parametrize("case", trace_scenes(), ids=lambda c: c[0])
+def test_any_hit_parity(ctx, case):
+    name, desc, res = case
+    scene = scenes.build(ctx, desc, res)
+    rays = trace_rays(name, desc, res)
+    ora = O.oracle_scene_from_product(desc, scene)
+    closest = ora.trace_closest(rays)
+    for tmax in (0.5, 2.0, 1e30):
+        r = nx.make_rays(rays["origin"], rays["direction"], tmax)
+        occ = scene.TraceAny(r)
+        assert (occ == ora.trace_any(r)).all()
+        # any-hit is consistent with closest-hit: occluded <=> the closest hit lies inside (0, tmax)
+        assert (occ.astype(bool) == (closest["t"] < np.float32(tmax))).all()
+    scene.close()
+
+
+def test_edge_cases(ctx):
+    """Empty batch, rays that miss everything, axis-parallel rays (zero direction components -> infinite reciprocals),
+    rays starting on a surface, a single-triangle mesh, and a batch that is not a multiple of the warp size."""
+    desc = scenes.with_triangle_data(scenes.cornell_box())
+    scene = scenes.build(ctx, desc, (64, 64))
+    ora = O.oracle_scene_from_product(desc, scene)
+    assert len(scene.TraceClosest(nx.make_rays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)))) == 0
+    o = np.array([[0, 1, 5], [0, 1, 0.5], [0, 1, 0.5], [0, 1, 0.5], [0.3, 0.0, 0.2], [5, 5, 5], [0, 1, 0.5]], np.float32)
+    d = np.array([[0, 0, 1], [1, 0, 0], [0, -1, 0], [0, 0, -1], [0, 1, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    rays = nx.make_rays(o, d)
+    got, want = scene.TraceClosest(rays), ora.trace_closest(rays)
+    assert (got["prim"] == want["prim"]).all() and (got["instance"] == want["instance"]).all()
+    assert (got["t"].view(np.uint32) == want["t"].view(np.uint32)).all()
+    assert got["t"][0] == nx.MISS_T and got["prim"][0] == 0xffffffff and got["t"][5] == nx.MISS_T
+    assert got["t"][2] == np.float32(1.0)             # straight down from y=1 to the floor at y=0
+    scene.close()
+    # one triangle, one instance
+    one = {"meshes": [{"name": "t", "triangles": np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), "material": 0}],
+           "instances": [{"mesh": 0, "material": -1, "position": (0, 0, -2), "rotation": (0, 0, 0), "scale": (2, 2, 2)}],
+           "materials": [nx.Material()], "lights": [], "camera": nx.Camera(), "settings": nx.RenderSettings()}
+    s1 = scenes.build(ctx, scenes.with_triangle_data(one), (8, 8))
+    h = s1.TraceClosest(nx.make_rays(np.array([[0.5, 0.5, 0]], np.float32), np.array([[0, 0, -1]], np.float32)))
+    assert h["prim"][0] == 0 and h["instance"][0] == 0 and h["t"][0] == np.float32(2.0)
+    assert abs(h["u"][0] - 0.25) < 1e-6 and abs(h["v"][0] - 0.25) < 1e-6
+    s1.close()
+
+
+def test_full_resolution_properties(ctx):
+    """At bench size (3840x2160 primary rays of a mid-size instanced scene) parity is checked through size-independent
+    properties: a random 100k subset equals the CPU oracle bit for bit, any-hit agrees with closest-hit, and tracing the
+    batch in two halves gives the same answers as tracing it at once (no dependence on queue position)."""
+    desc = scenes.with_triangle_data(scenes.instanced_scene(n_blas=32, n_instances=256, nu=40, nv=40))
+    res = (3840, 2160)
+    scene = scenes.build(ctx, desc, res)
+    o, d = scenes.camera_rays(desc["camera"], res)
+    rays = nx.make_rays(o, d)
+    got = scene.TraceClosest(rays)
+    idx = np.random.default_rng(1).choice(len(rays), 100_000, replace=False)
+    ora = O.oracle_scene_from_product(desc, scene)
+    want = ora.trace_closest(rays[idx])
+    assert (got["prim"][idx] == want["prim"]).all() and (got["instance"][idx] == want["instance"]).all()
+    assert (got["t"][idx].view(np.uint32) == want["t"].view(np.uint32)).all()
+    half = len(rays) // 2
+    a, b = scene.TraceClosest(rays[:half]), scene.TraceClosest(rays[half:])
+    assert (np.concatenate([a, b]).view(np.uint8) == got.view(np.uint8)).all()
+    occ = scene.TraceAny(rays)
+    assert (occ.astype(bool) == (got["t"] < nx.MISS_T)).all()
+    scene.close()
