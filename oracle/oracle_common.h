@@ -23,8 +23,12 @@ static inline f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; 
 static inline f3 operator*(float s, f3 a) { return {a.x * s, a.y * s, a.z * s}; }
 static inline f3 operator*(f3 a, f3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
 static inline f3 operator-(f3 a) { return {-a.x, -a.y, -a.z}; }
-static inline f3 vmin(f3 a, f3 b) { return {fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}; }
-static inline f3 vmax(f3 a, f3 b) { return {fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
+// PTX min.f32 / max.f32 order the zeros (-0 < +0); libm's fminf/fmaxf may return either.  Leaf bounds of triangles with a
+// vertex at -0 depend on it (seen on the UV sphere's pole rows), so the restatement pins the GPU behaviour.
+static inline float gmin(float a, float b) { if (a == 0.0f && b == 0.0f) return (std::signbit(a) || std::signbit(b)) ? -0.0f : 0.0f; return fminf(a, b); }
+static inline float gmax(float a, float b) { if (a == 0.0f && b == 0.0f) return (std::signbit(a) && std::signbit(b)) ? -0.0f : 0.0f; return fmaxf(a, b); }
+static inline f3 vmin(f3 a, f3 b) { return {gmin(a.x, b.x), gmin(a.y, b.y), gmin(a.z, b.z)}; }
+static inline f3 vmax(f3 a, f3 b) { return {gmax(a.x, b.x), gmax(a.y, b.y), gmax(a.z, b.z)}; }
 static inline float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline f3 cross(f3 a, f3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 static inline float length(f3 a) { return sqrtf(dot(a, a)); }

@@ -1,0 +1,118 @@
+"""CPU tests of the oracle (oracle/*.cpp, test infrastructure) against the committed outputs of the unmodified reference
+kernels (tests/golden/, see its README), plus structural invariants the reference implies.  No GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from golden_cases import builder_cases, trace_rays, trace_scenes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = builder_cases()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "builder_ref.npz"))
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_builder_oracle_equals_reference_trees(gold, case):
+    """Given the reference's own (fast-math) Morton keys, the CPU H-PLOC + collapse restatement reproduces the reference's
+    BVH2 and CWBVH8 bit for bit (canonical numbering)."""
+    name, prims, speed = case
+    n, tri, b64 = prims.shape[0], 1 if prims.shape[1] == 9 else 0, 0 if speed else 1
+    pb, sb = O.prim_bounds(prims, tri)
+    assert (sb == gold[name + "/bounds"]).all()
+    o2 = O.build_bvh2(pb, gold[name + "/morton"], b64)
+    if n > 1:
+        assert (O.canon_bvh2(o2, n) == gold[name + "/bvh2"]).all()
+    o8, op8 = O.build_bvh8(o2, n)
+    c8, cp8 = O.canon_bvh8(o8, op8)
+    assert c8.shape == gold[name + "/bvh8"].shape and (c8 == gold[name + "/bvh8"]).all()
+    assert (cp8 == gold[name + "/prim_idx"]).all()
+    assert O.check_bvh8(o8, op8, pb) == 0
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_builder_oracle_pure_cpu_pipeline(gold, case):
+    """Same with the oracle's own IEEE-division Morton keys: 32-bit keys agree with the GPU's exactly on every golden case;
+    64-bit keys may differ in the last quantisation cell for a few primitives (div.approx), counted here, and on these
+    cases never change the tree."""
+    name, prims, speed = case
+    n, tri, b64 = prims.shape[0], 1 if prims.shape[1] == 9 else 0, 0 if speed else 1
+    pb, sb = O.prim_bounds(prims, tri)
+    codes = O.morton(pb, sb, b64)
+    mism = int((codes != gold[name + "/morton"]).sum())
+    assert mism == 0 if not b64 else mism <= 0.3 * n + 4, mism   # 21-bit cells vs a 2-ulp approximate division
+    n8, pidx, _ = O.cpu_build_bvh8(prims, tri, b64)
+    c8, cp8 = O.canon_bvh8(n8, pidx)
+    assert c8.shape == gold[name + "/bvh8"].shape and (c8 == gold[name + "/bvh8"]).all() and (cp8 == gold[name + "/prim_idx"]).all()
+
+
+def test_sort_contract_and_bvh2_shape():
+    """Keys are sorted on bits [2,32) / [1,64) only, stably (Setup.cu:74-78); BVH2 = 2n-1 nodes, leaves first, root last."""
+    rng = np.random.default_rng(3)
+    import ctypes as C
+    codes = rng.integers(0, 1 << 30, 1000, dtype=np.uint64)
+    codes[100:200] = codes[100] ^ np.arange(100, dtype=np.uint64) % 4          # equal after dropping the two low bits
+    out_c, out_i = np.zeros(1000, np.uint64), np.zeros(1000, np.uint32)
+    O.oracle().orc_sort(O._p(codes), C.c_uint32(1000), C.c_int(0), O._p(out_c), O._p(out_i))
+    key = out_c >> np.uint64(2)
+    assert (np.diff(key.astype(np.int64)) >= 0).all()
+    same = np.nonzero(np.diff(key.astype(np.int64)) == 0)[0]
+    assert (out_i[same + 1] > out_i[same]).all()                                # stable
+    n = 777
+    c = rng.uniform(-3, 3, (n, 1, 3)).astype(np.float32)
+    prims = (c + rng.uniform(-0.1, 0.1, (n, 3, 3)).astype(np.float32)).reshape(n, 9)
+    pb, sb = O.prim_bounds(prims, 1)
+    n2 = O.build_bvh2(pb, O.morton(pb, sb, 0), 0)
+    leaf = n2[:, 6] == 0xffffffff
+    assert leaf[:n].all() and not leaf[n:].any() and (n2[:n, 7] == np.arange(n)).all()
+    kids = np.concatenate([n2[n:, 6], n2[n:, 7]])
+    assert len(np.unique(kids)) == 2 * n - 2 and 2 * n - 2 not in kids
+    f = n2.view(np.float32)
+    for i in range(n, 2 * n - 1):                                               # parent box = union of child boxes
+        l, r = n2[i, 6], n2[i, 7]
+        assert (f[i, :3] == np.minimum(f[l, :3], f[r, :3])).all() and (f[i, 3:6] == np.maximum(f[l, 3:6], f[r, 3:6])).all()
+    c2 = O.canon_bvh2(n2, n)
+    assert (O.canon_bvh2(c2, n) == c2).all()                                    # canonical form is a fixed point
+
+
+def test_bvh8_invariants_on_config1_mesh():
+    """BASELINE.json configs[0]: the ~100K-triangle tessellated mesh, host only."""
+    from nexus_b200 import scenes
+    prims = scenes.uv_sphere(224, 224)
+    n = prims.shape[0]
+    assert n == 100352
+    n8, pidx, sb = O.cpu_build_bvh8(prims, 1, 0)
+    assert len(n8) <= (4 * n - 1 + 6) // 7
+    assert (np.sort(pidx) == np.arange(n)).all()
+    pb, _ = O.prim_bounds(prims, 1)
+    assert O.check_bvh8(n8, pidx, pb) == 0
+    c8, cp = O.canon_bvh8(n8, pidx)
+    assert (O.canon_bvh8(c8, cp)[0] == c8).all()
+    cost = O.bvh8_cost(n8, sb)
+    assert 10.0 < cost < 1000.0
+
+
+@pytest.mark.parametrize("case", trace_scenes(), ids=lambda c: c[0])
+def test_trace_oracle_equals_reference_hits(case):
+    """CPU two-level traversal (own CPU-built BVHs) vs the reference TraceKernel's hits on the same rays: primitive and
+    instance ids equal except exact-distance ties, t within 1e-5 relative except a counted handful of ill-conditioned hits
+    (see oracle_lib.t_outliers) that must still meet the conditioning bound; brute force agrees with the BVH traversal."""
+    name, desc, res = case
+    gold = np.load(os.path.join(GOLD, "trace_ref.npz"))[name + "/hits"]
+    rays = trace_rays(name, desc, res)
+    ora = O.oracle_scene_from_desc(desc)
+    got = ora.trace_closest(rays)
+    cmp = O.compare_hits(ora, rays, got, gold, rel=1e-5)
+    assert cmp["hard"] == 0 and cmp["tie"] <= 0.001 * cmp["n"], cmp
+    bad, worse = O.t_outliers(rays, got, gold, rel=1e-5)
+    assert len(bad) <= 1e-3 * len(rays) and len(worse) == 0, (len(bad), len(worse))
+    brute = ora.trace_brute(rays[:1500])
+    cmp2 = O.compare_hits(ora, rays[:1500], got[:1500], brute, rel=1e-6)
+    assert cmp2["hard"] == 0 and cmp2["t_bad"] == 0, cmp2
+    occ = ora.trace_any(np.array(rays))
+    assert (occ.astype(bool) == (got["t"] < np.float32(1e30))).all()
