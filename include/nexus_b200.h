@@ -109,6 +109,10 @@ typedef struct nx_kernel_profile {
     float ms[4]; uint32_t launches[4];
     uint64_t closest_work[4];             /* nodes visited, triangles tested, instances entered, rays (flags & 2) */
     uint64_t any_work[4];
+    /* warp scheduling of the traversal loop (flags & 2), summed over warps: loop iterations, lanes that tested a node,
+     * triangle rounds, lanes in them, set-up (new ray / instance entry) rounds, lanes in them, instances culled by their sphere */
+    uint64_t closest_sched[7];
+    uint64_t any_sched[7];
 } nx_kernel_profile;
 
 /* ------------------------------------------------------------------------------------------------ context ---- */
@@ -119,6 +123,13 @@ const char* nx_last_error(const nx_ctx* ctx);
 int nx_ctx_synchronize(nx_ctx* ctx);
 int nx_ctx_sm_count(const nx_ctx* ctx);
 void* nx_ctx_stream(nx_ctx* ctx);                                   /* cudaStream_t all work is issued on */
+/* Traversal batching thresholds, in lanes of a warp: the triangle / instance-entry phase of the traversal kernels runs when
+ * at least this many lanes have such work (or one lane has nothing else to do).  Results do not depend on them (equal-distance
+ * hits are resolved by id); they trade SIMT efficiency against front-to-back culling.  The reference's counterpart is the
+ * compile-time 20 % postponing rule (BVH8Traversal.cuh:15-22,270-278).  Also settable with NX_TRACE_TUNE="tri,inst". */
+int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes);
+/* 0 switches the per-instance bounding-sphere test off (measurement only; results are identical either way). */
+int nx_ctx_set_sphere_cull(nx_ctx* ctx, int enabled);
 
 /* device memory helpers so a C / ctypes host needs no CUDA runtime of its own (replace N/Device/CudaMemory.h) */
 int nx_malloc(nx_ctx* ctx, size_t bytes, void** out_dev);

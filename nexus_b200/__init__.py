@@ -47,6 +47,12 @@ class Context:
     def synchronize(self):
         check(self._h, lib().nx_ctx_synchronize(self._h), "synchronize")
 
+    def SetTraceTuning(self, tri_lanes, inst_lanes):
+        check(self._h, lib().nx_ctx_set_trace_tuning(self._h, C.c_uint32(tri_lanes), C.c_uint32(inst_lanes)), "SetTraceTuning")
+
+    def SetSphereCull(self, enabled):
+        check(self._h, lib().nx_ctx_set_sphere_cull(self._h, C.c_int(int(enabled))), "SetSphereCull")
+
     @property
     def sm_count(self):
         return lib().nx_ctx_sm_count(self._h)
@@ -463,6 +469,8 @@ class PathTracer:
         out = {k: {"ms": p.ms[i], "launches": p.launches[i]} for i, k in enumerate(self.KERNELS)}
         for name, arr in (("closest_work", p.closest_work), ("any_work", p.any_work)):
             out[name] = {"nodes": arr[0], "tris": arr[1], "insts": arr[2], "rays": arr[3]}
+        for name, arr in (("closest_sched", p.closest_sched), ("any_sched", p.any_sched)):
+            out[name] = dict(zip(("iters", "lanes_node", "tri_rounds", "tri_lanes", "setup_rounds", "setup_lanes", "sphere_culled"), list(arr)))
         return out
 
     def ReadAccumulation(self, out=None):

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnexus_b200.so")
+LIB_PATH = os.environ.get("NEXUS_B200_LIB") or os.path.join(_HERE, "libnexus_b200.so")   # override: kernel-variant experiments only
 
 
 class NexusError(RuntimeError):
@@ -64,7 +64,8 @@ class FrameStats(C.Structure):
 
 
 class KernelProfile(C.Structure):
-    _fields_ = [("ms", C.c_float * 4), ("launches", C.c_uint32 * 4), ("closest_work", C.c_uint64 * 4), ("any_work", C.c_uint64 * 4)]
+    _fields_ = [("ms", C.c_float * 4), ("launches", C.c_uint32 * 4), ("closest_work", C.c_uint64 * 4), ("any_work", C.c_uint64 * 4),
+                ("closest_sched", C.c_uint64 * 7), ("any_sched", C.c_uint64 * 7)]
 
 
 assert C.sizeof(MaterialPod) == 92 and C.sizeof(Aabb) == 24

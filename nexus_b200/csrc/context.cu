@@ -1,6 +1,7 @@
 // Context, device-memory helpers and headless image output of the nexus_b200 C ABI.
 #include "nx_common.cuh"
 #include <fstream>
+#include <cstdlib>
 
 extern "C" {
 
@@ -27,6 +28,10 @@ int nx_ctx_create(int device, nx_ctx** out)
         uint64_t threshold = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
+    if (const char* t = std::getenv("NX_TRACE_TUNE")) {
+        unsigned a = 0, b = 0;
+        if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = a; ctx->tune_inst = b; }
+    }
     *out = ctx;
     return NX_OK;
 }
@@ -45,6 +50,20 @@ void nx_ctx_destroy(nx_ctx* ctx)
 const char* nx_last_error(const nx_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 int nx_ctx_sm_count(const nx_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 void* nx_ctx_stream(nx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes)
+{
+    if (!ctx || tri_lanes > 32 || inst_lanes > 32) return NX_ERR_INVALID;
+    ctx->tune_tri = tri_lanes; ctx->tune_inst = inst_lanes;
+    return NX_OK;
+}
+
+int nx_ctx_set_sphere_cull(nx_ctx* ctx, int enabled)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    ctx->tune_sphere = enabled ? 1u : 0u;
+    return NX_OK;
+}
 
 int nx_ctx_synchronize(nx_ctx* ctx)
 {

@@ -19,6 +19,8 @@ struct nx_ctx {
     cudaStream_t stream = nullptr;      // main stream: build, generate, closest-hit trace, shade
     cudaStream_t stream_aux = nullptr;  // shadow rays overlap the next extension trace
     std::string error;
+    // traversal batching thresholds in lanes (traverse.cuh TraceTuning); overridable with NX_TRACE_TUNE="tri,inst"
+    uint32_t tune_tri = 6, tune_inst = 6, tune_sphere = 1;
     // scratch reused by the builder's parity hook
     std::vector<uint64_t> dbg_codes;
 };

@@ -63,96 +63,44 @@ __device__ __forceinline__ void add_radiance(float* accum, uint32_t pixel, F3 L)
 }
 
 // ------------------------------------------------------------------------------------------ trace kernels ----
-// Persistent threads with warp-granular dynamic fetch: a warp reserves 32 queue slots with one atomic and hands them to
-// lanes as they finish, so lanes never idle while the queue still has rays (the reference fetches one ray per atomic).
-struct WarpFetcher {
-    uint32_t next = 0, end = 0;   // warp-uniform
-    __device__ __forceinline__ uint32_t take(uint32_t* cursor, bool want)
+// Persistent warps over a device-side queue; the loop itself is trace_loop() in traverse.cuh.
+struct ClosestSink {
+    nx_hit* hits;
+    __device__ __forceinline__ void finish(const TraceScene& sc, uint32_t rayIdx, uint32_t, float t, float u, float v, uint32_t prim, uint32_t slot, bool)
     {
-        const uint32_t mask = __ballot_sync(NX_FULL, want);
-        if (!mask) return NX_INVALID;
-        const uint32_t cnt = __popc(mask), rank = __popc(mask & lanemask_lt());
-        const uint32_t avail = end - next;
-        uint32_t fresh = 0;
-        if (cnt > avail) {
-            if (lane_id() == 0) fresh = atomicAdd(cursor, 32u);
-            fresh = __shfl_sync(NX_FULL, fresh, 0);
-        }
-        uint32_t idx = rank < avail ? next + rank : fresh + (rank - avail);
-        if (cnt > avail) { next = fresh + (cnt - avail); end = fresh + 32u; } else next += cnt;
-        return want ? idx : NX_INVALID;
+        nx_hit h; h.t = t; h.u = u; h.v = v; h.prim = prim;
+        h.instance = slot != NX_INVALID ? __ldg(sc.tlasPrimIdx + slot) : NX_INVALID;
+        hits[rayIdx] = h;
+    }
+};
+// Any-hit.  occluded != null: write occlusion flags (parity hook); else add the queued radiance to the pixel when unoccluded
+// (TraceShadowKernel's fused accumulate, PathTracer.cu:115-122 / BVH8Traversal.cuh:517-519).
+struct AnySink {
+    uint8_t* occluded; const float4* radiance; float* accum;
+    __device__ __forceinline__ void finish(const TraceScene&, uint32_t rayIdx, uint32_t pixel, float, float, float, uint32_t, uint32_t, bool occ)
+    {
+        if (occluded) occluded[rayIdx] = occ ? 1 : 0;
+        else if (!occ) { const float4 L = __ldg(radiance + rayIdx); add_radiance(accum, pixel, f3(L.x, L.y, L.z)); }
     }
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(NX_TRACE_BLOCK) trace_closest_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
-                                                                         uint32_t* cursor, nx_hit* __restrict__ hits, TraceStats* stats)
+__global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_closest_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+                                                                         uint32_t* cursor, nx_hit* __restrict__ hits, TraceStats* stats, TraceTuning tune)
 {
-    __shared__ uint2 sstack[NX_STACK_SHARED * NX_TRACE_BLOCK];
-    const uint32_t n = nPtr ? __ldg(nPtr) : nImm;
-    Traverser<false, STATS> tr; tr.st.sh = sstack + threadIdx.x;
-    WarpFetcher fetch;
-    bool need = true, dead = false;
-    uint32_t rayIdx = 0;
-    unsigned long long sN = 0, sT = 0, sI = 0, sR = 0;
-    while (true)
-    {
-        const uint32_t got = fetch.take(cursor, need && !dead);
-        if (need && !dead) {
-            if (got < n) {
-                const float4* r = reinterpret_cast<const float4*>(rays + got);
-                const float4 a = __ldg(r), b = __ldg(r + 1);
-                tr.begin(sc, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
-                rayIdx = got; need = false;
-            } else dead = true;
-        }
-        if (__all_sync(NX_FULL, dead)) break;
-        if (!dead && tr.step(sc)) {
-            nx_hit h; h.t = tr.hit.t; h.u = tr.hit.u; h.v = tr.hit.v; h.prim = tr.hit.prim;
-            h.instance = tr.hit.slot != NX_INVALID ? __ldg(sc.tlasPrimIdx + tr.hit.slot) : NX_INVALID;
-            hits[rayIdx] = h;
-            if (STATS) { sN += tr.cNodes; sT += tr.cTris; sI += tr.cInsts; sR++; }
-            need = true;
-        }
-    }
-    if (STATS) { atomicAdd(&stats->nodes, sN); atomicAdd(&stats->tris, sT); atomicAdd(&stats->insts, sI); atomicAdd(&stats->rays, sR); }
+    __shared__ __align__(16) uint32_t smem[NX_TRACE_SMEM_BYTES / 4];
+    ClosestSink sink{hits};
+    trace_loop<false, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
 }
 
-// Any-hit.  mode 0: write occlusion flags (parity hook); mode 1: add the queued radiance to the pixel when unoccluded
-// (TraceShadowKernel's fused accumulate, PathTracer.cu:115-122 / BVH8Traversal.cuh:517-519).
 template <bool STATS>
-__global__ void __launch_bounds__(NX_TRACE_BLOCK) trace_any_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+__global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_any_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
                                                                      uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum,
-                                                                     TraceStats* stats)
+                                                                     TraceStats* stats, TraceTuning tune)
 {
-    __shared__ uint2 sstack[NX_STACK_SHARED * NX_TRACE_BLOCK];
-    const uint32_t n = nPtr ? __ldg(nPtr) : nImm;
-    Traverser<true, STATS> tr; tr.st.sh = sstack + threadIdx.x;
-    WarpFetcher fetch;
-    bool need = true, dead = false;
-    uint32_t rayIdx = 0, pixel = 0;
-    unsigned long long sN = 0, sT = 0, sI = 0, sR = 0;
-    while (true)
-    {
-        const uint32_t got = fetch.take(cursor, need && !dead);
-        if (need && !dead) {
-            if (got < n) {
-                const float4* r = reinterpret_cast<const float4*>(rays + got);
-                const float4 a = __ldg(r), b = __ldg(r + 1);
-                tr.begin(sc, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
-                pixel = __float_as_uint(b.w);
-                rayIdx = got; need = false;
-            } else dead = true;
-        }
-        if (__all_sync(NX_FULL, dead)) break;
-        if (!dead && tr.step(sc)) {
-            if (occluded) occluded[rayIdx] = tr.occluded ? 1 : 0;
-            else if (!tr.occluded) { const float4 L = __ldg(radiance + rayIdx); add_radiance(accum, pixel, f3(L.x, L.y, L.z)); }
-            if (STATS) { sN += tr.cNodes; sT += tr.cTris; sI += tr.cInsts; sR++; }
-            need = true;
-        }
-    }
-    if (STATS) { atomicAdd(&stats->nodes, sN); atomicAdd(&stats->tris, sT); atomicAdd(&stats->insts, sI); atomicAdd(&stats->rays, sR); }
+    __shared__ __align__(16) uint32_t smem[NX_TRACE_SMEM_BYTES / 4];
+    AnySink sink{occluded, radiance, accum};
+    trace_loop<true, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
 }
 
 // --------------------------------------------------------------------------------------------- generate ----
@@ -405,6 +353,8 @@ __global__ void resolve_rgba8_kernel(const float* __restrict__ accum, uint32_t c
     }
 }
 
+TraceTuning trace_tuning(const nx_ctx* ctx) { TraceTuning t; t.triLanes = ctx->tune_tri; t.instLanes = ctx->tune_inst; t.sphereCull = ctx->tune_sphere; return t; }
+
 int persistent_grid(nx_ctx* ctx, const void* fn, int block, int* cache)
 {
     if (*cache) return *cache;
@@ -447,7 +397,7 @@ int nxi_trace_closest(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, ui
     const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    trace_closest_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dHits, nullptr);
+    trace_closest_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dHits, nullptr, trace_tuning(ctx));
     if (outMs) { cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1); cudaEventElapsedTime(outMs, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     cudaFreeAsync(cursor, ctx->stream);
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -464,7 +414,7 @@ int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32
     const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<false>, NX_TRACE_BLOCK, &g_gridAny);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    trace_any_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr);
+    trace_any_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr, trace_tuning(ctx));
     if (outMs) { cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1); cudaEventElapsedTime(outMs, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     cudaFreeAsync(cursor, ctx->stream);
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -483,7 +433,7 @@ extern "C" int nx_trace_stats(nx_scene* s, const nx_ray* dRays, uint32_t n, nx_h
     NX_CUDA(ctx, cudaMallocAsync((void**)&cursor, 4, ctx->stream)); NX_CUDA(ctx, cudaMallocAsync((void**)&st, sizeof(TraceStats), ctx->stream));
     NX_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream)); NX_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(TraceStats), ctx->stream));
     const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<true>, NX_TRACE_BLOCK, &g_gridClosestStats);
-    trace_closest_kernel<true><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(v.trace, dRays, n, nullptr, cursor, dHits, st);
+    trace_closest_kernel<true><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(v.trace, dRays, n, nullptr, cursor, dHits, st, trace_tuning(ctx));
     TraceStats h{};
     NX_CUDA(ctx, cudaMemcpyAsync(&h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -584,6 +534,7 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
     cudaStream_t s = ctx->stream, sa = ctx->stream_aux;
     const uint32_t L = sv.pathLength;
     const bool work = (r->profFlags & 2) != 0;
+    const TraceTuning tune = trace_tuning(ctx);
     const int gClosest = work ? persistent_grid(ctx, (const void*)trace_closest_kernel<true>, NX_TRACE_BLOCK, &g_gridClosestStats)
                               : persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
     const int gAny = work ? persistent_grid(ctx, (const void*)trace_any_kernel<true>, NX_TRACE_BLOCK, &g_gridAnyStats)
@@ -596,8 +547,8 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
 
     auto closest = [&](const nx_ray* q, uint32_t b) {
         r->prof_begin(1, s);
-        if (work) trace_closest_kernel<true><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, r->dWork);
-        else trace_closest_kernel<false><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, nullptr);
+        if (work) trace_closest_kernel<true><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, r->dWork, tune);
+        else trace_closest_kernel<false><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, nullptr, tune);
         r->prof_end(s);
         r->launches++;
     };
@@ -626,8 +577,8 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
             // shadow rays on the auxiliary stream overlap the extension trace (the reference's graph runs them as siblings)
             NX_CUDA(ctx, cudaStreamWaitEvent(sa, r->evShade, 0));
             r->prof_begin(3, sa);
-            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, r->dWork + 1);
-            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, nullptr);
+            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, r->dWork + 1, tune);
+            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, nullptr, tune);
             r->prof_end(sa);
             NX_CUDA(ctx, cudaEventRecord(r->evShadow, sa));
             r->launches++;
@@ -685,6 +636,8 @@ int nx_renderer_profile(nx_renderer* r, nx_kernel_profile* out)
         NX_CUDA(ctx, cudaMemcpy(h, r->dWork, sizeof(h), cudaMemcpyDeviceToHost));
         out->closest_work[0] = h[0].nodes; out->closest_work[1] = h[0].tris; out->closest_work[2] = h[0].insts; out->closest_work[3] = h[0].rays;
         out->any_work[0] = h[1].nodes; out->any_work[1] = h[1].tris; out->any_work[2] = h[1].insts; out->any_work[3] = h[1].rays;
+        const unsigned long long* a = &h[0].iters; const unsigned long long* b = &h[1].iters;
+        for (int k = 0; k < 7; k++) { out->closest_sched[k] = a[k]; out->any_sched[k] = b[k]; }
     }
     return NX_OK;
 }

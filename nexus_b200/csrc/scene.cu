@@ -69,6 +69,52 @@ nx_aabb transformed_bounds(const float* m, const nx_aabb& b)
     return r;
 }
 
+// Bounding sphere of a mesh's vertices: centre of their AABB, radius = farthest vertex (double precision, padded).
+void mesh_sphere(const nx_triangle* tris, uint32_t n, double out[4])
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    const float* v = (const float*)tris;
+    for (size_t i = 0; i < (size_t)n * 3; i++)
+        for (int k = 0; k < 3; k++) { const double x = v[3 * i + k]; lo[k] = x < lo[k] ? x : lo[k]; hi[k] = x > hi[k] ? x : hi[k]; }
+    for (int k = 0; k < 3; k++) out[k] = 0.5 * (lo[k] + hi[k]);
+    double r2 = 0.0;
+    for (size_t i = 0; i < (size_t)n * 3; i++) {
+        const double dx = v[3 * i] - out[0], dy = v[3 * i + 1] - out[1], dz = v[3 * i + 2] - out[2];
+        const double q = dx * dx + dy * dy + dz * dz;
+        r2 = q > r2 ? q : r2;
+    }
+    out[3] = std::sqrt(r2) * (1.0 + 1e-6);
+}
+
+// Largest singular value of the upper-left 3x3 of a row-major 4x4 (power iteration on A^T A, double): the factor by which the
+// instance transform can stretch a sphere radius.
+double max_stretch(const float* m)
+{
+    double a[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = m[4 * i + j];
+    double g[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { g[i][j] = 0; for (int k = 0; k < 3; k++) g[i][j] += a[k][i] * a[k][j]; }
+    double best = 0.0;
+    const double starts[3][3] = {{1, 0.3, 0.2}, {0.2, 1, 0.3}, {0.3, 0.2, 1}};
+    for (const auto& s0 : starts) {
+        double v[3] = {s0[0], s0[1], s0[2]}, lambda = 0.0;
+        for (int it = 0; it < 64; it++) {
+            double w[3] = {0, 0, 0};
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) w[i] += g[i][j] * v[j];
+            const double nrm = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+            if (nrm == 0.0) break;
+            lambda = nrm;
+            for (int i = 0; i < 3; i++) v[i] = w[i] / nrm;
+        }
+        best = lambda > best ? lambda : best;
+    }
+    // power iteration approaches the top eigenvalue from below: bound it by the Frobenius norm and pad
+    const double fro = g[0][0] + g[1][1] + g[2][2];
+    double sigma = std::sqrt(best) * (1.0 + 1e-3);
+    const double cap = std::sqrt(fro);
+    return sigma < cap ? sigma : cap;
+}
+
 bool material_emits(const nx_material& m)   // Scene::UpdateSceneLighting's test (Scene.cpp:162-185)
 {
     float mx = fmaxf(m.emission_color[0], fmaxf(m.emission_color[1], m.emission_color[2]));
@@ -204,6 +250,7 @@ int nx_scene_add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_da
     const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
     if (data) NX_CUDA(ctx, cudaMemcpyAsync(m.dTriData, data, 96 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     else default_tridata_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, n, m.dTriData);
+    mesh_sphere(tris, n, m.sphere);
     int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, 1 /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
     if (rc) return rc;
     leaf_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris);
@@ -330,6 +377,11 @@ int nx_scene_update(nx_scene* s)
         for (size_t k = 0; k < order.size(); k++) {
             const HostInstance& h = s->instances[order[k]];
             std::memcpy(&ti[k].r0, h.inv, 48);
+            const HostMesh& hm = s->meshes[h.meshIdx];
+            double c[3];
+            for (int r = 0; r < 3; r++) c[r] = (double)h.m[4 * r] * hm.sphere[0] + (double)h.m[4 * r + 1] * hm.sphere[1] + (double)h.m[4 * r + 2] * hm.sphere[2] + (double)h.m[4 * r + 3];
+            const double rad = hm.sphere[3] * max_stretch(h.m) * (1.0 + 1e-5) + 1e-30;
+            ti[k].sphere = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(rad * (1.0 + 1e-6)) + 1e-6f * (float)(std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2])));
             ti[k].nodes = (const float4*)s->meshes[h.meshIdx].bvh.nodes; ti[k].ltris = s->meshes[h.meshIdx].dLeafTris;
         }
         rc = upload_vec(ctx, &s->dTravInst, ti); if (rc) return rc;

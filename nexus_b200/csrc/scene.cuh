@@ -49,6 +49,7 @@ struct HostMesh {
     float4* dLeafTris = nullptr;
     nx_bvh8 bvh{};
     uint32_t materialIdx = 0;
+    double sphere[4] = {0, 0, 0, 0};   // object-space bounding sphere of the vertices (centre, radius)
 };
 
 struct HostInstance {

@@ -4,13 +4,22 @@
 // (src/Cuda/BVH/BVH8Traversal.cuh:56-521, src/Cuda/Geometry/Triangle.cuh:29-93).  Same 80-byte node, same octant-ordered
 // hit mask, same Moeller-Trumbore formulation, so the closest primitive / instance ids are the reference's.
 //
-// What is different, and why:
+// What is different, and why (ncu evidence in profiles/):
 //   * leaves index straight into a leaf-ordered, 48-byte, 16-byte-aligned triangle stream {v0 | primId, e0, e1}: three
 //     LDG.128 per triangle instead of one dependent index load plus nine 4-byte loads at 36-byte stride;
 //   * TLAS leaves index a 64-byte instance record {inverse 3x4, BLAS node pointer, BLAS triangle pointer} stored in TLAS
 //     leaf order: one 64-byte line instead of primIdx -> 160-byte instance -> 72-byte mesh (three dependent loads);
 //   * rays are fetched for the whole warp with one atomic (ballot + popc prefix) instead of one atomic per ray;
-//   * the traversal stack lives in shared memory (conflict-free, lane-interleaved) with a short local spill tail;
+//   * the warp runs in PHASES with convergent votes in between (pop/refill -> enter instance -> node -> triangles), so all
+//     lanes that have a node to test execute the 8-wide slab test together, and triangle / instance work is batched until
+//     enough lanes have some (or a lane has nothing else to do).  The first version ran one resumable state machine per
+//     lane and measured 12-13 active lanes per instruction (ncu smsp__thread_inst_executed_per_inst_executed);
+//   * all per-ray state lives in registers; the traversal stack is in shared memory (lane-interleaved, conflict-free) with
+//     a separate local spill array that only deep paths touch; the world-space ray is parked in shared memory while the
+//     lane is inside an instance;
+//   * equal-distance hits are resolved by (instance id, primitive id), not by visiting order, so the answer does not depend
+//     on which rays share a warp or on how triangle work is batched (the reference's result on exact ties is schedule
+//     dependent);
 //   * arithmetic uses explicit-rounding intrinsics, IEEE reciprocal included, so results do not depend on compiler
 //     contraction and the CPU oracle can reproduce every hit bit for bit.
 #pragma once
@@ -20,12 +29,17 @@
 #define NX_TRACE_BLOCK 128
 #endif
 #ifndef NX_STACK_SHARED
-#define NX_STACK_SHARED 10
+#define NX_STACK_SHARED 12
 #endif
-#define NX_STACK_TOTAL 32
+#ifndef NX_TRACE_MIN_BLOCKS
+#define NX_TRACE_MIN_BLOCKS 8
+#endif
+#define NX_STACK_TOTAL 40
 #define NX_MISS_T 1.0e30f   // miss sentinel of the reference (PathTracer.cu:140)
 
-struct DTravInst {           // 64 B, one cache-line half; TLAS-leaf order
+struct DTravInst {           // 80 B; TLAS-leaf order
+    float4 sphere;           // world-space bounding sphere of the instance's geometry (centre, radius): culls the loose
+                             // world AABB of a rotated object before the ray is transformed (a conservative test, results unchanged)
     float4 r0, r1, r2;       // rows of the inverse instance transform (world -> object), row-major 3x4
     const float4* nodes;     // BLAS nodes (5 x float4 each)
     const float4* ltris;     // BLAS leaf-ordered triangles (3 x float4 each)
@@ -37,18 +51,26 @@ struct TraceScene {
     const DTravInst* inst;         // TLAS leaf slot -> traversal record
 };
 
-struct HitRec { float t, u, v; uint32_t prim, slot; };
-
-struct TraceStats { unsigned long long nodes, tris, insts, rays; };
-
-// stack: first NX_STACK_SHARED entries in shared memory (entry e of thread t at [e * blockDim + t]), the rest in local memory
-struct TravStack {
-    uint2* sh; uint2 loc[NX_STACK_TOTAL - NX_STACK_SHARED]; int sp;
-    __device__ __forceinline__ void push(uint2 v) { if (sp < NX_STACK_SHARED) sh[sp * NX_TRACE_BLOCK] = v; else loc[sp - NX_STACK_SHARED] = v; sp++; }
-    __device__ __forceinline__ uint2 pop() { sp--; return sp < NX_STACK_SHARED ? sh[sp * NX_TRACE_BLOCK] : loc[sp - NX_STACK_SHARED]; }
+struct TraceTuning {               // batching thresholds (lanes): run a phase when at least this many lanes want it
+    uint32_t triLanes;             // triangle phase
+    uint32_t instLanes;            // new-ray / instance-entry phase
+    uint32_t sphereCull;           // 0 disables the per-instance bounding-sphere test (measurement only)
 };
 
-__device__ __forceinline__ uint32_t octant_inv(V3 d) { return 7u - (((d.x < 0.f) ? 4u : 0u) | ((d.y < 0.f) ? 2u : 0u) | ((d.z < 0.f) ? 1u : 0u)); }
+struct TraceStats {
+    unsigned long long nodes, tris, insts, rays;
+    // warp scheduling: loop iterations, lanes that tested a node, triangle rounds / lanes, set-up rounds / lanes (per warp, summed)
+    unsigned long long iters, lanesN, roundsT, lanesT, roundsX, lanesX, sphereCulled;
+};
+
+// Shared memory per block: stack entries [NX_STACK_SHARED][block] of uint2, then the parked world-space ray
+// (origin, direction, reciprocal direction) as [9][block] floats.
+#define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 9 * 4) * NX_TRACE_BLOCK)
+
+__device__ __forceinline__ uint32_t octant_inv4(V3 d)
+{
+    return (7u - (((d.x < 0.f) ? 4u : 0u) | ((d.y < 0.f) ? 2u : 0u) | ((d.z < 0.f) ? 1u : 0u))) * 0x01010101u;
+}
 __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 
 // Slab test of the eight quantised child boxes of one node.  Returns the inner-node group (childBase, hits<<24 | imask)
@@ -94,124 +116,219 @@ __device__ __forceinline__ void intersect_children(const float4* __restrict__ no
     leaves = make_uint2(__float_as_uint(n1.y), hits & 0x00ffffffu);
 }
 
-// Moeller-Trumbore on {v0, e0 = v1 - v0, e1 = v2 - v0}; no back-face culling; accepts 0 < t < best (strict), as
-// Triangle.cuh:29-62.  Returns true when the hit was accepted.
-__device__ __forceinline__ bool intersect_triangle(const float4* __restrict__ tri, V3 o, V3 d, float& best, float& bu, float& bv, uint32_t& prim)
+__device__ __forceinline__ V3 xform_point(float4 r0, float4 r1, float4 r2, V3 p)
 {
-    const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
-    const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
-    const V3 pv = xcross(d, e1);
-    const float det = xdot(e0, pv);
-    const float invDet = rcp_ieee(det);
-    const V3 s = o - v3(a.x, a.y, a.z);
-    const float u = __fmul_rn(invDet, xdot(s, pv));
-    if (u < 0.0f || u > 1.0f) return false;
-    const V3 qv = xcross(s, e0);
-    const float v = __fmul_rn(invDet, xdot(d, qv));
-    if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
-    const float t = __fmul_rn(invDet, xdot(e1, qv));
-    if (t > 0.0f && t < best) { best = t; bu = u; bv = v; prim = __float_as_uint(a.w); return true; }
-    return false;
+    return v3(__fmaf_rn(r0.x, p.x, __fmaf_rn(r0.y, p.y, __fmaf_rn(r0.z, p.z, r0.w))),
+              __fmaf_rn(r1.x, p.x, __fmaf_rn(r1.y, p.y, __fmaf_rn(r1.z, p.z, r1.w))),
+              __fmaf_rn(r2.x, p.x, __fmaf_rn(r2.y, p.y, __fmaf_rn(r2.z, p.z, r2.w))));
+}
+__device__ __forceinline__ V3 xform_vector(float4 r0, float4 r1, float4 r2, V3 p)
+{
+    return v3(__fmaf_rn(r0.x, p.x, __fmaf_rn(r0.y, p.y, __fmul_rn(r0.z, p.z))),
+              __fmaf_rn(r1.x, p.x, __fmaf_rn(r1.y, p.y, __fmul_rn(r1.z, p.z))),
+              __fmaf_rn(r2.x, p.x, __fmaf_rn(r2.y, p.y, __fmul_rn(r2.z, p.z))));
 }
 
-__device__ __forceinline__ V3 xform_point(const DTravInst& I, V3 p)
-{
-    return v3(__fmaf_rn(I.r0.x, p.x, __fmaf_rn(I.r0.y, p.y, __fmaf_rn(I.r0.z, p.z, I.r0.w))),
-              __fmaf_rn(I.r1.x, p.x, __fmaf_rn(I.r1.y, p.y, __fmaf_rn(I.r1.z, p.z, I.r1.w))),
-              __fmaf_rn(I.r2.x, p.x, __fmaf_rn(I.r2.y, p.y, __fmaf_rn(I.r2.z, p.z, I.r2.w))));
-}
-__device__ __forceinline__ V3 xform_vector(const DTravInst& I, V3 p)
-{
-    return v3(__fmaf_rn(I.r0.x, p.x, __fmaf_rn(I.r0.y, p.y, __fmul_rn(I.r0.z, p.z))),
-              __fmaf_rn(I.r1.x, p.x, __fmaf_rn(I.r1.y, p.y, __fmul_rn(I.r1.z, p.z))),
-              __fmaf_rn(I.r2.x, p.x, __fmaf_rn(I.r2.y, p.y, __fmul_rn(I.r2.z, p.z))));
-}
-
-// Per-lane traversal state machine.  One call to step() intersects one node (or pops) and then works off the leaf group.
-// Written as a resumable state so the persistent kernel can refill finished lanes between steps.
-template <bool ANY_HIT, bool STATS>
-struct Traverser {
-    V3 o, d, inv;          // current-space ray
-    V3 wo, wd;             // world-space ray (restored when leaving an instance)
-    float tmax;            // any-hit: fixed limit; closest-hit: shrinks with every accepted hit
-    HitRec hit;
-    uint2 ngroup, tgroup;
-    const float4* nodes; const float4* ltris;
-    uint32_t octinv4, curSlot;
-    int instDepth;         // stack depth at which the current instance was entered, -1 in the TLAS
-    bool occluded;
-    TravStack st;
-    uint32_t cNodes, cTris, cInsts;
-
-    __device__ __forceinline__ void begin(const TraceScene& sc, V3 ro, V3 rd, float limit)
+// Warp-granular dynamic fetch: a warp reserves 32 queue slots with one atomic and hands them to lanes as they finish, so
+// lanes never idle while the queue still has rays (the reference fetches one ray per atomic, BVH8Traversal.cuh:179).
+struct WarpFetcher {
+    uint32_t next = 0, end = 0;   // warp-uniform
+    __device__ __forceinline__ uint32_t take(uint32_t* cursor, uint32_t mask, uint32_t lane_lt)
     {
-        o = wo = ro; d = wd = rd;
-        inv = v3(rcp_ieee(rd.x), rcp_ieee(rd.y), rcp_ieee(rd.z));
-        tmax = limit; hit.t = NX_MISS_T; hit.u = hit.v = 0.f; hit.prim = NX_INVALID; hit.slot = NX_INVALID;
-        ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
-        nodes = sc.tlasNodes; ltris = nullptr;
-        octinv4 = octant_inv(rd) * 0x01010101u; curSlot = NX_INVALID; instDepth = -1; occluded = false; st.sp = 0;
-        if (STATS) cNodes = cTris = cInsts = 0;
-    }
-
-    // returns true when the ray is finished
-    __device__ __forceinline__ bool step(const TraceScene& sc)
-    {
-        if (ngroup.y & 0xff000000u)
-        {
-            const uint32_t bit = 31u - __clz(ngroup.y);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y & 0xff000000u) st.push(ngroup);
-            const uint32_t slot = (bit - 24u) ^ (octinv4 & 0xffu);
-            const uint32_t child = ngroup.x + __popc(ngroup.y & ((1u << slot) - 1u) & 0xffu);
-            intersect_children(nodes, child, o, d, inv, octinv4, ANY_HIT ? tmax : fminf(tmax, hit.t), ngroup, tgroup);
-            if (STATS) cNodes++;
+        const uint32_t cnt = __popc(mask), rank = __popc(mask & lane_lt);
+        const uint32_t avail = end - next;
+        uint32_t fresh = 0;
+        if (cnt > avail) {
+            if (lane_id() == 0) fresh = atomicAdd(cursor, 32u);
+            fresh = __shfl_sync(NX_FULL, fresh, 0);
         }
-        else { tgroup = ngroup; ngroup = make_uint2(0u, 0u); }
+        const uint32_t idx = rank < avail ? next + rank : fresh + (rank - avail);
+        if (cnt > avail) { next = fresh + (cnt - avail); end = fresh + 32u; } else next += cnt;
+        return idx;
+    }
+};
 
-        while (tgroup.y)
+// The traversal loop, shared by the closest-hit and the any-hit kernels.
+//   Sink::finish(rayIdx, pad, t, u, v, prim, slot, occluded) is called once per ray.
+template <bool ANY_HIT, bool STATS, typename Sink>
+__device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* __restrict__ rays, uint32_t n, uint32_t* cursor, TraceTuning tune,
+                                           uint32_t* smem, Sink& sink, TraceStats* stats)
+{
+    uint2* const sstack = reinterpret_cast<uint2*>(smem) + threadIdx.x;                       // entry e at sstack[e * NX_TRACE_BLOCK]
+    float* const park = reinterpret_cast<float*>(smem + 2 * NX_STACK_SHARED * NX_TRACE_BLOCK) + threadIdx.x;   // value k at park[k * NX_TRACE_BLOCK]
+    uint2 spill[NX_STACK_TOTAL - NX_STACK_SHARED];
+    uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
+
+    // per-lane state (registers)
+    V3 o = v3(0, 0, 0), d = v3(0, 0, 1), inv = v3(0, 0, 0);
+    float tmax = 0.f, hitT = NX_MISS_T, hitU = 0.f, hitV = 0.f;
+    uint32_t hitPrim = NX_INVALID, hitSlot = NX_INVALID;
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    const float4* nodes = sc.tlasNodes; const float4* ltris = nullptr;
+    uint32_t octinv4 = 0, curSlot = NX_INVALID, rayIdx = 0, rayPad = 0;
+    int sp = 0, instDepth = -1;
+    bool live = false, dead = false, occluded = false;
+    WarpFetcher fetch;
+    unsigned long long cN = 0, cT = 0, cI = 0, cR = 0, cS = 0;
+    unsigned long long wIt = 0, wLN = 0, wRT = 0, wLT = 0, wRX = 0, wLX = 0;   // lane 0 only
+
+    // deeper than NX_STACK_TOTAL entries (never seen; the reference's 32-entry stack has no check at all): the entry is dropped
+    auto push = [&](uint2 v) { if (sp < NX_STACK_SHARED) sstack[sp * NX_TRACE_BLOCK] = v; else if (sp < NX_STACK_TOTAL) spill[sp - NX_STACK_SHARED] = v; else return; sp++; };
+    auto pop = [&]() -> uint2 { sp--; return sp < NX_STACK_SHARED ? sstack[sp * NX_TRACE_BLOCK] : spill[sp - NX_STACK_SHARED]; };
+
+    while (true)
+    {
+        // ---------------------------------------------------------------- phase P: retire / pop (cheap, every iteration) ----
+        if (live && ((ANY_HIT && occluded) || (!(ngroup.y & 0xff000000u) && !tgroup.y)))
         {
-            const uint32_t bit = 31u - __clz(tgroup.y);
-            tgroup.y &= ~(1u << bit);
-            if (instDepth < 0)
-            {
-                // TLAS leaf: enter the instance.  What is left of this node goes on the stack first.
-                if (tgroup.y) st.push(tgroup);
-                if (ngroup.y & 0xff000000u) st.push(ngroup);
-                instDepth = st.sp;
+            if (sp == 0 || (ANY_HIT && occluded)) {
+                sink.finish(sc, rayIdx, rayPad, hitT, hitU, hitV, hitPrim, hitSlot, occluded);
+                if (STATS) cR++;
+                live = false; ngroup = make_uint2(0u, 0u); tgroup = make_uint2(0u, 0u);
+            } else {
+                if (sp == instDepth) {      // leaving an instance: restore the parked world-space ray
+                    o = v3(park[0], park[NX_TRACE_BLOCK], park[2 * NX_TRACE_BLOCK]);
+                    d = v3(park[3 * NX_TRACE_BLOCK], park[4 * NX_TRACE_BLOCK], park[5 * NX_TRACE_BLOCK]);
+                    inv = v3(park[6 * NX_TRACE_BLOCK], park[7 * NX_TRACE_BLOCK], park[8 * NX_TRACE_BLOCK]);
+                    octinv4 = octant_inv4(d);
+                    nodes = sc.tlasNodes; instDepth = -1;
+                }
+                const uint2 e = pop();
+                if (e.y & 0xff000000u) ngroup = e; else tgroup = e;
+            }
+        }
+        // what every lane could do next; phases other than N run when enough lanes want them or nobody has a node to test
+        const bool hasN = live && (ngroup.y & 0xff000000u) != 0u;
+        const bool needR = !live && !dead;
+        const bool wantI = live && instDepth < 0 && tgroup.y != 0u;
+        const uint32_t mN = __ballot_sync(NX_FULL, hasN);
+        const uint32_t mX = __ballot_sync(NX_FULL, needR || wantI);
+
+        // ---------------------------------------------------------------- phase X: new ray / enter an instance ----
+        // Both end in the same reciprocal-direction + octant set-up, so they share it.
+        if (STATS) { wIt++; wLN += __popc(mN); }
+        if (mX && (__popc(mX) >= tune.instLanes || mN == 0u))
+        {
+            if (STATS) { wRX++; wLX += __popc(mX); }
+            const uint32_t mR = __ballot_sync(NX_FULL, needR);
+            uint32_t got = 0;
+            if (mR) got = fetch.take(cursor, mR, lane_lt);
+            bool setup = false;
+            if (needR) {
+                if (got < n) {
+                    const float4* r = reinterpret_cast<const float4*>(rays + got);
+                    const float4 a = __ldg(r), b = __ldg(r + 1);
+                    o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); tmax = a.w;
+                    rayIdx = got; rayPad = __float_as_uint(b.w);
+                    hitT = NX_MISS_T; hitU = hitV = 0.f; hitPrim = NX_INVALID; hitSlot = NX_INVALID; occluded = false;
+                    nodes = sc.tlasNodes; curSlot = NX_INVALID; instDepth = -1; sp = 0;
+                    live = true; setup = true;
+                } else dead = true;
+            } else if (wantI) {
+                // first instance of the group whose bounding sphere the ray can reach before its current limit
+                const float dd = xdot(d, d), limit = ANY_HIT ? tmax : fminf(tmax, hitT);
+                uint32_t bit = 0; bool found = false;
+                while (tgroup.y && !found) {
+                    bit = 31u - __clz(tgroup.y);
+                    tgroup.y &= ~(1u << bit);
+                    const float4 sp4 = __ldg(&sc.inst[tgroup.x + bit].sphere);
+                    const V3 oc = v3(sp4.x - o.x, sp4.y - o.y, sp4.z - o.z);
+                    const float b = xdot(oc, d), c2 = xdot(oc, oc), r2 = sp4.w * sp4.w;
+                    // miss if the closest approach is outside the sphere (slack covers rounding), if the sphere lies behind
+                    // the origin, or if it starts beyond the current limit
+                    const bool miss = (c2 * dd - b * b) > (r2 + 1.0e-4f * c2) * dd || (b < 0.0f && c2 > r2) || (b - sp4.w * sqrtf(dd)) > limit * dd * 1.0001f;
+                    found = !miss || !tune.sphereCull;
+                    if (STATS && !found) cS++;
+                }
+                if (found) {
+                if (tgroup.y) push(tgroup);
+                if (ngroup.y & 0xff000000u) push(ngroup);
+                instDepth = sp;
                 curSlot = tgroup.x + bit;
                 const DTravInst* I = sc.inst + curSlot;
-                DTravInst T; T.r0 = __ldg(&I->r0); T.r1 = __ldg(&I->r1); T.r2 = __ldg(&I->r2);
+                const float4 r0 = __ldg(&I->r0), r1 = __ldg(&I->r1), r2 = __ldg(&I->r2);
                 const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&I->nodes));
                 nodes = reinterpret_cast<const float4*>(((uint64_t)ptrs.y << 32) | ptrs.x);
                 ltris = reinterpret_cast<const float4*>(((uint64_t)ptrs.w << 32) | ptrs.z);
-                o = xform_point(T, wo); d = xform_vector(T, wd);     // direction is not renormalised: t stays in world units
+                park[0] = o.x; park[NX_TRACE_BLOCK] = o.y; park[2 * NX_TRACE_BLOCK] = o.z;
+                park[3 * NX_TRACE_BLOCK] = d.x; park[4 * NX_TRACE_BLOCK] = d.y; park[5 * NX_TRACE_BLOCK] = d.z;
+                park[6 * NX_TRACE_BLOCK] = inv.x; park[7 * NX_TRACE_BLOCK] = inv.y; park[8 * NX_TRACE_BLOCK] = inv.z;
+                const V3 wo = o, wd = d;
+                o = xform_point(r0, r1, r2, wo); d = xform_vector(r0, r1, r2, wd);   // direction is not renormalised: t stays in world units
+                if (STATS) cI++;
+                setup = true;
+                }
+            }
+            if (setup) {
                 inv = v3(rcp_ieee(d.x), rcp_ieee(d.y), rcp_ieee(d.z));
-                octinv4 = octant_inv(d) * 0x01010101u;
+                octinv4 = octant_inv4(d);
                 ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
-                if (STATS) cInsts++;
-                return false;
             }
-            if (STATS) cTris++;
-            float best = ANY_HIT ? tmax : fminf(tmax, hit.t);
-            if (intersect_triangle(ltris + 3 * (size_t)(tgroup.x + bit), o, d, best, hit.u, hit.v, hit.prim))
-            {
-                if (ANY_HIT) { occluded = true; return true; }
-                hit.t = best; hit.slot = curSlot;
-            }
+            if (__all_sync(NX_FULL, dead)) break;
         }
 
-        if ((ngroup.y & 0xff000000u) == 0u)
+        // ---------------------------------------------------------------- phase N: one node per lane ----
+        if (live && (ngroup.y & 0xff000000u))
         {
-            if (st.sp == 0) return true;
-            if (st.sp == instDepth)
-            {
-                o = wo; d = wd; inv = v3(rcp_ieee(wd.x), rcp_ieee(wd.y), rcp_ieee(wd.z));
-                octinv4 = octant_inv(wd) * 0x01010101u;
-                nodes = sc.tlasNodes; instDepth = -1;
-            }
-            ngroup = st.pop();
+            if (tgroup.y) { push(tgroup); tgroup = make_uint2(0u, 0u); }     // postponed triangles / instances wait on the stack
+            const uint32_t bit = 31u - __clz(ngroup.y);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y & 0xff000000u) push(ngroup);
+            const uint32_t slot = (bit - 24u) ^ (octinv4 & 0xffu);
+            const uint32_t child = ngroup.x + __popc(ngroup.y & ((1u << slot) - 1u) & 0xffu);
+            intersect_children(nodes, child, o, d, inv, octinv4, ANY_HIT ? tmax : fminf(tmax, hitT), ngroup, tgroup);
+            if (STATS) cN++;
         }
-        return false;
+
+        // ---------------------------------------------------------------- phase T: triangles ----
+        while (true)
+        {
+            const bool wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded);
+            const uint32_t mT = __ballot_sync(NX_FULL, wantT);
+            if (!mT) break;
+            // lanes that still have a node to test after this one keep the warp busy; otherwise triangles are all there is
+            const uint32_t mN2 = __ballot_sync(NX_FULL, live && (ngroup.y & 0xff000000u) != 0u);
+            if (__popc(mT) < tune.triLanes && mN2 != 0u) break;
+            if (STATS) { wRT++; wLT += __popc(mT); }
+            if (wantT)
+            {
+                const uint32_t bit = 31u - __clz(tgroup.y);
+                tgroup.y &= ~(1u << bit);
+                if (STATS) cT++;
+                // Moeller-Trumbore on {v0, e0 = v1 - v0, e1 = v2 - v0}; no back-face culling (Triangle.cuh:29-62)
+                const float4* tri = ltris + 3 * (size_t)(tgroup.x + bit);
+                const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+                const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
+                const V3 pv = xcross(d, e1);
+                const float det = xdot(e0, pv);
+                const float invDet = rcp_ieee(det);
+                const V3 s = o - v3(a.x, a.y, a.z);
+                const float u = __fmul_rn(invDet, xdot(s, pv));
+                const V3 qv = xcross(s, e0);
+                const float v = __fmul_rn(invDet, xdot(d, qv));
+                const float t = __fmul_rn(invDet, xdot(e1, qv));
+                if (u >= 0.0f && u <= 1.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f && t > 0.0f)
+                {
+                    const uint32_t prim = __float_as_uint(a.w);
+                    if (ANY_HIT) { if (t < tmax) occluded = true; }
+                    else {
+                        bool take = t < fminf(tmax, hitT);
+                        if (!take && t == hitT && hitPrim != NX_INVALID) {
+                            // exact tie: the smaller (instance id, primitive id) wins, whatever the visiting order
+                            const uint32_t ia = __ldg(sc.tlasPrimIdx + curSlot), ib = __ldg(sc.tlasPrimIdx + hitSlot);
+                            take = ia < ib || (ia == ib && prim < hitPrim);
+                        }
+                        if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = curSlot; }
+                    }
+                }
+            }
+        }
     }
-};
+    if (STATS) {
+        atomicAdd(&stats->nodes, cN); atomicAdd(&stats->tris, cT); atomicAdd(&stats->insts, cI); atomicAdd(&stats->rays, cR); atomicAdd(&stats->sphereCulled, cS);
+        if (lane_id() == 0) {
+            atomicAdd(&stats->iters, wIt); atomicAdd(&stats->lanesN, wLN); atomicAdd(&stats->roundsT, wRT); atomicAdd(&stats->lanesT, wLT);
+            atomicAdd(&stats->roundsX, wRX); atomicAdd(&stats->lanesX, wLX);
+        }
+    }
+}

@@ -46,7 +46,23 @@ inline f3 xvector(const float* m, f3 p)
 }
 inline uint32_t octantInv(f3 d) { return 7u - (((d.x < 0.f) ? 4u : 0u) | ((d.y < 0.f) ? 2u : 0u) | ((d.z < 0.f) ? 1u : 0u)); }
 
-// Triangle.cuh:29-62 on (v0, e0 = v1 - v0, e1 = v2 - v0)
+// Triangle.cuh:29-62 on (v0, e0 = v1 - v0, e1 = v2 - v0).  Returns the distance of a valid intersection (t > 0) or -1.
+inline float triangleT(const float* t, f3 o, f3 d, float& u, float& v)
+{
+    f3 v0 = mk(t[0], t[1], t[2]);
+    f3 e0 = mk(t[3], t[4], t[5]) - v0, e1 = mk(t[6], t[7], t[8]) - v0;
+    f3 pv = xcross(d, e1);
+    float det = xdot(e0, pv);
+    float inv = 1.0f / det;
+    f3 s = o - v0;
+    u = inv * xdot(s, pv);
+    if (!(u >= 0.0f && u <= 1.0f)) return -1.0f;
+    f3 qv = xcross(s, e0);
+    v = inv * xdot(d, qv);
+    if (!(v >= 0.0f && u + v <= 1.0f)) return -1.0f;
+    float tt = inv * xdot(e1, qv);
+    return tt > 0.0f ? tt : -1.0f;
+}
 inline bool triangle(const float* t, f3 o, f3 d, float& best, float& bu, float& bv)
 {
     f3 v0 = mk(t[0], t[1], t[2]);
@@ -119,9 +135,17 @@ bool traverseBlas(const Mesh& M, f3 o, f3 d, float& best, Hit& hit, uint32_t ins
             tgroup.hits &= ~(1u << bit);
             uint32_t prim = M.primIdx[tgroup.base + bit];
             st.tris++;
-            if (triangle(&M.tris[9 * (size_t)prim], o, d, best, hit.u, hit.v)) {
-                hit.t = best; hit.prim = prim; hit.inst = instId;
-                if (ANY) return true;
+            float u, v;
+            const float tt = triangleT(&M.tris[9 * (size_t)prim], o, d, u, v);
+            if (tt > 0.0f) {
+                // closer hit, or an exact tie resolved by (instance id, primitive id) so that the visiting order cannot matter
+                // (the reference keeps whichever it met first, which depends on its warp schedule: SURVEY.md §7)
+                bool take = tt < best;
+                if (!ANY && !take && tt == hit.t && hit.prim != INVALID) take = instId < hit.inst || (instId == hit.inst && prim < hit.prim);
+                if (take) {
+                    best = tt; hit.t = tt; hit.u = u; hit.v = v; hit.prim = prim; hit.inst = instId;
+                    if (ANY) return true;
+                }
             }
         }
         if ((ngroup.hits & 0xff000000u) == 0) {
