@@ -7,6 +7,9 @@
 // (the reference evaluates 2*PI*u in fp64 because its PI is a double literal, src/Utils/Utils.h:7).
 #pragma once
 #include "nx_common.cuh"
+#ifndef NX_BSDF_INLINE
+#define NX_BSDF_INLINE __forceinline__
+#endif
 
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 f3(float x, float y, float z) { return {x, y, z}; }
@@ -261,7 +264,7 @@ __device__ __forceinline__ LobeSample plastic_sample(const nx_material& M, const
 }
 
 // Principled mix (PrincipledBSDF.cuh:12-83): eval sums the lobes with their selection weights, sample picks one lobe.
-__device__ __forceinline__ bool principled_eval(const nx_material& M, F3 wi, F3 wo, F3& f, float& pdf)
+__device__ NX_BSDF_INLINE bool principled_eval(const nx_material& M, F3 wi, F3 wo, F3& f, float& pdf)
 {
     const Ggx g(M.roughness, M.anisotropy);
     f = f3(0.f); pdf = 0.f;
@@ -277,7 +280,7 @@ __device__ __forceinline__ bool principled_eval(const nx_material& M, F3 wi, F3 
     }
     return pdf_ok(pdf);
 }
-__device__ __forceinline__ LobeSample principled_sample(const nx_material& M, F3 wi, uint32_t& rng)
+__device__ NX_BSDF_INLINE LobeSample principled_sample(const nx_material& M, F3 wi, uint32_t& rng)
 {
     const Ggx g(M.roughness, M.anisotropy);
     LobeSample s; float w;

@@ -19,6 +19,9 @@
 namespace {
 
 constexpr int kShadeBlock = 128;
+#ifndef NX_SHADE_MIN_BLOCKS
+#define NX_SHADE_MIN_BLOCKS 5
+#endif
 constexpr uint32_t kMaxBounce = 256;
 
 struct WaveCounters {                 // zeroed at the start of every frame
@@ -175,13 +178,14 @@ struct ShadeOut {
 };
 
 // Next-event estimation: one light picked uniformly, one point on it, MIS against the BSDF (PathTracer.cu:176-343).
+// The light-specific part only produces (direction, distance, pdf, emission); the BSDF is evaluated once, at one call site,
+// which keeps the kernel's code size (and with it the instruction-cache pressure ncu showed) down.
 __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_material& mat, const Surface& sf, const Frame& fr, F3 wi, F3 rayDir, F3 thr,
                                            uint32_t& rng, ShadeOut& out)
 {
     const uint32_t li = (uint32_t)floorf(rng_next(rng) * (float)sv.lightCount);
     const DLight L = sv.lights[min(li, sv.lightCount - 1u)];
-    F3 toLight, emissive, dir; float lightPdf, dist, weight = 1.0f;
-    F3 origin;
+    F3 toLight, emissive, dir, origin; float lightPdf, dist; bool mis = false;
     if (L.type == NX_LIGHT_MESH)
     {
         const DShadeInst I = sv.shadeInst[L.instance];
@@ -207,12 +211,9 @@ __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_materi
         lightPdf = 1.0f / ((float)sv.lightCount * (float)mesh.primCount * area);
         lightPdf *= dot(toLight, toLight) / cosL;                                // area measure -> solid angle
         if (!pdf_ok(lightPdf)) return;
-        F3 f; float bsdfPdf;
-        if (!principled_eval(mat, wi, fr.toLocal(dir), f, bsdfPdf)) return;
-        weight = power_heuristic(lightPdf, bsdfPdf);
-        const nx_material lm = sv.materials[I.materialIdx];
-        emissive = f3(lm.emission_color[0], lm.emission_color[1], lm.emission_color[2]) * lm.intensity;
-        out.shL = weight * thr * f * emissive / lightPdf;
+        const nx_material& lm = sv.materials[I.materialIdx];
+        emissive = f3(__ldg(&lm.emission_color[0]), __ldg(&lm.emission_color[1]), __ldg(&lm.emission_color[2])) * __ldg(&lm.intensity);
+        mis = true;
     }
     else if (L.type == NX_LIGHT_POINT || L.type == NX_LIGHT_DIRECTIONAL)
     {
@@ -226,11 +227,12 @@ __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_materi
         origin = offset_ray(sf.p, sf.gn * sign_or_one(dot(toLight, sf.n)));
         dist = point ? length(toLight) : NX_MISS_T;
         dir = point ? toLight / dist : normalize(toLight);
-        F3 f; float bsdfPdf;
-        if (!principled_eval(mat, wi, fr.toLocal(dir), f, bsdfPdf)) return;
-        out.shL = thr * f * emissive / lightPdf;
     }
     else return;   // spot lights are declared but have no NEE branch in the reference either (PathTracer.cu:274-334)
+    F3 f; float bsdfPdf;
+    if (!principled_eval(mat, wi, fr.toLocal(dir), f, bsdfPdf)) return;
+    const float weight = mis ? power_heuristic(lightPdf, bsdfPdf) : 1.0f;
+    out.shL = weight * thr * f * emissive / lightPdf;
     out.shadow = true; out.shO = origin; out.shD = dir; out.shDist = dist;
 }
 
@@ -294,7 +296,7 @@ __device__ __forceinline__ void shade_one(const DSceneView& sv, const WaveBuffer
     out.ext = true; out.extO = offset_ray(sf.p, sf.gn * sign_or_one(dot(wo, sf.n))); out.extD = wo; out.thr = thr * s.weight; out.pdf = s.pdf;
 }
 
-__global__ void __launch_bounds__(kShadeBlock) shade_kernel(const __grid_constant__ DSceneView sv, WaveBuffers wb, uint32_t bounce, uint32_t frame)
+__global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DSceneView sv, WaveBuffers wb, uint32_t bounce, uint32_t frame)
 {
     const uint32_t n = wb.counters->extCount[bounce - 1];
     const uint32_t in = (bounce - 1) & 1u, outQ = bounce & 1u;

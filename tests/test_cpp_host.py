@@ -1,0 +1,61 @@
+"""The C++ host layer (include/nexus_b200.hpp) over the C ABI: compiles with g++ alone (no CUDA headers), fails loudly
+without a GPU, and on a GPU renders the Cornell box headless to PFM + EXR."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "examples", "render_headless")
+
+
+def _build():
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "render_headless.cpp"),
+                           "-L" + os.path.join(ROOT, "nexus_b200"), "-lnexus_b200", "-Wl,-rpath,$ORIGIN/../nexus_b200", "-o", EXE])
+
+
+def test_cpp_host_compiles_without_cuda_headers():
+    _build()
+    assert os.path.exists(EXE)
+    src = open(os.path.join(ROOT, "include", "nexus_b200.hpp")).read()
+    assert "cuda" not in src.lower().replace("cuda headers", "").replace("no cuda", "").replace("usable cuda device", "")
+    for name in ("BuildBVH2", "BuildBVH8", "ToHost", "FreeDeviceBVH", "BenchmarkBuild", "class Scene", "class AssetManager", "class MeshInstance",
+                 "class PathTracer", "struct Material", "struct Light", "struct Camera", "struct RenderSettings", "CreateMeshInstance", "AddHDRMap",
+                 "ResetFrameNumber", "OnResize", "GetFrameNumber"):
+        assert name in src, name
+
+
+def test_cpp_host_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    if not os.path.exists(EXE):
+        _build()
+    r = subprocess.run([EXE, "32", "32", "1", "/tmp/nx_nogpu"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_renders_cornell(tmp_path):
+    if not os.path.exists(EXE):
+        _build()
+    out = str(tmp_path / "cornell")
+    r = subprocess.run([EXE, "160", "120", "64", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(out + ".pfm", "rb").read()
+    head, dims, scale, body = raw.split(b"\n", 3)
+    assert head == b"PF" and dims == b"160 120"
+    img = np.frombuffer(body, "<f4").reshape(120, 160, 3)
+    assert np.isfinite(img).all() and 0.1 < img.mean() < 1.0
+    # same scene through the Python mirror: the two host layers drive the same kernels, so the means agree to sampling noise
+    import nexus_b200 as nx
+    from nexus_b200 import scenes
+    ctx = nx.Context(0)
+    desc = scenes.cornell_box()
+    sc = scenes.build(ctx, desc, (160, 120))
+    pt = nx.PathTracer(ctx, (160, 120)); pt.Render(sc, frames=64)
+    ref = pt.ReadAccumulation()
+    assert abs(ref.mean() - img.mean()) < 0.02 * ref.mean()
+    assert os.path.getsize(out + ".exr") > 160 * 120 * 12
+    pt.close(); sc.close(); ctx.close()
