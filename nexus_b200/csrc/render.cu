@@ -355,7 +355,7 @@ __global__ void resolve_rgba8_kernel(const float* __restrict__ accum, uint32_t c
     }
 }
 
-TraceTuning trace_tuning(const nx_ctx* ctx) { TraceTuning t; t.triLanes = ctx->tune_tri; t.instLanes = ctx->tune_inst; t.sphereCull = ctx->tune_sphere; return t; }
+TraceTuning trace_tuning(const nx_ctx* ctx) { TraceTuning t; t.triLanes = ctx->tune_tri; t.instLanes = ctx->tune_inst; t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u; return t; }
 
 int persistent_grid(nx_ctx* ctx, const void* fn, int block, int* cache)
 {

@@ -55,6 +55,7 @@ struct TraceTuning {               // batching thresholds (lanes): run a phase w
     uint32_t triLanes;             // triangle phase
     uint32_t instLanes;            // new-ray / instance-entry phase
     uint32_t sphereCull;           // 0 disables the per-instance bounding-sphere test (measurement only)
+    uint32_t k47;                  // always 0x47000000 (see trace_loop: a constant the compiler must not see)
 };
 
 struct TraceStats {
@@ -73,10 +74,54 @@ __device__ __forceinline__ uint32_t octant_inv4(V3 d)
 }
 __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 
+// Which of the six quantised planes per child are converted byte -> float on the ALU pipe (PRMT into the mantissa of
+// 2^15, the bias folded into the FMA addend) instead of the XU pipe (I2F.U8): bit a = near plane of axis a, bit 3 + a =
+// far plane.  ncu (profiles/r01_trace_closest.md): 48 I2F.U8 per node kept the XU pipe at 54-61 % with the I2Fs holding
+// 15 % of all stall samples; splitting the conversions over both pipes removes that queue.
+#ifndef NX_MAGIC_PLANES
+#define NX_MAGIC_PLANES 0x2d
+#endif
+
+#ifndef NX_PREFETCH
+#define NX_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t shl_wrap(uint32_t v, uint32_t n) { uint32_t r; asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(v), "r"(n)); return r; }
+
+// Byte j of `word` as a float.  MAGIC: the byte is spliced into 0x4700qq00 = 32768 + q (one PRMT on the ALU pipe); the
+// caller folds -32768 * s into the addend.  Otherwise I2F.U8 on the XU pipe.
+template <bool MAGIC>
+__device__ __forceinline__ float plane_q(uint32_t word, int j, uint32_t k47)
+{
+    if (MAGIC) return __uint_as_float(__byte_perm(word, k47, 0x7504u | (uint32_t)(j << 4)));
+    return (float)((word >> (8 * j)) & 0xffu);
+}
+// {t0, t1} = {q0, q1} * s + {c0, c1}: one FFMA2 (sm_100 packed fp32, scalar-broadcast multiplier) = one issue slot for the
+// near and the far plane of an axis.  Each half is an IEEE fma, so the CPU oracle's fmaf() reproduces it.
+#ifndef NX_FFMA2
+#define NX_FFMA2 1
+#endif
+__device__ __forceinline__ void fma2_bcast(float& t0, float& t1, float q0, float q1, float s, float c0, float c1)
+{
+#if !NX_FFMA2
+    t0 = __fmaf_rn(q0, s, c0); t1 = __fmaf_rn(q1, s, c1); return;
+#endif
+    asm("{\n\t.reg .b64 ra, rs, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+        "fma.rn.f32x2 rd, ra, rs, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(t0), "=f"(t1) : "f"(q0), "f"(q1), "f"(s), "f"(c0), "f"(c1));
+}
+
 // Slab test of the eight quantised child boxes of one node.  Returns the inner-node group (childBase, hits<<24 | imask)
 // and the leaf group (primBase, hit bits 0..23).
-__device__ __forceinline__ void intersect_children(const float4* __restrict__ nodes, uint32_t idx, V3 o, V3 d, V3 inv, uint32_t octinv4, float tmax,
-                                                   uint2& inner, uint2& leaves)
+//
+// The test is CONSERVATIVE, not exact: `inv` is the hardware reciprocal approximation and every slab is widened by
+// eps = 2^-6 cell + 2^-20 |(p - o) * inv| per axis, which covers the approximation (2^-22 relative), the 2^-9 cell lost to
+// the folded bias and the roundings of the original formulation.  A widened box can only add node visits; which triangle
+// is the closest hit is decided by the triangle test alone (exact arithmetic, deterministic tie-break), so hits are
+// unchanged.  NaNs (0 * inf on axis-parallel rays) drop out of min/max, i.e. the axis is ignored: also conservative.
+__device__ __forceinline__ void intersect_children(const float4* __restrict__ nodes, uint32_t idx, V3 o, V3 inv, uint32_t octinv4, float tmax,
+                                                   uint32_t k47, uint2& inner, uint2& leaves)
 {
     const float4* nd = nodes + 5 * (size_t)idx;
     const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3), n4 = __ldg(nd + 4);
@@ -86,6 +131,20 @@ __device__ __forceinline__ void intersect_children(const float4* __restrict__ no
     const float sy = __fmul_rn(__uint_as_float(((eim >> 8) & 0xffu) << 23), inv.y);
     const float sz = __fmul_rn(__uint_as_float(((eim >> 16) & 0xffu) << 23), inv.z);
     const float ox = __fmul_rn(__fsub_rn(n0.x, o.x), inv.x), oy = __fmul_rn(__fsub_rn(n0.y, o.y), inv.y), oz = __fmul_rn(__fsub_rn(n0.z, o.z), inv.z);
+    const float ex = __fmaf_rn(fabsf(ox), 0x1p-20f, __fmul_rn(fabsf(sx), 0x1p-6f));
+    const float ey = __fmaf_rn(fabsf(oy), 0x1p-20f, __fmul_rn(fabsf(sy), 0x1p-6f));
+    const float ez = __fmaf_rn(fabsf(oz), 0x1p-20f, __fmul_rn(fabsf(sz), 0x1p-6f));
+    constexpr bool MNX = NX_MAGIC_PLANES & 1, MNY = NX_MAGIC_PLANES & 2, MNZ = NX_MAGIC_PLANES & 4;
+    constexpr bool MFX = NX_MAGIC_PLANES & 8, MFY = NX_MAGIC_PLANES & 16, MFZ = NX_MAGIC_PLANES & 32;
+    float nx_ = __fsub_rn(ox, ex), ny_ = __fsub_rn(oy, ey), nz_ = __fsub_rn(oz, ez);      // near-plane addends
+    float fx_ = __fadd_rn(ox, ex), fy_ = __fadd_rn(oy, ey), fz_ = __fadd_rn(oz, ez);      // far-plane addends
+    if (MNX) nx_ = __fmaf_rn(-32768.0f, sx, nx_);
+    if (MNY) ny_ = __fmaf_rn(-32768.0f, sy, ny_);
+    if (MNZ) nz_ = __fmaf_rn(-32768.0f, sz, nz_);
+    if (MFX) fx_ = __fmaf_rn(-32768.0f, sx, fx_);
+    if (MFY) fy_ = __fmaf_rn(-32768.0f, sy, fy_);
+    if (MFZ) fz_ = __fmaf_rn(-32768.0f, sz, fz_);
+    const bool negx = inv.x < 0.f, negy = inv.y < 0.f, negz = inv.z < 0.f;                // sign(inv) == sign(d), -0 included
     uint32_t hits = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -93,23 +152,25 @@ __device__ __forceinline__ void intersect_children(const float4* __restrict__ no
         const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
         const uint32_t inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;                 // bit 4 of a byte set <=> low5 >= 24 <=> inner child
         const uint32_t innerFF = (inner4 >> 4) * 0xffu;                               // 0xff in the bytes of inner children
-        const uint32_t bitIdx4 = (meta4 ^ (octinv4 & innerFF)) & 0x1f1f1f1fu;         // inner: 24 + (slot ^ octinv); leaf: first triangle bit
+        const uint32_t bitIdx4 = meta4 ^ (octinv4 & innerFF);                         // low 5 bits per byte: inner 24 + (slot ^ octinv); leaf first triangle bit
         const uint32_t bits4 = (meta4 >> 5) & 0x07070707u;                            // inner: 1; leaf: unary triangle count
         const uint32_t lox = __float_as_uint(h ? n2.y : n2.x), loy = __float_as_uint(h ? n2.w : n2.z), loz = __float_as_uint(h ? n3.y : n3.x);
         const uint32_t hix = __float_as_uint(h ? n3.w : n3.z), hiy = __float_as_uint(h ? n4.y : n4.x), hiz = __float_as_uint(h ? n4.w : n4.z);
-        const uint32_t nearx = d.x < 0.f ? hix : lox, farx = d.x < 0.f ? lox : hix;
-        const uint32_t neary = d.y < 0.f ? hiy : loy, fary = d.y < 0.f ? loy : hiy;
-        const uint32_t nearz = d.z < 0.f ? hiz : loz, farz = d.z < 0.f ? loz : hiz;
+        const uint32_t nearx = negx ? hix : lox, farx = negx ? lox : hix;
+        const uint32_t neary = negy ? hiy : loy, fary = negy ? loy : hiy;
+        const uint32_t nearz = negz ? hiz : loz, farz = negz ? loz : hiz;
 #pragma unroll
         for (int j = 0; j < 4; j++)
         {
-            const uint32_t sh = 8u * j;
-            const float t0x = __fmaf_rn((float)((nearx >> sh) & 0xffu), sx, ox), t1x = __fmaf_rn((float)((farx >> sh) & 0xffu), sx, ox);
-            const float t0y = __fmaf_rn((float)((neary >> sh) & 0xffu), sy, oy), t1y = __fmaf_rn((float)((fary >> sh) & 0xffu), sy, oy);
-            const float t0z = __fmaf_rn((float)((nearz >> sh) & 0xffu), sz, oz), t1z = __fmaf_rn((float)((farz >> sh) & 0xffu), sz, oz);
+            float t0x, t1x, t0y, t1y, t0z, t1z;
+            fma2_bcast(t0x, t1x, plane_q<MNX>(nearx, j, k47), plane_q<MFX>(farx, j, k47), sx, nx_, fx_);
+            fma2_bcast(t0y, t1y, plane_q<MNY>(neary, j, k47), plane_q<MFY>(fary, j, k47), sy, ny_, fy_);
+            fma2_bcast(t0z, t1z, plane_q<MNZ>(nearz, j, k47), plane_q<MFZ>(farz, j, k47), sz, nz_, fz_);
             const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
             const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-            if (tn <= tf) hits |= ((bits4 >> sh) & 0xffu) << ((bitIdx4 >> sh) & 0xffu);
+            // child bits shifted to the child's position: the shift uses the low 5 bits of its count only
+            const uint32_t c = shl_wrap(__byte_perm(bits4, 0u, 0x4440u | (uint32_t)j), bitIdx4 >> (8 * j));
+            if (tn <= tf) hits |= c;
         }
     }
     inner = make_uint2(__float_as_uint(n1.x), (hits & 0xff000000u) | (eim >> 24));
@@ -158,6 +219,10 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
     float* const park = reinterpret_cast<float*>(smem + 2 * NX_STACK_SHARED * NX_TRACE_BLOCK) + threadIdx.x;   // value k at park[k * NX_TRACE_BLOCK]
     uint2 spill[NX_STACK_TOTAL - NX_STACK_SHARED];
     uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
+    // 0x47000000 arrives as a kernel parameter so that ptxas cannot fold it: PRMT then takes the constant from the
+    // parameter bank / a register and its selector as the immediate, and the byte -> float splice is ONE instruction (with
+    // the constant known, ptxas makes IT the immediate and reloads the selector into a register before every PRMT)
+    const uint32_t k47 = tune.k47;
 
     // per-lane state (registers)
     V3 o = v3(0, 0, 0), d = v3(0, 0, 1), inv = v3(0, 0, 0);
@@ -190,7 +255,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                     o = v3(park[0], park[NX_TRACE_BLOCK], park[2 * NX_TRACE_BLOCK]);
                     d = v3(park[3 * NX_TRACE_BLOCK], park[4 * NX_TRACE_BLOCK], park[5 * NX_TRACE_BLOCK]);
                     inv = v3(park[6 * NX_TRACE_BLOCK], park[7 * NX_TRACE_BLOCK], park[8 * NX_TRACE_BLOCK]);
-                    octinv4 = octant_inv4(d);
+                    octinv4 = octant_inv4(inv);
                     nodes = sc.tlasNodes; instDepth = -1;
                 }
                 const uint2 e = pop();
@@ -259,9 +324,10 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                 setup = true;
                 }
             }
+            __syncwarp();   // new rays and instance entries reconverge here: one pass through the shared set-up, not one per branch
             if (setup) {
-                inv = v3(rcp_ieee(d.x), rcp_ieee(d.y), rcp_ieee(d.z));
-                octinv4 = octant_inv4(d);
+                inv = v3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
+                octinv4 = octant_inv4(inv);
                 ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
             }
             if (__all_sync(NX_FULL, dead)) break;
@@ -276,8 +342,21 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             if (ngroup.y & 0xff000000u) push(ngroup);
             const uint32_t slot = (bit - 24u) ^ (octinv4 & 0xffu);
             const uint32_t child = ngroup.x + __popc(ngroup.y & ((1u << slot) - 1u) & 0xffu);
-            intersect_children(nodes, child, o, d, inv, octinv4, ANY_HIT ? tmax : fminf(tmax, hitT), ngroup, tgroup);
+            intersect_children(nodes, child, o, inv, octinv4, ANY_HIT ? tmax : fminf(tmax, hitT), k47, ngroup, tgroup);
             if (STATS) cN++;
+#if NX_PREFETCH
+            // the lane's next fetch is known now; pull its lines into L1 while the votes / other phases run
+            if (ngroup.y & 0xff000000u) {
+                const uint32_t nb = 31u - __clz(ngroup.y);
+                const uint32_t ns = (nb - 24u) ^ (octinv4 & 0xffu);
+                const float4* pn = nodes + 5 * (size_t)(ngroup.x + __popc(ngroup.y & ((1u << ns) - 1u) & 0xffu));
+                prefetch_l1(pn); prefetch_l1(pn + 4);
+            } else if (tgroup.y) {
+                const uint32_t tb = 31u - __clz(tgroup.y);
+                if (instDepth >= 0) { const float4* pt = ltris + 3 * (size_t)(tgroup.x + tb); prefetch_l1(pt); prefetch_l1(pt + 2); }
+                else prefetch_l1(&sc.inst[tgroup.x + tb]);
+            }
+#endif
         }
 
         // ---------------------------------------------------------------- phase T: triangles ----
