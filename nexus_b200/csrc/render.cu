@@ -19,6 +19,9 @@
 namespace {
 
 constexpr int kShadeBlock = 128;
+#ifndef NX_TILED_PIXELS
+#define NX_TILED_PIXELS 1
+#endif
 #ifndef NX_SHADE_MIN_BLOCKS
 #define NX_SHADE_MIN_BLOCKS 5
 #endif
@@ -115,8 +118,16 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ D
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.counters->extCount[0] = count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
     {
-        const uint32_t py = i / cam.resX, px = i - py * cam.resX;
-        uint32_t rng = rng_seed(i, frame, 0u);
+        // Queue slot i -> pixel: 8x4 pixel tiles, so the 32 rays a warp fetches together cover a compact footprint (and, because
+        // every later queue inherits this order through compaction, so do their bounces).  Row-major order when the
+        // resolution is not a multiple of the tile.  The pixel index, not the slot, keys the RNG and addresses the image.
+        uint32_t px, py;
+        if (NX_TILED_PIXELS && (cam.resX & 7u) == 0u && (cam.resY & 3u) == 0u) {
+            const uint32_t tile = i >> 5, tilesX = cam.resX >> 3, ty = tile / tilesX, tx = tile - ty * tilesX;
+            px = tx * 8u + (i & 7u); py = ty * 4u + ((i >> 3) & 3u);
+        } else { py = i / cam.resX; px = i - py * cam.resX; }
+        const uint32_t pixel = py * cam.resX + px;
+        uint32_t rng = rng_seed(pixel, frame, 0u);
         const float x = ((float)px + rng_next(rng)) / (float)cam.resX;
         const float y = ((float)py + rng_next(rng)) / (float)cam.resY;
         const float u0 = rng_next(rng), u1 = rng_next(rng);   // concentric-free polar disk sample (Random.cuh:100-107)
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ D
         const F3 dir = normalize(target - pos - off);
         float4* out = reinterpret_cast<float4*>(wb.ext[0] + i);
         out[0] = make_float4(org.x, org.y, org.z, NX_MISS_T);
-        out[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(i));
+        out[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
         wb.state[0][i] = make_float4(1.f, 1.f, 1.f, 0.f);
     }
 }

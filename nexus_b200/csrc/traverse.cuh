@@ -29,7 +29,7 @@
 #define NX_TRACE_BLOCK 128
 #endif
 #ifndef NX_STACK_SHARED
-#define NX_STACK_SHARED 12
+#define NX_STACK_SHARED 8
 #endif
 #ifndef NX_TRACE_MIN_BLOCKS
 #define NX_TRACE_MIN_BLOCKS 8
@@ -64,13 +64,28 @@ struct TraceStats {
     unsigned long long iters, lanesN, roundsT, lanesT, roundsX, lanesX, sphereCulled;
 };
 
-// Shared memory per block: stack entries [NX_STACK_SHARED][block] of uint2, then the parked world-space ray
-// (origin, direction, reciprocal direction) as [9][block] floats.
+// Shared memory per block: stack entries [NX_STACK_SHARED][block] of uint2, then the parked world-space ray, 48 B per
+// thread: {origin, octant word} {direction, -} {reciprocal direction, -}.  Three LDS.128 / STS.128 per instance exit /
+// entry; a 48-byte thread stride keeps the 16-byte accesses of a quarter warp on distinct banks.
+#ifndef NX_PARK128
+#define NX_PARK128 1
+#endif
+#if NX_PARK128
+#define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 48) * NX_TRACE_BLOCK)
+#else
 #define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 9 * 4) * NX_TRACE_BLOCK)
+#endif
+#ifndef NX_TSINGLE
+#define NX_TSINGLE 0   // measured: one triangle round per iteration (1) is 4 % slower than looping over rounds (0)
+#endif
 
+// (7 - octant) replicated into four bytes, octant = sign bits of the direction (x: 4, y: 2, z: 1).  Any value works as long
+// as the same one decodes the hit mask it encoded (it only fixes the visiting order), so the sign BITS are used: shifts
+// and one multiply instead of three float compares and selects.
 __device__ __forceinline__ uint32_t octant_inv4(V3 d)
 {
-    return (7u - (((d.x < 0.f) ? 4u : 0u) | ((d.y < 0.f) ? 2u : 0u) | ((d.z < 0.f) ? 1u : 0u))) * 0x01010101u;
+    const uint32_t oct = ((__float_as_uint(d.x) >> 31) << 2) | ((__float_as_uint(d.y) >> 31) << 1) | (__float_as_uint(d.z) >> 31);
+    return (7u - oct) * 0x01010101u;
 }
 __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 
@@ -216,7 +231,11 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                                            uint32_t* smem, Sink& sink, TraceStats* stats)
 {
     uint2* const sstack = reinterpret_cast<uint2*>(smem) + threadIdx.x;                       // entry e at sstack[e * NX_TRACE_BLOCK]
+#if NX_PARK128
+    float4* const park4 = reinterpret_cast<float4*>(smem + 2 * NX_STACK_SHARED * NX_TRACE_BLOCK) + 3 * threadIdx.x;
+#else
     float* const park = reinterpret_cast<float*>(smem + 2 * NX_STACK_SHARED * NX_TRACE_BLOCK) + threadIdx.x;   // value k at park[k * NX_TRACE_BLOCK]
+#endif
     uint2 spill[NX_STACK_TOTAL - NX_STACK_SHARED];
     uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
     // 0x47000000 arrives as a kernel parameter so that ptxas cannot fold it: PRMT then takes the constant from the
@@ -241,6 +260,39 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
     auto push = [&](uint2 v) { if (sp < NX_STACK_SHARED) sstack[sp * NX_TRACE_BLOCK] = v; else if (sp < NX_STACK_TOTAL) spill[sp - NX_STACK_SHARED] = v; else return; sp++; };
     auto pop = [&]() -> uint2 { sp--; return sp < NX_STACK_SHARED ? sstack[sp * NX_TRACE_BLOCK] : spill[sp - NX_STACK_SHARED]; };
 
+    // One Moeller-Trumbore test for the highest set bit of the lane's triangle group; {v0, e0 = v1 - v0, e1 = v2 - v0},
+    // no back-face culling (Triangle.cuh:29-62).
+    auto test_triangle = [&]() {
+        const uint32_t bit = 31u - __clz(tgroup.y);
+        tgroup.y &= ~(1u << bit);
+        if (STATS) cT++;
+        const float4* tri = ltris + 3 * (size_t)(tgroup.x + bit);
+        const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+        const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
+        const V3 pv = xcross(d, e1);
+        const float det = xdot(e0, pv);
+        const float invDet = rcp_ieee(det);
+        const V3 s = o - v3(a.x, a.y, a.z);
+        const float u = __fmul_rn(invDet, xdot(s, pv));
+        const V3 qv = xcross(s, e0);
+        const float v = __fmul_rn(invDet, xdot(d, qv));
+        const float t = __fmul_rn(invDet, xdot(e1, qv));
+        if (u >= 0.0f && u <= 1.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f && t > 0.0f)
+        {
+            const uint32_t prim = __float_as_uint(a.w);
+            if (ANY_HIT) { if (t < tmax) occluded = true; }
+            else {
+                bool take = t < fminf(tmax, hitT);
+                if (!take && t == hitT && hitPrim != NX_INVALID) {
+                    // exact tie: the smaller (instance id, primitive id) wins, whatever the visiting order
+                    const uint32_t ia = __ldg(sc.tlasPrimIdx + curSlot), ib = __ldg(sc.tlasPrimIdx + hitSlot);
+                    take = ia < ib || (ia == ib && prim < hitPrim);
+                }
+                if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = curSlot; }
+            }
+        }
+    };
+
     while (true)
     {
         // ---------------------------------------------------------------- phase P: retire / pop (cheap, every iteration) ----
@@ -252,10 +304,16 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                 live = false; ngroup = make_uint2(0u, 0u); tgroup = make_uint2(0u, 0u);
             } else {
                 if (sp == instDepth) {      // leaving an instance: restore the parked world-space ray
+#if NX_PARK128
+                    const float4 p0 = park4[0], p1 = park4[1], p2 = park4[2];
+                    o = v3(p0.x, p0.y, p0.z); d = v3(p1.x, p1.y, p1.z); inv = v3(p2.x, p2.y, p2.z);
+                    octinv4 = __float_as_uint(p0.w);
+#else
                     o = v3(park[0], park[NX_TRACE_BLOCK], park[2 * NX_TRACE_BLOCK]);
                     d = v3(park[3 * NX_TRACE_BLOCK], park[4 * NX_TRACE_BLOCK], park[5 * NX_TRACE_BLOCK]);
                     inv = v3(park[6 * NX_TRACE_BLOCK], park[7 * NX_TRACE_BLOCK], park[8 * NX_TRACE_BLOCK]);
                     octinv4 = octant_inv4(inv);
+#endif
                     nodes = sc.tlasNodes; instDepth = -1;
                 }
                 const uint2 e = pop();
@@ -268,6 +326,12 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
         const bool wantI = live && instDepth < 0 && tgroup.y != 0u;
         const uint32_t mN = __ballot_sync(NX_FULL, hasN);
         const uint32_t mX = __ballot_sync(NX_FULL, needR || wantI);
+#if NX_TSINGLE
+        // one triangle round per iteration, decided by the same set of votes (the first version looped here with two more
+        // votes per round: 4 % of the kernel's instructions were those votes, profiles/r01b)
+        const bool wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded);
+        const uint32_t mT = __ballot_sync(NX_FULL, wantT);
+#endif
 
         // ---------------------------------------------------------------- phase X: new ray / enter an instance ----
         // Both end in the same reciprocal-direction + octant set-up, so they share it.
@@ -315,9 +379,15 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                 const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&I->nodes));
                 nodes = reinterpret_cast<const float4*>(((uint64_t)ptrs.y << 32) | ptrs.x);
                 ltris = reinterpret_cast<const float4*>(((uint64_t)ptrs.w << 32) | ptrs.z);
+#if NX_PARK128
+                park4[0] = make_float4(o.x, o.y, o.z, __uint_as_float(octinv4));
+                park4[1] = make_float4(d.x, d.y, d.z, 0.f);
+                park4[2] = make_float4(inv.x, inv.y, inv.z, 0.f);
+#else
                 park[0] = o.x; park[NX_TRACE_BLOCK] = o.y; park[2 * NX_TRACE_BLOCK] = o.z;
                 park[3 * NX_TRACE_BLOCK] = d.x; park[4 * NX_TRACE_BLOCK] = d.y; park[5 * NX_TRACE_BLOCK] = d.z;
                 park[6 * NX_TRACE_BLOCK] = inv.x; park[7 * NX_TRACE_BLOCK] = inv.y; park[8 * NX_TRACE_BLOCK] = inv.z;
+#endif
                 const V3 wo = o, wd = d;
                 o = xform_point(r0, r1, r2, wo); d = xform_vector(r0, r1, r2, wd);   // direction is not renormalised: t stays in world units
                 if (STATS) cI++;
@@ -332,6 +402,16 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             }
             if (__all_sync(NX_FULL, dead)) break;
         }
+
+#if NX_TSINGLE
+        // ---------------------------------------------------------------- phase T: one triangle per lane ----
+        // (lanes that took part in phase X were not in mT: wantT needs a lane inside an instance, wantI one outside)
+        if (mT && (__popc(mT) >= tune.triLanes || mN == 0u))
+        {
+            if (STATS) { wRT++; wLT += __popc(mT); }
+            if (wantT) test_triangle();
+        }
+#endif
 
         // ---------------------------------------------------------------- phase N: one node per lane ----
         if (live && (ngroup.y & 0xff000000u))
@@ -359,7 +439,8 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
 #endif
         }
 
-        // ---------------------------------------------------------------- phase T: triangles ----
+#if !NX_TSINGLE
+        // ---------------------------------------------------------------- phase T: triangles (rounds until too few lanes) ----
         while (true)
         {
             const bool wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded);
@@ -369,39 +450,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             const uint32_t mN2 = __ballot_sync(NX_FULL, live && (ngroup.y & 0xff000000u) != 0u);
             if (__popc(mT) < tune.triLanes && mN2 != 0u) break;
             if (STATS) { wRT++; wLT += __popc(mT); }
-            if (wantT)
-            {
-                const uint32_t bit = 31u - __clz(tgroup.y);
-                tgroup.y &= ~(1u << bit);
-                if (STATS) cT++;
-                // Moeller-Trumbore on {v0, e0 = v1 - v0, e1 = v2 - v0}; no back-face culling (Triangle.cuh:29-62)
-                const float4* tri = ltris + 3 * (size_t)(tgroup.x + bit);
-                const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
-                const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
-                const V3 pv = xcross(d, e1);
-                const float det = xdot(e0, pv);
-                const float invDet = rcp_ieee(det);
-                const V3 s = o - v3(a.x, a.y, a.z);
-                const float u = __fmul_rn(invDet, xdot(s, pv));
-                const V3 qv = xcross(s, e0);
-                const float v = __fmul_rn(invDet, xdot(d, qv));
-                const float t = __fmul_rn(invDet, xdot(e1, qv));
-                if (u >= 0.0f && u <= 1.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f && t > 0.0f)
-                {
-                    const uint32_t prim = __float_as_uint(a.w);
-                    if (ANY_HIT) { if (t < tmax) occluded = true; }
-                    else {
-                        bool take = t < fminf(tmax, hitT);
-                        if (!take && t == hitT && hitPrim != NX_INVALID) {
-                            // exact tie: the smaller (instance id, primitive id) wins, whatever the visiting order
-                            const uint32_t ia = __ldg(sc.tlasPrimIdx + curSlot), ib = __ldg(sc.tlasPrimIdx + hitSlot);
-                            take = ia < ib || (ia == ib && prim < hitPrim);
-                        }
-                        if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = curSlot; }
-                    }
-                }
-            }
+            if (wantT) test_triangle();
         }
+#endif
     }
     if (STATS) {
         atomicAdd(&stats->nodes, cN); atomicAdd(&stats->tris, cT); atomicAdd(&stats->insts, cI); atomicAdd(&stats->rays, cR); atomicAdd(&stats->sphereCulled, cS);
