@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline measurement of the wavefront path-tracing hot path (BASELINE.json / SURVEY.md §8d).
 
-  python bench.py --gpus N --steps K --warmup W [--workload instanced10m_4k|cornell_1080p] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--workload instanced10m_4k|cornell_1080p|sky10m_4k|build50m|build10m] [--impl reference]
 
 A step is one frame (1 sample per pixel) of the wavefront pipeline: generate -> closest-hit trace -> shade (+NEE) ->
 {closest-hit trace, any-hit shadow trace} per bounce -> accumulate.  Metric: Mrays/s = (extension + shadow rays traced) /
@@ -36,6 +36,13 @@ WORKLOADS = {
                             "dielectric/metal/translucent, NEE+MIS, pathLength 8, 3840x2160, 1 spp/step"),
     # BASELINE.json configs[1]
     "cornell_1080p": dict(res=(1920, 1080), desc="Cornell box (32 triangles, 8 instances, diffuse + 35x area light), NEE+MIS, pathLength 10, 1920x1080, 1 spp/step"),
+    # BASELINE.json configs[4]'s scene (8 GPUs: `--gpus 8`): configs[2]'s geometry lit only by a procedural HDR sky with a sun disc
+    "sky10m_4k": dict(res=(3840, 2160), desc="10M-triangle instanced scene (1024 BLAS, 1026 instances), no area light, procedural 4096x2048 RGBA32F HDR sky + sun disc, "
+                      "pathLength 8, 3840x2160, 1 spp/step"),
+    # BASELINE.json configs[3]: the NexusBVH benchmark mesh (Test/src/Main.cpp:31-64) at 50M triangles; metric Mprims/s
+    "build50m": dict(res=None, n=50_000_000, desc="H-PLOC BVH2 build + CWBVH8 collapse of the NexusBVH benchmark mesh (random small triangles on a 1000^3 lattice), "
+                     "50,000,000 triangles, 32-bit Morton keys (prioritizeSpeed), 1 build/step"),
+    "build10m": dict(res=None, n=10_000_000, desc="as build50m with 10,000,000 triangles (the size NexusBVH's README quotes)"),
     # reduced variant for quick functional checks (not a bench line)
     "instanced_small": dict(res=(640, 360), desc="64-BLAS reduced instanced scene, 640x360 (functional check only)"),
 }
@@ -47,6 +54,12 @@ def make_desc(workload):
         d = scenes.instanced_scene(n_blas=1024, n_instances=1024, path_length=8)
     elif workload == "cornell_1080p":
         d = scenes.cornell_box(path_length=10)
+    elif workload == "sky10m_4k":
+        d = scenes.instanced_scene(n_blas=1024, n_instances=1024, path_length=8)
+        # no area light: the emissive quad keeps its place in the instance list (same TLAS) but emits nothing
+        d["materials"][1].emissionColor = (0.0, 0.0, 0.0); d["materials"][1].intensity = 0.0
+        d["hdr"] = scenes.procedural_sky()
+        d["settings"].backgroundIntensity = 1.0
     elif workload == "instanced_small":
         d = scenes.instanced_scene(n_blas=64, n_instances=64, nu=24, nv=24, path_length=8)
     else:
@@ -293,6 +306,160 @@ def cpu_baseline(desc, scene, res, budget_s=15.0):
             "sample": f"{len(rays)} primary (camera) rays of this workload, closest-hit traversal only, {dt:.1f} s"}
 
 
+
+# ------------------------------------------------------------------------------------- builder workloads ----
+# algorithmic bytes per primitive with 32-bit keys, each BVH2 node counted once per phase.
+BUILD_BYTES_FIXED = 340           # + 80 * N8 / n for the CWBVH8 node writes
+HPLOC_BYTES_PER_PRIM = 32 + 32 + 16 + 8 + 8   # leaf bounds read, inner node write, clusterIdx load/store, parentIdx, two Morton neighbours
+
+
+def run_build_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nexus_b200 as nx
+    from nexus_b200 import scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    n = wl["n"]
+    speed = True
+    ctx = nx.Context(local)
+    stream = torch.cuda.ExternalStream(int(nx.lib().nx_ctx_stream(ctx._h)), device=torch.device("cuda", local))
+    t_gen = time.time()
+    host = torch.empty((n, 9), dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = scenes.test_triangles(n)
+    t_gen = time.time() - t_gen
+    dev_t = torch.empty((n, 9), dtype=torch.float32, device="cuda")
+    dev_t.copy_(host)
+    dev = dev_t.data_ptr()
+
+    def barrier():
+        ctx.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(W):
+        nx.BuildBVH8Device(ctx, dev, n, 1, speed).Free()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    nodes = 0
+    for _ in range(K):                       # replicas only: every rank builds the whole mesh (one hierarchy does not shard)
+        b = nx.BuildBVH8Device(ctx, dev, n, 1, speed)
+        nodes = b.nodeCount
+        b.Free()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms[0])
+    value = world * K * n / (ms_total * 1e-3) / 1e6
+
+    # per-stage device times (the builder's own CUDA events, BVHBuildMetrics layout) over K more builds, and the SAH costs
+    m = nx.BenchmarkBuild(ctx, dev, n, 1, speed, 1, K)
+    hbm, hbm_src = peaks()
+    hploc_ms = m["bvh2_ms"]
+    achieved = HPLOC_BYTES_PER_PRIM * n / (hploc_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload, {}).get("hploc_dram_bytes_per_launch")
+    whole_bytes = (BUILD_BYTES_FIXED + 80.0 * nodes / n) * n
+    roofline = {"bound": "hbm", "kernel": "hploc_kernel", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                "traffic": traffic, "peak_source": hbm_src, "avg_launch_ms": round(hploc_ms, 4), "launches": K,
+                "algorithmic_bytes_per_launch": int(HPLOC_BYTES_PER_PRIM * n),
+                "whole_build": {"bytes_per_prim": round(whole_bytes / n, 1), "achieved_gbs": round(whole_bytes / (ms_total / K * 1e-3) / 1e9, 1),
+                                "frac": round(whole_bytes / (ms_total / K * 1e-3) / 1e9 / hbm, 4)},
+                "stage_ms": {k: round(v, 4) for k, v in m.items() if k.endswith("_ms")}}
+
+    # e2e: what Mesh::Mesh does per mesh (N/Assets/Mesh.h:29-40): host triangles -> device, BuildBVH8, handle (bounds, counts) back
+    barrier()
+    t0 = time.time()
+    for _ in range(K):
+        with torch.cuda.stream(stream):
+            dev_t.copy_(host, non_blocking=True)
+        b = nx.BuildBVH8Device(ctx, dev, n, 1, speed)
+        ctx.synchronize()
+        _ = (b.nodeCount, b.bounds)
+        b.Free()
+    barrier()
+    e2e_s = torch.tensor([time.time() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": round(world * K * n / float(e2e_s[0]) / 1e6, 1), "unit": "Mprims/s", "h2d_bytes_per_step": 36 * n, "d2h_bytes_per_step": 48,
+           "ms_per_step": round(float(e2e_s[0]) * 1e3 / K, 3), "what": "pinned host triangles -> device copy -> BuildBVH8 -> handle (bounds, node count) on the host"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib as O
+        ns = 1_000_000
+        sample = host.numpy()[:ns]
+        t0 = time.time(); n8, _, _ = O.cpu_build_bvh8(sample, 1, 0); dt = time.time() - t0
+        cpu = {"value": round(ns / dt / 1e6, 4), "unit": "Mprims/s", "cores": 1, "kind": "port",
+               "sample": f"first {ns} triangles of this mesh through the CPU restatement of the whole pipeline (bounds, Morton, H-PLOC, collapse), single thread, {dt:.1f} s"}
+    if rank == 0:
+        line = {"metric": "Mprims/s", "value": round(value, 1), "unit": "Mprims/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": wl["desc"], "triangles": n, "prioritize_speed": speed,
+                           "partition": "replicas only: one global sort + one hierarchy does not shard; each rank builds the whole mesh" if world > 1 else "single GPU",
+                           "l2": "input (%.1f GB) and every intermediate array exceed the 126 MB L2; no flush needed" % (36e-9 * n)},
+                "bvh8_nodes": int(nodes), "bvh2_sah": round(m["bvh2_cost"], 4), "bvh8_sah": round(m["bvh8_cost"], 4), "avg_children_per_node": round(m["avg_children_per_node"], 3),
+                "host_generate_s": round(t_gen, 1), "gpu_launches": int(K * 4), "library_launches": int(K * 6), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_build_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import ctypes as C
+    import oracle_lib as O
+    from nexus_b200 import scenes      # scene/mesh generators only (numpy); the product library is not loaded on this arm
+    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    n = wl["n"]
+    if not O.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnexus_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    tris = scenes.test_triangles(n)
+    mm = np.zeros(9, np.float32); cnt = C.c_uint32(0); ms2 = np.zeros(2, np.float32)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start(); time.sleep(0.3)
+    rc = O.ref().nxref_benchmark_bvh8(tris.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, 1, W, K, mm.ctypes.data_as(C.c_void_p), C.byref(cnt), ms2.ctypes.data_as(C.c_void_p))
+    clocks = sampler.stop()
+    assert rc == 0
+    # The reference's own metric (BVHBuildMetrics::totalTime: the sum of its per-stage CUDA-event times, what NexusBVH's README
+    # quotes) is the value; what a caller of BuildBVH8 actually waits for (cudaMallocAsync + cudaFree of every array inside each
+    # build) is reported beside it as caller_ms_per_step and is several times longer.
+    ms = float(mm[5]) * K
+    value = K * n / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": "Mprims/s", "value": round(value, 1), "unit": "Mprims/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 4), "caller_ms_per_step": round(float(ms2[0]) / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": wl["desc"], "triangles": n, "prioritize_speed": True},
+            "bvh8_nodes": int(cnt.value), "bvh2_sah": round(float(mm[6]), 4), "bvh8_sah": round(float(mm[7]), 4), "avg_children_per_node": round(float(mm[8]), 3),
+            "stage_ms": {"computeSceneBoundsTime": round(float(mm[0]), 4), "computeMortonCodesTime": round(float(mm[1]), 4), "radixSortTime": round(float(mm[2]), 4),
+                         "bvhBuildTime": round(float(mm[3]), 4), "bvh8ConversionTime": round(float(mm[4]), 4), "totalTime": round(float(mm[5]), 4)},
+            "clocks": clocks,
+            "cpu_baseline": {"value": round(value, 1), "unit": "Mprims/s", "cores": 0, "kind": "reference",
+                             "sample": f"{K} builds of this mesh through the unmodified NexusBVH (compiled -arch=sm_100a --use_fast_math from /root/reference) on the same B200; "
+                                       "the reference has no CPU builder in this snapshot"},
+            "e2e": {"value": round(value, 1), "unit": "Mprims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
 # ----------------------------------------------------------------------------------------- reference arm ----
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -339,10 +506,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    build = args.workload.startswith("build")
     if args.impl == "reference":
-        run_reference(args)
+        (run_build_reference if build else run_reference)(args)
     else:
-        run_ours(args)
+        (run_build_ours if build else run_ours)(args)
 
 
 if __name__ == "__main__":

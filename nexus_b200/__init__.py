@@ -161,6 +161,16 @@ def BuildBVH8(ctx, prims, prioritizeSpeed=False, metrics=False):
     return (bvh, m.as_dict()) if metrics else bvh
 
 
+def BuildBVH8Device(ctx, prims_dev, n, prim_type=1, prioritizeSpeed=False, metrics=False):
+    """NXB::BuildBVH8<PrimT> on primitives already resident on the device (the reference's signature takes a device
+    pointer, BVHBuilder.h:31).  Asynchronous on the context's stream unless metrics are requested."""
+    cfg, m, out = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), Bvh8()
+    fn = lib().nx_bvh8_build_tri if prim_type else lib().nx_bvh8_build_aabb
+    check(ctx._h, fn(ctx._h, C.c_void_p(prims_dev), C.c_uint32(n), C.byref(cfg), C.byref(m) if metrics else None, C.byref(out)), "BuildBVH8")
+    bvh = BVH8(ctx, out)
+    return (bvh, m.as_dict()) if metrics else bvh
+
+
 def BenchmarkBuild(ctx, prims_dev, n, prim_type, prioritizeSpeed, warmup, iters):
     """NXB::BenchmarkBuild (BVHBuildMetrics.h:63-108) on primitives already resident on the device."""
     cfg, m, nodes = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), C.c_uint32(0)

@@ -150,6 +150,45 @@ int nxref_build_bvh8(const void* hostPrims, uint32_t n, int primType, int priori
     return 0;
 }
 
+// NXB::BenchmarkBuild's protocol (BVHBuildMetrics.h:63-108: warm-up builds, then the mean of the per-stage metrics over the
+// measured builds) without its std::cout report, on primitives uploaded once.  outMs2: [0] device time of the measured
+// builds back to back (CUDA events around the loop, FreeDeviceBVH included as in BenchmarkBuild), [1] host wall time.
+int nxref_benchmark_bvh8(const void* hostPrims, uint32_t n, int primType, int prioritizeSpeed, int warmup, int iters,
+                         float* outMetrics9, uint32_t* outNodeCount, float* outMs2)
+{
+    size_t stride = primType ? sizeof(NXB::Triangle) : sizeof(NXB::AABB);
+    void* dPrims = nullptr;
+    REF_CHECK(cudaMalloc(&dPrims, stride * n));
+    REF_CHECK(cudaMemcpy(dPrims, hostPrims, stride * n, cudaMemcpyHostToDevice));
+    NXB::BuildConfig cfg; cfg.prioritizeSpeed = prioritizeSpeed != 0;
+    NXB::BVHBuildMetrics agg{};
+    uint32_t nodes = 0;
+    auto build = [&](NXB::BVHBuildMetrics* m) {
+        NXB::BVH8 bvh = primType ? NXB::BuildBVH8<NXB::Triangle>((NXB::Triangle*)dPrims, n, cfg, m) : NXB::BuildBVH8<NXB::AABB>((NXB::AABB*)dPrims, n, cfg, m);
+        nodes = bvh.nodeCount;
+        NXB::FreeDeviceBVH(bvh);
+    };
+    for (int i = 0; i < warmup; i++) { NXB::BVHBuildMetrics dummy{}; build(&dummy); }
+    for (int i = 0; i < iters; i++) { NXB::BVHBuildMetrics m{}; build(&m); agg += m; }
+    agg = agg / (float)iters;
+    copyMetrics(agg, outMetrics9);
+    if (outNodeCount) *outNodeCount = nodes;
+    if (outMs2) {
+        // the same builds without per-stage metrics (no event synchronisation inside): what a caller of BuildBVH8 waits for
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        REF_CHECK(cudaDeviceSynchronize());
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters; i++) build(nullptr);
+        cudaEventRecord(e1, 0);
+        REF_CHECK(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&outMs2[0], e0, e1);
+        outMs2[1] = 0.f;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(dPrims);
+    return 0;
+}
+
 // The reference's own Morton keys: ComputeSceneBoundsKernel + ComputeMortonCodesKernel launched as BuildBVH2 /
 // BuildBVH2Impl launch them (B/src/BVHBuilder.cpp:119-153, 17-49).  outCodes: n x uint64 in primitive order.
 } // extern "C"
@@ -184,34 +223,6 @@ int nxref_morton(const void* hostPrims, uint32_t n, int primType, int bits64, ui
 {
     if (primType) return bits64 ? refMorton<NXB::Triangle, uint64_t>(hostPrims, n, outCodes, outBounds6) : refMorton<NXB::Triangle, uint32_t>(hostPrims, n, outCodes, outBounds6);
     return bits64 ? refMorton<NXB::AABB, uint64_t>(hostPrims, n, outCodes, outBounds6) : refMorton<NXB::AABB, uint32_t>(hostPrims, n, outCodes, outBounds6);
-}
-
-// NXB::BenchmarkBuild (B/include/NXB/BVHBuildMetrics.h:63-108) without the printing:
-// per-stage CUDA-event times averaged over `iters` builds after `warmup` builds.
-int nxref_bench_build8(const void* hostPrims, uint32_t n, int primType, int prioritizeSpeed,
-                       int warmup, int iters, float* outMetrics9, uint32_t* outNodeCount)
-{
-    size_t stride = primType ? sizeof(NXB::Triangle) : sizeof(NXB::AABB);
-    void* dPrims = nullptr;
-    REF_CHECK(cudaMalloc(&dPrims, stride * n));
-    REF_CHECK(cudaMemcpy(dPrims, hostPrims, stride * n, cudaMemcpyHostToDevice));
-    NXB::BuildConfig cfg; cfg.prioritizeSpeed = prioritizeSpeed != 0;
-    NXB::BVHBuildMetrics agg{};
-    uint32_t nodeCount = 0;
-    for (int i = 0; i < warmup + iters; i++)
-    {
-        NXB::BVHBuildMetrics m{};
-        NXB::BVH8 bvh = primType ? NXB::BuildBVH8<NXB::Triangle>((NXB::Triangle*)dPrims, n, cfg, &m)
-                                 : NXB::BuildBVH8<NXB::AABB>((NXB::AABB*)dPrims, n, cfg, &m);
-        nodeCount = bvh.nodeCount;
-        NXB::FreeDeviceBVH(bvh);
-        if (i >= warmup) agg += m;
-    }
-    if (iters > 0) agg = agg / (float)iters;
-    copyMetrics(agg, outMetrics9);
-    if (outNodeCount) *outNodeCount = nodeCount;
-    cudaFree(dPrims);
-    return 0;
 }
 
 // ------------------------------------------------------------------ scene ----

@@ -76,7 +76,7 @@ try:
             if O.have_ref():
                 import ctypes as C
                 mm = np.zeros(9, np.float32); cnt = C.c_uint32(0)
-                O.ref().nxref_bench_build8(tris.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, int(speed), 2, 5, mm.ctypes.data_as(C.c_void_p), C.byref(cnt))
+                O.ref().nxref_benchmark_bvh8(tris.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, int(speed), 2, 5, mm.ctypes.data_as(C.c_void_p), C.byref(cnt), None)
                 print(f"REF  n={n} speed={speed}: bounds={mm[0]:.3f} morton={mm[1]:.3f} sort={mm[2]:.3f} bvh2={mm[3]:.3f} bvh8={mm[4]:.3f} total={mm[5]:.3f} cost2={mm[6]:.3f} cost8={mm[7]:.3f} nodes={cnt.value}", flush=True)
         ctx.free(dev)
 except Exception:
