@@ -1,0 +1,282 @@
+// Ray generation, shading (logic + OpenPBR material + NEE/MIS) and the display transform of the wavefront path tracer.
+// Replaces GenerateKernel, LogicKernel, MaterialKernel + NextEventEstimation and AccumulateKernel of
+// src/Cuda/PathTracer/PathTracer.cu:60-95, 124-173, 176-511, 513-549.
+//
+// This translation unit is compiled with --use_fast_math, as the reference compiles all of its device code
+// (Nexus/CMakeLists.txt:75-78): divisions are MUFU.RCP + FMUL, square roots MUFU.RSQ/SQRT, denormals flush to zero.
+// Traversal (render.cu) is NOT: its arithmetic decides hit ids and is written with explicit IEEE roundings.
+#include "wave.cuh"
+
+namespace {
+
+// --------------------------------------------------------------------------------------------- generate ----
+// Camera rays with pixel jitter and thin-lens sampling (GenerateKernel, PathTracer.cu:60-95).
+__global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ DSceneView sv, WaveBuffers wb, uint32_t frame)
+{
+    const DCamera& cam = sv.camera;
+    const uint32_t count = cam.resX * cam.resY;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.counters->extCount[0] = count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        // Queue slot i -> pixel: 8x4 pixel tiles, so the 32 rays a warp fetches together cover a compact footprint (and, because
+        // every later queue inherits this order through compaction, so do their bounces).  Row-major order when the
+        // resolution is not a multiple of the tile.  The pixel index, not the slot, keys the RNG and addresses the image.
+        uint32_t px, py;
+        if (NX_TILED_PIXELS && (cam.resX & 7u) == 0u && (cam.resY & 3u) == 0u) {
+            const uint32_t tile = i >> 5, tilesX = cam.resX >> 3, ty = tile / tilesX, tx = tile - ty * tilesX;
+            px = tx * 8u + (i & 7u); py = ty * 4u + ((i >> 3) & 3u);
+        } else { py = i / cam.resX; px = i - py * cam.resX; }
+        const uint32_t pixel = py * cam.resX + px;
+        uint32_t rng = rng_seed(pixel, frame, 0u);
+        const float x = ((float)px + rng_next(rng)) / (float)cam.resX;
+        const float y = ((float)py + rng_next(rng)) / (float)cam.resY;
+        const float u0 = rng_next(rng), u1 = rng_next(rng);   // concentric-free polar disk sample (Random.cuh:100-107)
+        float sn, cs; __sincosf(NX_TWO_PI * u1, &sn, &cs);
+        const float r = cam.lensRadius * sqrtf(u0);
+        const F3 right = f3(cam.right[0], cam.right[1], cam.right[2]), up = f3(cam.up[0], cam.up[1], cam.up[2]);
+        const F3 off = right * (r * cs) + up * (r * sn);
+        const F3 pos = f3(cam.position[0], cam.position[1], cam.position[2]);
+        const F3 org = pos + off;
+        const F3 target = f3(cam.lowerLeft[0], cam.lowerLeft[1], cam.lowerLeft[2]) + x * f3(cam.viewportX[0], cam.viewportX[1], cam.viewportX[2]) +
+                          y * f3(cam.viewportY[0], cam.viewportY[1], cam.viewportY[2]);
+        const F3 dir = normalize(target - pos - off);
+        float4* out = reinterpret_cast<float4*>(wb.ext[0] + i);
+        out[0] = make_float4(org.x, org.y, org.z, NX_MISS_T);
+        out[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
+        wb.state[0][i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ shade ----
+__device__ __forceinline__ F3 load3(const float* p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+__device__ __forceinline__ F3 bary(F3 a, F3 b, F3 c, float u, float v) { return u * b + v * c + (1.0f - u - v) * a; }   // Utils.cuh:59-63
+__device__ __forceinline__ F3 xf_point(float4 r0, float4 r1, float4 r2, F3 p)
+{
+    return f3(r0.x * p.x + r0.y * p.y + r0.z * p.z + r0.w, r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w, r2.x * p.x + r2.y * p.y + r2.z * p.z + r2.w);
+}
+// (M^-1)^T * n: normals transform with the transposed inverse (PathTracer.cu:385-389)
+__device__ __forceinline__ F3 xf_normal(float4 i0, float4 i1, float4 i2, F3 n)
+{
+    return f3(i0.x * n.x + i1.x * n.y + i2.x * n.z, i0.y * n.x + i1.y * n.y + i2.y * n.z, i0.z * n.x + i1.z * n.y + i2.z * n.z);
+}
+// "A Fast and Robust Method for Avoiding Self-Intersection" (Ray Tracing Gems ch. 6; src/Cuda/Utils.cuh:65-86)
+__device__ __forceinline__ float offset_axis(float p, float n)
+{
+    const int of = (int)(256.0f * n);
+    const float pi = __int_as_float(__float_as_int(p) + (p < 0.0f ? -of : of));
+    return fabsf(p) < (1.0f / 32.0f) ? p + (1.0f / 65536.0f) * n : pi;
+}
+__device__ __forceinline__ F3 offset_ray(F3 p, F3 n) { return f3(offset_axis(p.x, n.x), offset_axis(p.y, n.y), offset_axis(p.z, n.z)); }
+__device__ __forceinline__ float power_heuristic(float a, float b) { return a * a / (a * a + b * b); }   // Sampler.cuh:22-25
+
+__device__ __forceinline__ F3 background(const DSceneView& sv, F3 d)   // SampleBackground, PathTracer.cu:40-58
+{
+    if (sv.hasHdr) {
+        const float theta = atan2f(d.z, d.x), phi = asinf(d.y);
+        const float u = (theta + NX_PI) * NX_INV_PI * 0.5f, v = 1.0f - (phi + NX_PI * 0.5f) * NX_INV_PI;
+        const float4 c = tex2D<float4>(sv.hdr, u, v);
+        return f3(c.x, c.y, c.z) * sv.bgIntensity;
+    }
+    return f3(sv.bg[0], sv.bg[1], sv.bg[2]) * sv.bgIntensity;
+}
+
+struct Surface { F3 p, n, gn; };
+
+struct ShadeOut {
+    bool ext, shadow;
+    F3 extO, extD, thr; float pdf;
+    F3 shO, shD, shL; float shDist;
+};
+
+// Next-event estimation: one light picked uniformly, one point on it, MIS against the BSDF (PathTracer.cu:176-343).
+// The light-specific part only produces (direction, distance, pdf, emission); the BSDF is evaluated once, at one call site,
+// which keeps the kernel's code size (and with it the instruction-cache pressure ncu showed) down.
+__device__ __forceinline__ void next_event(const DSceneView& sv, const nx_material& mat, const Surface& sf, const Frame& fr, F3 wi, F3 rayDir, F3 thr,
+                                           uint32_t& rng, ShadeOut& out)
+{
+    const uint32_t li = (uint32_t)floorf(rng_next(rng) * (float)sv.lightCount);
+    const DLight L = sv.lights[min(li, sv.lightCount - 1u)];
+    F3 toLight, emissive, dir, origin; float lightPdf, dist; bool mis = false;
+    if (L.type == NX_LIGHT_MESH)
+    {
+        const DShadeInst I = sv.shadeInst[L.instance];
+        const DMesh mesh = sv.meshes[I.meshIdx];
+        const uint32_t ti = min((uint32_t)floorf(rng_next(rng) * (float)mesh.primCount), mesh.primCount - 1u);
+        const float a = rng_next(rng), b = rng_next(rng), su = sqrtf(a);
+        const float u = 1.0f - su, v = b * su;                                   // uniform triangle sample (Sampler.cuh:41-48)
+        const float* t = mesh.tris + 9 * (size_t)ti; const float* td = mesh.tridata + 24 * (size_t)ti;
+        const F3 v0 = load3(t), v1 = load3(t + 3), v2 = load3(t + 6);
+        F3 lp = xf_point(I.m0, I.m1, I.m2, bary(v0, v1, v2, u, v));
+        const F3 lgn = normalize(xf_normal(I.i0, I.i1, I.i2, cross(v1 - v0, v2 - v0)));
+        const F3 ln = normalize(xf_normal(I.i0, I.i1, I.i2, bary(load3(td), load3(td + 3), load3(td + 6), u, v)));
+        toLight = lp - sf.p;
+        const bool sameSide = dot(-rayDir, sf.gn) * dot(toLight, sf.gn) > 0.0f;
+        if (!sameSide && mat.transmission == 0.0f) return;
+        origin = offset_ray(sf.p, sf.gn * sign_or_one(dot(toLight, sf.n)));
+        lp = offset_ray(lp, lgn * sign_or_one(dot(-toLight, ln)));
+        const F3 seg = lp - origin;
+        dist = length(seg); dir = seg / dist;
+        const float cosL = fabsf(dot(ln, dir));
+        const F3 w0 = xf_point(I.m0, I.m1, I.m2, v0), w1 = xf_point(I.m0, I.m1, I.m2, v1), w2 = xf_point(I.m0, I.m1, I.m2, v2);
+        const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+        lightPdf = 1.0f / ((float)sv.lightCount * (float)mesh.primCount * area);
+        lightPdf *= dot(toLight, toLight) / cosL;                                // area measure -> solid angle
+        if (!pdf_ok(lightPdf)) return;
+        const nx_material& lm = sv.materials[I.materialIdx];
+        emissive = f3(__ldg(&lm.emission_color[0]), __ldg(&lm.emission_color[1]), __ldg(&lm.emission_color[2])) * __ldg(&lm.intensity);
+        mis = true;
+    }
+    else if (L.type == NX_LIGHT_POINT || L.type == NX_LIGHT_DIRECTIONAL)
+    {
+        const bool point = L.type == NX_LIGHT_POINT;
+        toLight = point ? f3(L.px, L.py, L.pz) - sf.p : -f3(L.dx, L.dy, L.dz);
+        lightPdf = 1.0f / (float)sv.lightCount;
+        if (point) { lightPdf *= dot(toLight, toLight); if (!pdf_ok(lightPdf)) return; }
+        emissive = f3(L.cr, L.cg, L.cb) * L.intensity;
+        const bool sameSide = dot(-rayDir, sf.gn) * dot(toLight, sf.gn) > 0.0f;
+        if (!sameSide && mat.transmission == 0.0f) return;
+        origin = offset_ray(sf.p, sf.gn * sign_or_one(dot(toLight, sf.n)));
+        dist = point ? length(toLight) : NX_MISS_T;
+        dir = point ? toLight / dist : normalize(toLight);
+    }
+    else return;   // spot lights are declared but have no NEE branch in the reference either (PathTracer.cu:274-334)
+    F3 f; float bsdfPdf;
+    if (!principled_eval(mat, wi, fr.toLocal(dir), f, bsdfPdf)) return;
+    const float weight = mis ? power_heuristic(lightPdf, bsdfPdf) : 1.0f;
+    out.shL = weight * thr * f * emissive / lightPdf;
+    out.shadow = true; out.shO = origin; out.shD = dir; out.shDist = dist;
+}
+
+// LogicKernel + MaterialKernel for one traced ray (PathTracer.cu:124-173, 346-511).
+__device__ __forceinline__ void shade_one(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, const nx_hit& hit, F3 rayDir,
+                                          uint32_t pixel, F3 thr, float lastPdf, ShadeOut& out, bool& survived)
+{
+    if (hit.t == NX_MISS_T) { add_radiance(wb.accum, pixel, thr * background(sv, rayDir)); return; }
+
+    uint32_t rng = rng_seed(pixel, frame, bounce);
+    // Russian roulette on the largest throughput component, from the first bounce, no clamp (PathTracer.cu:158-166)
+    const float survive = max3(thr);
+    if (!(rng_next(rng) < survive)) return;
+    thr = thr / survive;
+    survived = true;
+
+    const DShadeInst I = sv.shadeInst[hit.instance];
+    const DMesh mesh = sv.meshes[I.meshIdx];
+    const float* t = mesh.tris + 9 * (size_t)hit.prim; const float* td = mesh.tridata + 24 * (size_t)hit.prim;
+    const F3 v0 = load3(t), v1 = load3(t + 3), v2 = load3(t + 6);
+    const nx_material mat = sv.materials[I.materialIdx];
+
+    Surface sf;
+    sf.p = xf_point(I.m0, I.m1, I.m2, bary(v0, v1, v2, hit.u, hit.v));
+    sf.n = normalize(xf_normal(I.i0, I.i1, I.i2, normalize(bary(load3(td), load3(td + 3), load3(td + 6), hit.u, hit.v))));
+    sf.gn = normalize(xf_normal(I.i0, I.i1, I.i2, cross(v1 - v0, v2 - v0)));
+    const Frame fr(sf.n);
+
+    // emission seen by the BSDF-sampled ray, MIS-weighted against light sampling except on primary hits (PathTracer.cu:414-447)
+    const F3 Le = f3(mat.emission_color[0], mat.emission_color[1], mat.emission_color[2]) * mat.intensity;
+    if (max3(Le) > 0.0f)
+    {
+        float w = 1.0f;
+        if (bounce > 1u && sv.useMIS) {
+            const float cosL = fabsf(dot(sf.n, rayDir));
+            const F3 w0 = xf_point(I.m0, I.m1, I.m2, v0), w1 = xf_point(I.m0, I.m1, I.m2, v1), w2 = xf_point(I.m0, I.m1, I.m2, v2);
+            const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+            float lightPdf = 1.0f / ((float)sv.lightCount * (float)mesh.primCount * area);
+            lightPdf *= sqr(hit.t) / cosL;
+            w = pdf_ok(lightPdf) ? power_heuristic(lastPdf, lightPdf) : 0.0f;
+        }
+        add_radiance(wb.accum, pixel, w * Le * thr);
+    }
+    if (bounce == sv.pathLength) return;
+
+    const F3 wi = fr.toLocal(-rayDir);
+    if (rng_next(rng) > mat.opacity)
+    {
+        // alpha pass-through: continue straight on, path state unchanged (PathTracer.cu:464-475)
+        const F3 wo = fr.toWorld(-wi);
+        out.ext = true; out.extO = offset_ray(sf.p, sf.gn * sign_or_one(dot(wo, sf.n))); out.extD = wo; out.thr = thr; out.pdf = lastPdf;
+        return;
+    }
+    if (sv.useMIS && sv.lightCount > 0u) next_event(sv, mat, sf, fr, wi, rayDir, thr, rng, out);
+
+    const LobeSample s = principled_sample(mat, wi, rng);
+    if (!s.ok) return;
+    const F3 wo = fr.toWorld(s.wo);
+    const bool sameSide = dot(-rayDir, sf.gn) * dot(wo, sf.gn) > 0.0f;
+    if (!sameSide && mat.transmission == 0.0f) return;
+    out.ext = true; out.extO = offset_ray(sf.p, sf.gn * sign_or_one(dot(wo, sf.n))); out.extD = wo; out.thr = thr * s.weight; out.pdf = s.pdf;
+}
+
+__global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DSceneView sv, WaveBuffers wb, uint32_t bounce, uint32_t frame)
+{
+    const uint32_t n = wb.counters->extCount[bounce - 1];
+    const uint32_t in = (bounce - 1) & 1u, outQ = bounce & 1u;
+    uint32_t shadedHere = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = base + threadIdx.x;
+        ShadeOut o; o.ext = false; o.shadow = false;
+        uint32_t pixel = 0;
+        if (i < n)
+        {
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(wb.ext[in] + i) + 1);
+            const float4 st = __ldg(wb.state[in] + i);
+            const nx_hit h = wb.hits[i];
+            pixel = __float_as_uint(d4.w);
+            bool survived = false;
+            shade_one(sv, wb, bounce, frame, h, f3(d4.x, d4.y, d4.z), pixel, f3(st.x, st.y, st.z), st.w, o, survived);
+            shadedHere += survived ? 1u : 0u;
+        }
+        const uint32_t e = warp_append(&wb.counters->extCount[bounce], o.ext);
+        if (o.ext) {
+            float4* r = reinterpret_cast<float4*>(wb.ext[outQ] + e);
+            r[0] = make_float4(o.extO.x, o.extO.y, o.extO.z, NX_MISS_T);
+            r[1] = make_float4(o.extD.x, o.extD.y, o.extD.z, __uint_as_float(pixel));
+            wb.state[outQ][e] = make_float4(o.thr.x, o.thr.y, o.thr.z, o.pdf);
+        }
+        const uint32_t s = warp_append(&wb.counters->shCount[bounce], o.shadow);
+        if (o.shadow) {
+            float4* r = reinterpret_cast<float4*>(wb.shadow + s);
+            r[0] = make_float4(o.shO.x, o.shO.y, o.shO.z, o.shDist);
+            r[1] = make_float4(o.shD.x, o.shD.y, o.shD.z, __uint_as_float(pixel));
+            wb.shadowRad[s] = make_float4(o.shL.x, o.shL.y, o.shL.z, 0.f);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) shadedHere += __shfl_xor_sync(NX_FULL, shadedHere, off);
+    if (lane_id() == 0 && shadedHere) atomicAdd(&wb.counters->shaded[bounce], shadedHere);
+}
+
+// Display transform of AccumulateKernel (PathTracer.cu:527-548) on the mean; tone curves other than NONE are added with
+// SURVEY.md §8 row f-1, until then every mode maps to exposure + gamma 2.2.
+__global__ void resolve_rgba8_kernel(const float* __restrict__ accum, uint32_t count, float invFrames, float exposure, uint32_t* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float s = invFrames * exp2f(exposure);
+        const float r = __powf(fmaxf(accum[3 * (size_t)i] * s, 0.f), 1.0f / 2.2f), g = __powf(fmaxf(accum[3 * (size_t)i + 1] * s, 0.f), 1.0f / 2.2f),
+                    b = __powf(fmaxf(accum[3 * (size_t)i + 2] * s, 0.f), 1.0f / 2.2f);
+        out[i] = (uint32_t)(__saturatef(r) * 255.0f) | ((uint32_t)(__saturatef(g) * 255.0f) << 8) | ((uint32_t)(__saturatef(b) * 255.0f) << 16) | 0xff000000u;
+    }
+}
+
+int g_gridShade = 0;
+
+} // namespace
+
+int nxi_shade_grid(nx_ctx* ctx)
+{
+    if (g_gridShade) return g_gridShade;
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void*)shade_kernel, kShadeBlock, 0);
+    if (perSm < 1) perSm = 1;
+    g_gridShade = perSm * ctx->sm_count;
+    return g_gridShade;
+}
+void nxi_launch_generate(const DSceneView& sv, const WaveBuffers& wb, uint32_t frame, int grid, cudaStream_t s) { generate_kernel<<<grid, 256, 0, s>>>(sv, wb, frame); }
+void nxi_launch_shade(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, int grid, cudaStream_t s)
+{
+    shade_kernel<<<grid, kShadeBlock, 0, s>>>(sv, wb, bounce, frame);
+}
+void nxi_launch_resolve(int grid, cudaStream_t s, const float* accum, uint32_t count, float invFrames, float exposure, uint32_t* out)
+{
+    resolve_rgba8_kernel<<<grid, 256, 0, s>>>(accum, count, invFrames, exposure, out);
+}
