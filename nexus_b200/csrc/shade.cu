@@ -147,18 +147,23 @@ __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_materi
     out.shadow = true; out.shO = origin; out.shD = dir; out.shDist = dist;
 }
 
-// LogicKernel + MaterialKernel for one traced ray (PathTracer.cu:124-173, 346-511).
-__device__ __forceinline__ void shade_one(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, const nx_hit& hit, F3 rayDir,
-                                          uint32_t pixel, F3 thr, float lastPdf, ShadeOut& out, bool& survived)
+// LogicKernel for one traced ray (PathTracer.cu:124-173): environment on a miss, Russian roulette.  Returns true when the
+// hit goes on to be shaded.
+__device__ __forceinline__ bool logic_one(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, float hitT, F3 rayDir, uint32_t pixel, F3 thr)
 {
-    if (hit.t == NX_MISS_T) { add_radiance(wb.accum, pixel, thr * background(sv, rayDir)); return; }
-
+    if (hitT == NX_MISS_T) { add_radiance(wb.accum, pixel, thr * background(sv, rayDir)); return false; }
     uint32_t rng = rng_seed(pixel, frame, bounce);
     // Russian roulette on the largest throughput component, from the first bounce, no clamp (PathTracer.cu:158-166)
-    const float survive = max3(thr);
-    if (!(rng_next(rng) < survive)) return;
-    thr = thr / survive;
-    survived = true;
+    return rng_next(rng) < max3(thr);
+}
+
+// MaterialKernel for one surviving hit (PathTracer.cu:346-511).
+__device__ __forceinline__ void material_one(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, const nx_hit& hit, F3 rayDir,
+                                             uint32_t pixel, F3 thr, float lastPdf, ShadeOut& out)
+{
+    uint32_t rng = rng_seed(pixel, frame, bounce);
+    rng_next(rng);                       // the roulette draw logic_one consumed
+    thr = thr / max3(thr);
 
     const DShadeInst I = sv.shadeInst[hit.instance];
     const DMesh mesh = sv.meshes[I.meshIdx];
@@ -207,25 +212,31 @@ __device__ __forceinline__ void shade_one(const DSceneView& sv, const WaveBuffer
     out.ext = true; out.extO = offset_ray(sf.p, sf.gn * sign_or_one(dot(wo, sf.n))); out.extD = wo; out.thr = thr * s.weight; out.pdf = s.pdf;
 }
 
+// Logic and material in ONE kernel, with the survivors compacted inside the block in between: every thread decides miss /
+// roulette for its own ray, survivors' queue indices go into a shared-memory ring, and the material code runs only when a
+// full block of survivors is available (plus one flush at the end), so its warps are full instead of carrying the 30-40 %
+// of lanes whose path just ended.  The reference gets the same effect with a 36-byte-per-ray material queue in HBM between
+// two kernels; here the intermediate is 4 bytes per survivor in shared memory.
 __global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DSceneView sv, WaveBuffers wb, uint32_t bounce, uint32_t frame)
 {
+    __shared__ uint32_t ring[2 * kShadeBlock];
+    __shared__ uint32_t ringCount;                 // survivors appended so far (monotone)
     const uint32_t n = wb.counters->extCount[bounce - 1];
     const uint32_t in = (bounce - 1) & 1u, outQ = bounce & 1u;
-    uint32_t shadedHere = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
-    {
-        const uint32_t i = base + threadIdx.x;
+    uint32_t shadedHere = 0, consumed = 0;         // consumed is block-uniform
+    if (threadIdx.x == 0) ringCount = 0;
+    __syncthreads();
+
+    auto material_round = [&](bool have, uint32_t i) {    // all threads of the block call this; `have`: the thread owns survivor i
         ShadeOut o; o.ext = false; o.shadow = false;
         uint32_t pixel = 0;
-        if (i < n)
+        if (have)
         {
             const float4 d4 = __ldg(reinterpret_cast<const float4*>(wb.ext[in] + i) + 1);
             const float4 st = __ldg(wb.state[in] + i);
             const nx_hit h = wb.hits[i];
             pixel = __float_as_uint(d4.w);
-            bool survived = false;
-            shade_one(sv, wb, bounce, frame, h, f3(d4.x, d4.y, d4.z), pixel, f3(st.x, st.y, st.z), st.w, o, survived);
-            shadedHere += survived ? 1u : 0u;
+            material_one(sv, wb, bounce, frame, h, f3(d4.x, d4.y, d4.z), pixel, f3(st.x, st.y, st.z), st.w, o);
         }
         const uint32_t e = warp_append(&wb.counters->extCount[bounce], o.ext);
         if (o.ext) {
@@ -241,7 +252,36 @@ __global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel
             r[1] = make_float4(o.shD.x, o.shD.y, o.shD.z, __uint_as_float(pixel));
             wb.shadowRad[s] = make_float4(o.shL.x, o.shL.y, o.shL.z, 0.f);
         }
+    };
+
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = base + threadIdx.x;
+        bool surv = false;
+        if (i < n)
+        {
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(wb.ext[in] + i) + 1);
+            const float4 st = __ldg(wb.state[in] + i);
+            surv = logic_one(sv, wb, bounce, frame, wb.hits[i].t, f3(d4.x, d4.y, d4.z), __float_as_uint(d4.w), f3(st.x, st.y, st.z));
+        }
+        const uint32_t mask = __ballot_sync(NX_FULL, surv);
+        if (mask) {
+            const uint32_t leader = __ffs(mask) - 1;
+            uint32_t pos = 0;
+            if (lane_id() == leader) pos = atomicAdd(&ringCount, __popc(mask));
+            pos = __shfl_sync(NX_FULL, pos, leader);
+            if (surv) ring[(pos + __popc(mask & lanemask_lt())) & (2 * kShadeBlock - 1)] = i;
+        }
+        shadedHere += surv ? 1u : 0u;
+        __syncthreads();                                         // this iteration's appends are visible
+        const uint32_t avail = ringCount - consumed;             // < 2 * kShadeBlock: at most kShadeBlock - 1 were left over
+        const bool full = avail >= kShadeBlock;                  // block-uniform
+        const uint32_t item = full ? ring[(consumed + threadIdx.x) & (2 * kShadeBlock - 1)] : 0u;
+        __syncthreads();                                         // count and ring slots read before anybody appends again
+        if (full) { material_round(true, item); consumed += kShadeBlock; }
     }
+    const uint32_t rest = ringCount - consumed;                  // no appends after the loop's last barrier
+    if (rest) material_round(threadIdx.x < rest, threadIdx.x < rest ? ring[(consumed + threadIdx.x) & (2 * kShadeBlock - 1)] : 0u);
     for (int off = 16; off > 0; off >>= 1) shadedHere += __shfl_xor_sync(NX_FULL, shadedHere, off);
     if (lane_id() == 0 && shadedHere) atomicAdd(&wb.counters->shaded[bounce], shadedHere);
 }
