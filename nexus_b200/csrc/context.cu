@@ -30,7 +30,11 @@ int nx_ctx_create(int device, nx_ctx** out)
     }
     if (const char* t = std::getenv("NX_TRACE_TUNE")) {
         unsigned a = 0, b = 0;
-        if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = a; ctx->tune_inst = b; }
+        if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = ctx->tune_tri_any = a; ctx->tune_inst = ctx->tune_inst_any = b; }
+    }
+    if (const char* t = std::getenv("NX_TRACE_TUNE_ANY")) {
+        unsigned a = 0, b = 0;
+        if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri_any = a; ctx->tune_inst_any = b; }
     }
     *out = ctx;
     return NX_OK;
@@ -55,6 +59,7 @@ int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes
 {
     if (!ctx || tri_lanes > 32 || inst_lanes > 32) return NX_ERR_INVALID;
     ctx->tune_tri = tri_lanes; ctx->tune_inst = inst_lanes;
+    if (!std::getenv("NX_TRACE_TUNE_ANY")) { ctx->tune_tri_any = tri_lanes; ctx->tune_inst_any = inst_lanes; }
     return NX_OK;
 }
 

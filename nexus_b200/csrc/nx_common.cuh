@@ -21,6 +21,7 @@ struct nx_ctx {
     std::string error;
     // traversal batching thresholds in lanes (traverse.cuh TraceTuning); overridable with NX_TRACE_TUNE="tri,inst"
     uint32_t tune_tri = 6, tune_inst = 6, tune_sphere = 1;
+    uint32_t tune_tri_any = 6, tune_inst_any = 6;   // any-hit kernel (NX_TRACE_TUNE_ANY)
     // scratch reused by the builder's parity hook
     std::vector<uint64_t> dbg_codes;
 };

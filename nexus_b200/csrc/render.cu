@@ -65,7 +65,10 @@ __global__ void frame_totals_kernel(WaveBuffers wb, uint32_t pathLength)
     wb.totals->ext += e; wb.totals->shadow += s; wb.totals->shaded += h; wb.totals->frames += 1;
 }
 
-TraceTuning trace_tuning(const nx_ctx* ctx) { TraceTuning t; t.triLanes = ctx->tune_tri; t.instLanes = ctx->tune_inst; t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u; return t; }
+TraceTuning trace_tuning(const nx_ctx* ctx, bool any = false)
+{
+    TraceTuning t; t.triLanes = any ? ctx->tune_tri_any : ctx->tune_tri; t.instLanes = any ? ctx->tune_inst_any : ctx->tune_inst; t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u; return t;
+}
 
 int persistent_grid(nx_ctx* ctx, const void* fn, int block, int* cache)
 {
@@ -126,7 +129,7 @@ int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32
     const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<false>, NX_TRACE_BLOCK, &g_gridAny);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    trace_any_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr, trace_tuning(ctx));
+    trace_any_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr, trace_tuning(ctx, true));
     if (outMs) { cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1); cudaEventElapsedTime(outMs, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     cudaFreeAsync(cursor, ctx->stream);
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -246,7 +249,7 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
     cudaStream_t s = ctx->stream, sa = ctx->stream_aux;
     const uint32_t L = sv.pathLength;
     const bool work = (r->profFlags & 2) != 0;
-    const TraceTuning tune = trace_tuning(ctx);
+    const TraceTuning tune = trace_tuning(ctx), tuneAny = trace_tuning(ctx, true);
     const int gClosest = work ? persistent_grid(ctx, (const void*)trace_closest_kernel<true>, NX_TRACE_BLOCK, &g_gridClosestStats)
                               : persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
     const int gAny = work ? persistent_grid(ctx, (const void*)trace_any_kernel<true>, NX_TRACE_BLOCK, &g_gridAnyStats)
@@ -289,8 +292,8 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
             // shadow rays on the auxiliary stream overlap the extension trace (the reference's graph runs them as siblings)
             NX_CUDA(ctx, cudaStreamWaitEvent(sa, r->evShade, 0));
             r->prof_begin(3, sa);
-            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, r->dWork + 1, tune);
-            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, nullptr, tune);
+            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, r->dWork + 1, tuneAny);
+            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, nullptr, tuneAny);
             r->prof_end(sa);
             NX_CUDA(ctx, cudaEventRecord(r->evShadow, sa));
             r->launches++;
