@@ -388,8 +388,10 @@ def run_build_ours(args):
     barrier()
     t0 = time.time()
     for _ in range(K):
-        with torch.cuda.stream(stream):
-            dev_t.copy_(host, non_blocking=True)
+        # the copy runs on torch's stream (its allocators must never see the context's stream, which is destroyed with the
+        # context); the builder's stream waits for it through an event
+        dev_t.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(); stream.wait_event(ev)
         b = nx.BuildBVH8Device(ctx, dev, n, 1, speed)
         ctx.synchronize()
         _ = (b.nodeCount, b.bounds)
@@ -418,6 +420,8 @@ def run_build_ours(args):
                 "bvh8_nodes": int(nodes), "bvh2_sah": round(m["bvh2_cost"], 4), "bvh8_sah": round(m["bvh8_cost"], 4), "avg_children_per_node": round(m["avg_children_per_node"], 3),
                 "host_generate_s": round(t_gen, 1), "gpu_launches": int(K * 4), "library_launches": int(K * 6), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    del dev_t, host
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

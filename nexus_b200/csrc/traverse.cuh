@@ -75,9 +75,6 @@ struct TraceStats {
 #else
 #define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 9 * 4) * NX_TRACE_BLOCK)
 #endif
-#ifndef NX_TSINGLE
-#define NX_TSINGLE 0   // measured: one triangle round per iteration (1) is 4 % slower than looping over rounds (0)
-#endif
 
 // (7 - octant) replicated into four bytes, octant = sign bits of the direction (x: 4, y: 2, z: 1).  Any value works as long
 // as the same one decodes the hit mask it encoded (it only fixes the visiting order), so the sign BITS are used: shifts
@@ -97,10 +94,6 @@ __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 #define NX_MAGIC_PLANES 0x2d
 #endif
 
-#ifndef NX_PREFETCH
-#define NX_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ uint32_t shl_wrap(uint32_t v, uint32_t n) { uint32_t r; asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(v), "r"(n)); return r; }
 
@@ -326,12 +319,6 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
         const bool wantI = live && instDepth < 0 && tgroup.y != 0u;
         const uint32_t mN = __ballot_sync(NX_FULL, hasN);
         const uint32_t mX = __ballot_sync(NX_FULL, needR || wantI);
-#if NX_TSINGLE
-        // one triangle round per iteration, decided by the same set of votes (the first version looped here with two more
-        // votes per round: 4 % of the kernel's instructions were those votes, profiles/r01b)
-        const bool wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded);
-        const uint32_t mT = __ballot_sync(NX_FULL, wantT);
-#endif
 
         // ---------------------------------------------------------------- phase X: new ray / enter an instance ----
         // Both end in the same reciprocal-direction + octant set-up, so they share it.
@@ -403,16 +390,6 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             if (__all_sync(NX_FULL, dead)) break;
         }
 
-#if NX_TSINGLE
-        // ---------------------------------------------------------------- phase T: one triangle per lane ----
-        // (lanes that took part in phase X were not in mT: wantT needs a lane inside an instance, wantI one outside)
-        if (mT && (__popc(mT) >= tune.triLanes || mN == 0u))
-        {
-            if (STATS) { wRT++; wLT += __popc(mT); }
-            if (wantT) test_triangle();
-        }
-#endif
-
         // ---------------------------------------------------------------- phase N: one node per lane ----
         if (live && (ngroup.y & 0xff000000u))
         {
@@ -424,22 +401,8 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             const uint32_t child = ngroup.x + __popc(ngroup.y & ((1u << slot) - 1u) & 0xffu);
             intersect_children(nodes, child, o, inv, octinv4, ANY_HIT ? tmax : fminf(tmax, hitT), k47, ngroup, tgroup);
             if (STATS) cN++;
-#if NX_PREFETCH
-            // the lane's next fetch is known now; pull its lines into L1 while the votes / other phases run
-            if (ngroup.y & 0xff000000u) {
-                const uint32_t nb = 31u - __clz(ngroup.y);
-                const uint32_t ns = (nb - 24u) ^ (octinv4 & 0xffu);
-                const float4* pn = nodes + 5 * (size_t)(ngroup.x + __popc(ngroup.y & ((1u << ns) - 1u) & 0xffu));
-                prefetch_l1(pn); prefetch_l1(pn + 4);
-            } else if (tgroup.y) {
-                const uint32_t tb = 31u - __clz(tgroup.y);
-                if (instDepth >= 0) { const float4* pt = ltris + 3 * (size_t)(tgroup.x + tb); prefetch_l1(pt); prefetch_l1(pt + 2); }
-                else prefetch_l1(&sc.inst[tgroup.x + tb]);
-            }
-#endif
         }
 
-#if !NX_TSINGLE
         // ---------------------------------------------------------------- phase T: triangles (rounds until too few lanes) ----
         while (true)
         {
@@ -452,7 +415,6 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             if (STATS) { wRT++; wLT += __popc(mT); }
             if (wantT) test_triangle();
         }
-#endif
     }
     if (STATS) {
         atomicAdd(&stats->nodes, cN); atomicAdd(&stats->tris, cT); atomicAdd(&stats->insts, cI); atomicAdd(&stats->rays, cR); atomicAdd(&stats->sphereCulled, cS);
