@@ -88,6 +88,9 @@ typedef struct nx_camera {                /* Camera ctor arguments, src/Scene/Ca
     float horizontal_fov_deg; float focus_distance; float defocus_angle_deg;
 } nx_camera;
 
+/* ColorUtils::ToneMapping, src/Utils/ColorUtils.h:9-16 */
+enum { NX_TONE_NONE = 0, NX_TONE_ACES = 1, NX_TONE_UNCHARTED2 = 2, NX_TONE_AGX_DEFAULT = 3, NX_TONE_AGX_GOLDEN = 4, NX_TONE_AGX_PUNCHY = 5 };
+
 typedef struct nx_render_settings {       /* RenderSettings, src/Renderer/RenderSettings.h:5-17 */
     int32_t use_mis; int32_t path_length;
     float background_color[3]; float background_intensity;
@@ -216,6 +219,9 @@ int nx_renderer_accum_device(nx_renderer* r, float** out_dev_sum, uint32_t* out_
 int nx_renderer_set_accum_frames(nx_renderer* r, uint32_t frames);                         /* after an external all-reduce */
 /* Tone-mapped RGBA8 (AccumulateKernel's display transform, PathTracer.cu:527-548), HOST buffer of w*h uint32. */
 int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* host_rgba);
+/* The same display transform (exposure, tone curve NX_TONE_*, gamma 2.2, RGBA8 pack: src/Utils/ColorUtils.h:27-212) applied on
+ * the device to a HOST linear float RGB image of `count` pixels; for previews of EXR/PFM output and for the parity tests. */
+int nx_display_transform(nx_ctx* ctx, const float* host_rgb, uint32_t count, int tone_mapping, float exposure, uint32_t* host_rgba);
 /* Headless output (north_star): PFM (little-endian float RGB) and EXR (uncompressed scanline, float RGB). */
 int nx_write_pfm(const char* path, const float* rgb, uint32_t w, uint32_t h);
 int nx_write_exr(const char* path, const float* rgb, uint32_t w, uint32_t h);

@@ -508,6 +508,17 @@ class PathTracer:
         return out
 
 
+TONE_NONE, TONE_ACES, TONE_UNCHARTED2, TONE_AGX_DEFAULT, TONE_AGX_GOLDEN, TONE_AGX_PUNCHY = range(6)   # ColorUtils::ToneMapping
+
+
+def display_transform(ctx, rgb, toneMapping=TONE_AGX_DEFAULT, exposure=0.0):
+    """AccumulateKernel's display transform (PathTracer.cu:527-548, ColorUtils.h:27-212) of a linear float RGB image -> packed RGBA8."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    out = np.empty(rgb.shape[:-1], np.uint32)
+    check(ctx._h, lib().nx_display_transform(ctx._h, _ptr(rgb), C.c_uint32(out.size), C.c_int(int(toneMapping)), C.c_float(exposure), _ptr(out)), "display_transform")
+    return out
+
+
 def write_pfm(path, rgb):
     rgb = np.ascontiguousarray(rgb, np.float32)
     rc = lib().nx_write_pfm(str(path).encode(), _ptr(rgb), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]))

@@ -379,6 +379,22 @@ int nx_renderer_accum_device(nx_renderer* r, float** outSum, uint32_t* outFrames
 }
 int nx_renderer_set_accum_frames(nx_renderer* r, uint32_t frames) { if (!r) return NX_ERR_INVALID; r->frames = frames; return NX_OK; }
 
+int nx_display_transform(nx_ctx* ctx, const float* hostRgb, uint32_t count, int toneMapping, float exposure, uint32_t* hostRgba)
+{
+    if (!ctx || !hostRgb || !hostRgba || toneMapping < NX_TONE_NONE || toneMapping > NX_TONE_AGX_PUNCHY) return NX_ERR_INVALID;
+    if (!count) return NX_OK;
+    DeviceGuard guard(ctx->device);
+    float* dIn = nullptr; uint32_t* dOut = nullptr;
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dIn, 12 * (size_t)count, ctx->stream));
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dOut, 4 * (size_t)count, ctx->stream));
+    NX_CUDA(ctx, cudaMemcpyAsync(dIn, hostRgb, 12 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    nxi_launch_resolve(ctx->sm_count * 4, ctx->stream, dIn, count, 1.0f, exposure, toneMapping, dOut);
+    NX_CUDA(ctx, cudaMemcpyAsync(hostRgba, dOut, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(dIn, ctx->stream); cudaFreeAsync(dOut, ctx->stream);
+    return NX_OK;
+}
+
 int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* hostRgba)
 {
     if (!r || !scene || !hostRgba) return NX_ERR_INVALID;
@@ -388,7 +404,7 @@ int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* hostRgba)
     uint32_t* d = nullptr;
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
     NX_CUDA(ctx, cudaMallocAsync((void**)&d, 4 * (size_t)count, ctx->stream));
-    nxi_launch_resolve(ctx->sm_count * 4, ctx->stream, r->wb.accum, count, r->frames ? 1.0f / (float)r->frames : 0.f, scene->settings.exposure, d);
+    nxi_launch_resolve(ctx->sm_count * 4, ctx->stream, r->wb.accum, count, r->frames ? 1.0f / (float)r->frames : 0.f, scene->settings.exposure, scene->settings.tone_mapping, d);
     NX_CUDA(ctx, cudaMemcpyAsync(hostRgba, d, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(d, ctx->stream);

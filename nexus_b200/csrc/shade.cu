@@ -286,16 +286,75 @@ __global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel
     if (lane_id() == 0 && shadedHere) atomicAdd(&wb.counters->shaded[bounce], shadedHere);
 }
 
-// Display transform of AccumulateKernel (PathTracer.cu:527-548) on the mean; tone curves other than NONE are added with
-// SURVEY.md §8 row f-1, until then every mode maps to exposure + gamma 2.2.
-__global__ void resolve_rgba8_kernel(const float* __restrict__ accum, uint32_t count, float invFrames, float exposure, uint32_t* __restrict__ out)
+// ------------------------------------------------------------------------------------------------ display ----
+// Display transform of AccumulateKernel (PathTracer.cu:527-548): exposure, one of the reference's six tone curves
+// (src/Utils/ColorUtils.h:9-16: NONE, ACES, UNCHARTED2, AGX_DEFAULT, AGX_GOLDEN, AGX_PUNCHY), gamma 2.2, RGBA8 pack.  The curves
+// are the published fits the reference cites: S. Hill's ACES RRT+ODT fit, J. Hable's Uncharted 2 operator with white point
+// 11.2, B. Wrensch's minimal AgX (7th-order sigmoid fit) with the golden / punchy ASC-CDL looks.
+__device__ __forceinline__ F3 mul3x3(const float (&m)[9], F3 v)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const float s = invFrames * exp2f(exposure);
-        const float r = __powf(fmaxf(accum[3 * (size_t)i] * s, 0.f), 1.0f / 2.2f), g = __powf(fmaxf(accum[3 * (size_t)i + 1] * s, 0.f), 1.0f / 2.2f),
-                    b = __powf(fmaxf(accum[3 * (size_t)i + 2] * s, 0.f), 1.0f / 2.2f);
-        out[i] = (uint32_t)(__saturatef(r) * 255.0f) | ((uint32_t)(__saturatef(g) * 255.0f) << 8) | ((uint32_t)(__saturatef(b) * 255.0f) << 16) | 0xff000000u;
-    }
+    return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ F3 pow3(F3 v, F3 e) { return f3(powf(v.x, e.x), powf(v.y, e.y), powf(v.z, e.z)); }
+
+__device__ __forceinline__ F3 tone_aces(F3 c)                                    // ColorUtils.h:72-97
+{
+    const float in[9] = {0.59719f, 0.35458f, 0.04823f, 0.07600f, 0.90834f, 0.01566f, 0.02840f, 0.13383f, 0.83777f};
+    const float outm[9] = {1.60475f, -0.53108f, -0.07367f, -0.10208f, 1.10813f, -0.00605f, -0.00327f, -0.07276f, 1.07602f};
+    const F3 v = mul3x3(in, c);
+    auto fit = [](float x) { return (x * (x + 0.0245786f) - 0.000090537f) / (x * (0.983729f * x + 0.4329510f) + 0.238081f); };
+    const F3 o = mul3x3(outm, f3(fit(v.x), fit(v.y), fit(v.z)));
+    return f3(clampf(o.x, 0.f, 1.f), clampf(o.y, 0.f, 1.f), clampf(o.z, 0.f, 1.f));
+}
+__device__ __forceinline__ float hable(float x)                                 // ColorUtils.h:99-110
+{
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return (x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F) - E / F;
+}
+__device__ __forceinline__ F3 tone_uncharted2(F3 c)                              // ColorUtils.h:112-117
+{
+    const float scale = 1.0f / hable(11.2f);
+    return f3(hable(1.6f * c.x) * scale, hable(1.6f * c.y) * scale, hable(1.6f * c.z) * scale);
+}
+__device__ __forceinline__ F3 tone_agx(F3 c, int mode)                           // ColorUtils.h:119-212
+{
+    const float inset[9] = {0.842479062253094f, 0.0784335999999992f, 0.0792237451477643f, 0.0423282422610123f, 0.878468636469772f, 0.0791661274605434f,
+                            0.0423756549057051f, 0.0784336f, 0.879142973793104f};
+    const float outset[9] = {1.19687900512017f, -0.0980208811401368f, -0.0990297440797205f, -0.0528968517574562f, 1.15190312990417f, -0.0989611768448433f,
+                             -0.0529716355144438f, -0.0980434501171241f, 1.15107367264116f};
+    const float minEv = -12.47393f, maxEv = 4.026069f;
+    F3 v = mul3x3(inset, c);
+    auto enc = [&](float x) { return (clampf(log2f(x), minEv, maxEv) - minEv) / (maxEv - minEv); };
+    auto sig = [](float x) {                                                     // 7th-order fit of the AgX default contrast curve
+        const float x2 = x * x, x4 = x2 * x2, x6 = x4 * x2;
+        return -17.86f * x6 * x + 78.01f * x6 - 126.7f * x4 * x + 92.06f * x4 - 28.72f * x2 * x + 4.361f * x2 - 0.1718f * x + 0.002857f;
+    };
+    v = f3(sig(enc(v.x)), sig(enc(v.y)), sig(enc(v.z)));
+    // look: ASC CDL slope / power, then saturation about the Rec.709 luma
+    F3 slope = f3(1.0f), power = f3(1.0f); float sat = 1.0f;
+    if (mode == NX_TONE_AGX_GOLDEN) { slope = f3(1.0f, 0.9f, 0.5f); power = f3(0.8f); sat = 0.8f; }
+    else if (mode == NX_TONE_AGX_PUNCHY) { power = f3(1.35f); sat = 1.4f; }
+    v = pow3(v * slope, power);
+    const float luma = 0.2126f * v.x + 0.7152f * v.y + 0.0722f * v.z;
+    v = f3(luma + sat * (v.x - luma), luma + sat * (v.y - luma), luma + sat * (v.z - luma));
+    return pow3(mul3x3(outset, v), f3(2.2f));                                    // outset, then linearise (gamma is re-applied below)
+}
+__device__ __forceinline__ uint32_t display_pixel(F3 c, int mode, float gain)
+{
+    c = c * gain;
+    if (mode == NX_TONE_ACES) c = tone_aces(c);
+    else if (mode == NX_TONE_UNCHARTED2) c = tone_uncharted2(c);
+    else if (mode >= NX_TONE_AGX_DEFAULT && mode <= NX_TONE_AGX_PUNCHY) c = tone_agx(c, mode);
+    c = pow3(c, f3(1.0f / 2.2f));
+    // ToColorUInt (ColorUtils.h:46-56): clamp (NaN -> 0), scale, truncate
+    return (uint32_t)(clampf(c.x, 0.f, 1.f) * 255.0f) | ((uint32_t)(clampf(c.y, 0.f, 1.f) * 255.0f) << 8) | ((uint32_t)(clampf(c.z, 0.f, 1.f) * 255.0f) << 16) | 0xff000000u;
+}
+__global__ void resolve_rgba8_kernel(const float* __restrict__ accum, uint32_t count, float invFrames, float exposure, int mode, uint32_t* __restrict__ out)
+{
+    const float gain = invFrames * exp2f(exposure);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        out[i] = display_pixel(f3(accum[3 * (size_t)i], accum[3 * (size_t)i + 1], accum[3 * (size_t)i + 2]), mode, gain);
 }
 
 int g_gridShade = 0;
@@ -316,7 +375,7 @@ void nxi_launch_shade(const DSceneView& sv, const WaveBuffers& wb, uint32_t boun
 {
     shade_kernel<<<grid, kShadeBlock, 0, s>>>(sv, wb, bounce, frame);
 }
-void nxi_launch_resolve(int grid, cudaStream_t s, const float* accum, uint32_t count, float invFrames, float exposure, uint32_t* out)
+void nxi_launch_resolve(int grid, cudaStream_t s, const float* accum, uint32_t count, float invFrames, float exposure, int mode, uint32_t* out)
 {
-    resolve_rgba8_kernel<<<grid, 256, 0, s>>>(accum, count, invFrames, exposure, out);
+    resolve_rgba8_kernel<<<grid, 256, 0, s>>>(accum, count, invFrames, exposure, mode, out);
 }

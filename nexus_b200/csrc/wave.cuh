@@ -58,4 +58,4 @@ __device__ __forceinline__ void add_radiance(float* accum, uint32_t pixel, F3 L)
 int nxi_shade_grid(nx_ctx* ctx);
 void nxi_launch_generate(const DSceneView& sv, const WaveBuffers& wb, uint32_t frame, int grid, cudaStream_t s);
 void nxi_launch_shade(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, int grid, cudaStream_t s);
-void nxi_launch_resolve(int grid, cudaStream_t s, const float* accum, uint32_t count, float invFrames, float exposure, uint32_t* out);
+void nxi_launch_resolve(int grid, cudaStream_t s, const float* accum, uint32_t count, float invFrames, float exposure, int mode, uint32_t* out);

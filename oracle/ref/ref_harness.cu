@@ -488,6 +488,29 @@ int nxref_read_accum(float* outRgb /* w*h*3 */)
     return 0;
 }
 
+// The reference's display transform (AccumulateKernel, N/Cuda/PathTracer/PathTracer.cu:513-549 with N/Utils/ColorUtils.h:27-212)
+// applied to a caller-supplied linear image: the image is written to pathState.radiance, frameNumber is set to 1 (so the
+// running mean becomes the image itself) and AccumulateKernel fills the RGBA8 render buffer.  count must be w*h of the last
+// nxref_render_init.  Overwrites the accumulation buffer.
+int nxref_display(int toneMapping, float exposure, const float* rgb, uint32_t count, uint32_t* outRgba)
+{
+    if ((size_t)count != (size_t)g.w * g.h) return -2;
+    D_PathStateSOA ps;
+    REF_CHECK(cudaMemcpy(&ps, GetDevicePathStateAddress(), sizeof(ps), cudaMemcpyDeviceToHost));
+    REF_CHECK(cudaMemcpy(ps.radiance, rgb, 12ull * count, cudaMemcpyHostToDevice));
+    g.settings.toneMapping = (ColorUtils::ToneMapping)toneMapping;
+    g.settings.exposure = exposure;
+    if (uploadSymbols()) return -1;
+    const uint32_t one = 1;
+    REF_CHECK(cudaMemcpy(GetDeviceFrameNumberAddress(), &one, 4, cudaMemcpyHostToDevice));
+    void** noArgs = nullptr;
+    REF_CHECK(cudaLaunchKernel((void*)AccumulateKernel, g.pixelGrid, dim3(BLOCK_SIZE), noArgs, 0, 0));
+    REF_CHECK(cudaDeviceSynchronize());
+    REF_CHECK(cudaMemcpy(outRgba, g.renderBuffer, 4ull * count, cudaMemcpyDeviceToHost));
+    g.settings.toneMapping = ColorUtils::ToneMapping::NONE; g.settings.exposure = 0.0f;
+    return uploadSymbols();
+}
+
 // Closest hit for a caller-supplied ray batch through the reference TraceKernel (bounce 0 queue).
 // n must be <= w*h of the last nxref_render_init.
 int nxref_trace(const float* origins, const float* dirs, uint32_t n,

@@ -68,3 +68,17 @@ def render_cases():
         ("cornell", scenes.with_triangle_data(scenes.cornell_box(path_length=6)), (128, 128), 2048, 8),
         ("instanced", scenes.with_triangle_data(scenes.instanced_scene(n_blas=6, n_instances=20, nu=16, nv=14, path_length=6)), (128, 72), 2048, 8),
     ]
+
+
+# ------------------------------------------------------------------ display transform (tests/golden/display_ref.npz) ----
+DISPLAY_EXPOSURES = (0.0, -1.5, 2.0)
+
+
+def display_image():
+    """64x64 linear HDR test image: log-uniform radiance over 1e-4..60 per channel, a grey ramp row, exact zeros and ones."""
+    rng = np.random.default_rng(3)
+    img = np.exp(rng.uniform(np.log(1e-4), np.log(60.0), (64, 64, 3))).astype(np.float32)
+    img[0] = (np.linspace(0.0, 4.0, 64, dtype=np.float32) ** 2)[:, None]
+    img[1, :8] = 0.0
+    img[1, 8:16] = 1.0
+    return img

@@ -13,6 +13,7 @@ import pytest
 import nexus_b200 as nx
 import oracle_lib as O
 from golden_cases import builder_cases
+from nexus_b200 import scenes
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "builder_ref.npz")
@@ -112,3 +113,28 @@ def test_rebuild_is_deterministic(ctx):
 def test_invalid_inputs_fail_loudly(ctx):
     with pytest.raises(nx.NexusError):
         nx.BuildBVH8(ctx, np.zeros((0, 9), np.float32))
+
+
+def test_bench_size_build_properties(ctx, have_ref):
+    """At bench size (10 M triangles of the NexusBVH benchmark mesh, BASELINE.json configs[3]'s generator) parity is checked
+    through size-independent properties: every primitive appears exactly once, every child box contains its subtree, the
+    node count respects the ceil((4n-1)/7) bound, rebuilding gives the same tree, and - when the compiled reference travelled
+    to the box - node count and both SAH costs (Eval.cu definitions) equal the reference's (1e-4: float-atomic summation order)."""
+    n = 10_000_000
+    prims = scenes.test_triangles(n)
+    b8, m = nx.BuildBVH8(ctx, prims, prioritizeSpeed=True, metrics=True)
+    n8, p8 = b8.ToHost(); b8.Free()
+    assert len(n8) <= (4 * n - 1 + 6) // 7
+    assert (np.bincount(p8, minlength=n) == 1).all()
+    pb, _ = O.prim_bounds(prims, 1)
+    assert O.check_bvh8(n8, p8, pb) == 0
+    b8b = nx.BuildBVH8(ctx, prims, prioritizeSpeed=True)
+    n8b, p8b = b8b.ToHost(); b8b.Free()
+    ca, cb = O.canon_bvh8(n8, p8), O.canon_bvh8(n8b, p8b)     # numbering inside a level follows the atomics; the tree does not
+    assert (ca[0] == cb[0]).all() and (ca[1] == cb[1]).all()
+    if have_ref:
+        import ctypes as C
+        mm = np.zeros(9, np.float32); cnt = C.c_uint32(0)
+        assert O.ref().nxref_benchmark_bvh8(prims.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, 1, 0, 1, mm.ctypes.data_as(C.c_void_p), C.byref(cnt), None) == 0
+        assert cnt.value == len(n8)
+        assert abs(m["bvh2_cost"] - mm[6]) <= 1e-4 * mm[6] and abs(m["bvh8_cost"] - mm[7]) <= 1e-4 * mm[7]

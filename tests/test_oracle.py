@@ -116,3 +116,26 @@ def test_trace_oracle_equals_reference_hits(case):
     assert cmp2["hard"] == 0 and cmp2["t_bad"] == 0, cmp2
     occ = ora.trace_any(np.array(rays))
     assert (occ.astype(bool) == (got["t"] < np.float32(1e30))).all()
+
+
+# ------------------------------------------------------------------ display transform ----
+@pytest.mark.parametrize("mode", range(6), ids=["none", "aces", "uncharted2", "agx", "agx_golden", "agx_punchy"])
+def test_display_oracle_equals_reference_render_buffer(mode):
+    """The numpy restatement of AccumulateKernel's display transform (oracle/oracle_display.py) against the RGBA8 buffers the
+    unmodified reference kernel produced for the same image (tests/golden/display_ref.npz).  Integer output: exact for the
+    rational curves; the AgX path goes through log2 / pow (fast-math in the reference), where a value that lands on a
+    quantisation boundary may differ by one code: at most 1 LSB on at most 0.2 % of the channels."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "oracle"))
+    import oracle_display as D
+    from golden_cases import DISPLAY_EXPOSURES, display_image
+    g = np.load(os.path.join(GOLD, "display_ref.npz"))
+    assert (g["image"] == display_image()).all()
+    for e in DISPLAY_EXPOSURES:
+        ref, got = D.unpack(g[f"m{mode}_e{e:+.1f}"]), D.unpack(D.display(g["image"], mode, e))
+        diff = np.abs(ref - got)
+        if mode <= D.UNCHARTED2:
+            assert diff.max() == 0, (mode, e)
+        else:
+            assert diff.max() <= 1 and (diff > 0).mean() <= 0.002, (mode, e, diff.max(), (diff > 0).mean())
+        assert (g[f"m{mode}_e{e:+.1f}"] >> 24 == 0xff).all()
