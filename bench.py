@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline measurement of the wavefront path-tracing hot path (BASELINE.json / SURVEY.md §8d).
 
-  python bench.py --gpus N --steps K --warmup W [--workload instanced10m_4k|cornell_1080p|sky10m_4k|build50m|build10m] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--workload instanced10m_4k|cornell_1080p|sky10m_4k|build50m|build10m|build100k] [--impl reference]
 
 A step is one frame (1 sample per pixel) of the wavefront pipeline: generate -> closest-hit trace -> shade (+NEE) ->
 {closest-hit trace, any-hit shadow trace} per bounce -> accumulate.  Metric: Mrays/s = (extension + shadow rays traced) /
@@ -43,6 +43,10 @@ WORKLOADS = {
     "build50m": dict(res=None, n=50_000_000, desc="H-PLOC BVH2 build + CWBVH8 collapse of the NexusBVH benchmark mesh (random small triangles on a 1000^3 lattice), "
                      "50,000,000 triangles, 32-bit Morton keys (prioritizeSpeed), 1 build/step"),
     "build10m": dict(res=None, n=10_000_000, desc="as build50m with 10,000,000 triangles (the size NexusBVH's README quotes)"),
+    # BASELINE.json configs[0]: the reference's CPU-runnable case.  Our arm builds the same mesh on the GPU; the CPU path (binned-SAH
+    # BVH2 + SAH-optimal BVH8 collapse, oracle/oracle_sah.cpp) is timed beside it on the host cores as cpu_baseline
+    "build100k": dict(res=None, n=100_352, mesh="uv_sphere", desc="procedurally tessellated UV sphere, 224 x 224 x 2 = 100,352 triangles: H-PLOC BVH2 build + CWBVH8 collapse on the GPU; "
+                      "cpu_baseline = CPU binned-SAH BVH2 build + SAH-optimal BVH8 collapse of the same mesh on the host cores"),
     # reduced variant for quick functional checks (not a bench line)
     "instanced_small": dict(res=(640, 360), desc="64-BLAS reduced instanced scene, 640x360 (functional check only)"),
 }
@@ -313,6 +317,32 @@ BUILD_BYTES_FIXED = 340           # + 80 * N8 / n for the CWBVH8 node writes
 HPLOC_BYTES_PER_PRIM = 32 + 32 + 16 + 8 + 8   # leaf bounds read, inner node write, clusterIdx load/store, parentIdx, two Morton neighbours
 
 
+def build_mesh(wl):
+    from nexus_b200 import scenes
+    if wl.get("mesh") == "uv_sphere":
+        return np.ascontiguousarray(scenes.uv_sphere(224, 224).reshape(-1, 9), np.float32)
+    return scenes.test_triangles(wl["n"])
+
+
+def cpu_sah_baseline(tris):
+    """BASELINE.json configs[0]'s CPU path on this box's host cores: binned-SAH BVH2 (all cores) + SAH-optimal collapse (sequential,
+    as the reference's recursive BVH8Builder is), best of 3."""
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    pb, sb = O.prim_bounds(tris, 1)
+    n = len(pb)
+    best = None
+    for _ in range(3):
+        t0 = time.time(); n2 = O.sah_build_bvh2(pb, threads=cores); t1 = time.time(); n8, pidx, root_cost = O.sah_collapse(n2, n); t2 = time.time()
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+    return {"value": round(n / best[0] / 1e6, 4), "unit": "Mprims/s", "cores": cores, "kind": "port",
+            "sample": f"all {n} triangles: binned-SAH BVH2 build {best[1] * 1e3:.1f} ms on {cores} threads + SAH-optimal BVH8 collapse {best[2] * 1e3:.1f} ms on 1 thread "
+                      "(oracle/oracle_sah.cpp; the reference snapshot contains no CPU BVH2 builder and its CPU collapse is dead code, SURVEY.md header note 1)",
+            "bvh8_nodes": int(len(n8)), "bvh2_sah_leaf_cost": round(O.sah_bvh2_cost(n2, n), 3), "collapse_root_cost": round(float(root_cost), 4),
+            "bvh8_sah": round(O.bvh8_cost(n8, sb), 4)}
+
+
 def run_build_ours(args):
     import torch
     import torch.distributed as dist
@@ -333,7 +363,7 @@ def run_build_ours(args):
     stream = torch.cuda.ExternalStream(int(nx.lib().nx_ctx_stream(ctx._h)), device=torch.device("cuda", local))
     t_gen = time.time()
     host = torch.empty((n, 9), dtype=torch.float32, pin_memory=True)
-    host.numpy()[:] = scenes.test_triangles(n)
+    host.numpy()[:] = build_mesh(wl)
     t_gen = time.time() - t_gen
     dev_t = torch.empty((n, 9), dtype=torch.float32, device="cuda")
     dev_t.copy_(host)
@@ -404,7 +434,9 @@ def run_build_ours(args):
            "ms_per_step": round(float(e2e_s[0]) * 1e3 / K, 3), "what": "pinned host triangles -> device copy -> BuildBVH8 -> handle (bounds, node count) on the host"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and wl.get("mesh") == "uv_sphere":
+        cpu = cpu_sah_baseline(host.numpy())
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle_lib as O
         ns = 1_000_000
         sample = host.numpy()[:ns]
@@ -439,7 +471,7 @@ def run_build_reference(args):
     if not O.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnexus_ref.so was not built (needs /root/reference at build time)"}))
         return
-    tris = scenes.test_triangles(n)
+    tris = build_mesh(wl)
     mm = np.zeros(9, np.float32); cnt = C.c_uint32(0); ms2 = np.zeros(2, np.float32)
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start(); time.sleep(0.3)

@@ -119,6 +119,32 @@ def check_bvh8(nodes, prim_idx, bounds):
                                    C.c_uint32(prim_idx.shape[0]), _p(np.ascontiguousarray(bounds, np.float32)))
 
 
+# ------------------------------------------------------------------ oracle: config 1 (CPU binned SAH + SAH-optimal collapse) ----
+def sah_build_bvh2(bounds, threads=1):
+    """Binned-SAH BVH2, root at node 0 (oracle/oracle_sah.cpp; parity unpinned: the reference snapshot has no such source)."""
+    bounds = np.ascontiguousarray(bounds, np.float32)
+    n = bounds.shape[0]
+    nodes = np.zeros((2 * n - 1, 8), np.uint32)
+    assert oracle().orc_sah_build_bvh2(_p(bounds), C.c_uint32(n), _p(nodes), C.c_int(threads)) == 0
+    return nodes
+
+
+def sah_collapse(bvh2_nodes, n, root=0):
+    """CPU BVH8Builder restatement (Ylitie et al. dynamic-programming collapse).  Returns nodes8, primIdx, C(root, 1)."""
+    cap = (4 * n - 1) // 7 + 1
+    nodes = np.zeros((cap, 20), np.uint32)
+    prim_idx = np.zeros(n, np.uint32)
+    cnt, cost = C.c_uint32(0), C.c_float(0)
+    rc = oracle().orc_sah_collapse(_p(np.ascontiguousarray(bvh2_nodes)), C.c_uint32(n), C.c_uint32(root), _p(nodes), _p(prim_idx), C.byref(cnt), C.byref(cost))
+    assert rc == 0, rc
+    return nodes[:cnt.value].copy(), prim_idx, cost.value
+
+
+def sah_bvh2_cost(bvh2_nodes, n):
+    oracle().orc_sah_bvh2_cost.restype = C.c_double
+    return oracle().orc_sah_bvh2_cost(_p(np.ascontiguousarray(bvh2_nodes)), C.c_uint32(n))
+
+
 # ------------------------------------------------------------------ oracle: traversal ----
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("tmax", np.float32), ("direction", np.float32, 3), ("pad", np.uint32)])
 HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.uint32), ("instance", np.uint32)])
