@@ -183,7 +183,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    pt.SetProfiling(events=True, work=False)
+    pt.SetProfiling(events=False, work=False)   # no per-launch events inside the headline region: they cost 7 % on the small Cornell launches
     barrier()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     wall0 = time.time()
@@ -199,7 +199,6 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_total, ms_reduce = e0.elapsed_time(e2), e1.elapsed_time(e2)
     st = pt.Stats()
-    prof = pt.Profile()
     rays_local = st["extension_rays"] + st["shadow_rays"]
     agg = torch.tensor([ms_total, ms_reduce], device="cuda", dtype=torch.float64)
     cnt = torch.tensor([rays_local, st["extension_rays"], st["shadow_rays"]], device="cuda", dtype=torch.float64)
@@ -211,7 +210,13 @@ def run_ours(args):
     value = rays_all / (ms_total * 1e-3) / 1e6
     mean_radiance = float(pt.ReadAccumulation().mean()) if rank == 0 else 0.0
 
-    # ---- roofline of the dominant kernel (closest-hit traversal): algorithmic bytes from a counted, untimed replay of the same frames
+    # ---- roofline of the dominant kernel (closest-hit traversal): the same K frames again with a CUDA event pair around every
+    # launch (on the stream it is launched on), then the algorithmic bytes from a counted, untimed replay of the same frames
+    pt.SetProfiling(events=True, work=False)
+    pt.ResetFrameNumber()
+    pt.Render(scene, frames=K, firstFrame=first)
+    ctx.synchronize()
+    prof = pt.Profile()
     pt.SetProfiling(events=False, work=True)
     pt.ResetFrameNumber()
     pt.Render(scene, frames=K, firstFrame=first)
@@ -266,6 +271,24 @@ def run_ours(args):
     e2e = {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": 48 + 32, "d2h_bytes_per_step": 4 * res[0] * res[1],
            "ms_per_step": round(float(e2e_t[0]) * 1e3 / K, 3), "what": "SetCamera+SetRenderSettings (host structs) -> Render(1 frame) -> ReadRGBA8 into pinned host memory"}
 
+    # ---- like for like (N = 1 only): the same frames on BLASes / TLAS collapsed by the reference GPU converter's rule, i.e. trees
+    # identical to the ones the reference renders with.  The headline above uses the product default, the SAH-optimal collapse of
+    # the reference's CPU BVH8Builder run on the GPU (same hits, fewer node visits); this line isolates what the trees contribute.
+    like = None
+    if world == 1 and not args.no_like_for_like:
+        ctx.SetSceneCollapse(nx.COLLAPSE_REFERENCE_GPU, 0)
+        scene_ref = scenes.build(ctx, desc, res)
+        ctx.SetSceneCollapse(nx.COLLAPSE_SAH_OPTIMAL, 2)
+        pt.ResetFrameNumber()
+        pt.Render(scene_ref, frames=3, firstFrame=1); ctx.synchronize()
+        pt.ResetFrameNumber()
+        kk = min(K, 8)
+        pt.Render(scene_ref, frames=kk, firstFrame=first); ctx.synchronize()
+        s2 = pt.Stats()
+        like = {"collapse": "reference_gpu (NexusBVH-identical trees)", "value": round((s2["extension_rays"] + s2["shadow_rays"]) / s2["device_ms"] / 1e3, 1), "unit": "Mrays/s",
+                "ms_per_step": round(s2["device_ms"] / kk, 4), "steps": kk}
+        scene_ref.close()
+
     # ---- CPU baseline (rank 0, N = 1 only): the CPU oracle's closest-hit traversal on a bounded sample of this workload's primary rays
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -277,13 +300,14 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "description": wl["desc"], "resolution": list(res), "path_length": desc["settings"].pathLength,
                            "partition": f"sample partition: rank g renders frames [1+g*K, (g+1)*K]; NCCL all-reduce(sum) of float[3*W*H] accumulation ({'%.1f' % (12e-6 * res[0] * res[1])} MB)" if world > 1 else "single GPU",
+                           "bvh": "BLAS / TLAS: H-PLOC BVH2 + SAH-optimal CWBVH8 collapse (reference CPU BVH8Builder's C(n,i) table on the GPU, <= 2 primitives per leaf); same hits as the reference's trees, see like_for_like",
                            "l2": "per-step working set (ray/hit/state queues %.0f MB at this resolution + BVH/triangles) exceeds the 126 MB L2; no flush needed" % (164e-6 * res[0] * res[1])},
                 "spp_per_s": round(world * K / (ms_total * 1e-3), 2),
                 "rays_per_step": int(rays_all / (K * world)), "extension_rays": int(cnt[1]), "shadow_rays": int(cnt[2]),
                 "primary_Mrays_per_s": round(world * K * res[0] * res[1] / (ms_total * 1e-3) / 1e6, 1),
                 "reduce_ms": round(ms_reduce, 3), "wall_s": round(wall, 3), "scene_setup_s": round(t_scene, 2),
                 "mean_radiance": round(mean_radiance, 5),
-                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "like_for_like": like}
         print(json.dumps(line), flush=True)
     pt.close(); scene.close(); ctx.close()
     if world > 1:
@@ -399,6 +423,7 @@ def run_build_ours(args):
 
     # per-stage device times (the builder's own CUDA events, BVHBuildMetrics layout) over K more builds, and the SAH costs
     m = nx.BenchmarkBuild(ctx, dev, n, 1, speed, 1, K)
+    mo = nx.BenchmarkBuild(ctx, dev, n, 1, speed, 1, K, collapse=nx.COLLAPSE_SAH_OPTIMAL, maxLeafPrims=2)
     hbm, hbm_src = peaks()
     hploc_ms = m["bvh2_ms"]
     achieved = HPLOC_BYTES_PER_PRIM * n / (hploc_ms * 1e-3) / 1e9
@@ -450,6 +475,9 @@ def run_build_ours(args):
                            "partition": "replicas only: one global sort + one hierarchy does not shard; each rank builds the whole mesh" if world > 1 else "single GPU",
                            "l2": "input (%.1f GB) and every intermediate array exceed the 126 MB L2; no flush needed" % (36e-9 * n)},
                 "bvh8_nodes": int(nodes), "bvh2_sah": round(m["bvh2_cost"], 4), "bvh8_sah": round(m["bvh8_cost"], 4), "avg_children_per_node": round(m["avg_children_per_node"], 3),
+                "sah_optimal_collapse": {"what": "same build with nx_build_config.collapse = NX_COLLAPSE_SAH_OPTIMAL, max_leaf_prims 2 (what the renderer builds its BLASes with)",
+                                         "total_ms": round(mo["total_ms"], 4), "bvh8_ms": round(mo["bvh8_ms"], 4), "bvh8_nodes": int(mo["node_count"]), "bvh8_sah": round(mo["bvh8_cost"], 4),
+                                         "Mprims_per_s": round(n / mo["total_ms"] / 1e3, 1)},
                 "host_generate_s": round(t_gen, 1), "gpu_launches": int(K * 4), "library_launches": int(K * 6), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize()
@@ -539,6 +567,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="instanced10m_4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-like-for-like", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -62,7 +62,13 @@ typedef struct nx_bvh8_node {
 typedef struct nx_bvh2 { nx_bvh2_node* nodes; uint32_t node_count; uint32_t prim_count; nx_aabb bounds; } nx_bvh2;
 typedef struct nx_bvh8 { nx_bvh8_node* nodes; uint32_t node_count; uint32_t* prim_idx; uint32_t prim_count; nx_aabb bounds; } nx_bvh8;
 
-typedef struct nx_build_config { int prioritize_speed; } nx_build_config;             /* NXB::BuildConfig           */
+/* NXB::BuildConfig (BuildConfig.h:6-12) plus the choice of BVH2 -> BVH8 collapse:
+ *   NX_COLLAPSE_REFERENCE_GPU  (0, default) the reference GPU converter's rule (WideConverter.cu:225-414): trees identical to NexusBVH's;
+ *   NX_COLLAPSE_SAH_OPTIMAL    the SAH-optimal collapse of the reference's CPU BVH8Builder (src/Geometry/BVH/BVH8Builder.cpp:31-199:
+ *                              C(n, i) table, C_PRIM 0.3, C_NODE 1.0), leaf children of up to max_leaf_prims (1..3, 0 = P_MAX = 3)
+ *                              primitives, on the GPU; node layout, slot assignment and quantisation as in the GPU converter. */
+enum { NX_COLLAPSE_REFERENCE_GPU = 0, NX_COLLAPSE_SAH_OPTIMAL = 1 };
+typedef struct nx_build_config { int prioritize_speed; int collapse; int max_leaf_prims; } nx_build_config;
 typedef struct nx_build_metrics {                                                       /* NXB::BVHBuildMetrics       */
     float scene_bounds_ms, morton_ms, sort_ms, bvh2_ms, bvh8_ms, total_ms;
     float bvh2_cost, bvh8_cost, avg_children_per_node;
@@ -131,6 +137,9 @@ void* nx_ctx_stream(nx_ctx* ctx);                                   /* cudaStrea
  * hits are resolved by id); they trade SIMT efficiency against front-to-back culling.  The reference's counterpart is the
  * compile-time 20 % postponing rule (BVH8Traversal.cuh:15-22,270-278).  Also settable with NX_TRACE_TUNE="tri,inst". */
 int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes);
+/* Collapse used for the BLASes / TLAS that nx_scene_* builds from now on (default NX_COLLAPSE_SAH_OPTIMAL, 2 primitives per leaf;
+ * NX_COLLAPSE_REFERENCE_GPU reproduces NexusBVH's trees).  Hit ids and distances do not depend on the choice. */
+int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims);
 /* 0 switches the per-instance bounding-sphere test off (measurement only; results are identical either way). */
 int nx_ctx_set_sphere_cull(nx_ctx* ctx, int enabled);
 

@@ -50,6 +50,11 @@ class Context:
     def SetTraceTuning(self, tri_lanes, inst_lanes):
         check(self._h, lib().nx_ctx_set_trace_tuning(self._h, C.c_uint32(tri_lanes), C.c_uint32(inst_lanes)), "SetTraceTuning")
 
+    def SetSceneCollapse(self, collapse, maxLeafPrims=0):
+        """BVH2 -> BVH8 collapse used for the BLASes / TLAS of scenes created afterwards (default: SAH-optimal, 2 primitives per
+        leaf; COLLAPSE_REFERENCE_GPU gives trees identical to the reference's NexusBVH)."""
+        check(self._h, lib().nx_ctx_set_scene_collapse(self._h, C.c_int(int(collapse)), C.c_int(int(maxLeafPrims))), "SetSceneCollapse")
+
     def SetSphereCull(self, enabled):
         check(self._h, lib().nx_ctx_set_sphere_cull(self._h, C.c_int(int(enabled))), "SetSphereCull")
 
@@ -148,10 +153,14 @@ def BuildBVH2(ctx, prims, prioritizeSpeed=False, metrics=False):
     return (bvh, m.as_dict()) if metrics else bvh
 
 
-def BuildBVH8(ctx, prims, prioritizeSpeed=False, metrics=False):
-    """NXB::BuildBVH8<PrimT> (BVHBuilder.h:31)."""
+COLLAPSE_REFERENCE_GPU, COLLAPSE_SAH_OPTIMAL = 0, 1
+
+
+def BuildBVH8(ctx, prims, prioritizeSpeed=False, metrics=False, collapse=COLLAPSE_REFERENCE_GPU, maxLeafPrims=0):
+    """NXB::BuildBVH8<PrimT> (BVHBuilder.h:31).  collapse: the reference GPU converter's rule (default, trees identical to
+    NexusBVH's) or the SAH-optimal collapse of the reference's CPU BVH8Builder (BVH8Builder.cpp:31-199) on the GPU."""
     prims, dev, tri = _prims_to_device(ctx, prims)
-    cfg, m, out = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), Bvh8()
+    cfg, m, out = BuildConfig(int(prioritizeSpeed), int(collapse), int(maxLeafPrims)), BuildMetrics(), Bvh8()
     fn = lib().nx_bvh8_build_tri if tri else lib().nx_bvh8_build_aabb
     try:
         check(ctx._h, fn(ctx._h, C.c_void_p(dev), C.c_uint32(prims.shape[0]), C.byref(cfg), C.byref(m) if metrics else None, C.byref(out)), "BuildBVH8")
@@ -161,19 +170,19 @@ def BuildBVH8(ctx, prims, prioritizeSpeed=False, metrics=False):
     return (bvh, m.as_dict()) if metrics else bvh
 
 
-def BuildBVH8Device(ctx, prims_dev, n, prim_type=1, prioritizeSpeed=False, metrics=False):
+def BuildBVH8Device(ctx, prims_dev, n, prim_type=1, prioritizeSpeed=False, metrics=False, collapse=COLLAPSE_REFERENCE_GPU, maxLeafPrims=0):
     """NXB::BuildBVH8<PrimT> on primitives already resident on the device (the reference's signature takes a device
     pointer, BVHBuilder.h:31).  Asynchronous on the context's stream unless metrics are requested."""
-    cfg, m, out = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), Bvh8()
+    cfg, m, out = BuildConfig(int(prioritizeSpeed), int(collapse), int(maxLeafPrims)), BuildMetrics(), Bvh8()
     fn = lib().nx_bvh8_build_tri if prim_type else lib().nx_bvh8_build_aabb
     check(ctx._h, fn(ctx._h, C.c_void_p(prims_dev), C.c_uint32(n), C.byref(cfg), C.byref(m) if metrics else None, C.byref(out)), "BuildBVH8")
     bvh = BVH8(ctx, out)
     return (bvh, m.as_dict()) if metrics else bvh
 
 
-def BenchmarkBuild(ctx, prims_dev, n, prim_type, prioritizeSpeed, warmup, iters):
+def BenchmarkBuild(ctx, prims_dev, n, prim_type, prioritizeSpeed, warmup, iters, collapse=COLLAPSE_REFERENCE_GPU, maxLeafPrims=0):
     """NXB::BenchmarkBuild (BVHBuildMetrics.h:63-108) on primitives already resident on the device."""
-    cfg, m, nodes = BuildConfig(int(prioritizeSpeed)), BuildMetrics(), C.c_uint32(0)
+    cfg, m, nodes = BuildConfig(int(prioritizeSpeed), int(collapse), int(maxLeafPrims)), BuildMetrics(), C.c_uint32(0)
     check(ctx._h, lib().nx_bvh8_benchmark(ctx._h, C.c_void_p(prims_dev), C.c_uint32(n), C.c_int(prim_type), C.byref(cfg), C.c_int(warmup),
                                           C.c_int(iters), C.byref(m), C.byref(nodes)), "BenchmarkBuild")
     d = m.as_dict()

@@ -24,7 +24,7 @@ class Bvh8(C.Structure):
 
 
 class BuildConfig(C.Structure):
-    _fields_ = [("prioritize_speed", C.c_int)]
+    _fields_ = [("prioritize_speed", C.c_int), ("collapse", C.c_int), ("max_leaf_prims", C.c_int)]
 
 
 class BuildMetrics(C.Structure):

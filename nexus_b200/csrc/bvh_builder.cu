@@ -276,6 +276,13 @@ __global__ void __launch_bounds__(kPlocBlock) hploc_kernel(PlocArgs a, const Key
 }
 
 // ---------------------------------------------------------------------------------------------- collapse ----
+__device__ __forceinline__ Box load_box2(const float4* n2, uint32_t i)
+{
+    const float4 p = __ldg(n2 + 2 * (size_t)i), q = __ldg(n2 + 2 * (size_t)i + 1);
+    Box b; b.lo = v3(p.x, p.y, p.z); b.hi = v3(p.w, q.x, q.y);
+    return b;
+}
+
 struct CollapseArgs {
     const float4* n2;      // BVH2 nodes
     float4* n8;            // CWBVH8 nodes, 5 x float4 each
@@ -283,14 +290,90 @@ struct CollapseArgs {
     uint32_t* bvh2Of;      // work map: BVH8 node index -> BVH2 node it collapses
     uint32_t* counters;    // [0] nodes allocated, [1] leaf slots allocated
     uint32_t n;
+    // SAH-optimal collapse only (NX_COLLAPSE_SAH_OPTIMAL): C(n, i) decisions of every BVH2 node, dp_eval_kernel
+    const unsigned long long* dpDec;
 };
 
-__device__ __forceinline__ Box load_box2(const float4* n2, uint32_t i)
+// ------------------------------------------------------------------------------- SAH-optimal collapse: the C(n, i) table ----
+// The reference's CPU BVH8Builder (Nexus/src/Geometry/BVH/BVH8Builder.cpp:31-145; Ylitie, Karras, Laine 2017 §3): for every
+// BVH2 node n and i = 1..7, C(n, i) is the cheapest way to turn n's subtree into at most i BVH8 children, with the
+// decision that achieves it - LEAF (at most max_leaf_prims primitives), INTERNAL (n becomes a BVH8 node: 7 roots shared
+// between its two children, plus C_NODE * area) or DISTRIBUTE (the roots are split k / i-1-k between the children).  The
+// recursion with a memo table becomes one bottom-up pass here: a thread starts at every leaf and climbs, the second
+// thread to arrive at a node (atomic counter) evaluates it from its finished children.
+// dpDec[n]: byte i = decision (bits 0-1) | left count (bits 2-4) | right count (bits 5-7) for i = 0..6; byte 7 = primitives
+// in the subtree, saturated at 255.  dpCost[n * 7 + i] = C(n, i + 1).
+constexpr uint32_t kDpLeaf = 0u, kDpInternal = 1u, kDpDistribute = 2u;
+constexpr float kCPrim = 0.3f, kCNode = 1.0f;      // BVH8Builder.h:7-8
+
+struct DpArgs {
+    const float4* n2; uint32_t n;
+    uint32_t* parent; uint32_t* arrived;           // arrived: one counter per inner node
+    float* cost; unsigned long long* dec;
+    uint32_t maxLeafPrims;
+};
+
+__global__ void dp_parent_kernel(DpArgs a)
 {
-    const float4 p = __ldg(n2 + 2 * (size_t)i), q = __ldg(n2 + 2 * (size_t)i + 1);
-    Box b; b.lo = v3(p.x, p.y, p.z); b.hi = v3(p.w, q.x, q.y);
-    return b;
+    for (uint32_t i = a.n + blockIdx.x * blockDim.x + threadIdx.x; i < 2 * a.n - 1; i += gridDim.x * blockDim.x) {
+        const float4 q = __ldg(a.n2 + 2 * (size_t)i + 1);
+        a.parent[__float_as_uint(q.z)] = i; a.parent[__float_as_uint(q.w)] = i;
+        a.arrived[i - a.n] = 0u;
+    }
 }
+
+__global__ void __launch_bounds__(128) dp_eval_kernel(DpArgs a)
+{
+    const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= a.n) return;
+    {
+        const float c = __fmul_rn(__fmul_rn(half_area_ref(load_box2(a.n2, leaf)), 1.0f), kCPrim);     // CLeaf(node, 1), :31-37
+        for (int i = 0; i < 7; i++) __stcg(a.cost + 7 * (size_t)leaf + i, c);
+        __stcg(a.dec + leaf, 1ull << 56);                                                             // LEAF for every i, one primitive
+    }
+    __threadfence();
+    uint32_t p = __ldcg(a.parent + leaf);
+    while (p != NX_INVALID)
+    {
+        if (atomicAdd(a.arrived + (p - a.n), 1u) == 0u) return;     // the sibling subtree is not finished: its thread continues
+        __threadfence();
+        const float4 q = __ldg(a.n2 + 2 * (size_t)p + 1);
+        const uint32_t L = __float_as_uint(q.z), R = __float_as_uint(q.w);
+        float cl[7], cr[7], c[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) { cl[i] = __ldcg(a.cost + 7 * (size_t)L + i); cr[i] = __ldcg(a.cost + 7 * (size_t)R + i); }
+        const uint32_t tris = min(255u, (uint32_t)(__ldcg(a.dec + L) >> 56) + (uint32_t)(__ldcg(a.dec + R) >> 56));
+        const float area = half_area_ref(load_box2(a.n2, p));
+        unsigned long long dec = (unsigned long long)tris << 56;
+        // CDistribute(node, j) (:39-57): best split of j - 1 ... wait for it ... roots: k to the left child, j - 1 - k to the right
+        auto distribute = [&](int j, uint32_t& l, uint32_t& r) {
+            float best = 1.0e30f;
+#pragma unroll
+            for (int k = 0; k < 7; k++) if (k < j) { const float v = __fadd_rn(cl[k], cr[j - 1 - k]); if (v < best) { best = v; l = (uint32_t)k; r = (uint32_t)(j - 1 - k); } }
+            return best;
+        };
+        {   // i = 0: leaf or internal (:92-113)
+            uint32_t l = 0, r = 0;
+            const float internal = __fadd_rn(distribute(7, l, r), __fmul_rn(area, kCNode));
+            const float leafCost = tris > a.maxLeafPrims ? 1.0e30f : __fmul_rn(__fmul_rn(area, (float)tris), kCPrim);
+            if (leafCost < internal) { c[0] = leafCost; dec |= kDpLeaf; }
+            else { c[0] = internal; dec |= kDpInternal | (l << 2) | (r << 5); }
+        }
+#pragma unroll
+        for (int i = 1; i < 7; i++) {   // i roots + 1: distribute, or keep the solution with one root fewer (:115-131)
+            uint32_t l = 0, r = 0;
+            const float d = distribute(i, l, r);
+            if (d < c[i - 1]) { c[i] = d; dec |= (unsigned long long)(kDpDistribute | (l << 2) | (r << 5)) << (8 * i); }
+            else { c[i] = c[i - 1]; dec |= ((dec >> (8 * (i - 1))) & 0xffull) << (8 * i); }
+        }
+#pragma unroll
+        for (int i = 0; i < 7; i++) __stcg(a.cost + 7 * (size_t)p + i, c[i]);
+        __stcg(a.dec + p, dec);
+        __threadfence();
+        p = __ldcg(a.parent + p);
+    }
+}
+
 __device__ __forceinline__ uint32_t ceil_log2_biased(float x)   // biased exponent of the smallest power of two >= x
 {
     const uint32_t u = __float_as_uint(x);
@@ -306,7 +389,11 @@ __device__ __forceinline__ uint32_t quant(float c, float p, float inv, bool up)
     return q & 0xffu;
 }
 
-// Collapses BVH2 node `root2` into BVH8 node `self`.
+// Collapses BVH2 node `root2` into BVH8 node `self`.  OPT = false: the reference GPU converter's rule (open the inner child in
+// the highest array position until eight children, WideConverter.cu:291-324).  OPT = true: the children the C(n, i) table
+// prescribes (GetChildrenIndices, BVH8Builder.cpp:165-199), leaf children holding up to max_leaf_prims primitives; slot
+// assignment, quantisation and node layout are the GPU converter's in both modes.
+template <bool OPT>
 __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root2)
 {
     const uint32_t lane = lane_id();
@@ -323,6 +410,33 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
         parent.lo = v3(p.x, p.y, p.z); parent.hi = v3(p.w, q.x, q.y);
         uint32_t l = __float_as_uint(q.z), r = __float_as_uint(q.w);
         int open = 0;
+        if (OPT)
+        {
+            // entries: node | count << 28 | expand flag << 31; the left entry is pushed last so that it is processed first and
+            // the children come out in the recursion's order
+            uint32_t stack[9]; int sp = 0;
+            auto decOf = [&](uint32_t node, uint32_t i) { return (uint32_t)(__ldg(a.dpDec + node) >> (8 * i)) & 0xffu; };
+            const uint32_t d0 = decOf(root2, 0);
+            if ((d0 & 3u) == kDpLeaf) stack[sp++] = root2;                  // the whole tree is one leaf child
+            else stack[sp++] = root2 | 0x80000000u;                          // count 0
+            while (sp)
+            {
+                const uint32_t e = stack[--sp], node = e & 0x0fffffffu;
+                if (!(e & 0x80000000u)) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (k == (int)count) child[k] = node;
+                    if ((decOf(node, 0) & 3u) == kDpInternal) innerMask |= 1u << count;
+                    count++;
+                    continue;
+                }
+                const uint32_t d = decOf(node, (e >> 28) & 7u), lc = (d >> 2) & 7u, rc = (d >> 5) & 7u;
+                const float4 nq = __ldg(a.n2 + 2 * (size_t)node + 1);
+                const uint32_t L = __float_as_uint(nq.z), R = __float_as_uint(nq.w);
+                stack[sp++] = R | (rc << 28) | ((decOf(R, rc) & 3u) == kDpDistribute ? 0x80000000u : 0u);
+                stack[sp++] = L | (lc << 28) | ((decOf(L, lc) & 3u) == kDpDistribute ? 0x80000000u : 0u);
+            }
+        }
+        else
         // Open inner children (highest array position first) until eight children or only leaves remain.  Of each opened
         // pair the smaller-area child takes the vacated position, the other is appended (WideConverter.cu:291-324).
         while (true)
@@ -382,7 +496,25 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
         const uint32_t c = (slotOf >> (4 * s)) & 0xfu;
         if (live && c != 0xfu) { if ((innerMask >> c) & 1u) slotInner |= 1u << s; else slotLeaf |= 1u << s; }
     }
-    const uint32_t nInner = __popc(slotInner), nLeaf = __popc(slotLeaf);
+    // primitives per leaf slot (4 bits each): one in the reference GPU mode, the subtree's count in the SAH-optimal mode
+    uint32_t slotPrims = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 8; s++) {
+        if (!((slotLeaf >> s) & 1u)) continue;
+        uint32_t cnt = 1;
+        if (OPT) {
+            const uint32_t c = (slotOf >> (4 * s)) & 0xfu;
+            uint32_t id = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k == (int)c) id = child[k];
+            cnt = (uint32_t)(__ldg(a.dpDec + id) >> 56);
+        }
+        slotPrims |= cnt << (4 * s);
+    }
+    uint32_t nLeaf = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 8; s++) nLeaf += (slotPrims >> (4 * s)) & 0xfu;
+    const uint32_t nInner = __popc(slotInner);
 
     // one atomic per warp and counter: inclusive scan of (inner | leaf << 16)
     uint32_t packed = nInner | (nLeaf << 16), scan = packed;
@@ -427,9 +559,22 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
             m = 0x20u | (24u + s);
             a.bvh2Of[childBase + bits_below(slotInner, s)] = id;
         } else {
-            const uint32_t off = bits_below(slotLeaf, s);
-            m = 0x20u | off;
-            a.primIdx[primBase + off] = id;   // a BVH2 leaf's index is its primitive id
+            uint32_t off = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < 8; t++) if (t < s) off += (slotPrims >> (4 * t)) & 0xfu;
+            const uint32_t cnt = (slotPrims >> (4 * s)) & 0xfu;
+            m = (((1u << cnt) - 1u) << 5) | off;              // unary primitive count | first primitive (1 -> 0x20 | off)
+            if (!OPT) a.primIdx[primBase + off] = id;         // a BVH2 leaf's index is its primitive id
+            else {
+                // the subtree's leaves, left to right (CountTriangles, BVH8Builder.cpp:282-293): at most three
+                uint32_t st[4]; int sp = 0; uint32_t k = 0;
+                st[sp++] = id;
+                while (sp) {
+                    const uint32_t u = st[--sp];
+                    if (u < n) a.primIdx[primBase + off + k++] = u;
+                    else { const float4 uq = __ldg(a.n2 + 2 * (size_t)u + 1); st[sp++] = __float_as_uint(uq.w); st[sp++] = __float_as_uint(uq.z); }
+                }
+            }
         }
         const Box cb = load_box2(a.n2, id);
         const uint32_t w = s >> 2, sh = (s & 3u) * 8u;
@@ -450,7 +595,8 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
 }
 
 // Persistent cooperative kernel: BVH8 level L is exactly the node index range allocated while level L-1 was processed.
-__global__ void __launch_bounds__(kCollapseBlock) collapse_kernel(CollapseArgs a)
+template <bool OPT>
+__global__ void __launch_bounds__(kCollapseBlock, 4) collapse_kernel(CollapseArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     uint32_t begin = 0, end = 1;
@@ -463,7 +609,7 @@ __global__ void __launch_bounds__(kCollapseBlock) collapse_kernel(CollapseArgs a
         {
             const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
             const uint32_t node = begin + k;
-            collapse_one(a, node, k < span ? __ldcg(a.bvh2Of + node) : NX_INVALID);   // whole warps call in, idle lanes pass INVALID
+            collapse_one<OPT>(a, node, k < span ? __ldcg(a.bvh2Of + node) : NX_INVALID);   // whole warps call in, idle lanes pass INVALID
         }
         __threadfence();
         grid.sync();
@@ -504,10 +650,10 @@ __global__ void bvh2_cost_kernel(const float4* __restrict__ n2, uint32_t nodeCou
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NX_FULL, v, o);
     if (lane_id() == 0) atomicAdd(out, v);
 }
-__global__ void bvh8_cost_kernel(const float4* __restrict__ n8, uint32_t nodeCount, Box scene, double* out)
+__global__ void bvh8_cost_kernel(const float4* __restrict__ n8, uint32_t nodeCount, Box scene, double* out)   // out[0] cost, out[1] children
 {
     const float rootArea = half_area_ref(scene);
-    double v = 0.0;
+    double v = 0.0, kids = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nodeCount; i += gridDim.x * blockDim.x) {
         const float4 h0 = __ldg(n8 + 5 * (size_t)i), h1 = __ldg(n8 + 5 * (size_t)i + 1), h2 = __ldg(n8 + 5 * (size_t)i + 2),
                      h3 = __ldg(n8 + 5 * (size_t)i + 3), h4 = __ldg(n8 + 5 * (size_t)i + 4);
@@ -521,14 +667,15 @@ __global__ void bvh8_cost_kernel(const float4* __restrict__ n8, uint32_t nodeCou
             const uint32_t w = s >> 2, sh = (s & 3u) * 8u;
             const uint32_t m = (meta[w] >> sh) & 0xffu;
             if (!m) continue;
+            kids += 1.0;
             Box b;
             b.lo = v3(__fmaf_rn(ex, (float)((lox[w] >> sh) & 0xffu), h0.x), __fmaf_rn(ey, (float)((loy[w] >> sh) & 0xffu), h0.y), __fmaf_rn(ez, (float)((loz[w] >> sh) & 0xffu), h0.z));
             b.hi = v3(__fmaf_rn(ex, (float)((hix[w] >> sh) & 0xffu), h0.x), __fmaf_rn(ey, (float)((hiy[w] >> sh) & 0xffu), h0.y), __fmaf_rn(ez, (float)((hiz[w] >> sh) & 0xffu), h0.z));
             v += (double)(((m & 0x1fu) >= 24u ? 2.0f : 3.0f) * __fdividef(half_area_ref(b), rootArea));
         }
     }
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NX_FULL, v, o);
-    if (lane_id() == 0) atomicAdd(out, v);
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(NX_FULL, v, o); kids += __shfl_xor_sync(NX_FULL, kids, o); }
+    if (lane_id() == 0) { atomicAdd(out, v); atomicAdd(out + 1, kids); }
 }
 
 // ------------------------------------------------------------------------------------------ host driver ----
@@ -646,7 +793,7 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     StageTimer timer(s, metrics != nullptr);
 
     const size_t cap = ((size_t)4 * n - 1 + 6) / 7;   // worst case node count (BVHBuilder.cpp:184-186)
-    CollapseArgs ca; ca.n2 = b2.nodes; ca.n = n;
+    CollapseArgs ca; ca.n2 = b2.nodes; ca.n = n; ca.dpDec = nullptr;
     NX_CUDA(ctx, allocAsync(&ca.n8, 5 * cap, s));
     NX_CUDA(ctx, allocAsync(&ca.primIdx, n, s));
     NX_CUDA(ctx, allocAsync(&ca.bvh2Of, cap, s));
@@ -655,15 +802,34 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     NX_CUDA(ctx, cudaMemcpyAsync(ca.counters, initCounters, 8, cudaMemcpyHostToDevice, s));
     NX_CUDA(ctx, cudaMemcpyAsync(ca.bvh2Of, &root2, 4, cudaMemcpyHostToDevice, s));
 
+    const bool optimal = cfg && cfg->collapse == NX_COLLAPSE_SAH_OPTIMAL && n > 1;
+    if (cfg && cfg->collapse != NX_COLLAPSE_REFERENCE_GPU && cfg->collapse != NX_COLLAPSE_SAH_OPTIMAL) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH8: unknown collapse mode %d", cfg->collapse);
+    DpArgs dp; std::memset(&dp, 0, sizeof(dp));
     timer.begin();
+    if (optimal)
+    {
+        if (2ull * n - 1 > 0x0fffffffull) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH8: the SAH-optimal collapse packs node ids into 28 bits (n = %u)", n);
+        dp.n2 = b2.nodes; dp.n = n;
+        dp.maxLeafPrims = cfg->max_leaf_prims >= 1 && cfg->max_leaf_prims <= 3 ? (uint32_t)cfg->max_leaf_prims : 3u;   // P_MAX, BVH8Builder.h:9
+        NX_CUDA(ctx, allocAsync(&dp.parent, 2 * (size_t)n - 1, s));
+        NX_CUDA(ctx, allocAsync(&dp.arrived, n, s));
+        NX_CUDA(ctx, allocAsync(&dp.cost, 7 * (2 * (size_t)n - 1), s));
+        NX_CUDA(ctx, allocAsync(&dp.dec, 2 * (size_t)n - 1, s));
+        NX_CUDA(ctx, cudaMemsetAsync(dp.parent, 0xff, 4 * (2 * (size_t)n - 1), s));
+        dp_parent_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp);
+        dp_eval_kernel<<<div_up(n, 128u), 128, 0, s>>>(dp);
+        ca.dpDec = dp.dec;
+    }
     if (n == 1) single_leaf_kernel<<<1, 1, 0, s>>>(ca);
     else {
         int perSm = 0;
-        NX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, collapse_kernel, kCollapseBlock, 0));
+        const void* fn = optimal ? (const void*)collapse_kernel<true> : (const void*)collapse_kernel<false>;
+        NX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, kCollapseBlock, 0));
         uint32_t grid = std::min<uint32_t>((uint32_t)(perSm * ctx->sm_count), std::max<uint32_t>(1u, div_up((uint32_t)cap, kCollapseBlock)));
         void* args[] = {&ca};
-        NX_CUDA(ctx, cudaLaunchCooperativeKernel((void*)collapse_kernel, dim3(grid), dim3(kCollapseBlock), args, 0, s));
+        NX_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCollapseBlock), args, 0, s));
     }
+    if (optimal) { cudaFreeAsync(dp.parent, s); cudaFreeAsync(dp.arrived, s); cudaFreeAsync(dp.cost, s); cudaFreeAsync(dp.dec, s); }
     if (metrics) { metrics->bvh8_ms = timer.end(); metrics->total_ms += metrics->bvh8_ms; }
     uint32_t counters[2] = {0, 0};
     NX_CUDA(ctx, cudaMemcpyAsync(counters, ca.counters, 8, cudaMemcpyDeviceToHost, s));
@@ -674,14 +840,14 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     out->nodes = (nx_bvh8_node*)ca.n8; out->node_count = counters[0]; out->prim_idx = ca.primIdx; out->prim_count = n; out->bounds = b2.bounds;
     if (metrics)
     {
-        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(&dCost, 1, s));
-        NX_CUDA(ctx, cudaMemsetAsync(dCost, 0, 8, s));
+        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(&dCost, 2, s));
+        NX_CUDA(ctx, cudaMemsetAsync(dCost, 0, 16, s));
         Box sb; sb.lo = v3(b2.bounds.bmin[0], b2.bounds.bmin[1], b2.bounds.bmin[2]); sb.hi = v3(b2.bounds.bmax[0], b2.bounds.bmax[1], b2.bounds.bmax[2]);
         bvh8_cost_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(ca.n8, counters[0], sb, dCost);
-        double cost = 0; NX_CUDA(ctx, cudaMemcpyAsync(&cost, dCost, 8, cudaMemcpyDeviceToHost, s));
+        double cost[2] = {0, 0}; NX_CUDA(ctx, cudaMemcpyAsync(cost, dCost, 16, cudaMemcpyDeviceToHost, s));
         NX_CUDA(ctx, cudaStreamSynchronize(s));
-        metrics->bvh8_cost = (float)cost;
-        metrics->avg_children_per_node = (float)(n + counters[0] - 1) / (float)counters[0];
+        metrics->bvh8_cost = (float)cost[0];
+        metrics->avg_children_per_node = (float)(cost[1] / (double)counters[0]);   // = (n + nodes - 1) / nodes with one primitive per leaf
         cudaFreeAsync(dCost, s);
     }
     cudaFreeAsync(b2.nodes, s); cudaFreeAsync(ca.bvh2Of, s); cudaFreeAsync(ca.counters, s);
@@ -694,7 +860,7 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
 // Internal entry used by the scene code (same translation-unit-free interface as the public C ABI).
 int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out)
 {
-    nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed;
+    nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed; cfg.collapse = ctx->scene_collapse; cfg.max_leaf_prims = ctx->scene_max_leaf_prims;
     return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out);
 }
 

@@ -32,6 +32,11 @@ int nx_ctx_create(int device, nx_ctx** out)
         unsigned a = 0, b = 0;
         if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = ctx->tune_tri_any = a; ctx->tune_inst = ctx->tune_inst_any = b; }
     }
+    if (const char* t = std::getenv("NX_SCENE_COLLAPSE")) {      // "mode,max_leaf_prims"
+        int a = 0, b = 0;
+        if (std::sscanf(t, "%d,%d", &a, &b) >= 1) { ctx->scene_collapse = a; ctx->scene_max_leaf_prims = b; }
+    }
+    if (const char* t = std::getenv("NX_SCENE_BLAS_SPEED")) ctx->scene_blas_speed = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_TRACE_TUNE_ANY")) {
         unsigned a = 0, b = 0;
         if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri_any = a; ctx->tune_inst_any = b; }
@@ -60,6 +65,13 @@ int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes
     if (!ctx || tri_lanes > 32 || inst_lanes > 32) return NX_ERR_INVALID;
     ctx->tune_tri = tri_lanes; ctx->tune_inst = inst_lanes;
     if (!std::getenv("NX_TRACE_TUNE_ANY")) { ctx->tune_tri_any = tri_lanes; ctx->tune_inst_any = inst_lanes; }
+    return NX_OK;
+}
+
+int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims)
+{
+    if (!ctx || (collapse != NX_COLLAPSE_REFERENCE_GPU && collapse != NX_COLLAPSE_SAH_OPTIMAL) || max_leaf_prims < 0 || max_leaf_prims > 3) return NX_ERR_INVALID;
+    ctx->scene_collapse = collapse; ctx->scene_max_leaf_prims = max_leaf_prims;
     return NX_OK;
 }
 

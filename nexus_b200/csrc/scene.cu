@@ -251,7 +251,7 @@ int nx_scene_add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_da
     if (data) NX_CUDA(ctx, cudaMemcpyAsync(m.dTriData, data, 96 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     else default_tridata_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, n, m.dTriData);
     mesh_sphere(tris, n, m.sphere);
-    int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, 1 /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
+    int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
     if (rc) return rc;
     leaf_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris);
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -406,6 +406,113 @@ int orc_build_bvh8(const void* bvh2Nodes, uint32_t n, void* outNodes8, uint32_t*
     return leafCounter == n ? 0 : -2;
 }
 
+// SAH-optimal collapse on the GPU builder's conventions: the C(n, i) table and child selection of the reference's CPU
+// BVH8Builder (Nexus/src/Geometry/BVH/BVH8Builder.cpp:31-199, constants BVH8Builder.h:7-9; restated in full, with its own slot
+// ordering and quantisation, in oracle_sah.cpp), emitted with the GPU converter's slot assignment (GreedyAssignment,
+// WideConverter.cu:106-153), quantisation and node layout (CreateBVH8Node, :156-206), in FIFO (= canonical) order.  This is
+// what nx_build_config::collapse = NX_COLLAPSE_SAH_OPTIMAL builds.  bvh2: root at 2n-2, leaves [0, n) in primitive order.
+int orc_build_bvh8_optimal(const void* bvh2Nodes, uint32_t n, uint32_t maxLeafPrims, void* outNodes8, uint32_t* outPrimIdx, uint32_t* outNodeCount)
+{
+    if (n == 1) return orc_build_bvh8(bvh2Nodes, n, outNodes8, outPrimIdx, outNodeCount);
+    const uint32_t total = 2 * n - 1, root = 2 * n - 2;
+    std::vector<Node2> n2(total);
+    std::memcpy(n2.data(), bvh2Nodes, total * sizeof(Node2));
+    enum { LEAF = 0, INTERNAL = 1, DISTRIBUTE = 2, UNDEF = 3 };
+    struct Ev { float cost; uint8_t dec = UNDEF, l = 0, r = 0; };
+    std::vector<Ev> ev((size_t)total * 7);
+    std::vector<uint32_t> tris(total, 0);
+    // children before parents: post-order from the root, iterative
+    std::vector<uint32_t> order; order.reserve(total);
+    { std::vector<uint32_t> st{root}; while (!st.empty()) { uint32_t u = st.back(); st.pop_back(); order.push_back(u); if (n2[u].left != INVALID) { st.push_back(n2[u].left); st.push_back(n2[u].right); } } }
+    for (size_t k = order.size(); k-- > 0;) {
+        const uint32_t u = order[k];
+        const Node2& nd = n2[u];
+        const float area = ftz(nd.bounds.area());
+        Ev* e = &ev[(size_t)u * 7];
+        if (nd.left == INVALID) { tris[u] = 1; for (int i = 0; i < 7; i++) { e[i].cost = (area * 1.0f) * 0.3f; e[i].dec = LEAF; } continue; }
+        tris[u] = std::min(255u, tris[nd.left] + tris[nd.right]);
+        const Ev* cl = &ev[(size_t)nd.left * 7]; const Ev* cr = &ev[(size_t)nd.right * 7];
+        auto distribute = [&](int j, uint8_t& l, uint8_t& r) {
+            float best = 1.0e30f;
+            for (int k2 = 0; k2 < j; k2++) { const float v = cl[k2].cost + cr[j - 1 - k2].cost; if (v < best) { best = v; l = (uint8_t)k2; r = (uint8_t)(j - 1 - k2); } }
+            return best;
+        };
+        { uint8_t l = 0, r = 0;
+          const float internal = distribute(7, l, r) + area * 1.0f;
+          const float leaf = tris[u] > maxLeafPrims ? 1.0e30f : (area * (float)tris[u]) * 0.3f;
+          if (leaf < internal) { e[0].cost = leaf; e[0].dec = LEAF; } else { e[0].cost = internal; e[0].dec = INTERNAL; e[0].l = l; e[0].r = r; } }
+        for (int i = 1; i < 7; i++) {
+            uint8_t l = 0, r = 0;
+            const float d = distribute(i, l, r);
+            if (d < e[i - 1].cost) { e[i].cost = d; e[i].dec = DISTRIBUTE; e[i].l = l; e[i].r = r; } else e[i] = e[i - 1];
+        }
+    }
+    auto dec = [&](uint32_t u, int i) -> const Ev& { return ev[(size_t)u * 7 + i]; };
+
+    Node8* out = (Node8*)outNodes8;
+    uint32_t nodeCounter = 1, leafCounter = 0;
+    std::queue<std::pair<uint32_t, uint32_t>> work;
+    work.push({root, 0});
+    while (!work.empty()) {
+        auto [i2, i8] = work.front(); work.pop();
+        const Node2& node = n2[i2];
+        uint32_t child[8], childCount = 0, innerMask = 0;
+        // GetChildrenIndices (BVH8Builder.cpp:165-199), iteratively: entries are (node, count, expand)
+        struct Ent { uint32_t node; int cnt; bool expand; };
+        std::vector<Ent> st;
+        if (dec(i2, 0).dec == LEAF) st.push_back({i2, 0, false}); else st.push_back({i2, 0, true});
+        while (!st.empty()) {
+            Ent e = st.back(); st.pop_back();
+            if (!e.expand) { if (dec(e.node, 0).dec == INTERNAL) innerMask |= 1u << childCount; child[childCount++] = e.node; continue; }
+            const Ev& d = dec(e.node, e.cnt);
+            const uint32_t L = n2[e.node].left, R = n2[e.node].right;
+            st.push_back({R, d.r, dec(R, d.r).dec == DISTRIBUTE});
+            st.push_back({L, d.l, dec(L, d.l).dec == DISTRIBUTE});
+        }
+        // GreedyAssignment, WideConverter.cu:106-153
+        f3 parentCentroid = node.bounds.bMin + node.bounds.bMax;
+        uint32_t assignments = INVALID;
+        for (uint32_t c = 0; c < childCount; c++) {
+            const AABB& cb = n2[child[c]].bounds;
+            f3 off = parentCentroid - (cb.bMax + cb.bMin);
+            float best = -FLT_MAX; uint32_t bestSlot = 0xf;
+            for (uint32_t s = 0; s < 8; s++) {
+                if (nibble(assignments, s) != 0xf) continue;
+                float cost = ((s >> 2) & 1 ? -1.0f : 1.0f) * off.x + ((s >> 1) & 1 ? -1.0f : 1.0f) * off.y + (s & 1 ? -1.0f : 1.0f) * off.z;
+                if (cost > best) { best = cost; bestSlot = s; }
+            }
+            setNibble(assignments, bestSlot, c);
+        }
+        uint32_t newInner = 0, leafMask = 0, leafPrims = 0, primsOf[8] = {0};
+        for (uint32_t i = 0; i < 8; i++) {
+            uint32_t a = nibble(assignments, i);
+            if (a == 0xf) continue;
+            bool bit = (innerMask >> a) & 1;
+            newInner |= (uint32_t)bit << i; leafMask |= (uint32_t)(!bit) << i;
+            if (!bit) { primsOf[i] = tris[child[a]]; leafPrims += primsOf[i]; }
+        }
+        innerMask = newInner;
+        uint32_t innerCount = __builtin_popcount(innerMask);
+        uint32_t childBase = innerCount ? nodeCounter : 0; nodeCounter += innerCount;
+        uint32_t primBase = leafPrims ? leafCounter : 0; leafCounter += leafPrims;
+        Node8 nd = makeNode8(n2, node.bounds, child, childBase, primBase, assignments, innerMask, leafMask);
+        uint32_t off = 0;
+        for (uint32_t i = 0; i < 8; i++) {
+            uint32_t a = nibble(assignments, i);
+            if (a == 0xf) continue;
+            if (innerMask & (1u << i)) { work.push({child[a], childBase + bitsBelow(innerMask, i)}); continue; }
+            nd.meta[i] = (uint8_t)((((1u << primsOf[i]) - 1u) << 5) | off);
+            // the subtree's leaves left to right (CountTriangles, BVH8Builder.cpp:282-293)
+            std::vector<uint32_t> ls{child[a]}; uint32_t k = 0;
+            while (!ls.empty()) { uint32_t u = ls.back(); ls.pop_back(); if (n2[u].left == INVALID) outPrimIdx[primBase + off + k++] = n2[u].right; else { ls.push_back(n2[u].right); ls.push_back(n2[u].left); } }
+            off += primsOf[i];
+        }
+        out[i8] = nd;
+    }
+    *outNodeCount = nodeCounter;
+    return leafCounter == n ? 0 : -2;
+}
+
 // Canonical renumbering of a BVH8 (root = node 0): breadth-first, children in slot order.  Node payloads are copied
 // byte for byte except childBaseIdx / primBaseIdx.  Returns 0, or <0 if the input is structurally broken.
 int orc_canon_bvh8(const void* nodesIn, const uint32_t* primIdxIn, uint32_t nodeCount, uint32_t primCount,

@@ -5,7 +5,7 @@
 # 3. launch list + --set full capture of the builder kernels (H-PLOC, collapse) on the 10M-triangle benchmark mesh
 TAG=${1:-r01}; WL=${2:-instanced10m_4k}
 OUT=gpurun_out/prof_$TAG; mkdir -p $OUT
-CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-like-for-like"
 K='regex:trace_closest_kernel|trace_any_kernel|shade_kernel|generate_kernel|frame_totals_kernel|resolve_rgba8_kernel'
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 140 --csv --log-file $OUT/launches_$WL.csv $CMD > $OUT/launches_$WL.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:trace_closest_kernel -s 32 -c 3 -f -o $OUT/trace_closest_$WL $CMD > $OUT/full_closest_$WL.log 2>&1

@@ -85,6 +85,17 @@ def build_bvh8(bvh2_nodes, n):
     return nodes[:cnt.value].copy(), prim_idx
 
 
+def build_bvh8_optimal(bvh2_nodes, n, max_leaf_prims=3):
+    """SAH-optimal collapse (reference CPU BVH8Builder's C(n, i) table) in the GPU builder's node conventions."""
+    cap = (4 * n - 1 + 6) // 7
+    nodes = np.zeros((cap, 20), np.uint32)
+    prim_idx = np.zeros(n, np.uint32)
+    cnt = C.c_uint32(0)
+    rc = oracle().orc_build_bvh8_optimal(_p(np.ascontiguousarray(bvh2_nodes)), C.c_uint32(n), C.c_uint32(max_leaf_prims), _p(nodes), _p(prim_idx), C.byref(cnt))
+    assert rc == 0, rc
+    return nodes[:cnt.value].copy(), prim_idx
+
+
 def canon_bvh8(nodes, prim_idx):
     nodes = np.ascontiguousarray(nodes).view(np.uint32).reshape(-1, 20)
     prim_idx = np.ascontiguousarray(prim_idx, np.uint32)

@@ -138,3 +138,44 @@ def test_bench_size_build_properties(ctx, have_ref):
         assert O.ref().nxref_benchmark_bvh8(prims.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, 1, 0, 1, mm.ctypes.data_as(C.c_void_p), C.byref(cnt), None) == 0
         assert cnt.value == len(n8)
         assert abs(m["bvh2_cost"] - mm[6]) <= 1e-4 * mm[6] and abs(m["bvh8_cost"] - mm[7]) <= 1e-4 * mm[7]
+
+
+@pytest.mark.parametrize("pmax", [1, 2, 3])
+@pytest.mark.parametrize("case", builder_cases(), ids=lambda c: c[0])
+def test_sah_optimal_collapse_equals_cpu_restatement(ctx, case, pmax):
+    """nx_build_config::collapse = NX_COLLAPSE_SAH_OPTIMAL (SURVEY.md §8 row a20 on the GPU): the C(n, i) table and child
+    selection of the reference's CPU BVH8Builder, run bottom-up on the device, against the CPU restatement
+    (oracle_bvh.cpp: orc_build_bvh8_optimal) applied to the device's own BVH2: canonical CWBVH8 and leaf order bit for bit."""
+    name, prims, speed = case
+    n = prims.shape[0]
+    tri = 1 if prims.shape[1] == 9 else 0
+    b2 = nx.BuildBVH2(ctx, prims, prioritizeSpeed=speed)
+    n2 = b2.ToHost(); b2.Free()
+    b8 = nx.BuildBVH8(ctx, prims, prioritizeSpeed=speed, collapse=nx.COLLAPSE_SAH_OPTIMAL, maxLeafPrims=pmax)
+    n8, p8 = b8.ToHost(); b8.Free()
+    pb, _ = O.prim_bounds(prims, tri)
+    assert O.check_bvh8(n8, p8, pb) == 0
+    o8, op8 = O.build_bvh8_optimal(n2, n, pmax)
+    c8, cp8 = O.canon_bvh8(n8, p8)
+    oc8, ocp8 = O.canon_bvh8(o8, op8)
+    assert c8.shape == oc8.shape and (c8 == oc8).all() and (cp8 == ocp8).all()
+    meta = n8.view(np.uint8).reshape(-1, 80)[:, 24:32]
+    leaf = (meta != 0) & ((meta & 0x1f) < 24)
+    assert np.isin(meta[leaf] >> 5, [1, 3, 7][:pmax]).all()          # unary primitive counts 1..pmax
+
+
+def test_sah_optimal_collapse_large_and_fewer_nodes(ctx):
+    """500k triangles of the NexusBVH benchmark mesh: same equality at size."""
+    prims = scenes.test_triangles(500_000)
+    n = len(prims)
+    b2 = nx.BuildBVH2(ctx, prims, prioritizeSpeed=True)
+    n2 = b2.ToHost(); b2.Free()
+    for pmax in (1, 3):
+        b8 = nx.BuildBVH8(ctx, prims, prioritizeSpeed=True, collapse=nx.COLLAPSE_SAH_OPTIMAL, maxLeafPrims=pmax)
+        n8, p8 = b8.ToHost(); b8.Free()
+        o8, op8 = O.build_bvh8_optimal(n2, n, pmax)
+        c8, cp8 = O.canon_bvh8(n8, p8)
+        oc8, ocp8 = O.canon_bvh8(o8, op8)
+        assert c8.shape == oc8.shape and (c8 == oc8).all() and (cp8 == ocp8).all()
+    with pytest.raises(nx.NexusError):
+        nx.BuildBVH8(ctx, prims[:100], collapse=7)
