@@ -125,3 +125,30 @@ def test_full_resolution_properties(ctx):
     occ = scene.TraceAny(rays)
     assert (occ.astype(bool) == (got["t"] < nx.MISS_T)).all()
     scene.close()
+
+
+def test_hits_do_not_depend_on_the_collapse(ctx):
+    """The scene code builds its BLASes / TLAS with the SAH-optimal collapse by default; with the reference GPU converter's rule
+    (NexusBVH-identical trees) every closest hit - ids, t, u, v - and every any-hit answer is the same, bit for bit: the tree
+    only decides which boxes are visited, the triangle test and the deterministic tie-break decide the hit."""
+    desc = scenes.with_triangle_data(scenes.instanced_scene(n_blas=16, n_instances=64, nu=30, nv=30))
+    res = (640, 360)
+    o, d = scenes.camera_rays(desc["camera"], res)
+    rng = np.random.default_rng(4)
+    ro = rng.uniform(-12, 12, (60000, 3)).astype(np.float32); ro[:, 1] = rng.uniform(0.2, 6.0, 60000)
+    rd = rng.normal(size=(60000, 3)).astype(np.float32); rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    rays = nx.make_rays(np.concatenate([o, ro]), np.concatenate([d, rd]))
+    shadow = nx.make_rays(rays["origin"], rays["direction"], 3.0)
+    out = []
+    try:
+        for mode, pmax in ((nx.COLLAPSE_SAH_OPTIMAL, 2), (nx.COLLAPSE_SAH_OPTIMAL, 3), (nx.COLLAPSE_REFERENCE_GPU, 0)):
+            ctx.SetSceneCollapse(mode, pmax)
+            scene = scenes.build(ctx, desc, res)
+            n8, _ = scene.MeshBVH(2).ToHost()
+            out.append((scene.TraceClosest(rays), scene.TraceAny(shadow), len(n8)))
+            scene.close()
+    finally:
+        ctx.SetSceneCollapse(nx.COLLAPSE_SAH_OPTIMAL, 2)
+    for hits, occ, _ in out[:-1]:
+        assert (hits.view(np.uint8) == out[-1][0].view(np.uint8)).all() and (occ == out[-1][1]).all()
+    assert out[0][2] < out[-1][2]          # the optimal collapse of a rock BLAS needs fewer nodes than the reference rule
