@@ -361,6 +361,31 @@ int nx_scene_update(nx_scene* s)
         }
         rc = upload_vec(ctx, &s->dShadeInst, si); if (rc) return rc;
 
+        // world-space bounding sphere of every instance's geometry (conservative: radius and centre rounding padded)
+        std::vector<float4> spheres(s->instances.size());
+        for (size_t i = 0; i < spheres.size(); i++) {
+            const HostInstance& h = s->instances[i];
+            const HostMesh& hm = s->meshes[h.meshIdx];
+            double c[3];
+            for (int r = 0; r < 3; r++) c[r] = (double)h.m[4 * r] * hm.sphere[0] + (double)h.m[4 * r + 1] * hm.sphere[1] + (double)h.m[4 * r + 2] * hm.sphere[2] + (double)h.m[4 * r + 3];
+            const double rad = hm.sphere[3] * max_stretch(h.m) * (1.0 + 1e-5) + 1e-30;
+            spheres[i] = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(rad * (1.0 + 1e-6)) + 1e-6f * (float)(std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2])));
+        }
+        // The reference bounds an instance by the world AABB of the eight transformed corners of its mesh AABB
+        // (MeshInstance::GetBounds, N/Scene/MeshInstance.h:42-66), which for a rotated object is up to sqrt(3) too wide.  Outside
+        // the NexusBVH-identical mode the TLAS is built over that box clipped to the bounding sphere's box: still conservative,
+        // and the node test then rejects what the per-instance sphere test would otherwise have to.
+        if (ctx->scene_collapse != NX_COLLAPSE_REFERENCE_GPU)
+            for (size_t i = 0; i < bounds.size(); i++) {
+                const float4 sp = spheres[i];
+                const float c3[3] = {sp.x, sp.y, sp.z};
+                for (int a = 0; a < 3; a++) {
+                    const float lo = std::nextafterf(c3[a] - sp.w, -INFINITY), hi = std::nextafterf(c3[a] + sp.w, INFINITY);
+                    const float nlo = std::max(bounds[i].bmin[a], lo), nhi = std::min(bounds[i].bmax[a], hi);
+                    if (nlo <= nhi) { bounds[i].bmin[a] = nlo; bounds[i].bmax[a] = nhi; }
+                }
+            }
+
         // Scene::BuildTLAS (src/Scene/Scene.cpp:65-78): BuildBVH8<AABB> over the instance bounds, default config (64-bit keys)
         nx_aabb* dBounds = nullptr;
         rc = upload_vec(ctx, &dBounds, bounds); if (rc) return rc;
@@ -377,11 +402,7 @@ int nx_scene_update(nx_scene* s)
         for (size_t k = 0; k < order.size(); k++) {
             const HostInstance& h = s->instances[order[k]];
             std::memcpy(&ti[k].r0, h.inv, 48);
-            const HostMesh& hm = s->meshes[h.meshIdx];
-            double c[3];
-            for (int r = 0; r < 3; r++) c[r] = (double)h.m[4 * r] * hm.sphere[0] + (double)h.m[4 * r + 1] * hm.sphere[1] + (double)h.m[4 * r + 2] * hm.sphere[2] + (double)h.m[4 * r + 3];
-            const double rad = hm.sphere[3] * max_stretch(h.m) * (1.0 + 1e-5) + 1e-30;
-            ti[k].sphere = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(rad * (1.0 + 1e-6)) + 1e-6f * (float)(std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2])));
+            ti[k].sphere = spheres[order[k]];
             ti[k].nodes = (const float4*)s->meshes[h.meshIdx].bvh.nodes; ti[k].ltris = s->meshes[h.meshIdx].dLeafTris;
         }
         rc = upload_vec(ctx, &s->dTravInst, ti); if (rc) return rc;
