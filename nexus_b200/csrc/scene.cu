@@ -137,6 +137,33 @@ __global__ void leaf_triangles_kernel(const float* __restrict__ tris, const uint
 }
 
 // Default shading data when the caller passes none: flat geometric normal, zero tangents and texture coordinates.
+// World-space AABB of an instance's actual geometry: one block per instance transforms every vertex of its mesh with the
+// instance matrix (row-major 3x4) and reduces min / max.  out: 6 floats per instance.
+struct InstGeom { const float* tris; uint32_t triCount; float m[12]; };
+__global__ void __launch_bounds__(256) instance_geometry_bounds_kernel(const InstGeom* __restrict__ inst, float* __restrict__ out)
+{
+    const InstGeom g = inst[blockIdx.x];
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (uint32_t v = threadIdx.x; v < 3u * g.triCount; v += blockDim.x) {
+        const float x = __ldg(g.tris + 3 * (size_t)v), y = __ldg(g.tris + 3 * (size_t)v + 1), z = __ldg(g.tris + 3 * (size_t)v + 2);
+        for (int a = 0; a < 3; a++) {
+            const float w = g.m[4 * a] * x + g.m[4 * a + 1] * y + g.m[4 * a + 2] * z + g.m[4 * a + 3];
+            lo[a] = fminf(lo[a], w); hi[a] = fmaxf(hi[a], w);
+        }
+    }
+    __shared__ float red[6][8];
+    for (int a = 0; a < 3; a++) {
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(NX_FULL, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(NX_FULL, hi[a], o)); }
+        if ((threadIdx.x & 31) == 0) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[threadIdx.x][0];
+        for (int w = 1; w < 8; w++) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+        out[6 * (size_t)blockIdx.x + threadIdx.x] = v;
+    }
+}
+
 __global__ void default_tridata_kernel(const float* __restrict__ tris, uint32_t n, float* __restrict__ out)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -376,6 +403,28 @@ int nx_scene_update(nx_scene* s)
         // the NexusBVH-identical mode the TLAS is built over that box clipped to the bounding sphere's box: still conservative,
         // and the node test then rejects what the per-instance sphere test would otherwise have to.
         if (ctx->scene_collapse != NX_COLLAPSE_REFERENCE_GPU)
+        {
+            // ... and to the box of the transformed vertices themselves (padded for the rounding of the transform)
+            std::vector<InstGeom> ig(s->instances.size());
+            for (size_t i = 0; i < ig.size(); i++) {
+                const HostInstance& h = s->instances[i];
+                ig[i].tris = s->meshes[h.meshIdx].dTris; ig[i].triCount = s->meshes[h.meshIdx].bvh.prim_count; std::memcpy(ig[i].m, h.m, 48);
+            }
+            InstGeom* dIg = nullptr; float* dGb = nullptr;
+            rc = upload_vec(ctx, &dIg, ig); if (rc) return rc;
+            NX_CUDA(ctx, cudaMallocAsync((void**)&dGb, 24 * ig.size(), ctx->stream));
+            instance_geometry_bounds_kernel<<<(uint32_t)ig.size(), 256, 0, ctx->stream>>>(dIg, dGb);
+            std::vector<float> gb(6 * ig.size());
+            NX_CUDA(ctx, cudaMemcpyAsync(gb.data(), dGb, 24 * ig.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFreeAsync(dIg, ctx->stream); cudaFreeAsync(dGb, ctx->stream);
+            for (size_t i = 0; i < bounds.size(); i++)
+                for (int a = 0; a < 3; a++) {
+                    const float ext = gb[6 * i + 3 + a] - gb[6 * i + a], mag = std::max(std::fabs(gb[6 * i + a]), std::fabs(gb[6 * i + 3 + a]));
+                    const float pad = 1.0e-5f * ext + 4.0e-6f * mag + 1.0e-30f;
+                    const float nlo = std::max(bounds[i].bmin[a], gb[6 * i + a] - pad), nhi = std::min(bounds[i].bmax[a], gb[6 * i + 3 + a] + pad);
+                    if (nlo <= nhi) { bounds[i].bmin[a] = nlo; bounds[i].bmax[a] = nhi; }
+                }
             for (size_t i = 0; i < bounds.size(); i++) {
                 const float4 sp = spheres[i];
                 const float c3[3] = {sp.x, sp.y, sp.z};
@@ -385,6 +434,7 @@ int nx_scene_update(nx_scene* s)
                     if (nlo <= nhi) { bounds[i].bmin[a] = nlo; bounds[i].bmax[a] = nhi; }
                 }
             }
+        }
 
         // Scene::BuildTLAS (src/Scene/Scene.cpp:65-78): BuildBVH8<AABB> over the instance bounds, default config (64-bit keys)
         nx_aabb* dBounds = nullptr;
