@@ -32,6 +32,18 @@ int nx_ctx_create(int device, nx_ctx** out)
         unsigned a = 0, b = 0;
         if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = ctx->tune_tri_any = a; ctx->tune_inst = ctx->tune_inst_any = b; }
     }
+    // L2 persistence for the top level of the scene (north_star: "L2-persistence hints for top-level nodes"): a small set-aside,
+    // the window itself is set when a scene's TLAS is built (scene.cu).  NX_L2_PERSIST_MB=0 turns the hints off.
+    {
+        int maxPersist = 0, maxWindow = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        size_t want = 4u << 20;
+        if (const char* t = std::getenv("NX_L2_PERSIST_MB")) want = (size_t)std::max(0, std::atoi(t)) << 20;
+        want = std::min(want, (size_t)std::max(maxPersist, 0));
+        if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) { ctx->l2_persist_bytes = want; ctx->l2_window_max = (size_t)std::max(maxWindow, 0); }
+        cudaGetLastError();
+    }
     if (const char* t = std::getenv("NX_SCENE_COLLAPSE")) {      // "mode,max_leaf_prims"
         int a = 0, b = 0;
         if (std::sscanf(t, "%d,%d", &a, &b) >= 1) { ctx->scene_collapse = a; ctx->scene_max_leaf_prims = b; }

@@ -28,6 +28,8 @@ struct nx_ctx {
     // NX_SCENE_COLLAPSE="0,0" restore trees identical to NexusBVH's.
     int scene_collapse = NX_COLLAPSE_SAH_OPTIMAL, scene_max_leaf_prims = 2;
     int scene_blas_speed = 1;   // Mesh::Mesh builds its BLAS with prioritizeSpeed = true (32-bit Morton keys), N/Assets/Mesh.h:37
+    // L2 set-aside for persisting accesses (top-level nodes + instance records of the scene being rendered); 0 = hints off
+    size_t l2_persist_bytes = 0, l2_window_max = 0;
     // scratch reused by the builder's parity hook
     std::vector<uint64_t> dbg_codes;
 };

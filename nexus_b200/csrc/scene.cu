@@ -213,7 +213,7 @@ int nxi_scene_view(nx_scene* s, DSceneView* v)
 {
     if (s->dirtyInstances || s->dirtyMaterials || s->dirtyLights) { int rc = nx_scene_update(s); if (rc) return rc; }
     std::memset(v, 0, sizeof(*v));
-    v->trace.tlasNodes = (const float4*)s->tlas.nodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst;
+    v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst;
     v->shadeInst = s->dShadeInst; v->meshes = s->dMeshes; v->materials = s->dMaterials; v->lights = s->dLights;
     v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr;
     v->camera = nxi_camera_to_device(s->camera, s->width, s->height);
@@ -245,7 +245,14 @@ void nx_scene_destroy(nx_scene* s)
     cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
     for (auto& m : s->meshes) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); nx_bvh8_free(ctx, &m.bvh); }
     if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
-    cudaFree(s->dTravInst); cudaFree(s->dShadeInst); cudaFree(s->dMeshes); cudaFree(s->dMaterials); cudaFree(s->dLights);
+    if (s->dTop && ctx->l2_persist_bytes) {   // drop the window that points at this scene's top-level block
+        cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaStreamSetAttribute(ctx->stream_aux, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
+    cudaFree(s->dTop); cudaFree(s->dShadeInst); cudaFree(s->dMeshes); cudaFree(s->dMaterials); cudaFree(s->dLights);
     if (s->hasHdr) { cudaDestroyTextureObject(s->hdr); cudaFreeArray(s->hdrArray); }
     cudaStreamSynchronize(ctx->stream);
     delete s;
@@ -455,7 +462,29 @@ int nx_scene_update(nx_scene* s)
             ti[k].sphere = spheres[order[k]];
             ti[k].nodes = (const float4*)s->meshes[h.meshIdx].bvh.nodes; ti[k].ltris = s->meshes[h.meshIdx].dLeafTris;
         }
-        rc = upload_vec(ctx, &s->dTravInst, ti); if (rc) return rc;
+        // top-level block: TLAS nodes + traversal records, one allocation, L2-persisting window on the two trace streams
+        {
+            const size_t nodeBytes = 80 * (size_t)s->tlas.node_count, recBytes = sizeof(DTravInst) * ti.size();
+            if (s->dTop) { cudaFreeAsync(s->dTop, ctx->stream); s->dTop = nullptr; }
+            s->topBytes = nodeBytes + recBytes;
+            NX_CUDA(ctx, cudaMallocAsync(&s->dTop, s->topBytes, ctx->stream));
+            s->dTopNodes = (const float4*)s->dTop;
+            s->dTravInst = (DTravInst*)((char*)s->dTop + nodeBytes);
+            NX_CUDA(ctx, cudaMemcpyAsync(s->dTop, s->tlas.nodes, nodeBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            NX_CUDA(ctx, cudaMemcpyAsync(s->dTravInst, ti.data(), recBytes, cudaMemcpyHostToDevice, ctx->stream));
+            NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // ti is a local
+            if (ctx->l2_persist_bytes) {
+                cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
+                attr.accessPolicyWindow.base_ptr = s->dTop;
+                attr.accessPolicyWindow.num_bytes = std::min(s->topBytes, ctx->l2_window_max);
+                attr.accessPolicyWindow.hitRatio = s->topBytes <= ctx->l2_persist_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)s->topBytes;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaStreamSetAttribute(ctx->stream_aux, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaGetLastError();   // a hint: failure to set it is not an error
+            }
+        }
     }
 
     if (s->dirtyLights || s->dirtyInstances || s->dirtyMaterials)

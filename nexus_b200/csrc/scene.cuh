@@ -72,7 +72,10 @@ struct nx_scene {
 
     // device mirrors
     nx_bvh8 tlas{};
-    DTravInst* dTravInst = nullptr;
+    DTravInst* dTravInst = nullptr;        // inside dTop
+    // Everything a ray touches before it enters an instance, in ONE allocation so that one L2 access-policy window covers it:
+    // [copy of the TLAS nodes | traversal records in TLAS leaf order].  Marked persisting in L2 on both trace streams.
+    void* dTop = nullptr; size_t topBytes = 0; const float4* dTopNodes = nullptr;
     DShadeInst* dShadeInst = nullptr;
     DMesh* dMeshes = nullptr;
     nx_material* dMaterials = nullptr;
