@@ -20,8 +20,10 @@ int nx_ctx_create(int device, nx_ctx** out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return NX_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NX_ERR_CUDA; }
+    int prLeast = 0, prGreatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);     // main stream: highest priority; auxiliary (shadow rays): lowest
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prLeast) != cudaSuccess) { delete ctx; return NX_ERR_CUDA; }
     // keep freed blocks in the stream-ordered pool: builds and per-frame scratch reuse them without going to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

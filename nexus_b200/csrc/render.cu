@@ -88,7 +88,7 @@ struct nx_renderer {
     uint32_t width = 0, height = 0;
     WaveBuffers wb{};
     uint32_t frames = 0;            // frames in the accumulation
-    cudaEvent_t evStart = nullptr, evStop = nullptr, evShade = nullptr, evShadow = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evShade = nullptr, evShadow[2] = {nullptr, nullptr};
     bool timed = false;
     uint32_t launches = 0;
     uint32_t pathLengthLast = 0;
@@ -164,8 +164,8 @@ int free_buffers(nx_renderer* r)
     nx_ctx* ctx = r->ctx;
     cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
     WaveBuffers& w = r->wb;
-    cudaFree(w.ext[0]); cudaFree(w.ext[1]); cudaFree(w.state[0]); cudaFree(w.state[1]); cudaFree(w.hits); cudaFree(w.shadow);
-    cudaFree(w.shadowRad); cudaFree(w.accum); cudaFree(w.counters); cudaFree(w.totals);
+    cudaFree(w.ext[0]); cudaFree(w.ext[1]); cudaFree(w.state[0]); cudaFree(w.state[1]); cudaFree(w.hits); cudaFree(w.shadow[0]); cudaFree(w.shadow[1]);
+    cudaFree(w.shadowRad[0]); cudaFree(w.shadowRad[1]); cudaFree(w.accum); cudaFree(w.counters); cudaFree(w.totals);
     w = WaveBuffers{};
     return NX_OK;
 }
@@ -179,7 +179,7 @@ int alloc_buffers(nx_renderer* r, uint32_t w, uint32_t h)
     NX_CUDA(ctx, cudaMalloc((void**)&b.ext[0], sizeof(nx_ray) * px)); NX_CUDA(ctx, cudaMalloc((void**)&b.ext[1], sizeof(nx_ray) * px));
     NX_CUDA(ctx, cudaMalloc((void**)&b.state[0], 16 * px)); NX_CUDA(ctx, cudaMalloc((void**)&b.state[1], 16 * px));
     NX_CUDA(ctx, cudaMalloc((void**)&b.hits, sizeof(nx_hit) * px));
-    NX_CUDA(ctx, cudaMalloc((void**)&b.shadow, sizeof(nx_ray) * px)); NX_CUDA(ctx, cudaMalloc((void**)&b.shadowRad, 16 * px));
+    for (int k = 0; k < 2; k++) { NX_CUDA(ctx, cudaMalloc((void**)&b.shadow[k], sizeof(nx_ray) * px)); NX_CUDA(ctx, cudaMalloc((void**)&b.shadowRad[k], 16 * px)); }
     NX_CUDA(ctx, cudaMalloc((void**)&b.accum, 12 * px));
     NX_CUDA(ctx, cudaMalloc((void**)&b.counters, sizeof(WaveCounters))); NX_CUDA(ctx, cudaMalloc((void**)&b.totals, sizeof(WaveTotals)));
     NX_CUDA(ctx, cudaMemsetAsync(b.accum, 0, 12 * px, ctx->stream));
@@ -200,7 +200,8 @@ int nx_renderer_create(nx_ctx* ctx, uint32_t width, uint32_t height, nx_renderer
     int rc = alloc_buffers(r, width, height);
     if (rc) { delete r; return rc; }
     cudaEventCreate(&r->evStart); cudaEventCreate(&r->evStop);
-    cudaEventCreateWithFlags(&r->evShade, cudaEventDisableTiming); cudaEventCreateWithFlags(&r->evShadow, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&r->evShade, cudaEventDisableTiming);
+    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&r->evShadow[k], cudaEventDisableTiming);
     if (cudaMalloc((void**)&r->dWork, 2 * sizeof(TraceStats)) != cudaSuccess || cudaMemset(r->dWork, 0, 2 * sizeof(TraceStats)) != cudaSuccess) {
         ctx->error = "nx_renderer_create: cudaMalloc failed"; nx_renderer_destroy(r); return NX_ERR_CUDA;
     }
@@ -213,7 +214,7 @@ void nx_renderer_destroy(nx_renderer* r)
     if (!r) return;
     DeviceGuard guard(r->ctx->device);
     free_buffers(r);
-    cudaEventDestroy(r->evStart); cudaEventDestroy(r->evStop); cudaEventDestroy(r->evShade); cudaEventDestroy(r->evShadow);
+    cudaEventDestroy(r->evStart); cudaEventDestroy(r->evStop); cudaEventDestroy(r->evShade); cudaEventDestroy(r->evShadow[0]); cudaEventDestroy(r->evShadow[1]);
     for (cudaEvent_t e : r->evPool) cudaEventDestroy(e);
     cudaFree(r->dWork);
     delete r;
@@ -282,24 +283,27 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
         closest(wb.ext[0], 0);
         for (uint32_t b = 1; b <= L; b++)
         {
-            // the shadow rays of bounce b-1 must have been consumed before shade(b) refills the shadow queue
-            if (b > 1) NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evShadow, 0));
+            // two shadow queues: shade(b) refills queue b & 1, which the shadow trace of bounce b-2 must have consumed; the shadow
+            // trace of bounce b-1 may still be running and overlaps this shade and the next extension trace
+            if (b > 2) NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evShadow[b & 1u], 0));
             r->prof_begin(2, s);
             nxi_launch_shade(sv, wb, b, frame, gShade, s);
             r->prof_end(s);
             r->launches++;
             NX_CUDA(ctx, cudaEventRecord(r->evShade, s));
-            // shadow rays on the auxiliary stream overlap the extension trace (the reference's graph runs them as siblings)
+            // The extension trace is on the critical path (the next shade waits for it), so it is launched first and its stream
+            // has the higher priority; the shadow rays on the auxiliary stream fill in behind it and under the next shade
+            // (the reference's graph runs the two traces as siblings).
+            if (b < L) closest(wb.ext[b & 1u], b);
             NX_CUDA(ctx, cudaStreamWaitEvent(sa, r->evShade, 0));
             r->prof_begin(3, sa);
-            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, r->dWork + 1, tuneAny);
-            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow, 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad, wb.accum, nullptr, tuneAny);
+            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow[b & 1u], 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad[b & 1u], wb.accum, r->dWork + 1, tuneAny);
+            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow[b & 1u], 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad[b & 1u], wb.accum, nullptr, tuneAny);
             r->prof_end(sa);
-            NX_CUDA(ctx, cudaEventRecord(r->evShadow, sa));
+            NX_CUDA(ctx, cudaEventRecord(r->evShadow[b & 1u], sa));
             r->launches++;
-            if (b < L) closest(wb.ext[b & 1u], b);
         }
-        NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evShadow, 0));
+        NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evShadow[L & 1u], 0));      // the auxiliary stream is in order: the last shadow trace is the last to finish
         frame_totals_kernel<<<1, 32, 0, s>>>(wb, L);
         r->launches++;
     }

@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel
         }
         const uint32_t s = warp_append(&wb.counters->shCount[bounce], o.shadow);
         if (o.shadow) {
-            float4* r = reinterpret_cast<float4*>(wb.shadow + s);
+            float4* r = reinterpret_cast<float4*>(wb.shadow[bounce & 1u] + s);
             r[0] = make_float4(o.shO.x, o.shO.y, o.shO.z, o.shDist);
             r[1] = make_float4(o.shD.x, o.shD.y, o.shD.z, __uint_as_float(pixel));
-            wb.shadowRad[s] = make_float4(o.shL.x, o.shL.y, o.shL.z, 0.f);
+            wb.shadowRad[bounce & 1u][s] = make_float4(o.shL.x, o.shL.y, o.shL.z, 0.f);
         }
     };
 

@@ -26,8 +26,8 @@ struct WaveBuffers {
     nx_ray* ext[2];        // extension-ray queues (ping-pong); nx_ray::pad carries the pixel index
     float4* state[2];      // (throughput.rgb, last bsdf pdf) of the path that owns the ray
     nx_hit* hits;          // closest hits, same index as the traced queue
-    nx_ray* shadow;        // shadow rays; tmax = distance to the light sample, pad = pixel index
-    float4* shadowRad;     // radiance to add when the shadow ray is unoccluded
+    nx_ray* shadow[2];     // shadow rays of bounce b in shadow[b & 1]; tmax = distance to the light sample, pad = pixel index
+    float4* shadowRad[2];  // radiance to add when the shadow ray is unoccluded
     float* accum;          // running SUM of radiance, 3 floats per pixel, row 0 = bottom row like the reference
     WaveCounters* counters;
     WaveTotals* totals;
