@@ -94,6 +94,7 @@ __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 #define NX_MAGIC_PLANES 0x2d
 #endif
 
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // one MUFU; 2^-22 relative
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ uint32_t shl_wrap(uint32_t v, uint32_t n) { uint32_t r; asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(v), "r"(n)); return r; }
 
@@ -343,6 +344,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             } else if (wantI) {
                 // first instance of the group whose bounding sphere the ray can reach before its current limit
                 const float dd = xdot(d, d), limit = ANY_HIT ? tmax : fminf(tmax, hitT);
+                const float dlen = sqrt_fast(dd), far = limit * dd * 1.0001f;   // the 1e-4 slack also covers the approximate root
                 uint32_t bit = 0; bool found = false;
                 while (tgroup.y && !found) {
                     bit = 31u - __clz(tgroup.y);
@@ -352,7 +354,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                     const float b = xdot(oc, d), c2 = xdot(oc, oc), r2 = sp4.w * sp4.w;
                     // miss if the closest approach is outside the sphere (slack covers rounding), if the sphere lies behind
                     // the origin, or if it starts beyond the current limit
-                    const bool miss = (c2 * dd - b * b) > (r2 + 1.0e-4f * c2) * dd || (b < 0.0f && c2 > r2) || (b - sp4.w * sqrtf(dd)) > limit * dd * 1.0001f;
+                    const bool miss = (c2 * dd - b * b) > (r2 + 1.0e-4f * c2) * dd || (b < 0.0f && c2 > r2) || (b - sp4.w * dlen) > far;
                     found = !miss || !tune.sphereCull;
                     if (STATS && !found) cS++;
                 }
