@@ -175,3 +175,37 @@ def test_read_rgba8_uses_the_scene_tone_mapping(ctx):
     with pytest.raises(nx.NexusError):
         nx.display_transform(ctx, lin, 9, 0.0)
     pt.close(); scene.close()
+
+
+def test_dynamic_scene_updates_rebuild_the_tlas(ctx):
+    """SURVEY.md §8 row f-4 (core): MeshInstance::SetTransform / AssetManager::InvalidateMaterial mark the scene dirty and the next
+    Update rebuilds the TLAS, the traversal records and the light list (Scene::Update, Scene.cpp:34-63; the reference rebuilds
+    its TLAS from scratch on any instance change).  An edited scene must behave exactly like one created in the final state:
+    identical closest hits (bit for bit) and an identical frame (the RNG is keyed on pixel, frame and bounce)."""
+    res = (160, 120)
+
+    def make(final):
+        desc = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=9, nu=16, nv=16, path_length=4))
+        if final:
+            desc["instances"][3]["position"] = (1.5, 2.0, -0.5); desc["instances"][3]["rotation"] = (10.0, 200.0, 35.0); desc["instances"][3]["scale"] = (1.3, 1.3, 1.3)
+            desc["materials"][2].baseColor = (0.1, 0.8, 0.2); desc["materials"][2].roughness = 0.6
+        return desc, scenes.build(ctx, desc, res)
+
+    desc_a, a = make(False)
+    desc_b, b = make(True)
+    o, d = scenes.camera_rays(desc_a["camera"], res)
+    rays = nx.make_rays(o, d)
+    before = a.TraceClosest(rays)
+    # edit scene a into scene b's state through the host API
+    nx.MeshInstance(a, 3, desc_a["instances"][3]["mesh"]).SetTransform((1.5, 2.0, -0.5), (10.0, 200.0, 35.0), (1.3, 1.3, 1.3))
+    m = desc_a["materials"][2]; m.baseColor = (0.1, 0.8, 0.2); m.roughness = 0.6
+    a.GetAssetManager().InvalidateMaterial(2, m)
+    a.Update()
+    after, want = a.TraceClosest(rays), b.TraceClosest(rays)
+    assert (after.view(np.uint8) == want.view(np.uint8)).all()
+    assert not (after.view(np.uint8) == before.view(np.uint8)).all()          # the edit is visible
+    pa, pb = nx.PathTracer(ctx, res), nx.PathTracer(ctx, res)
+    pa.Render(a, frames=2, firstFrame=1); pb.Render(b, frames=2, firstFrame=1)
+    ia, ib = pa.ReadAccumulation(), pb.ReadAccumulation()
+    assert np.allclose(ia, ib, rtol=1e-4, atol=1e-5)                          # float atomics: summation order only
+    pa.close(); pb.close(); a.close(); b.close()
