@@ -185,6 +185,9 @@ int nx_scene_set_instance_transform(nx_scene* scene, uint32_t inst, const float 
 int nx_scene_add_light(nx_scene* scene, const nx_light* light);                         /* Scene::AddLight */
 int nx_scene_set_camera(nx_scene* scene, const nx_camera* cam);
 int nx_scene_set_render_settings(nx_scene* scene, const nx_render_settings* rs);
+/* AssetManager::AddTexture + Texture::ToDevice (src/Assets/Texture.cpp:12-46): HOST RGBA8 (is_hdr 0; srgb: decode in the sampler) or RGBA32F
+ * (is_hdr 1) pixels, wrap addressing, linear filtering.  Returns the index nx_material::*_map refers to, or < 0. */
+int nx_scene_add_texture(nx_scene* s, const void* host_rgba, uint32_t w, uint32_t h, int is_hdr, int srgb);
 int nx_scene_set_hdr_map(nx_scene* scene, const float* rgba, uint32_t w, uint32_t h);   /* Scene::AddHDRMap (RGBA32F equirect) */
 /* Scene::Update: uploads dirty instances/materials, rebuilds the TLAS (BuildBVH8<AABB>, default config) and maintains the
  * emissive-mesh light list (Scene::UpdateSceneLighting, src/Scene/Scene.cpp:157-219). */

@@ -84,6 +84,7 @@ struct Material {                       // src/Assets/Material.h:6-26, same defa
     float3 baseColor{0.8f, 0.8f, 0.8f}; float metalness = 0.0f, roughness = 0.3f, anisotropy = 0.0f, specularWeight = 1.0f;
     float3 specularColor{1.0f, 1.0f, 1.0f}; float ior = 1.5f, transmission = 0.0f;
     float3 emissionColor{1.0f, 1.0f, 1.0f}; float intensity = 0.0f, opacity = 1.0f;
+    int32_t baseColorMapId = -1, emissiveMapId = -1, normalMapId = -1, roughnessMapId = -1, metalnessMapId = -1, metallicRoughnessMapId = -1;
     nx_material pod() const
     {
         nx_material m{};
@@ -93,7 +94,8 @@ struct Material {                       // src/Assets/Material.h:6-26, same defa
         m.ior = ior; m.transmission = transmission;
         m.emission_color[0] = emissionColor.x; m.emission_color[1] = emissionColor.y; m.emission_color[2] = emissionColor.z;
         m.intensity = intensity; m.opacity = opacity;
-        m.base_color_map = m.emissive_map = m.normal_map = m.roughness_map = m.metalness_map = m.metallic_roughness_map = -1;
+        m.base_color_map = baseColorMapId; m.emissive_map = emissiveMapId; m.normal_map = normalMapId;
+        m.roughness_map = roughnessMapId; m.metalness_map = metalnessMapId; m.metallic_roughness_map = metallicRoughnessMapId;
         return m;
     }
 };
@@ -129,6 +131,8 @@ public:
     // AddMesh builds the BLAS immediately (Mesh::Mesh, src/Assets/Mesh.h:15-46: BuildBVH8<Triangle>, prioritizeSpeed = true)
     uint32_t AddMesh(const std::string& name, uint32_t materialIdx, const std::vector<NXB::Triangle>& triangles, const std::vector<nx_triangle_data>& triangleData = {});
     void InvalidateMaterial(uint32_t idx, const Material& m);
+    // AddTexture + Texture::ToDevice (src/Assets/Texture.cpp:12-46): RGBA8 (isHDR false) or RGBA32F pixels; returns the id Material::*MapId uses
+    uint32_t AddTexture(const void* rgbaPixels, uint32_t width, uint32_t height, bool isHDR = false, bool sRGB = false);
 private:
     Scene* scene_;
 };
@@ -184,6 +188,7 @@ inline void MeshInstance::SetTransform(float3 position, float3 rotationDeg, floa
     scene_->context().check(nx_scene_set_instance_transform(scene_->handle(), idx_, p, r, s), "SetTransform");
 }
 inline uint32_t AssetManager::AddMaterial(const Material& m) { const nx_material p = m.pod(); return (uint32_t)scene_->context().check(nx_scene_add_material(scene_->handle(), &p), "AddMaterial"); }
+inline uint32_t AssetManager::AddTexture(const void* px, uint32_t w, uint32_t h, bool isHDR, bool sRGB) { return (uint32_t)scene_->context().check(nx_scene_add_texture(scene_->handle(), px, w, h, isHDR, sRGB), "AddTexture"); }
 inline void AssetManager::InvalidateMaterial(uint32_t idx, const Material& m) { const nx_material p = m.pod(); scene_->context().check(nx_scene_set_material(scene_->handle(), idx, &p), "InvalidateMaterial"); }
 inline uint32_t AssetManager::AddMesh(const std::string& name, uint32_t materialIdx, const std::vector<NXB::Triangle>& tris, const std::vector<nx_triangle_data>& data)
 {

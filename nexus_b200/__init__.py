@@ -217,6 +217,7 @@ class Material:
         self.emissionColor = (1.0, 1.0, 1.0)
         self.intensity = 0.0
         self.opacity = 1.0
+        self.baseColorMap = self.emissiveMap = self.normalMap = self.roughnessMap = self.metalnessMap = self.metallicRoughnessMap = -1
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -230,7 +231,8 @@ class Material:
         p.ior, p.transmission = self.ior, self.transmission
         p.emission_color[:] = self.emissionColor
         p.intensity, p.opacity = self.intensity, self.opacity
-        p.base_color_map = p.emissive_map = p.normal_map = p.roughness_map = p.metalness_map = p.metallic_roughness_map = -1
+        p.base_color_map, p.emissive_map, p.normal_map = self.baseColorMap, self.emissiveMap, self.normalMap
+        p.roughness_map, p.metalness_map, p.metallic_roughness_map = self.roughnessMap, self.metalnessMap, self.metallicRoughnessMap
         return p
 
 
@@ -312,6 +314,15 @@ class AssetManager:
             raise ValueError("triangleData must have one row per triangle")
         return check(self.scene.ctx._h, lib().nx_scene_add_mesh(self.scene._h, _ptr(tris), _ptr(td) if td is not None else None,
                                                                  C.c_uint32(tris.shape[0]), C.c_uint32(materialIdx)), f"AddMesh({name})")
+
+    def AddTexture(self, pixels, sRGB=False):
+        """AddTexture (AssetManager.h:31) + Texture::ToDevice (Texture.cpp:12-46).  pixels: (h, w, 4) uint8 (normalised reads,
+        sRGB decoded by the sampler when sRGB) or float32 (HDR).  Returns the index Material.*Map refers to."""
+        pixels = np.ascontiguousarray(pixels)
+        if pixels.ndim != 3 or pixels.shape[2] != 4 or pixels.dtype not in (np.uint8, np.float32):
+            raise ValueError("texture pixels must be (h, w, 4) uint8 or float32")
+        return check(self.scene.ctx._h, lib().nx_scene_add_texture(self.scene._h, _ptr(pixels), C.c_uint32(pixels.shape[1]), C.c_uint32(pixels.shape[0]),
+                                                                    C.c_int(int(pixels.dtype == np.float32)), C.c_int(int(sRGB))), "AddTexture")
 
     def InvalidateMaterial(self, index, material):
         p = material.pod()

@@ -211,11 +211,11 @@ DCamera nxi_camera_to_device(const nx_camera& c, uint32_t w, uint32_t h)
 
 int nxi_scene_view(nx_scene* s, DSceneView* v)
 {
-    if (s->dirtyInstances || s->dirtyMaterials || s->dirtyLights) { int rc = nx_scene_update(s); if (rc) return rc; }
+    if (s->dirtyInstances || s->dirtyMaterials || s->dirtyLights || s->dirtyTextures) { int rc = nx_scene_update(s); if (rc) return rc; }
     std::memset(v, 0, sizeof(*v));
     v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst;
     v->shadeInst = s->dShadeInst; v->meshes = s->dMeshes; v->materials = s->dMaterials; v->lights = s->dLights;
-    v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr;
+    v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr; v->textures = s->dTextures;
     v->camera = nxi_camera_to_device(s->camera, s->width, s->height);
     v->useMIS = s->settings.use_mis ? 1u : 0u; v->pathLength = (uint32_t)s->settings.path_length;
     for (int k = 0; k < 3; k++) v->bg[k] = s->settings.background_color[k];
@@ -252,6 +252,8 @@ void nx_scene_destroy(nx_scene* s)
         cudaCtxResetPersistingL2Cache();
         cudaGetLastError();
     }
+    for (size_t i = 0; i < s->textures.size(); i++) { cudaDestroyTextureObject(s->textures[i]); cudaFreeArray(s->textureArrays[i]); }
+    cudaFree(s->dTextures);
     cudaFree(s->dTop); cudaFree(s->dShadeInst); cudaFree(s->dMeshes); cudaFree(s->dMaterials); cudaFree(s->dLights);
     if (s->hasHdr) { cudaDestroyTextureObject(s->hdr); cudaFreeArray(s->hdrArray); }
     cudaStreamSynchronize(ctx->stream);
@@ -340,6 +342,33 @@ int nx_scene_add_light(nx_scene* s, const nx_light* l)
     s->userLights.push_back(*l); s->dirtyLights = true;
     return (int)s->userLights.size() - 1;
 }
+// AssetManager::AddTexture + Texture::ToDevice (src/Assets/AssetManager.h:31, src/Assets/Texture.cpp:12-46): RGBA8 (normalised float
+// reads, optional sRGB decode in the sampler) or RGBA32F pixels into a CUDA array behind a texture object with wrap addressing,
+// linear filtering and normalised coordinates.  Returns the texture index that nx_material::*_map refers to.
+int nx_scene_add_texture(nx_scene* s, const void* rgba, uint32_t w, uint32_t h, int isHdr, int srgb)
+{
+    if (!s || !rgba || !w || !h) return NX_ERR_INVALID;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    const cudaChannelFormatDesc desc = isHdr ? cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat) : cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+    cudaArray_t arr = nullptr;
+    NX_CUDA(ctx, cudaMallocArray(&arr, &desc, w, h));
+    const size_t pitch = (size_t)w * (isHdr ? 16 : 4);
+    NX_CUDA(ctx, cudaMemcpy2DToArray(arr, 0, 0, rgba, pitch, pitch, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc res; std::memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+    cudaTextureDesc tex; std::memset(&tex, 0, sizeof(tex));
+    tex.addressMode[0] = tex.addressMode[1] = cudaAddressModeWrap;
+    tex.sRGB = (srgb && !isHdr) ? 1 : 0;
+    tex.filterMode = cudaFilterModeLinear;
+    tex.readMode = isHdr ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+    tex.normalizedCoords = 1;
+    cudaTextureObject_t obj = 0;
+    NX_CUDA(ctx, cudaCreateTextureObject(&obj, &res, &tex, nullptr));
+    s->textures.push_back(obj); s->textureArrays.push_back(arr); s->dirtyTextures = true;
+    return (int)s->textures.size() - 1;
+}
+
 int nx_scene_set_camera(nx_scene* s, const nx_camera* c) { if (!s || !c) return NX_ERR_INVALID; s->camera = *c; return NX_OK; }
 int nx_scene_set_render_settings(nx_scene* s, const nx_render_settings* r)
 {
@@ -375,7 +404,11 @@ int nx_scene_update(nx_scene* s)
     if (s->materials.empty()) NX_FAIL(ctx, NX_ERR_STATE, "Scene::Update: the scene has no materials");
     for (const auto& i : s->instances) if (i.materialIdx >= s->materials.size()) NX_FAIL(ctx, NX_ERR_INVALID, "instance refers to material %u of %zu", i.materialIdx, s->materials.size());
 
+    for (const auto& m : s->materials)
+        for (int32_t id : {m.base_color_map, m.emissive_map, m.normal_map, m.roughness_map, m.metalness_map, m.metallic_roughness_map})
+            if (id < -1 || id >= (int32_t)s->textures.size()) NX_FAIL(ctx, NX_ERR_INVALID, "a material refers to texture %d of %zu", id, s->textures.size());
     if (s->dirtyMaterials) { int rc = upload_vec(ctx, &s->dMaterials, s->materials); if (rc) return rc; }
+    if (s->dirtyTextures) { int rc = upload_vec(ctx, &s->dTextures, s->textures); if (rc) return rc; s->dirtyTextures = false; }
 
     if (s->dirtyInstances)
     {

@@ -39,6 +39,7 @@ struct DSceneView {            // kernel parameter block (replaces the __constan
     uint32_t lightCount;
     uint32_t hasHdr;
     cudaTextureObject_t hdr;
+    const cudaTextureObject_t* textures;   // material maps (D_Scene::textures, src/Cuda/Scene/Scene.cuh:30), indexed by nx_material::*_map
     DCamera camera;
     uint32_t useMIS, pathLength;
     float bg[3], bgIntensity;
@@ -81,6 +82,8 @@ struct nx_scene {
     nx_material* dMaterials = nullptr;
     DLight* dLights = nullptr;
     cudaTextureObject_t hdr = 0; cudaArray_t hdrArray = nullptr; bool hasHdr = false;
+    std::vector<cudaTextureObject_t> textures; std::vector<cudaArray_t> textureArrays;   // AssetManager::AddTexture
+    cudaTextureObject_t* dTextures = nullptr; bool dirtyTextures = false;
     uint32_t dMeshCount = 0;
 };
 

@@ -123,7 +123,14 @@ __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_materi
         lightPdf *= dot(toLight, toLight) / cosL;                                // area measure -> solid angle
         if (!pdf_ok(lightPdf)) return;
         const nx_material& lm = sv.materials[I.materialIdx];
-        emissive = f3(__ldg(&lm.emission_color[0]), __ldg(&lm.emission_color[1]), __ldg(&lm.emission_color[2])) * __ldg(&lm.intensity);
+        const int32_t emap = __ldg(&lm.emissive_map);
+        if (emap != -1) {   // the map REPLACES the emission colour here (PathTracer.cu:263-269), unlike in the material kernel
+            const float tu = u * __ldg(td + 20) + v * __ldg(td + 22) + (1.0f - u - v) * __ldg(td + 18);
+            const float tv = u * __ldg(td + 21) + v * __ldg(td + 23) + (1.0f - u - v) * __ldg(td + 19);
+            const float4 c = tex2D<float4>(sv.textures[emap], tu, tv);
+            emissive = f3(c.x, c.y, c.z) * __ldg(&lm.intensity);
+        }
+        else emissive = f3(__ldg(&lm.emission_color[0]), __ldg(&lm.emission_color[1]), __ldg(&lm.emission_color[2])) * __ldg(&lm.intensity);
         mis = true;
     }
     else if (L.type == NX_LIGHT_POINT || L.type == NX_LIGHT_DIRECTIONAL)
@@ -169,11 +176,41 @@ __device__ __forceinline__ void material_one(const DSceneView& sv, const WaveBuf
     const DMesh mesh = sv.meshes[I.meshIdx];
     const float* t = mesh.tris + 9 * (size_t)hit.prim; const float* td = mesh.tridata + 24 * (size_t)hit.prim;
     const F3 v0 = load3(t), v1 = load3(t + 3), v2 = load3(t + 6);
-    const nx_material mat = sv.materials[I.materialIdx];
+    nx_material mat = sv.materials[I.materialIdx];
 
     Surface sf;
     sf.p = xf_point(I.m0, I.m1, I.m2, bary(v0, v1, v2, hit.u, hit.v));
-    sf.n = normalize(xf_normal(I.i0, I.i1, I.i2, normalize(bary(load3(td), load3(td + 3), load3(td + 6), hit.u, hit.v))));
+    F3 nObj = normalize(bary(load3(td), load3(td + 3), load3(td + 6), hit.u, hit.v));
+    // material maps (PathTracer.cu:373-411): all six indices are -1 <=> their AND is -1
+    if ((mat.base_color_map & mat.emissive_map & mat.normal_map & mat.roughness_map & mat.metalness_map & mat.metallic_roughness_map) != -1)
+    {
+        const float w0 = 1.0f - hit.u - hit.v;
+        const float tu = hit.u * __ldg(td + 20) + hit.v * __ldg(td + 22) + w0 * __ldg(td + 18);
+        const float tv = hit.u * __ldg(td + 21) + hit.v * __ldg(td + 23) + w0 * __ldg(td + 19);
+        if (mat.normal_map != -1) {
+            // tangent-space normal about (normal, Gram-Schmidt tangent) (TangentFrame(n, t), src/Math/TangentFrame.h:24-29)
+            const float4 c = tex2D<float4>(sv.textures[mat.normal_map], tu, tv);
+            const F3 tn = normalize(2.0f * f3(c.x, c.y, c.z) - f3(1.0f));
+            const F3 tg = bary(load3(td + 9), load3(td + 12), load3(td + 15), hit.u, hit.v);
+            const F3 t = normalize(tg - dot(tg, nObj) * nObj), b = cross(nObj, t);
+            nObj = t * tn.x + b * tn.y + nObj * tn.z;
+        }
+        if (mat.base_color_map != -1) {
+            const float4 c = tex2D<float4>(sv.textures[mat.base_color_map], tu, tv);
+            mat.base_color[0] *= c.x; mat.base_color[1] *= c.y; mat.base_color[2] *= c.z; mat.opacity *= c.w;
+        }
+        if (mat.emissive_map != -1) {
+            const float4 c = tex2D<float4>(sv.textures[mat.emissive_map], tu, tv);
+            mat.emission_color[0] *= c.x; mat.emission_color[1] *= c.y; mat.emission_color[2] *= c.z;
+        }
+        if (mat.roughness_map != -1) mat.roughness *= tex2D<float4>(sv.textures[mat.roughness_map], tu, tv).x;
+        if (mat.metalness_map != -1) mat.metalness *= tex2D<float4>(sv.textures[mat.metalness_map], tu, tv).x;
+        if (mat.metallic_roughness_map != -1) {
+            const float4 c = tex2D<float4>(sv.textures[mat.metallic_roughness_map], tu, tv);   // glTF packing: G roughness, B metalness
+            mat.roughness *= c.y; mat.metalness *= c.z;
+        }
+    }
+    sf.n = normalize(xf_normal(I.i0, I.i1, I.i2, nObj));
     sf.gn = normalize(xf_normal(I.i0, I.i1, I.i2, cross(v1 - v0, v2 - v0)));
     const Frame fr(sf.n);
 

@@ -64,6 +64,57 @@ def cornell_box(path_length=10):
     }
 
 
+def planar_triangle_data(tris, scale=1.0):
+    """D_TriangleData rows (n, 24) for flat-shaded geometry with texture coordinates: the geometric normal at every vertex, a
+    unit tangent along the triangle's first edge and (u, v) = the vertex position projected on the two axes most orthogonal
+    to the normal, times `scale`."""
+    tris = np.asarray(tris, np.float32).reshape(-1, 3, 3)
+    out = flat_triangle_data(tris.reshape(-1, 9))
+    n = out[:, 0:3]
+    e = tris[:, 1] - tris[:, 0]
+    t = e - (e * n).sum(1, keepdims=True) * n
+    t = t / np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-30)
+    out[:, 9:12] = out[:, 12:15] = out[:, 15:18] = t.astype(np.float32)
+    drop = np.abs(n).argmax(1)
+    for k in range(tris.shape[0]):
+        ax = [a for a in range(3) if a != drop[k]]
+        for v in range(3):
+            out[k, 18 + 2 * v: 20 + 2 * v] = tris[k, v, ax] * scale
+    return out
+
+
+def textured_cornell(path_length=6):
+    """the Cornell box with every kind of material map the reference samples (PathTracer.cu:373-411,
+    263-269): sRGB RGBA8 checker base colour (with alpha < 1 squares: texture transparency) on the floor, a linear RGBA8
+    normal map on the back wall, an RGBA8 roughness ramp on the short box, a glTF metallic-roughness map on the tall box and
+    an RGBA32F emissive map on the light."""
+    d = cornell_box(path_length)
+    for m in d["meshes"]:
+        m["triangle_data"] = planar_triangle_data(m["triangles"], scale=1.5)
+    yy, xx = np.mgrid[0:64, 0:64]
+    checker = np.zeros((64, 64, 4), np.uint8)
+    on = ((xx // 8 + yy // 8) % 2).astype(bool)
+    checker[..., 0], checker[..., 1], checker[..., 2] = np.where(on, 230, 60), np.where(on, 200, 90), np.where(on, 120, 200)
+    checker[..., 3] = np.where((xx // 16 + yy // 16) % 4 == 0, 160, 255)
+    normal = np.zeros((32, 32, 4), np.uint8)
+    nx_, ny_ = 0.35 * np.sin(xx[:32, :32] * (2 * np.pi / 16)), 0.35 * np.cos(yy[:32, :32] * (2 * np.pi / 16))
+    nz_ = np.sqrt(np.maximum(1.0 - nx_ ** 2 - ny_ ** 2, 0.0))
+    normal[..., 0], normal[..., 1], normal[..., 2], normal[..., 3] = (nx_ * 0.5 + 0.5) * 255, (ny_ * 0.5 + 0.5) * 255, (nz_ * 0.5 + 0.5) * 255, 255
+    rough = np.zeros((16, 16, 4), np.uint8); rough[..., 0] = np.linspace(40, 255, 16)[None, :]; rough[..., 1:] = 255
+    mr = np.zeros((16, 16, 4), np.uint8); mr[..., 1] = np.linspace(30, 200, 16)[:, None]; mr[..., 2] = np.where((xx[:16, :16] // 4) % 2, 255, 40); mr[..., 0] = mr[..., 3] = 255
+    emis = np.ones((8, 8, 4), np.float32)
+    emis[..., 0], emis[..., 1], emis[..., 2] = 1.0, 0.55 + 0.45 * ((xx[:8, :8] + yy[:8, :8]) % 2), 0.3 + 0.7 * (xx[:8, :8] / 7.0)
+    d["textures"] = [(checker, True), (normal, False), (rough, False), (mr, False), (emis, False)]
+    mats = d["materials"]
+    mats[0].baseColorMap = 0
+    mats[2].normalMap = 1; mats[2].roughness = 0.35; mats[2].specularWeight = 1.0; mats[2].ior = 1.5
+    mats[5].roughnessMap = 2; mats[5].roughness = 1.0; mats[5].specularWeight = 1.0; mats[5].ior = 1.5
+    mats[6].metallicRoughnessMap = 3; mats[6].metalness = 1.0; mats[6].roughness = 1.0; mats[6].baseColor = (0.95, 0.8, 0.5)
+    mats[7].emissiveMap = 4
+    d["name"] = "cornell_textured"
+    return d
+
+
 def uv_sphere(nu=224, nv=224, radius=1.0, displace=None):
     """Tessellated sphere, 2*nu*nv triangles (224 x 224 x 2 = 100,352: config 1's mesh).  Pole rows keep their (degenerate)
     second triangle so the count is exact."""
@@ -189,6 +240,8 @@ def build(ctx, desc, resolution):
     """Instantiates a scene description through the reference-shaped host API."""
     scene = Scene(ctx, resolution)
     am = scene.GetAssetManager()
+    for t in desc.get("textures", []):          # [(pixels, sRGB)]: indices in order of appearance
+        am.AddTexture(t[0], t[1])
     for m in desc["materials"]:
         am.AddMaterial(m)
     for m in desc["meshes"]:

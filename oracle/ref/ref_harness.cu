@@ -50,6 +50,7 @@ struct RefState {
     cudaTextureObject_t hdr = 0;
     cudaArray_t hdrArray = nullptr;
     bool hasHdr = false;
+    std::vector<cudaTextureObject_t> textures; std::vector<cudaArray_t> textureArrays; cudaTextureObject_t* dTextures = nullptr;
     D_Camera camera{};
     D_RenderSettings settings{};
 
@@ -237,6 +238,9 @@ int nxref_scene_reset()
     if (g.dLights) cudaFree(g.dLights), g.dLights = nullptr;
     if (g.hasTlas) NXB::FreeDeviceBVH(g.tlas), g.hasTlas = false;
     if (g.hasHdr) { cudaDestroyTextureObject(g.hdr); cudaFreeArray(g.hdrArray); g.hasHdr = false; }
+    for (size_t i = 0; i < g.textures.size(); i++) { cudaDestroyTextureObject(g.textures[i]); cudaFreeArray(g.textureArrays[i]); }
+    g.textures.clear(); g.textureArrays.clear();
+    if (g.dTextures) cudaFree(g.dTextures), g.dTextures = nullptr;
     g.instanceCount = g.lightCount = 0;
     return 0;
 }
@@ -300,6 +304,27 @@ int nxref_set_materials(const void* mats, uint32_t n)
     return 0;
 }
 
+// Texture::ToDevice (N/Assets/Texture.cpp:12-46) for one material map; returns its index in D_Scene::textures.
+int nxref_add_texture(const void* rgba, uint32_t w, uint32_t h, int isHdr, int srgb)
+{
+    cudaChannelFormatDesc desc = isHdr ? cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat) : cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+    cudaArray_t arr = nullptr;
+    REF_CHECK(cudaMallocArray(&arr, &desc, w, h));
+    const size_t pitch = (size_t)w * (isHdr ? 16 : 4);
+    REF_CHECK(cudaMemcpy2DToArray(arr, 0, 0, rgba, pitch, pitch, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc res; std::memset(&res, 0, sizeof(res)); res.resType = cudaResourceTypeArray; res.res.array.array = arr;
+    cudaTextureDesc tex; std::memset(&tex, 0, sizeof(tex));
+    tex.addressMode[0] = tex.addressMode[1] = cudaAddressModeWrap; tex.sRGB = (srgb && !isHdr) ? 1 : 0;
+    tex.filterMode = cudaFilterModeLinear; tex.readMode = isHdr ? cudaReadModeElementType : cudaReadModeNormalizedFloat; tex.normalizedCoords = 1;
+    cudaTextureObject_t obj = 0;
+    REF_CHECK(cudaCreateTextureObject(&obj, &res, &tex, nullptr));
+    g.textures.push_back(obj); g.textureArrays.push_back(arr);
+    if (g.dTextures) cudaFree(g.dTextures);
+    REF_CHECK(cudaMalloc((void**)&g.dTextures, sizeof(cudaTextureObject_t) * g.textures.size()));
+    REF_CHECK(cudaMemcpy(g.dTextures, g.textures.data(), sizeof(cudaTextureObject_t) * g.textures.size(), cudaMemcpyHostToDevice));
+    return (int)g.textures.size() - 1;
+}
+
 int nxref_set_lights(const void* lights, uint32_t n)
 {
     static_assert(sizeof(D_Light) == 52, "D_Light layout");
@@ -354,7 +379,7 @@ int nxref_set_hdr(const float* rgba, uint32_t w, uint32_t h)
 static int uploadSymbols()
 {
     D_Scene s; std::memset(&s, 0, sizeof(s));
-    s.hasHdrMap = g.hasHdr; s.hdrMap = g.hdr; s.textures = nullptr;
+    s.hasHdrMap = g.hasHdr; s.hdrMap = g.hdr; s.textures = g.dTextures;
     s.lights = g.dLights; s.lightCount = g.lightCount;
     s.materials = g.dMaterials; s.camera = g.camera;
     s.meshInstances = g.dInstances;

@@ -70,6 +70,12 @@ def render_cases():
     ]
 
 
+def textured_render_cases():
+    """SURVEY.md §8 row f-2 (material maps): same protocol as render_cases(), golden file render_textured_ref.npz."""
+    from nexus_b200 import scenes
+    return [("cornell_textured", scenes.textured_cornell(path_length=6), (128, 128), 2048, 8)]
+
+
 # ------------------------------------------------------------------ display transform (tests/golden/display_ref.npz) ----
 DISPLAY_EXPOSURES = (0.0, -1.5, 2.0)
 

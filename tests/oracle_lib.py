@@ -297,6 +297,13 @@ def ref_build_bvh2(prims, prioritize_speed):
     return nodes, bounds
 
 
+def _ref_textures(R, desc):
+    for k, (pixels, srgb) in enumerate(desc.get("textures", [])):
+        pixels = np.ascontiguousarray(pixels)
+        idx = R.nxref_add_texture(_p(pixels), C.c_uint32(pixels.shape[1]), C.c_uint32(pixels.shape[0]), C.c_int(int(pixels.dtype == np.float32)), C.c_int(int(srgb)))
+        assert idx == k, (idx, k)
+
+
 def ref_load_scene(desc, scene, resolution):
     """Feeds the reference harness the same scene the product got: identical triangles, shading data, materials, and the
     instance matrices / camera / light list exported by the product's host layer in the reference's device layouts."""
@@ -308,6 +315,7 @@ def ref_load_scene(desc, scene, resolution):
         assert R.nxref_add_mesh(_p(tris), _p(td), C.c_uint32(tris.shape[0])) >= 0
     inst = scene.ExportInstances()
     assert R.nxref_set_instances(_p(inst), C.c_uint32(inst.shape[0])) == 0
+    _ref_textures(R, desc)
     mats = np.frombuffer(b"".join(bytes(m.pod()) for m in desc["materials"]), np.uint8).copy()
     assert R.nxref_set_materials(_p(mats), C.c_uint32(len(desc["materials"]))) == 0
     lights = scene.ExportLights()
@@ -456,6 +464,7 @@ def ref_load_scene_standalone(desc, resolution):
         mesh_bounds.append(b)
     inst, mats_of = host_instances(desc, mesh_bounds)
     assert R.nxref_set_instances(_p(inst), C.c_uint32(inst.shape[0])) == 0
+    _ref_textures(R, desc)
     mats = np.frombuffer(b"".join(bytes(m.pod()) for m in desc["materials"]), np.uint8).copy()
     assert R.nxref_set_materials(_p(mats), C.c_uint32(len(desc["materials"]))) == 0
     lights = []

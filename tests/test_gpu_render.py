@@ -209,3 +209,60 @@ def test_dynamic_scene_updates_rebuild_the_tlas(ctx):
     ia, ib = pa.ReadAccumulation(), pb.ReadAccumulation()
     assert np.allclose(ia, ib, rtol=1e-4, atol=1e-5)                          # float atomics: summation order only
     pa.close(); pb.close(); a.close(); b.close()
+
+
+# ------------------------------------------------------------------ material maps ----
+def test_textured_converged_image_matches_reference(ctx):
+    """Base colour (sRGB RGBA8, with transparency), normal, roughness, metallic-roughness and emissive (RGBA32F) maps: converged
+    block means against the reference renderer's (tests/golden/render_textured_ref.npz, scripts/make_golden_textured.py),
+    same bound as the untextured cases: relative RMSE <= 3 x the reference's own noise floor, means within 1 - 1.5 %."""
+    from golden_cases import textured_render_cases
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "render_textured_ref.npz"))
+    for name, desc, res, spp, block in textured_render_cases():
+        ref_a, ref_b = gold[name + "/mean_a"].astype(np.float64), gold[name + "/mean_b"].astype(np.float64)
+        scene = scenes.build(ctx, desc, res)
+        pt = nx.PathTracer(ctx, res)
+        pt.Render(scene, frames=spp)
+        ours = _blocks(pt.ReadAccumulation().astype(np.float64), block)
+        ref = 0.5 * (ref_a + ref_b)
+        floor = np.sqrt(((ref_a - ref_b) ** 2).mean()) / ref.mean()
+        rmse = np.sqrt(((ours - ref) ** 2).mean()) / ref.mean()
+        assert rmse <= 3.0 * floor + 1e-3, (rmse, floor)
+        assert abs(ours.mean() - ref.mean()) <= 0.01 * ref.mean(), (ours.mean(), ref.mean())
+        for c in range(3):
+            assert abs(ours[..., c].mean() - ref[..., c].mean()) <= 0.015 * ref[..., c].mean()
+        pt.close(); scene.close()
+
+
+def test_constant_maps_equal_scaled_materials(ctx):
+    """A constant map multiplies the material parameter (PathTracer.cu:394-411): a scene whose floor carries a uniform 0.5-grey
+    base-colour map and whose box a uniform roughness map renders the same frames as the scene with the parameters pre-multiplied
+    and no maps (same RNG keys, so the comparison is per pixel, not statistical)."""
+    res = (96, 96)
+
+    def make(maps):
+        d = scenes.cornell_box(path_length=4)
+        for m in d["meshes"]:
+            m["triangle_data"] = scenes.planar_triangle_data(m["triangles"])
+        half = np.full((4, 4, 4), 0.5, np.float32); half[..., 3] = 1.0
+        quarter = np.full((4, 4, 4), 0.25, np.float32)
+        d["materials"][5].specularWeight = 1.0; d["materials"][5].ior = 1.5; d["materials"][5].roughness = 0.8
+        if maps:
+            d["textures"] = [(half, False), (quarter, False)]
+            d["materials"][0].baseColorMap = 0
+            d["materials"][5].roughnessMap = 1
+        else:
+            d["materials"][0].baseColor = tuple(0.5 * c for c in d["materials"][0].baseColor)
+            d["materials"][5].roughness = 0.8 * 0.25
+        return d, scenes.build(ctx, d, res)
+
+    (da, a), (db, b) = make(True), make(False)
+    pa, pb = nx.PathTracer(ctx, res), nx.PathTracer(ctx, res)
+    pa.Render(a, frames=4, firstFrame=1); pb.Render(b, frames=4, firstFrame=1)
+    ia, ib = pa.ReadAccumulation(), pb.ReadAccumulation()
+    assert ia.mean() > 0 and np.allclose(ia, ib, rtol=2e-3, atol=1e-5)
+    pa.close(); pb.close(); a.close(); b.close()
+    # a material that names a texture the scene does not have is rejected at Update
+    d = scenes.with_triangle_data(scenes.cornell_box(path_length=2)); d["materials"][0].baseColorMap = 3
+    with pytest.raises(nx.NexusError):
+        scenes.build(ctx, d, (8, 8)).TraceClosest(nx.make_rays(np.zeros((1, 3), np.float32), np.array([[0, 0, -1]], np.float32)))
