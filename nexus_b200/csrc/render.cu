@@ -247,7 +247,9 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
     if (scene->width != r->width || scene->height != r->height) NX_FAIL(ctx, NX_ERR_INVALID, "scene resolution %ux%u != renderer %ux%u", scene->width, scene->height, r->width, r->height);
     DeviceGuard guard(ctx->device);
     DSceneView sv; int rc = nxi_scene_view(scene, &sv); if (rc) return rc;
-    cudaStream_t s = ctx->stream, sa = ctx->stream_aux;
+    // with per-launch profiling events on, the shadow trace runs on the main stream too: kernels then execute one at a time and
+    // the event pairs measure each kernel alone (comparable with ncu's serialised launch list) instead of two overlapping ones
+    cudaStream_t s = ctx->stream, sa = (r->profFlags & 1) ? ctx->stream : ctx->stream_aux;
     const uint32_t L = sv.pathLength;
     const bool work = (r->profFlags & 2) != 0;
     const TraceTuning tune = trace_tuning(ctx), tuneAny = trace_tuning(ctx, true);
