@@ -247,7 +247,10 @@ def build(ctx, desc, resolution):
     for m in desc["meshes"]:
         am.AddMesh(m["name"], m["material"], m["triangles"], m.get("triangle_data"))
     for i in desc["instances"]:
-        scene.CreateMeshInstance(i["mesh"], i.get("material", -1), i["position"], i["rotation"], i["scale"])
+        if "matrix" in i:      # imported assets carry the accumulated node transform (nexus_b200.gltf)
+            scene.CreateMeshInstanceMatrix(i["mesh"], i["matrix"], i.get("material", -1))
+        else:
+            scene.CreateMeshInstance(i["mesh"], i.get("material", -1), i["position"], i["rotation"], i["scale"])
     for l in desc.get("lights", []):
         scene.AddLight(l)
     scene.SetCamera(desc["camera"])
