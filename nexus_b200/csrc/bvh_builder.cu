@@ -737,7 +737,7 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
 }
 
 int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics,
-               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1)
+               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1, bool finalSync = true)
 {
     if (!dPrims || n == 0) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: empty primitive list");
     if (n > 0x7fffffffu / 2) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: primitive count %u exceeds 2^30", n);
@@ -777,7 +777,8 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         cudaFreeAsync(dCost, s);
     }
     cudaFreeAsync(dScene, s); cudaFreeAsync(dSceneOut, s);
-    NX_CUDA(ctx, cudaStreamSynchronize(s));
+    // BuildBVH8 continues on the same stream and synchronises once at its end: out->bounds is valid from then on
+    if (finalSync) NX_CUDA(ctx, cudaStreamSynchronize(s));
     NX_CUDA(ctx, cudaGetLastError());
     out->nodes = nodes;
     return NX_OK;
@@ -786,7 +787,7 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
 int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out)
 {
     Bvh2Result b2;
-    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2);
+    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2, nullptr, -1, /*finalSync=*/false);
     if (rc) return rc;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = ctx->stream;
