@@ -250,16 +250,24 @@ def run_ours(args):
     pt.ResetFrameNumber()
     host_rgba = torch.empty((res[1], res[0]), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
     cam = desc["camera"]
+    # one untimed warm-up of this exact call sequence: the first read-back after the counted replay above carries a one-time
+    # cost of tens of milliseconds (first use of the display kernel / stream-ordered pool growth) that is not part of a step
+    scene.SetCamera(cam); scene.SetRenderSettings(desc["settings"])
+    pt.Render(scene, frames=1, firstFrame=first); pt.ReadRGBA8(scene, out=host_rgba); pt.Stats()
+    pt.ResetFrameNumber()
     barrier()
     t0 = time.time()
     e2e_rays = 0
+    step_ms = []
     for i in range(K):
+        ts = time.time()
         scene.SetCamera(cam)
         scene.SetRenderSettings(desc["settings"])
         pt.Render(scene, frames=1, firstFrame=first + i)
         pt.ReadRGBA8(scene, out=host_rgba)
         s1 = pt.Stats()
         e2e_rays += s1["extension_rays"] + s1["shadow_rays"]
+        step_ms.append((time.time() - ts) * 1e3)
     barrier()
     e2e_s = time.time() - t0
     e2e_t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -270,7 +278,8 @@ def run_ours(args):
     e2e_value = float(e2e_c[0]) / float(e2e_t[0]) / 1e6
     # H2D per step: nx_camera (48 B) + nx_render_settings (32 B), marshalled into the kernels' parameter block
     e2e = {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": 48 + 32, "d2h_bytes_per_step": 4 * res[0] * res[1],
-           "ms_per_step": round(float(e2e_t[0]) * 1e3 / K, 3), "what": "SetCamera+SetRenderSettings (host structs) -> Render(1 frame) -> ReadRGBA8 into pinned host memory"}
+           "ms_per_step": round(float(e2e_t[0]) * 1e3 / K, 3), "ms_per_step_median": round(float(np.median(step_ms)), 3), "ms_per_step_max": round(float(np.max(step_ms)), 3),
+           "what": "SetCamera+SetRenderSettings (host structs) -> Render(1 frame) -> ReadRGBA8 into pinned host memory"}
 
     # ---- like for like (N = 1 only): the same frames on BLASes / TLAS collapsed by the reference GPU converter's rule, i.e. trees
     # identical to the ones the reference renders with.  The headline above uses the product default, the SAH-optimal collapse of
