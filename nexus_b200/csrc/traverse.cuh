@@ -67,14 +67,7 @@ struct TraceStats {
 // Shared memory per block: stack entries [NX_STACK_SHARED][block] of uint2, then the parked world-space ray, 48 B per
 // thread: {origin, octant word} {direction, -} {reciprocal direction, -}.  Three LDS.128 / STS.128 per instance exit /
 // entry; a 48-byte thread stride keeps the 16-byte accesses of a quarter warp on distinct banks.
-#ifndef NX_PARK128
-#define NX_PARK128 1
-#endif
-#if NX_PARK128
 #define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 48) * NX_TRACE_BLOCK)
-#else
-#define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 9 * 4) * NX_TRACE_BLOCK)
-#endif
 
 // (7 - octant) replicated into four bytes, octant = sign bits of the direction (x: 4, y: 2, z: 1).  Any value works as long
 // as the same one decodes the hit mask it encoded (it only fixes the visiting order), so the sign BITS are used: shifts
@@ -225,11 +218,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                                            uint32_t* smem, Sink& sink, TraceStats* stats)
 {
     uint2* const sstack = reinterpret_cast<uint2*>(smem) + threadIdx.x;                       // entry e at sstack[e * NX_TRACE_BLOCK]
-#if NX_PARK128
     float4* const park4 = reinterpret_cast<float4*>(smem + 2 * NX_STACK_SHARED * NX_TRACE_BLOCK) + 3 * threadIdx.x;
-#else
-    float* const park = reinterpret_cast<float*>(smem + 2 * NX_STACK_SHARED * NX_TRACE_BLOCK) + threadIdx.x;   // value k at park[k * NX_TRACE_BLOCK]
-#endif
     uint2 spill[NX_STACK_TOTAL - NX_STACK_SHARED];
     uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
     // 0x47000000 arrives as a kernel parameter so that ptxas cannot fold it: PRMT then takes the constant from the
@@ -298,16 +287,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                 live = false; ngroup = make_uint2(0u, 0u); tgroup = make_uint2(0u, 0u);
             } else {
                 if (sp == instDepth) {      // leaving an instance: restore the parked world-space ray
-#if NX_PARK128
                     const float4 p0 = park4[0], p1 = park4[1], p2 = park4[2];
                     o = v3(p0.x, p0.y, p0.z); d = v3(p1.x, p1.y, p1.z); inv = v3(p2.x, p2.y, p2.z);
                     octinv4 = __float_as_uint(p0.w);
-#else
-                    o = v3(park[0], park[NX_TRACE_BLOCK], park[2 * NX_TRACE_BLOCK]);
-                    d = v3(park[3 * NX_TRACE_BLOCK], park[4 * NX_TRACE_BLOCK], park[5 * NX_TRACE_BLOCK]);
-                    inv = v3(park[6 * NX_TRACE_BLOCK], park[7 * NX_TRACE_BLOCK], park[8 * NX_TRACE_BLOCK]);
-                    octinv4 = octant_inv4(inv);
-#endif
                     nodes = sc.tlasNodes; instDepth = -1;
                 }
                 const uint2 e = pop();
@@ -368,15 +350,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                 const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&I->nodes));
                 nodes = reinterpret_cast<const float4*>(((uint64_t)ptrs.y << 32) | ptrs.x);
                 ltris = reinterpret_cast<const float4*>(((uint64_t)ptrs.w << 32) | ptrs.z);
-#if NX_PARK128
                 park4[0] = make_float4(o.x, o.y, o.z, __uint_as_float(octinv4));
                 park4[1] = make_float4(d.x, d.y, d.z, 0.f);
                 park4[2] = make_float4(inv.x, inv.y, inv.z, 0.f);
-#else
-                park[0] = o.x; park[NX_TRACE_BLOCK] = o.y; park[2 * NX_TRACE_BLOCK] = o.z;
-                park[3 * NX_TRACE_BLOCK] = d.x; park[4 * NX_TRACE_BLOCK] = d.y; park[5 * NX_TRACE_BLOCK] = d.z;
-                park[6 * NX_TRACE_BLOCK] = inv.x; park[7 * NX_TRACE_BLOCK] = inv.y; park[8 * NX_TRACE_BLOCK] = inv.z;
-#endif
                 const V3 wo = o, wd = d;
                 o = xform_point(r0, r1, r2, wo); d = xform_vector(r0, r1, r2, wd);   // direction is not renormalised: t stays in world units
                 if (STATS) cI++;
