@@ -174,6 +174,14 @@ int nx_scene_set_material(nx_scene* scene, uint32_t idx, const nx_material* m); 
 /* AssetManager::AddMesh: host triangles + per-triangle shading data (may be NULL => geometric normals); builds the BLAS
  * with prioritizeSpeed = true exactly like Mesh::Mesh (src/Assets/Mesh.h:15-46).  Returns mesh index >= 0. */
 int nx_scene_add_mesh(nx_scene* scene, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t material_idx);
+/* Sharded BLAS builds ("BVH build, many meshes"): BLAS builds are independent units, so ranks build disjoint
+ * subsets and exchange the results.  nx_scene_build_blas builds one mesh's BLAS from HOST triangles exactly as nx_scene_add_mesh
+ * would (the context's scene collapse mode, leaf size and Morton width) and returns an owned handle (free with nx_bvh8_free).
+ * nx_scene_add_mesh_prebuilt is nx_scene_add_mesh with the BLAS supplied instead of built: `d_nodes` / `d_prim_idx` are DEVICE
+ * pointers (e.g. into an NCCL all-gather buffer) and are copied; the result is indistinguishable from a locally built mesh. */
+int nx_scene_build_blas(nx_ctx* ctx, const nx_triangle* host_tris, uint32_t n, nx_bvh8* out);
+int nx_scene_add_mesh_prebuilt(nx_scene* scene, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t material_idx,
+                               const nx_bvh8_node* d_nodes, uint32_t node_count, const uint32_t* d_prim_idx, const nx_aabb* bounds);
 int nx_scene_mesh_bounds(nx_scene* scene, uint32_t mesh_idx, nx_aabb* out);
 int nx_scene_mesh_bvh(nx_scene* scene, uint32_t mesh_idx, nx_bvh8* out);                /* borrowed handle */
 /* Scene::CreateMeshInstance + MeshInstance::SetTransform (T * Rz * Ry * Rx * S, Euler degrees). Returns instance index. */
@@ -231,6 +239,22 @@ int nx_renderer_accum_device(nx_renderer* r, float** out_dev_sum, uint32_t* out_
 int nx_renderer_set_accum_frames(nx_renderer* r, uint32_t frames);                         /* after an external all-reduce */
 /* Tone-mapped RGBA8 (AccumulateKernel's display transform, PathTracer.cu:527-548), HOST buffer of w*h uint32. */
 int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* host_rgba);
+/* Pipelined display read-back, the headless counterpart of the reference's pixel-buffer path (PathTracer::Render maps a GL PBO
+ * and returns without synchronising, src/Renderer/PathTracer.cpp:170-199; Renderer::UnpackToTexture consumes it a frame later,
+ * src/Renderer/Renderer.cpp:41-48).  nx_renderer_present resolves the current accumulation to RGBA8 on the render stream into
+ * one of two device images and queues its copy to `host_rgba` (w*h uint32, PINNED host memory for a truly asynchronous copy) on
+ * a copy stream, together with the queue totals of the last nx_renderer_render call; it returns at once with a ticket
+ * (0 or 1, alternating).  nx_renderer_present_wait blocks until that ticket's image and totals are in host memory.  A slot is
+ * reused two presents later: wait for a ticket before presenting twice more into the same host buffer. */
+int nx_renderer_present(nx_renderer* r, nx_scene* scene, uint32_t* host_rgba, int* out_ticket);
+int nx_renderer_present_wait(nx_renderer* r, int ticket, nx_frame_stats* out_stats /* may be NULL; device_ms is 0 */);
+/* PathTracer::SetPixelQuery / PixelQueryPending / SynchronizePixelQuery (src/Renderer/PathTracer.h:23-27, PathTracer.cpp:221-240;
+ * device side PathTracer.cu:150-151, 459-460): the instance under pixel (x, y) — row 0 is the bottom row — as seen by the
+ * primary ray of the next rendered frame; -1 when that ray leaves the scene.  Synchronise returns the instance id and clears the
+ * pending flag; without a rendered frame in between it returns the previous answer (-1 initially), like the reference. */
+int nx_renderer_set_pixel_query(nx_renderer* r, uint32_t x, uint32_t y);
+int nx_renderer_pixel_query_pending(const nx_renderer* r);
+int nx_renderer_sync_pixel_query(nx_renderer* r, int32_t* out_instance);
 /* The same display transform (exposure, tone curve NX_TONE_*, gamma 2.2, RGBA8 pack: src/Utils/ColorUtils.h:27-212) applied on
  * the device to a HOST linear float RGB image of `count` pixels; for previews of EXR/PFM output and for the parity tests. */
 int nx_display_transform(nx_ctx* ctx, const float* host_rgb, uint32_t count, int tone_mapping, float exposure, uint32_t* host_rgba);

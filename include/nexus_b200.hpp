@@ -211,9 +211,18 @@ public:
     nx_frame_stats Stats() { nx_frame_stats s{}; ctx_.check(nx_renderer_stats(h_, &s), "Stats"); return s; }
     std::vector<float> ReadAccumulation() { std::vector<float> v(3ull * res_.x * res_.y); ctx_.check(nx_renderer_read_accum(h_, v.data()), "ReadAccumulation"); return v; }
     std::vector<uint32_t> ReadRGBA8(Scene& scene) { std::vector<uint32_t> v((size_t)res_.x * res_.y); ctx_.check(nx_renderer_read_rgba8(h_, scene.handle(), v.data()), "ReadRGBA8"); return v; }
+    // Pipelined display read-back (the reference's PBO path): Present queues resolve + copy into a caller-owned (pinned) image
+    // and returns a ticket; PresentWait blocks until that image is on the host and returns the render call's queue totals.
+    int Present(Scene& scene, uint32_t* hostRgba) { int t = 0; ctx_.check(nx_renderer_present(h_, scene.handle(), hostRgba, &t), "Present"); return t; }
+    nx_frame_stats PresentWait(int ticket) { nx_frame_stats s{}; ctx_.check(nx_renderer_present_wait(h_, ticket, &s), "PresentWait"); return s; }
+    // src/Renderer/PathTracer.h:23-27
+    void SetPixelQuery(uint32_t x, uint32_t y) { ctx_.check(nx_renderer_set_pixel_query(h_, x, y), "SetPixelQuery"); }
+    bool PixelQueryPending() const { return nx_renderer_pixel_query_pending(h_) == 1; }
+    int32_t SynchronizePixelQuery() { ctx_.check(nx_renderer_sync_pixel_query(h_, &selected_), "SynchronizePixelQuery"); return selected_; }
+    int32_t GetSelectedInstance() const { return selected_; }
     nx_renderer* handle() const { return h_; }
 private:
-    Context& ctx_; nx_renderer* h_ = nullptr; uint2 res_; uint32_t frame_ = 0;
+    Context& ctx_; nx_renderer* h_ = nullptr; uint2 res_; uint32_t frame_ = 0; int32_t selected_ = -1;
 };
 
 inline void WritePFM(const std::string& path, const std::vector<float>& rgb, uint2 res) { if (nx_write_pfm(path.c_str(), rgb.data(), res.x, res.y) != NX_OK) throw Error("cannot write " + path); }

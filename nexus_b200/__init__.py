@@ -527,6 +527,40 @@ class PathTracer:
         check(self.ctx._h, lib().nx_renderer_read_rgba8(self._h, scene._h, _ptr(out)), "ReadRGBA8")
         return out
 
+    def Present(self, scene, out):
+        """Pipelined display read-back (the reference's PBO path, PathTracer.cpp:170-199 + Renderer.cpp:41-48): queues the
+        display transform of the current accumulation and its copy into `out` ((h, w) uint32, pinned host memory for a truly
+        asynchronous copy) behind the frames already submitted and returns a ticket at once."""
+        w, h = self.resolution
+        assert out.dtype == np.uint32 and out.size == w * h and out.flags["C_CONTIGUOUS"]
+        t = C.c_int(0)
+        check(self.ctx._h, lib().nx_renderer_present(self._h, scene._h, _ptr(out), C.byref(t)), "Present")
+        return t.value
+
+    def PresentWait(self, ticket):
+        """Blocks until the image of `ticket` is in host memory; returns the queue totals of the render call it shows."""
+        st = FrameStats()
+        check(self.ctx._h, lib().nx_renderer_present_wait(self._h, C.c_int(ticket), C.byref(st)), "PresentWait")
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+    def SetPixelQuery(self, x, y):
+        """PathTracer::SetPixelQuery (PathTracer.cpp:233-240): asks for the instance under pixel (x, y), row 0 = bottom row."""
+        check(self.ctx._h, lib().nx_renderer_set_pixel_query(self._h, C.c_uint32(x), C.c_uint32(y)), "SetPixelQuery")
+
+    def PixelQueryPending(self):
+        return lib().nx_renderer_pixel_query_pending(self._h) == 1
+
+    def SynchronizePixelQuery(self):
+        """PathTracer::SynchronizePixelQuery (PathTracer.cpp:221-231): instance id seen by the queried pixel's primary ray in
+        the frame rendered after SetPixelQuery, -1 for a miss."""
+        v = C.c_int32(-1)
+        check(self.ctx._h, lib().nx_renderer_sync_pixel_query(self._h, C.byref(v)), "SynchronizePixelQuery")
+        self._selected = v.value
+        return v.value
+
+    def GetSelectedInstance(self):
+        return getattr(self, "_selected", -1)
+
 
 TONE_NONE, TONE_ACES, TONE_UNCHARTED2, TONE_AGX_DEFAULT, TONE_AGX_GOLDEN, TONE_AGX_PUNCHY = range(6)   # ColorUtils::ToneMapping
 

@@ -65,6 +65,14 @@ __global__ void frame_totals_kernel(WaveBuffers wb, uint32_t pathLength)
     wb.totals->ext += e; wb.totals->shadow += s; wb.totals->shaded += h; wb.totals->frames += 1;
 }
 
+// Pixel query (LogicKernel / MaterialKernel at bounce 1, PathTracer.cu:150-151, 459-460): the primary hit of one pixel.  The
+// primary-ray queue is in generation order, so the pixel's queue slot is known on the host (pixel_to_slot, wave.cuh).
+__global__ void pixel_query_kernel(const nx_hit* __restrict__ hits, uint32_t slot, int32_t* out)
+{
+    const nx_hit h = hits[slot];
+    *out = h.prim == NX_INVALID ? -1 : (int32_t)h.instance;
+}
+
 TraceTuning trace_tuning(const nx_ctx* ctx, bool any = false)
 {
     TraceTuning t; t.triLanes = any ? ctx->tune_tri_any : ctx->tune_tri; t.instLanes = any ? ctx->tune_inst_any : ctx->tune_inst; t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u; return t;
@@ -97,6 +105,16 @@ struct nx_renderer {
     std::vector<cudaEvent_t> evPool; size_t evUsed = 0;
     std::vector<std::pair<int, size_t>> evLaunches;   // (kernel class, index of the start event; stop = index + 1)
     TraceStats* dWork = nullptr;                      // [0] closest-hit traversal work, [1] any-hit traversal work
+    // pipelined display read-back (nx_renderer_present): two device RGBA8 images, a copy stream, pinned totals per ticket
+    cudaStream_t copyStream = nullptr;
+    uint32_t* dRgba[2] = {nullptr, nullptr};
+    cudaEvent_t evResolved[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
+    bool slotUsed[2] = {false, false};
+    WaveTotals* hTotals = nullptr;                    // pinned, [2]
+    int presentNext = 0;
+    // pixel query (SetPixelQuery / SynchronizePixelQuery)
+    int32_t* dQuery = nullptr; int32_t* hQuery = nullptr;   // device slot, pinned host mirror
+    int64_t queryPixel = -1; bool queryPending = false;
 
     cudaEvent_t next_event() { if (evUsed == evPool.size()) { cudaEvent_t e; cudaEventCreate(&e); evPool.push_back(e); } return evPool[evUsed++]; }
     void prof_begin(int cls, cudaStream_t st) { if (profFlags & 1) { evLaunches.push_back({cls, evUsed}); cudaEventRecord(next_event(), st); next_event(); } }
@@ -167,6 +185,9 @@ int free_buffers(nx_renderer* r)
     cudaFree(w.ext[0]); cudaFree(w.ext[1]); cudaFree(w.state[0]); cudaFree(w.state[1]); cudaFree(w.hits); cudaFree(w.shadow[0]); cudaFree(w.shadow[1]);
     cudaFree(w.shadowRad[0]); cudaFree(w.shadowRad[1]); cudaFree(w.accum); cudaFree(w.counters); cudaFree(w.totals);
     w = WaveBuffers{};
+    if (r->copyStream) cudaStreamSynchronize(r->copyStream);
+    for (int k = 0; k < 2; k++) { cudaFree(r->dRgba[k]); r->dRgba[k] = nullptr; r->slotUsed[k] = false; }
+    r->queryPixel = -1; r->queryPending = false;
     return NX_OK;
 }
 
@@ -205,6 +226,13 @@ int nx_renderer_create(nx_ctx* ctx, uint32_t width, uint32_t height, nx_renderer
     if (cudaMalloc((void**)&r->dWork, 2 * sizeof(TraceStats)) != cudaSuccess || cudaMemset(r->dWork, 0, 2 * sizeof(TraceStats)) != cudaSuccess) {
         ctx->error = "nx_renderer_create: cudaMalloc failed"; nx_renderer_destroy(r); return NX_ERR_CUDA;
     }
+    bool ok = cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; k++)
+        ok = cudaEventCreateWithFlags(&r->evResolved[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&r->evCopied[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&r->hTotals, 2 * sizeof(WaveTotals)) == cudaSuccess && cudaMallocHost((void**)&r->hQuery, 4) == cudaSuccess
+            && cudaMalloc((void**)&r->dQuery, 4) == cudaSuccess && cudaMemset(r->dQuery, 0xff, 4) == cudaSuccess;
+    if (!ok) { ctx->error = "nx_renderer_create: read-back resources"; nx_renderer_destroy(r); return NX_ERR_CUDA; }
+    *r->hQuery = -1;
     *out = r;
     return NX_OK;
 }
@@ -217,6 +245,9 @@ void nx_renderer_destroy(nx_renderer* r)
     cudaEventDestroy(r->evStart); cudaEventDestroy(r->evStop); cudaEventDestroy(r->evShade); cudaEventDestroy(r->evShadow[0]); cudaEventDestroy(r->evShadow[1]);
     for (cudaEvent_t e : r->evPool) cudaEventDestroy(e);
     cudaFree(r->dWork);
+    for (int k = 0; k < 2; k++) { if (r->evResolved[k]) cudaEventDestroy(r->evResolved[k]); if (r->evCopied[k]) cudaEventDestroy(r->evCopied[k]); }
+    if (r->copyStream) cudaStreamDestroy(r->copyStream);
+    cudaFreeHost(r->hTotals); cudaFreeHost(r->hQuery); cudaFree(r->dQuery);
     delete r;
 }
 
@@ -283,6 +314,10 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
         r->prof_end(s);
         r->launches++;
         closest(wb.ext[0], 0);
+        if (r->queryPixel >= 0 && f == 0) {
+            pixel_query_kernel<<<1, 1, 0, s>>>(wb.hits, pixel_to_slot((uint32_t)r->queryPixel, r->width, r->height), r->dQuery);
+            r->queryPixel = -1;                                              // answered by this frame (pixelIdx = -1 in the reference)
+        }
         for (uint32_t b = 1; b <= L; b++)
         {
             // two shadow queues: shade(b) refills queue b & 1, which the shadow trace of bounce b-2 must have consumed; the shadow
@@ -414,6 +449,66 @@ int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* hostRgba)
     NX_CUDA(ctx, cudaMemcpyAsync(hostRgba, d, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(d, ctx->stream);
+    return NX_OK;
+}
+
+int nx_renderer_present(nx_renderer* r, nx_scene* scene, uint32_t* hostRgba, int* outTicket)
+{
+    if (!r || !scene || !hostRgba || !outTicket) return NX_ERR_INVALID;
+    nx_ctx* ctx = r->ctx;
+    DeviceGuard guard(ctx->device);
+    const uint32_t count = r->width * r->height;
+    const int k = r->presentNext;
+    cudaStream_t s = ctx->stream;
+    if (!r->dRgba[k]) NX_CUDA(ctx, cudaMalloc((void**)&r->dRgba[k], 4 * (size_t)count));
+    // nx_renderer_render leaves the render stream ordered after the shadow stream, so the accumulation is complete here.  The
+    // device image of this slot may still be on its way to the host from two presents ago: the resolve waits for that copy.
+    if (r->slotUsed[k]) NX_CUDA(ctx, cudaStreamWaitEvent(s, r->evCopied[k], 0));
+    nxi_launch_resolve(ctx->sm_count * 4, s, r->wb.accum, count, r->frames ? 1.0f / (float)r->frames : 0.f, scene->settings.exposure, scene->settings.tone_mapping, r->dRgba[k]);
+    NX_CUDA(ctx, cudaMemcpyAsync(r->hTotals + k, r->wb.totals, sizeof(WaveTotals), cudaMemcpyDeviceToHost, s));   // before the next render call clears them
+    NX_CUDA(ctx, cudaEventRecord(r->evResolved[k], s));
+    NX_CUDA(ctx, cudaStreamWaitEvent(r->copyStream, r->evResolved[k], 0));
+    NX_CUDA(ctx, cudaMemcpyAsync(hostRgba, r->dRgba[k], 4 * (size_t)count, cudaMemcpyDeviceToHost, r->copyStream));
+    NX_CUDA(ctx, cudaEventRecord(r->evCopied[k], r->copyStream));
+    r->slotUsed[k] = true; r->presentNext = k ^ 1;
+    *outTicket = k;
+    return NX_OK;
+}
+
+int nx_renderer_present_wait(nx_renderer* r, int ticket, nx_frame_stats* out)
+{
+    if (!r || ticket < 0 || ticket > 1) return NX_ERR_INVALID;
+    nx_ctx* ctx = r->ctx;
+    if (!r->slotUsed[ticket]) NX_FAIL(ctx, NX_ERR_STATE, "nx_renderer_present_wait: ticket %d was never presented", ticket);
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaEventSynchronize(r->evCopied[ticket]));
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        const WaveTotals& t = r->hTotals[ticket];
+        out->extension_rays = t.ext; out->shadow_rays = t.shadow; out->shaded_hits = t.shaded; out->frames = t.frames;
+        out->kernel_launches = r->launches;
+    }
+    return NX_OK;
+}
+
+int nx_renderer_set_pixel_query(nx_renderer* r, uint32_t x, uint32_t y)
+{
+    if (!r) return NX_ERR_INVALID;
+    if (x >= r->width || y >= r->height) NX_FAIL(r->ctx, NX_ERR_INVALID, "SetPixelQuery: pixel (%u, %u) outside %ux%u", x, y, r->width, r->height);
+    r->queryPixel = (int64_t)y * r->width + x;      // PathTracer.cpp:236
+    r->queryPending = true;
+    return NX_OK;
+}
+int nx_renderer_pixel_query_pending(const nx_renderer* r) { return r ? (r->queryPending ? 1 : 0) : NX_ERR_INVALID; }
+int nx_renderer_sync_pixel_query(nx_renderer* r, int32_t* outInstance)
+{
+    if (!r || !outInstance) return NX_ERR_INVALID;
+    nx_ctx* ctx = r->ctx;
+    DeviceGuard guard(ctx->device);
+    NX_CUDA(ctx, cudaMemcpyAsync(r->hQuery, r->dQuery, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->queryPending = false;
+    *outInstance = *r->hQuery;
     return NX_OK;
 }
 

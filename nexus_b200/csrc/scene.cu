@@ -273,9 +273,11 @@ int nx_scene_set_material(nx_scene* s, uint32_t idx, const nx_material* m)
     return NX_OK;
 }
 
-int nx_scene_add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx)
+// Mesh::Mesh (N/Assets/Mesh.h:29-40).  With `pre` the BLAS is taken from the caller (device arrays, copied) instead of built here.
+struct PrebuiltBlas { const nx_bvh8_node* dNodes; uint32_t nodeCount; const uint32_t* dPrimIdx; nx_aabb bounds; };
+
+static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx, const PrebuiltBlas* pre)
 {
-    if (!s || !tris || !n) return NX_ERR_INVALID;
     nx_ctx* ctx = s->ctx;
     DeviceGuard guard(ctx->device);
     HostMesh m; m.materialIdx = materialIdx;
@@ -287,13 +289,49 @@ int nx_scene_add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_da
     if (data) NX_CUDA(ctx, cudaMemcpyAsync(m.dTriData, data, 96 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     else default_tridata_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, n, m.dTriData);
     mesh_sphere(tris, n, m.sphere);
-    int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
-    if (rc) return rc;
+    if (pre) {
+        // same allocator as the builder's outputs, so nx_bvh8_free / scene destruction treat both kinds alike
+        NX_CUDA(ctx, cudaMallocAsync((void**)&m.bvh.nodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, ctx->stream));
+        NX_CUDA(ctx, cudaMallocAsync((void**)&m.bvh.prim_idx, 4 * (size_t)n, ctx->stream));
+        NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.nodes, pre->dNodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, cudaMemcpyDeviceToDevice, ctx->stream));
+        NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.prim_idx, pre->dPrimIdx, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        m.bvh.node_count = pre->nodeCount; m.bvh.prim_count = n; m.bvh.bounds = pre->bounds;
+    } else {
+        int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
+        if (rc) return rc;
+    }
     leaf_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris);
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     NX_CUDA(ctx, cudaGetLastError());
     s->meshes.push_back(m);
     return (int)s->meshes.size() - 1;
+}
+
+int nx_scene_add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx)
+{
+    if (!s || !tris || !n) return NX_ERR_INVALID;
+    return add_mesh(s, tris, data, n, materialIdx, nullptr);
+}
+
+int nx_scene_add_mesh_prebuilt(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx,
+                               const nx_bvh8_node* dNodes, uint32_t nodeCount, const uint32_t* dPrimIdx, const nx_aabb* bounds)
+{
+    if (!s || !tris || !n || !dNodes || !dPrimIdx || !bounds) return NX_ERR_INVALID;
+    if (!nodeCount || (size_t)nodeCount > ((size_t)4 * n - 1 + 6) / 7) NX_FAIL(s->ctx, NX_ERR_INVALID, "AddMesh(prebuilt): %u nodes for %u triangles", nodeCount, n);
+    const PrebuiltBlas pre{dNodes, nodeCount, dPrimIdx, *bounds};
+    return add_mesh(s, tris, data, n, materialIdx, &pre);
+}
+
+int nx_scene_build_blas(nx_ctx* ctx, const nx_triangle* hostTris, uint32_t n, nx_bvh8* out)
+{
+    if (!ctx || !hostTris || !n || !out) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    float* d = nullptr;
+    NX_CUDA(ctx, cudaMallocAsync((void**)&d, 36 * (size_t)n, ctx->stream));
+    NX_CUDA(ctx, cudaMemcpyAsync(d, hostTris, 36 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = nxi_build_bvh8(ctx, d, n, 1, ctx->scene_blas_speed, out);   // synchronises the stream
+    cudaFreeAsync(d, ctx->stream);
+    return rc;
 }
 
 int nx_scene_mesh_bounds(nx_scene* s, uint32_t meshIdx, nx_aabb* out)

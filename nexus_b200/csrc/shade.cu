@@ -22,10 +22,7 @@ __global__ void __launch_bounds__(256) generate_kernel(const __grid_constant__ D
         // every later queue inherits this order through compaction, so do their bounces).  Row-major order when the
         // resolution is not a multiple of the tile.  The pixel index, not the slot, keys the RNG and addresses the image.
         uint32_t px, py;
-        if (NX_TILED_PIXELS && (cam.resX & 7u) == 0u && (cam.resY & 3u) == 0u) {
-            const uint32_t tile = i >> 5, tilesX = cam.resX >> 3, ty = tile / tilesX, tx = tile - ty * tilesX;
-            px = tx * 8u + (i & 7u); py = ty * 4u + ((i >> 3) & 3u);
-        } else { py = i / cam.resX; px = i - py * cam.resX; }
+        slot_to_pixel(i, cam.resX, cam.resY, px, py);
         const uint32_t pixel = py * cam.resX + px;
         uint32_t rng = rng_seed(pixel, frame, 0u);
         const float x = ((float)px + rng_next(rng)) / (float)cam.resX;

@@ -33,6 +33,22 @@ struct WaveBuffers {
     WaveTotals* totals;
 };
 
+// Primary-ray queue order (generate_kernel): 8x4 pixel tiles when the resolution allows, row-major otherwise.
+__host__ __device__ __forceinline__ bool pixels_tiled(uint32_t resX, uint32_t resY) { return NX_TILED_PIXELS && (resX & 7u) == 0u && (resY & 3u) == 0u; }
+__host__ __device__ __forceinline__ void slot_to_pixel(uint32_t i, uint32_t resX, uint32_t resY, uint32_t& px, uint32_t& py)
+{
+    if (pixels_tiled(resX, resY)) {
+        const uint32_t tile = i >> 5, tilesX = resX >> 3, ty = tile / tilesX, tx = tile - ty * tilesX;
+        px = tx * 8u + (i & 7u); py = ty * 4u + ((i >> 3) & 3u);
+    } else { py = i / resX; px = i - py * resX; }
+}
+__host__ __device__ __forceinline__ uint32_t pixel_to_slot(uint32_t pixel, uint32_t resX, uint32_t resY)
+{
+    if (!pixels_tiled(resX, resY)) return pixel;
+    const uint32_t py = pixel / resX, px = pixel - py * resX;
+    return (((py >> 2) * (resX >> 3) + (px >> 3)) << 5) | ((py & 3u) << 3) | (px & 7u);
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 // one atomic per warp; every lane of the warp must call this (convergent point)

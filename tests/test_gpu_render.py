@@ -266,3 +266,72 @@ def test_constant_maps_equal_scaled_materials(ctx):
     d = scenes.with_triangle_data(scenes.cornell_box(path_length=2)); d["materials"][0].baseColorMap = 3
     with pytest.raises(nx.NexusError):
         scenes.build(ctx, d, (8, 8)).TraceClosest(nx.make_rays(np.zeros((1, 3), np.float32), np.array([[0, 0, -1]], np.float32)))
+
+
+def test_present_is_a_pipelined_read_rgba8(ctx):
+    """nx_renderer_present / present_wait (the reference's PBO path: Render returns without synchronising and the display reads the
+    pixel buffer a frame later, PathTracer.cpp:170-199): the image and queue totals a ticket delivers are those of the frames
+    submitted before Present, even though later frames were queued behind it before anybody waited."""
+    import torch
+    desc = scenes.with_triangle_data(scenes.cornell_box(path_length=4))
+    res = (128, 96)
+    scene = scenes.build(ctx, desc, res)
+    pt = nx.PathTracer(ctx, res)
+    bufs = [torch.zeros((res[1], res[0]), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32) for _ in range(2)]
+    tickets, want_img, want_stats = [], [], []
+    # reference answers with the synchronous calls
+    for f in (1, 2, 3):
+        pt.Render(scene, frames=1, firstFrame=f)
+        want_stats.append(pt.Stats()); want_img.append(pt.ReadRGBA8(scene).copy())
+    pt.ResetFrameNumber()
+    got_img, got_stats = [], []
+    for f in (1, 2, 3):
+        pt.Render(scene, frames=1, firstFrame=f)
+        tickets.append(pt.Present(scene, bufs[(f - 1) & 1]))
+        if f > 1:       # wait for the previous frame only after this one has been queued
+            got_stats.append(pt.PresentWait(tickets[-2])); got_img.append(bufs[(f - 2) & 1].copy())
+    got_stats.append(pt.PresentWait(tickets[-1])); got_img.append(bufs[0].copy())
+    assert tickets == [0, 1, 0]
+    for k in range(3):
+        assert (got_img[k] == want_img[k]).all(), k
+        for key in ("extension_rays", "shadow_rays", "shaded_hits", "frames"):
+            assert got_stats[k][key] == want_stats[k][key], (k, key)
+    fresh = nx.PathTracer(ctx, res)
+    with pytest.raises(nx.NexusError):
+        fresh.PresentWait(1)
+    fresh.close(); pt.close(); scene.close()
+
+
+def test_pixel_query_returns_the_primary_hit_instance(ctx):
+    """PathTracer::SetPixelQuery / SynchronizePixelQuery (PathTracer.cpp:221-240, PathTracer.cu:150-151, 459-460): the instance the
+    pixel's primary ray hits in the next frame, -1 for a miss.  Checked on pixels whose whole 3x3 neighbourhood of centre rays
+    agrees (the primary ray is jittered inside the pixel), at a tiled (8x4) and a non-tiled resolution."""
+    desc = scenes.with_triangle_data(scenes.instanced_scene(n_blas=3, n_instances=12, nu=12, nv=12, path_length=2))
+    for res in ((160, 120), (150, 90)):
+        scene = scenes.build(ctx, desc, res)
+        pt = nx.PathTracer(ctx, res)
+        assert not pt.PixelQueryPending() and pt.SynchronizePixelQuery() == -1
+        o, d = scenes.camera_rays(desc["camera"], res)
+        hits = scene.TraceClosest(nx.make_rays(o, d))
+        inst = np.where(hits["prim"] == 0xffffffff, -1, hits["instance"].astype(np.int64)).reshape(res[1], res[0])
+        stable = np.ones_like(inst, bool)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                stable &= np.roll(np.roll(inst, dy, 0), dx, 1) == inst
+        stable[0, :] = stable[-1, :] = False; stable[:, 0] = stable[:, -1] = False
+        ys, xs = np.nonzero(stable)
+        rs = np.random.RandomState(3)
+        picks = list(rs.choice(len(ys), 24, replace=False))
+        seen = set()
+        for frame, i in enumerate(picks, start=1):
+            x, y = int(xs[i]), int(ys[i])
+            pt.SetPixelQuery(x, y)
+            assert pt.PixelQueryPending()
+            pt.Render(scene, frames=1, firstFrame=frame)
+            got = pt.SynchronizePixelQuery()
+            assert got == inst[y, x] and pt.GetSelectedInstance() == got and not pt.PixelQueryPending(), (res, x, y, got, inst[y, x])
+            seen.add(got)
+        assert len(seen) >= 3                        # several different instances (and usually the background) were picked
+        with pytest.raises(nx.NexusError):
+            pt.SetPixelQuery(res[0], 0)
+        pt.close(); scene.close()
