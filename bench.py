@@ -154,7 +154,17 @@ def run_ours(args):
     ctx = nx.Context(local)          # raises when the CUDA library or a GPU is missing: there is no fallback
     desc = make_desc(args.workload)
     t_scene = time.time()
-    scene = scenes.build(ctx, desc, res)
+    # N > 1: the BLAS builds are sharded (rank g builds meshes g, g + N, ...; one NCCL all-gather hands every rank every BLAS,
+    # SURVEY.md 8(e)); the TLAS is built by every rank.  --replicated-build makes every rank build everything.
+    sharded = world > 1 and len(desc["meshes"]) > 1 and not args.replicated_build
+    if world > 1:                                      # NCCL communicator set-up (lazy, ~1 s) is not a scene cost: do it before the clock starts
+        dist.all_reduce(torch.zeros(1, device="cuda")); torch.cuda.synchronize()
+        t_scene = time.time()
+    if sharded:
+        from nexus_b200.multigpu import build_scene_sharded
+        scene = build_scene_sharded(ctx, desc, res)
+    else:
+        scene = scenes.build(ctx, desc, res)
     ctx.synchronize()
     t_scene = time.time() - t_scene
     pt = nx.PathTracer(ctx, res)
@@ -336,6 +346,7 @@ def run_ours(args):
                 "rays_per_step": int(rays_all / (K * world)), "extension_rays": int(cnt[1]), "shadow_rays": int(cnt[2]),
                 "primary_Mrays_per_s": round(world * K * res[0] * res[1] / (ms_total * 1e-3) / 1e6, 1),
                 "reduce_ms": round(ms_reduce, 3), "wall_s": round(wall, 3), "scene_setup_s": round(t_scene, 2),
+                "blas_builds": f"sharded round-robin over {world} ranks + NCCL all-gather" if sharded else "every rank builds every BLAS",
                 "mean_radiance": round(mean_radiance, 5),
                 "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "like_for_like": like}
         print(json.dumps(line), flush=True)
@@ -598,6 +609,7 @@ def main():
     ap.add_argument("--workload", default="instanced10m_4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-like-for-like", action="store_true")
+    ap.add_argument("--replicated-build", action="store_true", help="N > 1: every rank builds every BLAS instead of sharding the builds")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -180,6 +180,16 @@ def BuildBVH8Device(ctx, prims_dev, n, prim_type=1, prioritizeSpeed=False, metri
     return (bvh, m.as_dict()) if metrics else bvh
 
 
+def BuildBLAS(ctx, triangles):
+    """The BLAS Mesh::Mesh (N/Assets/Mesh.h:29-40) builds for a mesh, as a standalone unit of work: host (n, 9) triangles in, an owned
+    BVH8 out, built with the context's scene settings (collapse mode, leaf size, Morton width) exactly as AssetManager.AddMesh
+    would.  What a rank of a sharded scene build runs for the meshes it owns (nexus_b200.multigpu.build_scene_sharded)."""
+    tris = np.ascontiguousarray(triangles, np.float32).reshape(-1, 9)
+    out = Bvh8()
+    check(ctx._h, lib().nx_scene_build_blas(ctx._h, _ptr(tris), C.c_uint32(tris.shape[0]), C.byref(out)), "BuildBLAS")
+    return BVH8(ctx, out)
+
+
 def BenchmarkBuild(ctx, prims_dev, n, prim_type, prioritizeSpeed, warmup, iters, collapse=COLLAPSE_REFERENCE_GPU, maxLeafPrims=0):
     """NXB::BenchmarkBuild (BVHBuildMetrics.h:63-108) on primitives already resident on the device."""
     cfg, m, nodes = BuildConfig(int(prioritizeSpeed), int(collapse), int(maxLeafPrims)), BuildMetrics(), C.c_uint32(0)
@@ -314,6 +324,19 @@ class AssetManager:
             raise ValueError("triangleData must have one row per triangle")
         return check(self.scene.ctx._h, lib().nx_scene_add_mesh(self.scene._h, _ptr(tris), _ptr(td) if td is not None else None,
                                                                  C.c_uint32(tris.shape[0]), C.c_uint32(materialIdx)), f"AddMesh({name})")
+
+    def AddMeshPrebuilt(self, name, materialIdx, triangles, triangleData, nodes_dev, node_count, prim_idx_dev, bounds):
+        """AddMesh with the BLAS supplied (DEVICE pointers to node_count 80-byte nodes and one uint32 per triangle, e.g. inside an
+        all-gather buffer; copied) instead of built: the receiving side of a sharded scene build."""
+        tris = np.ascontiguousarray(triangles, np.float32).reshape(-1, 9)
+        td = None if triangleData is None else np.ascontiguousarray(triangleData, np.float32).reshape(-1, 24)
+        if td is not None and td.shape[0] != tris.shape[0]:
+            raise ValueError("triangleData must have one row per triangle")
+        b = np.asarray(bounds, np.float32).reshape(6)
+        box = Aabb((C.c_float * 3)(*b[:3]), (C.c_float * 3)(*b[3:]))
+        return check(self.scene.ctx._h, lib().nx_scene_add_mesh_prebuilt(self.scene._h, _ptr(tris), _ptr(td) if td is not None else None,
+                                                                          C.c_uint32(tris.shape[0]), C.c_uint32(materialIdx), C.c_void_p(int(nodes_dev)),
+                                                                          C.c_uint32(int(node_count)), C.c_void_p(int(prim_idx_dev)), C.byref(box)), f"AddMeshPrebuilt({name})")
 
     def AddTexture(self, pixels, sRGB=False):
         """AddTexture (AssetManager.h:31) + Texture::ToDevice (Texture.cpp:12-46).  pixels: (h, w, 4) uint8 (normalised reads,

@@ -236,16 +236,21 @@ def test_triangles(n, seed=12345, grid=1000):
     return out
 
 
-def build(ctx, desc, resolution):
-    """Instantiates a scene description through the reference-shaped host API."""
+def build(ctx, desc, resolution, blas=None):
+    """Instantiates a scene description through the reference-shaped host API.  blas: optional {mesh index: (nodes_dev, node_count,
+    prim_idx_dev, bounds)} of BLASes built elsewhere (nexus_b200.multigpu.build_scene_sharded); those meshes are imported, the
+    others built here."""
     scene = Scene(ctx, resolution)
     am = scene.GetAssetManager()
     for t in desc.get("textures", []):          # [(pixels, sRGB)]: indices in order of appearance
         am.AddTexture(t[0], t[1])
     for m in desc["materials"]:
         am.AddMaterial(m)
-    for m in desc["meshes"]:
-        am.AddMesh(m["name"], m["material"], m["triangles"], m.get("triangle_data"))
+    for k, m in enumerate(desc["meshes"]):
+        if blas is not None and k in blas:
+            am.AddMeshPrebuilt(m["name"], m["material"], m["triangles"], m.get("triangle_data"), *blas[k])
+        else:
+            am.AddMesh(m["name"], m["material"], m["triangles"], m.get("triangle_data"))
     for i in desc["instances"]:
         if "matrix" in i:      # imported assets carry the accumulated node transform (nexus_b200.gltf)
             scene.CreateMeshInstanceMatrix(i["mesh"], i["matrix"], i.get("material", -1))

@@ -48,3 +48,65 @@ def test_two_rank_reduce_equals_single_process(tmp_path):
         got = np.load(tmp_path / f"r{r}.npy")
         assert int(got[0]) == world * k
         assert np.allclose(got[1:], want, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------- sharded BLAS builds ----
+def _fake_blas(k):
+    """Stand-in for the BLAS of mesh k: deterministic, mesh-dependent sizes and bit patterns (negative words, -0.0 bounds)."""
+    rng = np.random.default_rng(77 + k)
+    nodes = rng.integers(-2**31, 2**31 - 1, 20 * (1 + k % 5), dtype=np.int64).astype(np.int32)
+    prim = rng.permutation(3 + 7 * (k % 4)).astype(np.int32)
+    bounds = rng.uniform(-5, 5, 6).astype(np.float32)
+    if k == 1:
+        bounds[0] = -0.0
+    return nodes, prim, bounds
+
+
+def _blas_worker(rank, world, port, n_meshes, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nexus_b200.multigpu import exchange_blas, mesh_owner
+    local = {k: tuple(torch.from_numpy(a) for a in _fake_blas(k)) for k in range(n_meshes) if mesh_owner(k, world) == rank}
+    got = exchange_blas(local, n_meshes, torch.device("cpu"))
+    np.savez(os.path.join(out_dir, f"b{rank}.npz"), **{f"{k}_{j}": t.numpy() for k, v in got.items() for j, t in enumerate(v)})
+    bad = False
+    try:                                                   # a rank that supplies somebody else's mesh is refused
+        exchange_blas({k: v for k, v in local.items()} | {(rank + 1) % world: local[next(iter(local))]}, n_meshes, torch.device("cpu"))
+    except ValueError:
+        bad = True
+    assert bad
+    dist.destroy_process_group()
+
+
+def test_blas_layout_partitions_every_payload():
+    from nexus_b200.multigpu import NODE_WORDS, blas_layout, mesh_owner
+    nodes, prims = [3, 1, 4, 1, 5, 9, 2], [10, 20, 30, 40, 50, 60, 70]
+    for world in (1, 2, 3, 8):
+        offsets, sizes = blas_layout(nodes, prims, world)
+        assert len(sizes) == world and sum(sizes) == NODE_WORDS * sum(nodes) + sum(prims)
+        for g in range(world):                             # the slices of a rank's meshes tile its payload exactly
+            spans = sorted((a, a + NODE_WORDS * nodes[k]) for k, (a, b) in enumerate(offsets) if mesh_owner(k, world) == g) + \
+                    sorted((b, b + prims[k]) for k, (a, b) in enumerate(offsets) if mesh_owner(k, world) == g)
+            covered = sorted(spans)
+            assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+            assert (covered[0][0] == 0 and covered[-1][1] == sizes[g]) if covered else sizes[g] == 0
+
+
+def test_two_rank_blas_exchange_delivers_every_mesh_bit_for_bit(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    world, n_meshes = 2, 7
+    mp.start_processes(_blas_worker, args=(world, port, n_meshes, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    for r in range(world):
+        got = np.load(tmp_path / f"b{r}.npz")
+        for k in range(n_meshes):
+            for j, want in enumerate(_fake_blas(k)):
+                assert got[f"{k}_{j}"].dtype == want.dtype and got[f"{k}_{j}"].tobytes() == want.tobytes(), (r, k, j)
+
+
+def test_single_process_blas_exchange_is_the_identity():
+    from nexus_b200.multigpu import exchange_blas
+    local = {k: tuple(torch.from_numpy(a) for a in _fake_blas(k)) for k in range(4)}
+    got = exchange_blas(local, 4, torch.device("cpu"))
+    for k in range(4):
+        for j, want in enumerate(_fake_blas(k)):
+            assert got[k][j].numpy().tobytes() == want.tobytes()
