@@ -84,7 +84,9 @@ def test_obj_reader_rejects_what_it_cannot_represent(tmp_path):
 @pytest.mark.gpu
 def test_obj_scene_renders_like_the_same_scene_built_directly(tmp_path):
     d = obj.load_obj(_write(tmp_path), path_length=3)
-    d["camera"] = nx.Camera(position=(0.5, 0.5, 4.0), forward=(0.0, 0.0, -1.0), horizontalFOV=40.0)
+    # seen from below and in front: the emissive y = 0 face is in view, and a grey sky lights the rest
+    d["camera"] = nx.Camera(position=(0.5, -2.0, 4.0), forward=(0.0, 0.5547002, -0.8320503), horizontalFOV=40.0)
+    d["settings"].backgroundColor = (0.4, 0.5, 0.6)
     d["materials"][0].opacity = 1.0
     res = (96, 64)
     ctx = nx.Context(0)
