@@ -190,7 +190,13 @@ int nx_scene_add_instance(nx_scene* scene, uint32_t mesh_idx, int32_t material_i
 /* Same, with an explicit row-major 4x4 (used by parity tests so both arms see identical matrices). */
 int nx_scene_add_instance_matrix(nx_scene* scene, uint32_t mesh_idx, int32_t material_idx, const float m[16]);
 int nx_scene_set_instance_transform(nx_scene* scene, uint32_t inst, const float position[3], const float rotation_deg[3], const float scale[3]);
+int nx_scene_set_instance_material(nx_scene* scene, uint32_t inst, int32_t material_idx);      /* MeshInstance::AssignMaterial + InvalidateMeshInstance */
+int nx_scene_instance_matrix(nx_scene* scene, uint32_t inst, float out_row_major[16]);         /* MeshInstance::GetTransfromationMatrix */
+int nx_scene_instance_bounds(nx_scene* scene, uint32_t inst, nx_aabb* out);                    /* MeshInstance::GetBounds (world AABB) */
 int nx_scene_add_light(nx_scene* scene, const nx_light* light);                         /* Scene::AddLight */
+int nx_scene_set_light(nx_scene* scene, uint32_t idx, const nx_light* light);           /* GetLights()[idx] = ...; InvalidateLight(idx) */
+int nx_scene_remove_light(nx_scene* scene, uint32_t idx);                               /* Scene::RemoveLight */
+int nx_scene_light_count(nx_scene* scene);                                              /* lights added through AddLight (mesh lights are automatic) */
 int nx_scene_set_camera(nx_scene* scene, const nx_camera* cam);
 int nx_scene_set_render_settings(nx_scene* scene, const nx_render_settings* rs);
 /* AssetManager::AddTexture + Texture::ToDevice (src/Assets/Texture.cpp:12-46): HOST RGBA8 (is_hdr 0; srgb: decode in the sampler) or RGBA32F

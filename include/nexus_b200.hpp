@@ -16,6 +16,9 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <deque>
+#include <memory>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -64,6 +67,7 @@ inline BVH8 BuildBVH8(nexus::Context& ctx, const AABB* dPrims, uint32_t n, Build
 { BVH8 b; nx_build_config c{cfg.prioritizeSpeed}; ctx.check(nx_bvh8_build_aabb(ctx.handle(), dPrims, n, &c, m, &b.h), "BuildBVH8<AABB>"); return b; }
 inline std::vector<nx_bvh2_node> ToHost(nexus::Context& ctx, const BVH2& b)
 { std::vector<nx_bvh2_node> v(b.h.node_count); ctx.check(nx_bvh2_to_host(ctx.handle(), &b.h, v.data()), "ToHost"); return v; }
+inline void FreeHostBVH(std::vector<nx_bvh2_node>& hostNodes) { std::vector<nx_bvh2_node>().swap(hostNodes); }   // NXB::FreeHostBVH (BVHBuilder.h:42)
 inline void FreeDeviceBVH(nexus::Context& ctx, BVH2& b) { nx_bvh2_free(ctx.handle(), &b.h); }
 inline void FreeDeviceBVH(nexus::Context& ctx, BVH8& b) { nx_bvh8_free(ctx.handle(), &b.h); }
 // BenchmarkBuild(BuildBVH8<PrimT>, warmup, iterations, ...) (NXB/BVHBuildMetrics.h:63-108): averaged per-stage times
@@ -103,10 +107,36 @@ struct Material {                       // src/Assets/Material.h:6-26, same defa
 struct Light {                          // src/Scene/Light.h:10-54
     enum class Type { POINT = 0, SPOT = 1, DIRECTIONAL = 2, MESH = 3 } type = Type::POINT;
     float3 position{0, 0, 0}, direction{0, -1, 0}, color{1, 1, 1}; float intensity = 1.0f; uint32_t meshId = 0;
+    nx_light pod() const
+    {
+        nx_light p{}; p.type = (int32_t)type;
+        p.position[0] = position.x; p.position[1] = position.y; p.position[2] = position.z;
+        p.direction[0] = direction.x; p.direction[1] = direction.y; p.direction[2] = direction.z;
+        p.color[0] = color.x; p.color[1] = color.y; p.color[2] = color.z; p.intensity = intensity; p.instance = meshId;
+        return p;
+    }
 };
 
-struct Camera {                         // src/Scene/Camera.h:9-52 (ctor arguments)
+struct Camera {                         // src/Scene/Camera.h:9-52 (ctor arguments, setters, invalid flag)
     float3 position{0.0f, 4.0f, 14.0f}, forward{0.0f, 0.0f, -1.0f}; float horizontalFOV = 45.0f, focusDistance = 5.0f, defocusAngle = 0.0f;
+    float3 right{0.0f, 0.0f, 0.0f};     // zero: derived as cross(forward, +Y)
+    float& GetHorizontalFOV() { return horizontalFOV; }
+    void SetHorizontalFOV(float v) { horizontalFOV = v; }
+    float& GetDefocusAngle() { return defocusAngle; }
+    void SetDefocusAngle(float v) { defocusAngle = v; }
+    float& GetFocusDist() { return focusDistance; }
+    void SetFocusDist(float v) { focusDistance = v; }
+    float3& GetPosition() { return position; }
+    void SetPosition(const float3& v) { position = v; }
+    float3& GetForwardDirection() { return forward; }
+    void SetForwardDirection(const float3& v) { forward = v; }
+    float3& GetRightDirection() { return right; }
+    void SetRightDirection(const float3& v) { right = v; }
+    bool IsInvalid() const { return invalid_; }
+    void SetInvalid(bool v) { invalid_ = v; }
+    void Invalidate() { invalid_ = true; }
+private:
+    bool invalid_ = true;
 };
 
 struct RenderSettings {                 // src/Renderer/RenderSettings.h:5-17
@@ -115,81 +145,173 @@ struct RenderSettings {                 // src/Renderer/RenderSettings.h:5-17
 
 class Scene;
 
-class MeshInstance {                    // src/Scene/MeshInstance.h:9-77
+// src/Scene/MeshInstance.h:9-77: host object; edits reach the device at the next Scene::Update() after
+// Scene::InvalidateMeshInstance(index) - the setters below also invalidate by themselves.  (The reference's SetRotationY / SetRotationZ
+// write `position`, MeshInstance.h:24-25; that bug is not reproduced.)
+class MeshInstance {
 public:
-    MeshInstance(Scene* s, uint32_t idx) : scene_(s), idx_(idx) {}
-    void SetTransform(float3 position, float3 rotationDeg, float3 scale);
+    MeshInstance(Scene* s, uint32_t idx, uint32_t mesh, int material, float3 p, float3 r, float3 sc)
+        : name("instance " + std::to_string(idx)), position(p), rotation(r), scale(sc), meshIdx(mesh), materialIdx(material), scene_(s), idx_(idx) {}
+    void SetPosition(float3 p) { position = p; Edited(); }
+    void SetRotationX(float r) { rotation.x = r; Edited(); }
+    void SetRotationY(float r) { rotation.y = r; Edited(); }
+    void SetRotationZ(float r) { rotation.z = r; Edited(); }
+    void SetScale(float s) { scale = float3{s, s, s}; Edited(); }
+    void SetScale(float3 s) { scale = s; Edited(); }
+    void SetTransform(float3 p, float3 r, float3 s);          // applied at once
+    void AssignMaterial(int mIdx);
+    std::array<float, 16> GetTransfromationMatrix();           // T * Rz * Ry * Rx * S, row-major (MeshInstance.h:36-40; the reference's spelling)
+    NXB::AABB GetBounds();                                     // world AABB of the mesh box's eight corners (MeshInstance.h:42-53)
     uint32_t index() const { return idx_; }
+    std::string name;
+    float3 position, rotation, scale;
+    uint32_t meshIdx; int materialIdx;
 private:
-    Scene* scene_; uint32_t idx_;
+    friend class Scene;
+    void Edited();
+    Scene* scene_; uint32_t idx_; bool trsEdited_ = false, materialEdited_ = false;
 };
 
 class AssetManager {                    // src/Assets/AssetManager.h:13-57
 public:
     explicit AssetManager(Scene* s) : scene_(s) {}
     uint32_t AddMaterial(const Material& m);
+    std::vector<Material>& GetMaterials() { return materials_; }        // edit an entry, then InvalidateMaterial(index)
     // AddMesh builds the BLAS immediately (Mesh::Mesh, src/Assets/Mesh.h:15-46: BuildBVH8<Triangle>, prioritizeSpeed = true)
     uint32_t AddMesh(const std::string& name, uint32_t materialIdx, const std::vector<NXB::Triangle>& triangles, const std::vector<nx_triangle_data>& triangleData = {});
-    void InvalidateMaterial(uint32_t idx, const Material& m);
+    void InvalidateMaterial(uint32_t idx) { if (idx >= materials_.size()) throw Error("InvalidateMaterial: no such material"); invalid_.insert(idx); }
+    void InvalidateMaterial(uint32_t idx, const Material& m) { if (idx >= materials_.size()) throw Error("InvalidateMaterial: no such material"); materials_[idx] = m; invalid_.insert(idx); SendDataToDevice(); }
+    bool SendDataToDevice();                                            // AssetManager.cpp:74-84: uploads the invalidated materials
+    bool IsInvalid() const { return !invalid_.empty(); }
     // AddTexture + Texture::ToDevice (src/Assets/Texture.cpp:12-46): RGBA8 (isHDR false) or RGBA32F pixels; returns the id Material::*MapId uses
     uint32_t AddTexture(const void* rgbaPixels, uint32_t width, uint32_t height, bool isHDR = false, bool sRGB = false);
 private:
-    Scene* scene_;
+    Scene* scene_; std::vector<Material> materials_; std::set<uint32_t> invalid_;
 };
 
 class Scene {                           // src/Scene/Scene.h:16-77
 public:
-    Scene(Context& ctx, uint2 resolution) : ctx_(ctx), assets_(this), res_(resolution) { ctx.check(nx_scene_create(ctx.handle(), resolution.x, resolution.y, &h_), "Scene"); }
+    Scene(Context& ctx, uint2 resolution) : ctx_(ctx), assets_(this), res_(resolution), camera_(std::make_shared<Camera>()) { ctx.check(nx_scene_create(ctx.handle(), resolution.x, resolution.y, &h_), "Scene"); }
     ~Scene() { nx_scene_destroy(h_); }
     Scene(const Scene&) = delete; Scene& operator=(const Scene&) = delete;
+    std::shared_ptr<Camera> GetCamera() { return camera_; }               // edit, Invalidate(), Update()
     AssetManager& GetAssetManager() { return assets_; }
     uint32_t AddMaterial(const Material& m) { return assets_.AddMaterial(m); }
-    MeshInstance CreateMeshInstance(uint32_t meshId, float3 position = {0, 0, 0}, float3 rotationDeg = {0, 0, 0}, float3 scale = {1, 1, 1}, int materialIdx = -1)
+    std::vector<Material>& GetMaterials() { return assets_.GetMaterials(); }
+    RenderSettings& GetRenderSettings() { return settings_; }             // edits are uploaded by the next Update()
+    const RenderSettings& GetRenderSettings() const { return settings_; }
+    bool IsEmpty() const { return instances_.empty(); }
+    bool IsInvalid() const { return !invalidInstances_.empty() || !invalidLights_.empty() || camera_->IsInvalid() || assets_.IsInvalid(); }
+    MeshInstance& CreateMeshInstance(uint32_t meshId, float3 position = {0, 0, 0}, float3 rotationDeg = {0, 0, 0}, float3 scale = {1, 1, 1}, int materialIdx = -1)
     {
         const float p[3] = {position.x, position.y, position.z}, r[3] = {rotationDeg.x, rotationDeg.y, rotationDeg.z}, s[3] = {scale.x, scale.y, scale.z};
-        return MeshInstance(this, (uint32_t)ctx_.check(nx_scene_add_instance(h_, meshId, materialIdx, p, r, s), "CreateMeshInstance"));
+        const uint32_t idx = (uint32_t)ctx_.check(nx_scene_add_instance(h_, meshId, materialIdx, p, r, s), "CreateMeshInstance");
+        instances_.emplace_back(this, idx, meshId, materialIdx, position, rotationDeg, scale);
+        return instances_.back();
     }
-    void AddLight(const Light& l)
+    std::deque<MeshInstance>& GetMeshInstances() { return instances_; }   // a deque: references stay valid as instances are added
+    void InvalidateMeshInstance(uint32_t instanceId) { invalidInstances_.insert(instanceId); }
+    size_t AddLight(const Light& l)
     {
-        nx_light p{}; p.type = (int32_t)l.type;
-        p.position[0] = l.position.x; p.position[1] = l.position.y; p.position[2] = l.position.z;
-        p.direction[0] = l.direction.x; p.direction[1] = l.direction.y; p.direction[2] = l.direction.z;
-        p.color[0] = l.color.x; p.color[1] = l.color.y; p.color[2] = l.color.z; p.intensity = l.intensity; p.instance = l.meshId;
-        ctx_.check(nx_scene_add_light(h_, &p), "AddLight");
+        const nx_light p = l.pod();
+        const size_t idx = (size_t)ctx_.check(nx_scene_add_light(h_, &p), "AddLight");
+        lights_.push_back(l);
+        return idx;
+    }
+    std::vector<Light>& GetLights() { return lights_; }                   // edit an entry, then InvalidateLight(index)
+    void InvalidateLight(uint32_t lightIdx) { if (lightIdx >= lights_.size()) throw Error("InvalidateLight: no such light"); invalidLights_.insert(lightIdx); }
+    void RemoveLight(size_t index)
+    {
+        if (index >= lights_.size()) throw Error("RemoveLight: no such light");
+        ctx_.check(nx_scene_remove_light(h_, (uint32_t)index), "RemoveLight");
+        lights_.erase(lights_.begin() + (std::ptrdiff_t)index);
+        std::set<uint32_t> moved;
+        for (uint32_t i : invalidLights_) if (i != index) moved.insert(i > index ? i - 1 : i);
+        invalidLights_.swap(moved);
     }
     void AddHDRMap(const float* rgba, uint32_t w, uint32_t h) { ctx_.check(nx_scene_set_hdr_map(h_, rgba, w, h), "AddHDRMap"); }
     void SetCamera(const Camera& c)
     {
+        *camera_ = c;
         nx_camera p{}; p.position[0] = c.position.x; p.position[1] = c.position.y; p.position[2] = c.position.z;
         p.forward[0] = c.forward.x; p.forward[1] = c.forward.y; p.forward[2] = c.forward.z;
+        p.right[0] = c.right.x; p.right[1] = c.right.y; p.right[2] = c.right.z;
         p.horizontal_fov_deg = c.horizontalFOV; p.focus_distance = c.focusDistance; p.defocus_angle_deg = c.defocusAngle;
         ctx_.check(nx_scene_set_camera(h_, &p), "SetCamera");
+        camera_->SetInvalid(false);
     }
     void SetRenderSettings(const RenderSettings& r)
     {
+        settings_ = r;
         nx_render_settings p{}; p.use_mis = r.useMIS; p.path_length = r.pathLength;
         p.background_color[0] = r.backgroundColor.x; p.background_color[1] = r.backgroundColor.y; p.background_color[2] = r.backgroundColor.z;
         p.background_intensity = r.backgroundIntensity; p.tone_mapping = r.toneMapping; p.exposure = r.exposure;
         ctx_.check(nx_scene_set_render_settings(h_, &p), "SetRenderSettings");
     }
-    void Update() { ctx_.check(nx_scene_update(h_), "Scene::Update"); }      // uploads dirty state, rebuilds the TLAS, refreshes the light list
-    void BuildTLAS() { Update(); }
+    // Scene::Update (Scene.cpp:34-63): uploads what was invalidated (camera, settings, materials, instances, lights), rebuilds the TLAS
+    // when an instance changed, refreshes the light list
+    void Update()
+    {
+        if (camera_->IsInvalid()) SetCamera(Camera(*camera_));
+        SetRenderSettings(RenderSettings(settings_));                     // a host-side struct copy; no device work
+        assets_.SendDataToDevice();
+        for (uint32_t i : std::set<uint32_t>(invalidInstances_)) if (i < instances_.size()) Flush(instances_[i]);
+        invalidInstances_.clear();
+        for (uint32_t i : invalidLights_) { const nx_light p = lights_[i].pod(); ctx_.check(nx_scene_set_light(h_, i, &p), "InvalidateLight"); }
+        invalidLights_.clear();
+        ctx_.check(nx_scene_update(h_), "Scene::Update");
+    }
+    void BuildTLAS() { Update(); }                                        // the library rebuilds the TLAS inside Update when an instance changed
     NXB::BVH8 GetTLAS() { NXB::BVH8 b; ctx_.check(nx_scene_tlas(h_, &b.h), "TLAS"); return b; }
     nx_scene* handle() const { return h_; }
     Context& context() const { return ctx_; }
     uint2 resolution() const { return res_; }
 private:
+    friend class MeshInstance;
+    void Flush(MeshInstance& m)
+    {
+        if (m.trsEdited_) {
+            const float p[3] = {m.position.x, m.position.y, m.position.z}, r[3] = {m.rotation.x, m.rotation.y, m.rotation.z}, s[3] = {m.scale.x, m.scale.y, m.scale.z};
+            ctx_.check(nx_scene_set_instance_transform(h_, m.idx_, p, r, s), "InvalidateMeshInstance");
+        }
+        if (m.materialEdited_) ctx_.check(nx_scene_set_instance_material(h_, m.idx_, m.materialIdx), "AssignMaterial");
+        m.trsEdited_ = m.materialEdited_ = false;
+        invalidInstances_.erase(m.idx_);
+    }
     Context& ctx_; nx_scene* h_ = nullptr; AssetManager assets_; uint2 res_;
+    std::shared_ptr<Camera> camera_; RenderSettings settings_;
+    std::deque<MeshInstance> instances_; std::set<uint32_t> invalidInstances_;
+    std::vector<Light> lights_; std::set<uint32_t> invalidLights_;
 };
 
-inline void MeshInstance::SetTransform(float3 position, float3 rotationDeg, float3 scale)
+inline void MeshInstance::Edited() { trsEdited_ = true; scene_->InvalidateMeshInstance(idx_); }
+inline void MeshInstance::SetTransform(float3 p, float3 r, float3 s) { position = p; rotation = r; scale = s; Edited(); scene_->Flush(*this); }
+inline void MeshInstance::AssignMaterial(int mIdx) { materialIdx = mIdx; materialEdited_ = true; scene_->InvalidateMeshInstance(idx_); }
+inline std::array<float, 16> MeshInstance::GetTransfromationMatrix()
 {
-    const float p[3] = {position.x, position.y, position.z}, r[3] = {rotationDeg.x, rotationDeg.y, rotationDeg.z}, s[3] = {scale.x, scale.y, scale.z};
-    scene_->context().check(nx_scene_set_instance_transform(scene_->handle(), idx_, p, r, s), "SetTransform");
+    scene_->Flush(*this);
+    std::array<float, 16> m{}; scene_->context().check(nx_scene_instance_matrix(scene_->handle(), idx_, m.data()), "GetTransfromationMatrix"); return m;
 }
-inline uint32_t AssetManager::AddMaterial(const Material& m) { const nx_material p = m.pod(); return (uint32_t)scene_->context().check(nx_scene_add_material(scene_->handle(), &p), "AddMaterial"); }
+inline NXB::AABB MeshInstance::GetBounds()
+{
+    scene_->Flush(*this);
+    NXB::AABB b{}; scene_->context().check(nx_scene_instance_bounds(scene_->handle(), idx_, &b), "GetBounds"); return b;
+}
+inline uint32_t AssetManager::AddMaterial(const Material& m)
+{
+    const nx_material p = m.pod();
+    const uint32_t idx = (uint32_t)scene_->context().check(nx_scene_add_material(scene_->handle(), &p), "AddMaterial");
+    materials_.push_back(m);
+    return idx;
+}
+inline bool AssetManager::SendDataToDevice()
+{
+    const bool any = !invalid_.empty();
+    for (uint32_t i : invalid_) { const nx_material p = materials_[i].pod(); scene_->context().check(nx_scene_set_material(scene_->handle(), i, &p), "InvalidateMaterial"); }
+    invalid_.clear();
+    return any;
+}
 inline uint32_t AssetManager::AddTexture(const void* px, uint32_t w, uint32_t h, bool isHDR, bool sRGB) { return (uint32_t)scene_->context().check(nx_scene_add_texture(scene_->handle(), px, w, h, isHDR, sRGB), "AddTexture"); }
-inline void AssetManager::InvalidateMaterial(uint32_t idx, const Material& m) { const nx_material p = m.pod(); scene_->context().check(nx_scene_set_material(scene_->handle(), idx, &p), "InvalidateMaterial"); }
 inline uint32_t AssetManager::AddMesh(const std::string& name, uint32_t materialIdx, const std::vector<NXB::Triangle>& tris, const std::vector<nx_triangle_data>& data)
 {
     if (!data.empty() && data.size() != tris.size()) throw Error("AddMesh(" + name + "): triangleData must have one entry per triangle");
@@ -207,6 +329,8 @@ public:
     void Render(Scene& scene) { Render(scene, 1); }
     void Render(Scene& scene, uint32_t frames) { ctx_.check(nx_renderer_render(h_, scene.handle(), frame_ + 1, frames), "Render"); frame_ += frames; }
     uint32_t GetFrameNumber() const { return frame_; }
+    void Reset() { ResetFrameNumber(); }                                  // PathTracer::Reset (PathTracer.cpp:61-159): the queues here are sized once per resolution
+    void UpdateDeviceScene(Scene& scene) { scene.Update(); }              // PathTracer.cpp:216-219: the scene view is a per-call parameter block; flush pending edits
     uint2 GetResolution() const { return res_; }
     nx_frame_stats Stats() { nx_frame_stats s{}; ctx_.check(nx_renderer_stats(h_, &s), "Stats"); return s; }
     std::vector<float> ReadAccumulation() { std::vector<float> v(3ull * res_.x * res_.y); ctx_.check(nx_renderer_read_accum(h_, v.data()), "ReadAccumulation"); return v; }

@@ -270,6 +270,24 @@ class Camera:
     def __init__(self, position=(0.0, 4.0, 14.0), forward=(0.0, 0.0, -1.0), horizontalFOV=45.0, focusDistance=5.0, defocusAngle=0.0, right=(0.0, 0.0, 0.0)):
         self.position, self.forward, self.right = position, forward, right
         self.horizontalFOV, self.focusDistance, self.defocusAngle = horizontalFOV, focusDistance, defocusAngle
+        self._invalid = True
+
+    # Camera.h:19-35: the setters do not invalidate by themselves in the reference either; Scene::Update pushes an invalid camera
+    def GetHorizontalFOV(self): return self.horizontalFOV
+    def SetHorizontalFOV(self, v): self.horizontalFOV = float(v)
+    def GetDefocusAngle(self): return self.defocusAngle
+    def SetDefocusAngle(self, v): self.defocusAngle = float(v)
+    def GetFocusDist(self): return self.focusDistance
+    def SetFocusDist(self, v): self.focusDistance = float(v)
+    def GetPosition(self): return self.position
+    def SetPosition(self, v): self.position = tuple(float(x) for x in v)
+    def GetForwardDirection(self): return self.forward
+    def SetForwardDirection(self, v): self.forward = tuple(float(x) for x in v)
+    def GetRightDirection(self): return self.right
+    def SetRightDirection(self, v): self.right = tuple(float(x) for x in v)
+    def IsInvalid(self): return self._invalid
+    def SetInvalid(self, invalid): self._invalid = bool(invalid)
+    def Invalidate(self): self._invalid = True
 
     def pod(self):
         p = CameraPod()
@@ -296,14 +314,61 @@ class RenderSettings:
 
 
 class MeshInstance:
-    """MeshInstance (src/Scene/MeshInstance.h:9-77): handle returned by Scene.CreateMeshInstance."""
+    """MeshInstance (src/Scene/MeshInstance.h:9-77): host object with position / rotation (Euler degrees) / scale, mesh and material
+    index.  As in the reference, edits take effect at the next Scene.Update() after Scene.InvalidateMeshInstance(index); the
+    setters here also invalidate by themselves, so forgetting the call is harmless.  (The reference's SetRotationY / SetRotationZ
+    write `position`, MeshInstance.h:24-25; that bug is not reproduced.)"""
 
-    def __init__(self, scene, index, meshIdx):
-        self.scene, self.index, self.meshIdx = scene, index, meshIdx
+    def __init__(self, scene, index, meshIdx, materialIdx=-1, position=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0), scale=(1.0, 1.0, 1.0), matrix=None):
+        self.scene, self.index, self.meshIdx, self.materialIdx = scene, int(index), int(meshIdx), int(materialIdx)
+        self.position, self.rotation, self.scale = tuple(map(float, position)), tuple(map(float, rotation)), tuple(map(float, scale))
+        self._matrix = None if matrix is None else np.array(matrix, np.float32).reshape(4, 4)    # explicit-matrix instances (asset import)
+        self.name = f"instance {index}"
+        self._material_edited = self._trs_edited = False
+
+    def _edited(self):
+        self._matrix = None
+        self._trs_edited = True
+        self.scene.InvalidateMeshInstance(self.index)
+
+    def SetPosition(self, p):
+        self.position = tuple(map(float, p)); self._edited()
+
+    def SetRotationX(self, r):
+        self.rotation = (float(r), self.rotation[1], self.rotation[2]); self._edited()
+
+    def SetRotationY(self, r):
+        self.rotation = (self.rotation[0], float(r), self.rotation[2]); self._edited()
+
+    def SetRotationZ(self, r):
+        self.rotation = (self.rotation[0], self.rotation[1], float(r)); self._edited()
+
+    def SetScale(self, s):
+        self.scale = (float(s),) * 3 if np.isscalar(s) else tuple(map(float, s)); self._edited()
 
     def SetTransform(self, position, rotation, scale):
-        p, r, s = (np.asarray(v, np.float32) for v in (position, rotation, scale))
-        check(self.scene.ctx._h, lib().nx_scene_set_instance_transform(self.scene._h, C.c_uint32(self.index), _ptr(p), _ptr(r), _ptr(s)), "SetTransform")
+        self.position, self.rotation, self.scale = tuple(map(float, position)), tuple(map(float, rotation)), tuple(map(float, scale))
+        self._edited()
+        self.scene._flush_instance(self)        # applied at once (older callers trace right after SetTransform without Update)
+
+    def AssignMaterial(self, materialIdx):
+        self.materialIdx = int(materialIdx)
+        self._material_edited = True
+        self.scene.InvalidateMeshInstance(self.index)
+
+    def GetTransfromationMatrix(self):
+        """T * Rz * Ry * Rx * S (MeshInstance.h:36-40; the spelling is the reference's), row-major 4x4, as the device sees it."""
+        self.scene._flush_instance(self)
+        m = np.zeros(16, np.float32)
+        check(self.scene.ctx._h, lib().nx_scene_instance_matrix(self.scene._h, C.c_uint32(self.index), _ptr(m)), "GetTransfromationMatrix")
+        return m.reshape(4, 4)
+
+    def GetBounds(self):
+        """World AABB of the eight transformed corners of the mesh's box (MeshInstance.h:42-53): (bmin, bmax) as 6 floats."""
+        self.scene._flush_instance(self)
+        b = Aabb()
+        check(self.scene.ctx._h, lib().nx_scene_instance_bounds(self.scene._h, C.c_uint32(self.index), C.byref(b)), "GetBounds")
+        return np.array(list(b.bmin) + list(b.bmax), np.float32)
 
 
 class AssetManager:
@@ -311,10 +376,29 @@ class AssetManager:
 
     def __init__(self, scene):
         self.scene = scene
+        self._materials, self._invalid_materials = [], set()
 
     def AddMaterial(self, material):
         p = material.pod()
-        return check(self.scene.ctx._h, lib().nx_scene_add_material(self.scene._h, C.byref(p)), "AddMaterial")
+        idx = check(self.scene.ctx._h, lib().nx_scene_add_material(self.scene._h, C.byref(p)), "AddMaterial")
+        self._materials.append(material)
+        return idx
+
+    def GetMaterials(self):
+        """The host materials (AssetManager.h:24); edit one, then InvalidateMaterial(index)."""
+        return self._materials
+
+    def SendDataToDevice(self):
+        """AssetManager::SendDataToDevice (AssetManager.cpp:74-84): pushes the invalidated materials; True if there were any."""
+        dirty = sorted(self._invalid_materials)
+        for i in dirty:
+            p = self._materials[i].pod()
+            check(self.scene.ctx._h, lib().nx_scene_set_material(self.scene._h, C.c_uint32(i), C.byref(p)), "InvalidateMaterial")
+        self._invalid_materials.clear()
+        return bool(dirty)
+
+    def IsInvalid(self):
+        return bool(self._invalid_materials)
 
     def AddMesh(self, name, materialIdx, triangles, triangleData=None):
         """AddMesh(name, materialIdx, triangles, triangleData) (AssetManager.cpp:24-33): builds the BLAS immediately."""
@@ -347,9 +431,16 @@ class AssetManager:
         return check(self.scene.ctx._h, lib().nx_scene_add_texture(self.scene._h, _ptr(pixels), C.c_uint32(pixels.shape[1]), C.c_uint32(pixels.shape[0]),
                                                                     C.c_int(int(pixels.dtype == np.float32)), C.c_int(int(sRGB))), "AddTexture")
 
-    def InvalidateMaterial(self, index, material):
-        p = material.pod()
-        check(self.scene.ctx._h, lib().nx_scene_set_material(self.scene._h, C.c_uint32(index), C.byref(p)), "InvalidateMaterial")
+    def InvalidateMaterial(self, index, material=None):
+        """AssetManager::InvalidateMaterial (AssetManager.h:36): marks GetMaterials()[index] for upload at the next Scene.Update().
+        With `material` given it replaces the entry and uploads at once."""
+        if not (0 <= index < len(self._materials)):
+            raise NexusError(f"InvalidateMaterial: material {index} of {len(self._materials)}")
+        if material is not None:
+            self._materials[index] = material
+        self._invalid_materials.add(int(index))
+        if material is not None:
+            self.SendDataToDevice()
 
 
 class Scene:
@@ -361,6 +452,9 @@ class Scene:
         self._h = C.c_void_p()
         check(ctx._h, lib().nx_scene_create(ctx._h, C.c_uint32(self.resolution[0]), C.c_uint32(self.resolution[1]), C.byref(self._h)), "Scene")
         self._assets = AssetManager(self)
+        self._camera, self._settings = Camera(), RenderSettings()       # Scene::Scene defaults (Scene.cpp:8-12, RenderSettings.h:5-17)
+        self._instances, self._invalid_instances = [], set()
+        self._lights, self._invalid_lights = [], set()
 
     def close(self):
         if self._h:
@@ -373,27 +467,93 @@ class Scene:
     def AddMaterial(self, material):
         return self._assets.AddMaterial(material)
 
+    def GetMaterials(self):
+        return self._assets.GetMaterials()
+
     def CreateMeshInstance(self, meshId, materialIdx=-1, position=(0, 0, 0), rotation=(0, 0, 0), scale=(1, 1, 1)):
         p, r, s = (np.asarray(v, np.float32) for v in (position, rotation, scale))
         idx = check(self.ctx._h, lib().nx_scene_add_instance(self._h, C.c_uint32(meshId), C.c_int32(materialIdx), _ptr(p), _ptr(r), _ptr(s)), "CreateMeshInstance")
-        return MeshInstance(self, idx, meshId)
+        inst = MeshInstance(self, idx, meshId, materialIdx, position, rotation, scale)
+        self._instances.append(inst)
+        return inst
 
     def CreateMeshInstanceMatrix(self, meshId, matrix, materialIdx=-1):
         m = np.ascontiguousarray(matrix, np.float32).reshape(16)
         idx = check(self.ctx._h, lib().nx_scene_add_instance_matrix(self._h, C.c_uint32(meshId), C.c_int32(materialIdx), _ptr(m)), "CreateMeshInstance")
-        return MeshInstance(self, idx, meshId)
+        inst = MeshInstance(self, idx, meshId, materialIdx, matrix=m)
+        self._instances.append(inst)
+        return inst
+
+    def GetMeshInstances(self):
+        return self._instances
+
+    def IsEmpty(self):
+        return not self._instances
+
+    def InvalidateMeshInstance(self, instanceId):
+        """Scene::InvalidateMeshInstance (Scene.cpp:109-112): the instance's transform / material are re-read at the next Update()."""
+        self._invalid_instances.add(int(instanceId))
+
+    def _flush_instance(self, inst):
+        if inst.index not in self._invalid_instances:
+            return
+        if inst._matrix is None and inst._trs_edited:        # position / rotation / scale were set: T * Rz * Ry * Rx * S, composed by the library
+            p, r, s = (np.asarray(v, np.float32) for v in (inst.position, inst.rotation, inst.scale))
+            check(self.ctx._h, lib().nx_scene_set_instance_transform(self._h, C.c_uint32(inst.index), _ptr(p), _ptr(r), _ptr(s)), "InvalidateMeshInstance")
+        if inst._material_edited:
+            check(self.ctx._h, lib().nx_scene_set_instance_material(self._h, C.c_uint32(inst.index), C.c_int32(inst.materialIdx)), "AssignMaterial")
+            inst._material_edited = False
+        self._invalid_instances.discard(inst.index)
 
     def AddLight(self, light):
         p = light.pod()
-        return check(self.ctx._h, lib().nx_scene_add_light(self._h, C.byref(p)), "AddLight")
+        idx = check(self.ctx._h, lib().nx_scene_add_light(self._h, C.byref(p)), "AddLight")
+        self._lights.append(light)
+        return idx
+
+    def GetLights(self):
+        """The lights added through AddLight (Scene.h:46); edit one, then InvalidateLight(index).  Emissive instances become
+        lights by themselves (Scene.cpp:157-219) and are not in this list."""
+        return self._lights
+
+    def InvalidateLight(self, lightIdx):
+        if not (0 <= lightIdx < len(self._lights)):
+            raise NexusError(f"InvalidateLight: light {lightIdx} of {len(self._lights)}")
+        self._invalid_lights.add(int(lightIdx))
+
+    def RemoveLight(self, index):
+        """Scene::RemoveLight (Scene.cpp:129-132): later lights move down by one."""
+        if not (0 <= index < len(self._lights)):
+            raise NexusError(f"RemoveLight: light {index} of {len(self._lights)}")
+        check(self.ctx._h, lib().nx_scene_remove_light(self._h, C.c_uint32(index)), "RemoveLight")
+        del self._lights[index]
+        self._invalid_lights = {i - (i > index) for i in self._invalid_lights if i != index}
+
+    def GetCamera(self):
+        """The host camera (Scene.h:22); edit it, call Invalidate() on it, and the next Update() uploads it."""
+        return self._camera
 
     def SetCamera(self, camera):
         p = camera.pod()
         check(self.ctx._h, lib().nx_scene_set_camera(self._h, C.byref(p)), "SetCamera")
+        self._camera = camera
+        camera.SetInvalid(False)
+
+    def GetRenderSettings(self):
+        """The host render settings (Scene.h:27-28); edits are uploaded by the next Update()."""
+        return self._settings
 
     def SetRenderSettings(self, rs):
         p = rs.pod()
         check(self.ctx._h, lib().nx_scene_set_render_settings(self._h, C.byref(p)), "SetRenderSettings")
+        self._settings = rs
+        self._settings_sent = (rs.useMIS, rs.pathLength, tuple(rs.backgroundColor), rs.backgroundIntensity, rs.toneMapping, rs.exposure)
+
+    def IsInvalid(self):
+        """Scene::IsInvalid (Scene.h:32): something was edited since the last Update()."""
+        rs = self._settings
+        return bool(self._invalid_instances or self._invalid_lights or self._camera.IsInvalid() or self._assets.IsInvalid()
+                    or getattr(self, "_settings_sent", None) != (rs.useMIS, rs.pathLength, tuple(rs.backgroundColor), rs.backgroundIntensity, rs.toneMapping, rs.exposure))
 
     def AddHDRMap(self, rgba):
         """Scene::AddHDRMap with pixels instead of a file: (h, w, 4) float32 equirect."""
@@ -401,7 +561,26 @@ class Scene:
         check(self.ctx._h, lib().nx_scene_set_hdr_map(self._h, _ptr(rgba), C.c_uint32(rgba.shape[1]), C.c_uint32(rgba.shape[0])), "AddHDRMap")
 
     def Update(self):
+        """Scene::Update (Scene.cpp:34-63): uploads what was invalidated (camera, render settings, materials, instances, lights),
+        rebuilds the TLAS when an instance changed and refreshes the light list."""
+        if self._camera.IsInvalid():
+            self.SetCamera(self._camera)
+        rs = self._settings
+        if getattr(self, "_settings_sent", None) != (rs.useMIS, rs.pathLength, tuple(rs.backgroundColor), rs.backgroundIntensity, rs.toneMapping, rs.exposure):
+            self.SetRenderSettings(rs)
+        self._assets.SendDataToDevice()
+        for i in sorted(self._invalid_instances):
+            self._flush_instance(self._instances[i]) if i < len(self._instances) else self._invalid_instances.discard(i)
+        for i in sorted(self._invalid_lights):
+            p = self._lights[i].pod()
+            check(self.ctx._h, lib().nx_scene_set_light(self._h, C.c_uint32(i), C.byref(p)), "InvalidateLight")
+        self._invalid_lights.clear()
         check(self.ctx._h, lib().nx_scene_update(self._h), "Scene::Update")
+
+    def BuildTLAS(self):
+        """Scene::BuildTLAS (Scene.cpp:65-78).  The library rebuilds the TLAS inside Update whenever an instance changed; this is
+        Update under the reference's name for callers that drive the two steps themselves."""
+        self.Update()
 
     def MeshBounds(self, meshId):
         b = Aabb()
@@ -504,6 +683,16 @@ class PathTracer:
 
     def GetFrameNumber(self):
         return lib().nx_renderer_frame_count(self._h)
+
+    def Reset(self):
+        """PathTracer::Reset (PathTracer.cpp:61-159) re-allocates the queues for the current resolution and clears the
+        accumulation; the queues here are sized once per resolution, so this is ResetFrameNumber."""
+        self.ResetFrameNumber()
+
+    def UpdateDeviceScene(self, scene):
+        """PathTracer::UpdateDeviceScene (PathTracer.cpp:216-219) copies the D_Scene into the device symbol; here the scene view is
+        a kernel parameter block assembled per Render call, so all that is left is flushing the scene's pending edits."""
+        scene.Update()
 
     def Stats(self):
         st = FrameStats()

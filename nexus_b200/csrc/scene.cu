@@ -374,12 +374,48 @@ int nx_scene_set_instance_transform(nx_scene* s, uint32_t idx, const float pos[3
     return NX_OK;
 }
 
+// MeshInstance::AssignMaterial + Scene::InvalidateMeshInstance (MeshInstance.h:35, Scene.cpp:109-112); < 0 = the mesh's own material
+int nx_scene_set_instance_material(nx_scene* s, uint32_t idx, int32_t materialIdx)
+{
+    if (!s || idx >= s->instances.size()) return NX_ERR_INVALID;
+    if (materialIdx >= 0 && (size_t)materialIdx >= s->materials.size()) NX_FAIL(s->ctx, NX_ERR_INVALID, "AssignMaterial: material %d of %zu", materialIdx, s->materials.size());
+    HostInstance& inst = s->instances[idx];
+    inst.materialIdx = materialIdx >= 0 ? (uint32_t)materialIdx : s->meshes[inst.meshIdx].materialIdx;
+    s->dirtyInstances = true; s->dirtyLights = true;          // an emissive material turns the instance into a light (Scene.cpp:157-219)
+    return NX_OK;
+}
+// MeshInstance::GetTransfromationMatrix / GetBounds (MeshInstance.h:36-53): row-major 4x4; world AABB of the mesh box's eight corners
+int nx_scene_instance_matrix(nx_scene* s, uint32_t idx, float out[16])
+{
+    if (!s || !out || idx >= s->instances.size()) return NX_ERR_INVALID;
+    std::memcpy(out, s->instances[idx].m, 64); return NX_OK;
+}
+int nx_scene_instance_bounds(nx_scene* s, uint32_t idx, nx_aabb* out)
+{
+    if (!s || !out || idx >= s->instances.size()) return NX_ERR_INVALID;
+    *out = s->instances[idx].bounds; return NX_OK;
+}
+
 int nx_scene_add_light(nx_scene* s, const nx_light* l)
 {
     if (!s || !l) return NX_ERR_INVALID;
     s->userLights.push_back(*l); s->dirtyLights = true;
     return (int)s->userLights.size() - 1;
 }
+// Scene::InvalidateLight after editing GetLights()[idx] (Scene.cpp:114-117), Scene::RemoveLight (Scene.cpp:129-132; later lights move down)
+int nx_scene_set_light(nx_scene* s, uint32_t idx, const nx_light* l)
+{
+    if (!s || !l || idx >= s->userLights.size()) return NX_ERR_INVALID;
+    s->userLights[idx] = *l; s->dirtyLights = true;
+    return NX_OK;
+}
+int nx_scene_remove_light(nx_scene* s, uint32_t idx)
+{
+    if (!s || idx >= s->userLights.size()) return NX_ERR_INVALID;
+    s->userLights.erase(s->userLights.begin() + idx); s->dirtyLights = true;
+    return NX_OK;
+}
+int nx_scene_light_count(nx_scene* s) { return s ? (int)s->userLights.size() : NX_ERR_INVALID; }
 // AssetManager::AddTexture + Texture::ToDevice (src/Assets/AssetManager.h:31, src/Assets/Texture.cpp:12-46): RGBA8 (normalised float
 // reads, optional sRGB decode in the sampler) or RGBA32F pixels into a CUDA array behind a texture object with wrap addressing,
 // linear filtering and normalised coordinates.  Returns the texture index that nx_material::*_map refers to.

@@ -10,9 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "examples", "render_headless")
 
 
+API_EXE = os.path.join(ROOT, "examples", "host_api_check")
+
+
 def _build():
-    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "render_headless.cpp"),
-                           "-L" + os.path.join(ROOT, "nexus_b200"), "-lnexus_b200", "-Wl,-rpath,$ORIGIN/../nexus_b200", "-o", EXE])
+    for exe in (EXE, API_EXE):
+        subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), exe + ".cpp",
+                               "-L" + os.path.join(ROOT, "nexus_b200"), "-lnexus_b200", "-Wl,-rpath,$ORIGIN/../nexus_b200", "-o", exe])
 
 
 def test_cpp_host_compiles_without_cuda_headers():
@@ -22,7 +26,12 @@ def test_cpp_host_compiles_without_cuda_headers():
     assert "cuda" not in src.lower().replace("cuda headers", "").replace("no cuda", "").replace("usable cuda device", "")
     for name in ("BuildBVH2", "BuildBVH8", "ToHost", "FreeDeviceBVH", "BenchmarkBuild", "class Scene", "class AssetManager", "class MeshInstance",
                  "class PathTracer", "struct Material", "struct Light", "struct Camera", "struct RenderSettings", "CreateMeshInstance", "AddHDRMap",
-                 "ResetFrameNumber", "OnResize", "GetFrameNumber"):
+                 "ResetFrameNumber", "OnResize", "GetFrameNumber",
+                 # the rest of the kept host API: Scene.h:19-49, MeshInstance.h:22-53, Camera.h:19-35, AssetManager.h:18-44, PathTracer.h:12-29
+                 "GetCamera", "GetMaterials", "GetRenderSettings", "GetMeshInstances", "InvalidateMeshInstance", "InvalidateLight", "RemoveLight", "GetLights",
+                 "BuildTLAS", "IsInvalid", "SetPosition", "SetRotationY", "SetScale", "AssignMaterial", "GetTransfromationMatrix", "GetBounds",
+                 "SetHorizontalFOV", "SetFocusDist", "SetDefocusAngle", "SetForwardDirection", "InvalidateMaterial", "SendDataToDevice", "AddTexture",
+                 "UpdateDeviceScene", "SetPixelQuery", "PixelQueryPending", "SynchronizePixelQuery", "GetSelectedInstance", "FreeHostBVH", "Present"):
         assert name in src, name
 
 
@@ -59,3 +68,12 @@ def test_cpp_host_renders_cornell(tmp_path):
     assert abs(ref.mean() - img.mean()) < 0.02 * ref.mean()
     assert os.path.getsize(out + ".exr") > 160 * 120 * 12
     pt.close(); sc.close(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_cpp_host_api_mirror():
+    """examples/host_api_check.cpp: host objects edited in place + Invalidate* + Update (instances, materials, lights, camera), pixel
+    query and the pipelined read-back, all through the C++ layer; every check is in the program, which prints its failing line."""
+    _build()
+    r = subprocess.run([API_EXE], capture_output=True, text=True)
+    assert r.returncode == 0 and "host api ok" in r.stdout, r.stderr
