@@ -14,8 +14,10 @@ demo scenes use.  Assimp is not available here, so this reader covers exactly wh
   camera     the first perspective camera (yfov + aspect -> horizontal FOV); otherwise the reference's default camera
              (position (0, 4, 14), forward (0, 0, -1), 45 degrees, focus 5: src/Scene/Scene.cpp:9-10)
 
-Texture images (embedded PNG / JPEG) need an image decoder; assets that use them are rejected with a clear error unless a
-`decode_image(bytes) -> (h, w, 4) uint8` callable is supplied.  Pure host code: numpy only, no GPU.
+Texture images (embedded PNG / JPEG) are decoded with Pillow when it is installed (the reference uses stb_image,
+src/Assets/IMGLoader.cpp:13-43: 8-bit RGBA, rows top to bottom), or with a caller-supplied
+`decode_image(bytes) -> (h, w, 4) uint8`; without either, assets that use textures are rejected with a clear error.
+Pure host code: numpy (+ optional Pillow), no GPU.
 """
 import json
 import struct
@@ -30,6 +32,18 @@ _WIDTH = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT4": 16}
 
 class GltfError(ValueError):
     pass
+
+
+def _pillow_decoder():
+    try:
+        from PIL import Image
+    except ImportError:
+        return None
+    import io
+
+    def decode(data):
+        return np.asarray(Image.open(io.BytesIO(bytes(data))).convert("RGBA"), np.uint8)
+    return decode
 
 
 def _chunks(blob):
@@ -143,12 +157,14 @@ def load_glb(path, path_length=10, decode_image=None):
     with open(path, "rb") as f:
         js, binary = _chunks(f.read())
     textures, texture_of = [], {}
+    if decode_image is None:
+        decode_image = _pillow_decoder()
 
     def texture_id(tex_index, srgb):
         key = (tex_index, srgb)
         if key not in texture_of:
             if decode_image is None:
-                raise GltfError("the asset uses texture images; pass decode_image(bytes) -> (h, w, 4) uint8 to load them")
+                raise GltfError("the asset uses texture images; install Pillow or pass decode_image(bytes) -> (h, w, 4) uint8 to load them")
             image = js["images"][js["textures"][tex_index]["source"]]
             view = js["bufferViews"][image["bufferView"]]
             data = binary[view.get("byteOffset", 0): view.get("byteOffset", 0) + view["byteLength"]]

@@ -120,3 +120,33 @@ def test_imported_scene_renders_like_the_same_scene_built_directly(tmp_path):
     # same RNG keys on both sides; only pixels on silhouettes / at rounding-sensitive hits may differ
     assert ia.mean() > 0 and np.abs(ia - ib).mean() <= 0.01 * ia.mean() and (np.abs(ia - ib) > 1e-3 * ia.max()).mean() < 0.02
     pa.close(); pb.close(); a.close(); b.close(); ctx.close()
+
+
+def test_embedded_png_textures_are_decoded(tmp_path):
+    """A .glb whose material has a base-colour and a normal texture stored as embedded PNGs: decoded with Pillow by default (the
+    reference decodes with stb_image, IMGLoader.cpp:13-43), base colour flagged sRGB and the normal map linear, shared images
+    decoded once per (image, colour space)."""
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    rs = np.random.RandomState(5)
+    px = rs.randint(0, 256, (4, 6, 4)).astype(np.uint8)
+    buf = io.BytesIO(); PIL.fromarray(px, "RGBA").save(buf, format="PNG")
+    png = buf.getvalue()
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    binary = pos.tobytes() + png
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "material": 0}]}],
+          "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}, "normalTexture": {"index": 0}, "emissiveTexture": {"index": 0}}],
+          "textures": [{"source": 0}], "images": [{"bufferView": 1, "mimeType": "image/png"}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}],
+          "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": pos.nbytes}, {"buffer": 0, "byteOffset": pos.nbytes, "byteLength": len(png)}],
+          "buffers": [{"byteLength": len(binary)}]}
+    _write_glb(tmp_path / "t.glb", js, binary)
+    d = gltf.load_glb(tmp_path / "t.glb")
+    m = d["materials"][0]
+    assert len(d["textures"]) == 2 and m.baseColorMap == m.emissiveMap and m.normalMap != m.baseColorMap
+    (a, a_srgb), (b, b_srgb) = d["textures"][m.baseColorMap], d["textures"][m.normalMap]
+    assert a_srgb and not b_srgb and (a == px).all() and (b == px).all() and a.dtype == np.uint8
+    # a caller-supplied decoder takes precedence
+    d2 = gltf.load_glb(tmp_path / "t.glb", decode_image=lambda data: np.full((2, 2, 4), 7, np.uint8))
+    assert (d2["textures"][0][0] == 7).all()
