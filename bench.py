@@ -401,11 +401,20 @@ def cpu_sah_baseline(tris):
         t0 = time.time(); n2 = O.sah_build_bvh2(pb, threads=cores); t1 = time.time(); n8, pidx, root_cost = O.sah_collapse(n2, n); t2 = time.time()
         if best is None or t2 - t0 < best[0]:
             best = (t2 - t0, t1 - t0, t2 - t1)
-    return {"value": round(n / best[0] / 1e6, 4), "unit": "Mprims/s", "cores": cores, "kind": "port",
-            "sample": f"all {n} triangles: binned-SAH BVH2 build {best[1] * 1e3:.1f} ms on {cores} threads + SAH-optimal BVH8 collapse {best[2] * 1e3:.1f} ms on 1 thread "
-                      "(oracle/oracle_sah.cpp; the reference snapshot contains no CPU BVH2 builder and its CPU collapse is dead code, SURVEY.md header note 1)",
-            "bvh8_nodes": int(len(n8)), "bvh2_sah_leaf_cost": round(O.sah_bvh2_cost(n2, n), 3), "collapse_root_cost": round(float(root_cost), 4),
-            "bvh8_sah": round(O.bvh8_cost(n8, sb), 4)}
+    out = {"value": round(n / best[0] / 1e6, 4), "unit": "Mprims/s", "cores": cores, "kind": "port",
+           "sample": f"all {n} triangles: binned-SAH BVH2 build {best[1] * 1e3:.1f} ms on {cores} threads + SAH-optimal BVH8 collapse {best[2] * 1e3:.1f} ms on 1 thread "
+                     "(oracle/oracle_sah.cpp; the reference snapshot contains no CPU BVH2 builder and its CPU collapse is dead code, SURVEY.md header note 1)",
+           "bvh8_nodes": int(len(n8)), "bvh2_sah_leaf_cost": round(O.sah_bvh2_cost(n2, n), 3), "collapse_root_cost": round(float(root_cost), 4),
+           "bvh8_sah": round(O.bvh8_cost(n8, sb), 4)}
+    if O.have_refcpu():
+        # the collapse half also through the reference's own code: Nexus/src/Geometry/BVH/BVH8Builder.cpp compiled unmodified (oracle/_ref)
+        tr = []
+        for _ in range(3):
+            t0 = time.time(); rn, rp, rc = O.ref_cpu_collapse(n2, n); tr.append(time.time() - t0)
+        out["reference_collapse"] = {"ms": round(min(tr) * 1e3, 1), "what": "the same BVH2 through the unmodified reference BVH8Builder (g++ -O2, 1 thread)",
+                                     "identical_to_port": bool((rn == n8).all() and (rp == pidx).all() and rc == root_cost),
+                                     "Mprims_per_s_with_it": round(n / (best[1] + min(tr)) / 1e6, 4)}
+    return out
 
 
 def run_build_ours(args):

@@ -51,6 +51,12 @@ struct AABB {
         float dx = bMax.x - bMin.x, dy = bMax.y - bMin.y, dz = bMax.z - bMin.z;
         return fmaf(dx, dz, fmaf(dx, dy, dy * dz));
     }
+    // The same expression as a host compiler evaluates it (x86-64 without FMA: three products, two sums, each rounded): what the
+    // reference's CPU BVH8Builder computes.  The translation unit is built with -ffp-contract=off, so this stays uncontracted.
+    float areaHost() const {
+        float dx = bMax.x - bMin.x, dy = bMax.y - bMin.y, dz = bMax.z - bMin.z;
+        return dx * dy + dy * dz + dz * dx;
+    }
 };
 
 // NXB::BVH2::Node, B/include/NXB/BVH.h:20-29 (32 B)

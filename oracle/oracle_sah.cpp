@@ -7,6 +7,12 @@
 //     :261).  The restatement keeps its semantics - C(n, i) table with LEAF / INTERNAL / DISTRIBUTE decisions, C_PRIM 0.3,
 //     C_NODE 1.0, P_MAX 3, greedy global-minimum slot assignment, e = ceil(log2(extent / 255)) quantisation - and only adds
 //     what it needs to run: the primIdx allocation, a guard for zero-extent axes, and a root that may be a single leaf.
+//     PINNED against the reference's own code: BVH8Builder.cpp compiles unmodified with g++ (oracle/Makefile target `refcpu`,
+//     harness oracle/ref/ref_cpu_collapse.cpp allocates primIdx and calls Init() / CollapseNode()); on 10 inputs from 1 to
+//     100,352 triangles this restatement reproduces its nodes, primitive order and C(root, 1) bit for bit
+//     (tests/golden/cpu_collapse_ref.npz, tests/test_oracle.py).  Areas are evaluated as the host compiler does (areaHost(), no
+//     FMA contraction), not as the GPU builder does.  Not pinned: inputs with a zero-extent axis, where the reference takes
+//     log2f(0) and casts NaN to uint8_t (undefined behaviour).
 // (2) Binned SAH BVH2: the reference README advertises "Standard SAH-based BVH (BVH2) using binned building"
 //     (README.md:31) but the snapshot contains no such source; this is written from that description with the choices
 //     SURVEY.md §8(c) records: 8 bins per axis over the centroid bounds, cost A(L)·N(L) + A(R)·N(R), one primitive per leaf
@@ -115,7 +121,7 @@ struct Collapse {
         triCount[n] = nd.left == INVALID ? 1u : countTris(nd.left) + countTris(nd.right);
         return triCount[n];
     }
-    float cLeaf(const Node2& nd, uint32_t tris) { return tris > (uint32_t)kPMax ? 1.0e30f : nd.bounds.area() * (float)tris * kCPrim; }   // :31-37
+    float cLeaf(const Node2& nd, uint32_t tris) { return tris > (uint32_t)kPMax ? 1.0e30f : nd.bounds.areaHost() * (float)tris * kCPrim; }   // :31-37
     float cDistribute(const Node2& nd, int j, int8_t& l, int8_t& r)                                                            // :39-57
     {
         float best = 1.0e30f;
@@ -134,7 +140,7 @@ struct Collapse {
         if (i == 0) {
             int8_t l = 0, r = 0;
             const float leaf = cLeaf(nd, triCount[n]);
-            const float internal = cDistribute(nd, 7, l, r) + nd.bounds.area() * kCNode;      // CInternal, :59-62
+            const float internal = cDistribute(nd, 7, l, r) + nd.bounds.areaHost() * kCNode;      // CInternal, :59-62
             Eval& e0 = ev(n, 0);
             if (leaf < internal) { e0.decision = LEAF; e0.cost = leaf; }
             else { e0.decision = INTERNAL; e0.cost = internal; e0.leftCount = l; e0.rightCount = r; }

@@ -88,3 +88,18 @@ def display_image():
     img[1, :8] = 0.0
     img[1, 8:16] = 1.0
     return img
+
+
+def cpu_collapse_cases():
+    """(name, triangles (n, 9), keep arrays in the golden file) for the reference CPU collapse golden (scripts/make_golden_cpu_collapse.py).
+    No input with a zero-extent axis: there the reference evaluates log2f(0) and casts NaN to uint8_t (BVH8Builder.cpp:305-307,
+    346-353), which is undefined behaviour; the restatement gives such an axis the smallest normal cell instead (oracle_sah.cpp)."""
+    from nexus_b200 import scenes
+    rng = np.random.default_rng(2024)
+    cases = [("sphere32", np.asarray(scenes.uv_sphere(32, 32), np.float32).reshape(-1, 9), True),
+             ("rock912", np.asarray(scenes.rock(3, 24, 20), np.float32).reshape(-1, 9), True),
+             ("soup1", _rand_tris(rng, 1), True), ("soup2", _rand_tris(rng, 2), True), ("soup3", _rand_tris(rng, 3), True),
+             ("soup9", _rand_tris(rng, 9), True), ("soup500", _rand_tris(rng, 500), True), ("soup1900", _rand_tris(rng, 1900, spread=2.0, size=0.3), True),
+             ("rock9798", np.asarray(scenes.rock(11), np.float32).reshape(-1, 9), False),
+             ("sphere224", np.asarray(scenes.uv_sphere(224, 224), np.float32).reshape(-1, 9), False)]
+    return cases

@@ -41,6 +41,31 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+# The UNMODIFIED reference CPU collapse (Nexus/src/Geometry/BVH/BVH8Builder.cpp), oracle/Makefile target `refcpu`: plain g++, runs anywhere.
+REFCPU_SO = os.path.join(os.path.dirname(REF_SO), "libnexus_refcpu.so")
+_refcpu = None
+
+
+def have_refcpu():
+    return os.path.exists(REFCPU_SO)
+
+
+def ref_cpu_collapse(bvh2_nodes, n):
+    """BVH8Builder::Init + CollapseNode of the reference itself on a host BVH2 with its root at node 0.  Returns nodes8, primIdx,
+    C(root, 1) — the same triple as sah_collapse, the restatement it pins."""
+    global _refcpu
+    if _refcpu is None:
+        _refcpu = C.CDLL(REFCPU_SO)
+    bvh2 = np.ascontiguousarray(bvh2_nodes)
+    cap = (4 * n - 1) // 7 + 1
+    nodes = np.zeros((cap, 20), np.uint32)
+    prim_idx = np.zeros(n, np.uint32)
+    cnt, cost = C.c_uint32(0), C.c_float(0)
+    rc = _refcpu.ref_cpu_bvh8_collapse(_p(bvh2), C.c_uint32(bvh2.shape[0]), C.c_uint32(n), _p(nodes), _p(prim_idx), C.byref(cnt), C.byref(cost))
+    assert rc == 0, rc
+    return nodes[:cnt.value].copy(), prim_idx, cost.value
+
+
 def ref():
     """The unmodified reference kernels + our headless driver (needs a GPU to *run*; loading works anywhere)."""
     global _ref

@@ -202,3 +202,38 @@ def _root_last(n2, n):
     out[new[inner], 6] = new[n2[inner, 6]]
     out[new[inner], 7] = new[n2[inner, 7]]
     return out
+
+
+# ------------------------------------------------------------------ CPU collapse pinned against the reference's own code ----
+CPU_COLLAPSE_GOLD = os.path.join(os.path.dirname(__file__), "golden", "cpu_collapse_ref.npz")
+
+
+def _sha(*arrays):
+    import hashlib
+    return np.frombuffer(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in arrays)).digest(), np.uint8)
+
+
+@pytest.mark.parametrize("case", [c[0] for c in __import__("golden_cases").cpu_collapse_cases()])
+def test_cpu_collapse_restatement_equals_the_reference_bvh8builder(case):
+    """The oracle's restatement of the reference's CPU collapse (oracle_sah.cpp, orc_sah_collapse) against the golden output of the
+    UNMODIFIED Nexus/src/Geometry/BVH/BVH8Builder.cpp (scripts/make_golden_cpu_collapse.py): same CWBVH8 nodes byte for byte, same
+    primitive order, same C(root, 1) bit for bit - decisions, child order (greedy slot assignment), quantisation, numbering.  When
+    the compiled reference travelled with the repository it is also run live on the same input."""
+    from golden_cases import cpu_collapse_cases
+    g = np.load(CPU_COLLAPSE_GOLD)
+    tris = next(c[1] for c in cpu_collapse_cases() if c[0] == case)
+    n = len(tris)
+    if case + "/bvh2" in g.files:
+        bvh2 = g[case + "/bvh2"]
+    else:                                        # big cases: the input is rebuilt and checked against its digest
+        pb, _ = O.prim_bounds(tris, 1)
+        bvh2 = O.sah_build_bvh2(pb, threads=4)
+        assert (_sha(bvh2) == g[case + "/bvh2_sha256"]).all(), "the oracle's BVH2 builder changed: regenerate the golden file"
+    nodes, prim, cost = O.sah_collapse(bvh2, n)
+    assert len(nodes) == int(g[case + "/node_count"]) and np.float32(cost) == g[case + "/cost"]
+    assert (_sha(nodes, prim) == g[case + "/sha256"]).all()
+    if case + "/nodes" in g.files:
+        assert (nodes == g[case + "/nodes"]).all() and (prim == g[case + "/prim_idx"]).all()
+    if O.have_refcpu():
+        rn, rp, rc = O.ref_cpu_collapse(bvh2, n)
+        assert (rn == nodes).all() and (rp == prim).all() and rc == cost
