@@ -237,3 +237,51 @@ def test_cpu_collapse_restatement_equals_the_reference_bvh8builder(case):
     if O.have_refcpu():
         rn, rp, rc = O.ref_cpu_collapse(bvh2, n)
         assert (rn == nodes).all() and (rp == prim).all() and rc == cost
+
+
+def _subtree_prim_sets(nodes8, prim_idx):
+    """Topology of a CWBVH8 independent of node numbering, child order and quantisation: the primitive set under every node and
+    the primitive group of every leaf child, as sorted tuples."""
+    nodes8 = np.ascontiguousarray(nodes8).view(np.uint32).reshape(-1, 20)
+    meta = nodes8.view(np.uint8).reshape(-1, 80)[:, 24:32]
+    inner_sets, leaf_groups = [], []
+
+    def walk(i):
+        prims = []
+        imask, child_base, prim_base = int(nodes8[i, 3] >> 24), int(nodes8[i, 4]), int(nodes8[i, 5])
+        for s in range(8):
+            m = int(meta[i, s])
+            if not m:
+                continue
+            if (imask >> s) & 1:
+                prims += walk(child_base + bin(imask & ((1 << s) - 1)).count("1"))
+            else:
+                cnt, first = bin(m >> 5).count("1"), m & 0x1f
+                group = sorted(int(p) for p in prim_idx[prim_base + first: prim_base + first + cnt])
+                leaf_groups.append(tuple(group)); prims += group
+        inner_sets.append(tuple(sorted(prims)))
+        return prims
+
+    import sys
+    sys.setrecursionlimit(10000)
+    walk(0)
+    return sorted(inner_sets), sorted(leaf_groups)
+
+
+@pytest.mark.skipif(not O.have_refcpu(), reason="oracle/_ref/libnexus_refcpu.so (the compiled reference BVH8Builder) is not present")
+@pytest.mark.parametrize("case", ["sphere32", "rock912", "soup500", "soup1900"])
+def test_gpu_mode_optimal_collapse_takes_the_reference_builders_decisions(case):
+    """NX_COLLAPSE_SAH_OPTIMAL (the GPU kernels dp_eval_kernel + collapse_kernel<true>) is checked bit for bit against its CPU
+    restatement orc_build_bvh8_optimal (tests/test_gpu_builder.py).  Here that restatement - GPU-form areas, the GPU converter's slot
+    assignment and quantisation, root-last BVH2 numbering - is checked against the UNMODIFIED reference CPU BVH8Builder on the same
+    tree with P_MAX = 3: the same BVH8 topology (primitive set under every node, primitive group of every leaf), i.e. the same
+    LEAF / INTERNAL / DISTRIBUTE decisions, although node numbering, child order and quantisation are the GPU converter's."""
+    from golden_cases import cpu_collapse_cases
+    tris = next(c[1] for c in cpu_collapse_cases() if c[0] == case)
+    n = len(tris)
+    pb, _ = O.prim_bounds(tris, 1)
+    bvh2 = O.sah_build_bvh2(pb, threads=4)
+    ref_nodes, ref_prim, _ = O.ref_cpu_collapse(bvh2, n)
+    got_nodes, got_prim = O.build_bvh8_optimal(_root_last(bvh2, n), n, max_leaf_prims=3)[:2]
+    assert len(got_nodes) == len(ref_nodes)
+    assert _subtree_prim_sets(got_nodes, got_prim) == _subtree_prim_sets(ref_nodes, ref_prim)
