@@ -406,6 +406,8 @@ def cpu_sah_baseline(tris):
                      "(oracle/oracle_sah.cpp; the reference snapshot contains no CPU BVH2 builder and its CPU collapse is dead code, SURVEY.md header note 1)",
            "bvh8_nodes": int(len(n8)), "bvh2_sah_leaf_cost": round(O.sah_bvh2_cost(n2, n), 3), "collapse_root_cost": round(float(root_cost), 4),
            "bvh8_sah": round(O.bvh8_cost(n8, sb), 4)}
+    t0 = time.time(); O.sah_build_bvh2(pb, threads=1); t1 = time.time() - t0       # single-thread figure beside the all-core one
+    out["single_thread"] = {"bvh2_build_ms": round(t1 * 1e3, 1), "Mprims_per_s": round(n / (t1 + best[2]) / 1e6, 4)}
     if O.have_refcpu():
         # the collapse half also through the reference's own code: Nexus/src/Geometry/BVH/BVH8Builder.cpp compiled unmodified (oracle/_ref)
         tr = []
@@ -474,6 +476,7 @@ def run_build_ours(args):
     # per-stage device times (the builder's own CUDA events, BVHBuildMetrics layout) over K more builds, and the SAH costs
     m = nx.BenchmarkBuild(ctx, dev, n, 1, speed, 1, K)
     mo = nx.BenchmarkBuild(ctx, dev, n, 1, speed, 1, K, collapse=nx.COLLAPSE_SAH_OPTIMAL, maxLeafPrims=2)
+    m64 = nx.BenchmarkBuild(ctx, dev, n, 1, False, 1, min(K, 4))       # prioritizeSpeed = false: 64-bit Morton keys (SURVEY.md 8d, config 4 reports both)
     hbm, hbm_src = peaks()
     hploc_ms = m["bvh2_ms"]
     achieved = HPLOC_BYTES_PER_PRIM * n / (hploc_ms * 1e-3) / 1e9
@@ -528,6 +531,9 @@ def run_build_ours(args):
                 "sah_optimal_collapse": {"what": "same build with nx_build_config.collapse = NX_COLLAPSE_SAH_OPTIMAL, max_leaf_prims 2 (what the renderer builds its BLASes with)",
                                          "total_ms": round(mo["total_ms"], 4), "bvh8_ms": round(mo["bvh8_ms"], 4), "bvh8_nodes": int(mo["node_count"]), "bvh8_sah": round(mo["bvh8_cost"], 4),
                                          "Mprims_per_s": round(n / mo["total_ms"] / 1e3, 1)},
+                "morton64": {"what": "same build with prioritizeSpeed = false (64-bit Morton keys, sort over bits [1, 64))", "total_ms": round(m64["total_ms"], 4),
+                             "Mprims_per_s": round(n / m64["total_ms"] / 1e3, 1), "stage_ms": {k: round(v, 4) for k, v in m64.items() if k.endswith("_ms")},
+                             "bvh8_nodes": int(m64["node_count"]), "bvh2_sah": round(m64["bvh2_cost"], 4), "bvh8_sah": round(m64["bvh8_cost"], 4)},
                 "host_generate_s": round(t_gen, 1), "gpu_launches": int(K * 4), "library_launches": int(K * 6), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize()
@@ -556,6 +562,9 @@ def run_build_reference(args):
     rc = O.ref().nxref_benchmark_bvh8(tris.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, 1, W, K, mm.ctypes.data_as(C.c_void_p), C.byref(cnt), ms2.ctypes.data_as(C.c_void_p))
     clocks = sampler.stop()
     assert rc == 0
+    mm64 = np.zeros(9, np.float32); cnt64 = C.c_uint32(0); ms64 = np.zeros(2, np.float32)      # prioritizeSpeed = false (64-bit Morton keys)
+    rc = O.ref().nxref_benchmark_bvh8(tris.ctypes.data_as(C.c_void_p), C.c_uint32(n), 1, 0, 1, min(K, 4), mm64.ctypes.data_as(C.c_void_p), C.byref(cnt64), ms64.ctypes.data_as(C.c_void_p))
+    assert rc == 0
     # The reference's own metric (BVHBuildMetrics::totalTime: the sum of its per-stage CUDA-event times, what NexusBVH's README
     # quotes) is the value; what a caller of BuildBVH8 actually waits for (cudaMallocAsync + cudaFree of every array inside each
     # build) is reported beside it as caller_ms_per_step and is several times longer.
@@ -567,6 +576,8 @@ def run_build_reference(args):
             "bvh8_nodes": int(cnt.value), "bvh2_sah": round(float(mm[6]), 4), "bvh8_sah": round(float(mm[7]), 4), "avg_children_per_node": round(float(mm[8]), 3),
             "stage_ms": {"computeSceneBoundsTime": round(float(mm[0]), 4), "computeMortonCodesTime": round(float(mm[1]), 4), "radixSortTime": round(float(mm[2]), 4),
                          "bvhBuildTime": round(float(mm[3]), 4), "bvh8ConversionTime": round(float(mm[4]), 4), "totalTime": round(float(mm[5]), 4)},
+            "morton64": {"what": "same build with prioritizeSpeed = false (64-bit Morton keys)", "total_ms": round(float(mm64[5]), 4),
+                         "Mprims_per_s": round(n / float(mm64[5]) / 1e3, 1), "bvh8_nodes": int(cnt64.value), "bvh2_sah": round(float(mm64[6]), 4), "bvh8_sah": round(float(mm64[7]), 4)},
             "clocks": clocks,
             "cpu_baseline": {"value": round(value, 1), "unit": "Mprims/s", "cores": 0, "kind": "reference",
                              "sample": f"{K} builds of this mesh through the unmodified NexusBVH (compiled -arch=sm_100a --use_fast_math from /root/reference) on the same B200; "
