@@ -527,6 +527,9 @@ def run_build_ours(args):
                 "config": {"workload": args.workload, "description": wl["desc"], "triangles": n, "prioritize_speed": speed,
                            "partition": "replicas only: one global sort + one hierarchy does not shard; each rank builds the whole mesh" if world > 1 else "single GPU",
                            "l2": "input (%.1f GB) and every intermediate array exceed the 126 MB L2; no flush needed" % (36e-9 * n)},
+                # the reference's own metric (BVHBuildMetrics::totalTime = the sum of the per-stage CUDA-event times, which is what
+                # the reference arm reports as its value): the same definition for this arm, beside the stricter whole-step `value`
+                "Mprims_per_s_stage_sum": round(n / m["total_ms"] / 1e3, 1),
                 "bvh8_nodes": int(nodes), "bvh2_sah": round(m["bvh2_cost"], 4), "bvh8_sah": round(m["bvh8_cost"], 4), "avg_children_per_node": round(m["avg_children_per_node"], 3),
                 "sah_optimal_collapse": {"what": "same build with nx_build_config.collapse = NX_COLLAPSE_SAH_OPTIMAL, max_leaf_prims 2 (what the renderer builds its BLASes with)",
                                          "total_ms": round(mo["total_ms"], 4), "bvh8_ms": round(mo["bvh8_ms"], 4), "bvh8_nodes": int(mo["node_count"]), "bvh8_sah": round(mo["bvh8_cost"], 4),
