@@ -11,6 +11,8 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "instanced10m_4k"
 res = bench.WORKLOADS[wl]["res"]
 ctx = nx.Context(0)
 desc = bench.make_desc(wl)
+if os.environ.get("NX_PATHLEN"):      # e.g. 1: primary rays only, to tune the first (coherent) launch by itself
+    desc["settings"].pathLength = int(os.environ["NX_PATHLEN"])
 scene = scenes.build(ctx, desc, res)
 pt = nx.PathTracer(ctx, res)
 pt.Render(scene, frames=2); ctx.synchronize()
