@@ -152,3 +152,59 @@ def test_hits_do_not_depend_on_the_collapse(ctx):
     for hits, occ, _ in out[:-1]:
         assert (hits.view(np.uint8) == out[-1][0].view(np.uint8)).all() and (occ == out[-1][1]).all()
     assert out[0][2] < out[-1][2]          # the optimal collapse of a rock BLAS needs fewer nodes than the reference rule
+
+
+def test_exact_ties_and_degenerate_triangles(ctx):
+    """Collisions as this domain has them.  (1) Coincident geometry: the same mesh instanced twice at the same place and a mesh that
+    contains every triangle twice give exact-distance ties on every hit; the product resolves them by (instance id, primitive id),
+    smallest first, whatever the visiting order or warp composition (traverse.cuh; the reference's answer is schedule dependent), so
+    every hit must name instance 0 and the first copy of its triangle, on both collapse modes and for a shuffled ray order.
+    (2) Degenerate triangles (zero area: repeated vertex, collinear vertices) and a zero-extent mesh never produce a hit, a NaN or a
+    hang, and do not disturb the hits on the proper triangles around them."""
+    rock = np.asarray(scenes.rock(21, 18, 16), np.float32).reshape(-1, 9)
+    n = len(rock)
+    doubled = np.concatenate([rock, rock])                                   # primitive i and i + n coincide
+    desc = {"meshes": [{"name": "doubled", "triangles": doubled, "material": 0}],
+            "instances": [{"mesh": 0, "material": -1, "position": (0, 0, 0), "rotation": (0, 30, 0), "scale": (1, 1, 1)},
+                          {"mesh": 0, "material": -1, "position": (0, 0, 0), "rotation": (0, 30, 0), "scale": (1, 1, 1)}],
+            "materials": [nx.Material()], "lights": [], "settings": nx.RenderSettings(),
+            "camera": nx.Camera(position=(0.0, 0.5, 4.0), forward=(0.0, -0.1, -1.0), horizontalFOV=40.0)}
+    desc = scenes.with_triangle_data(desc)
+    res = (128, 96)
+    o, d = scenes.camera_rays(desc["camera"], res)
+    rays = nx.make_rays(o, d)
+    perm = np.random.default_rng(4).permutation(len(rays))
+    answers = []
+    for collapse, leaf in ((nx.COLLAPSE_SAH_OPTIMAL, 2), (nx.COLLAPSE_REFERENCE_GPU, 0)):
+        ctx.SetSceneCollapse(collapse, leaf)
+        scene = scenes.build(ctx, desc, res)
+        h = scene.TraceClosest(rays)
+        hit = h["prim"] != 0xffffffff
+        assert hit.mean() > 0.15 and (h["instance"][hit] == 0).all() and (h["prim"][hit] < n).all()
+        hp = scene.TraceClosest(rays[perm])
+        assert hp.tobytes() == h[perm].tobytes()
+        answers.append(h)
+        scene.close()
+    ctx.SetSceneCollapse(nx.COLLAPSE_SAH_OPTIMAL, 2)
+    assert answers[0].tobytes() == answers[1].tobytes()
+
+    # degenerate triangles mixed into a proper mesh
+    quad = np.array([[-1, -1, 0, 1, -1, 0, 1, 1, 0], [-1, -1, 0, 1, 1, 0, -1, 1, 0]], np.float32)
+    junk = np.array([[0, 0, 1, 0, 0, 1, 0, 0, 1],            # a point
+                     [0, 0, 1, 0.5, 0, 1, 1, 0, 1],          # collinear
+                     [0.2, 0.2, 1, 0.2, 0.2, 1, 0.7, 0.3, 1]], np.float32)   # repeated vertex
+    mixed = {"meshes": [{"name": "mixed", "triangles": np.concatenate([junk, quad, junk]), "material": 0},
+                        {"name": "point cloud", "triangles": np.tile(np.array([[0.3, 0.3, 0.5] * 3], np.float32), (5, 1)), "material": 0}],
+             "instances": [{"mesh": 0, "material": -1, "position": (0, 0, 0), "rotation": (0, 0, 0), "scale": (1, 1, 1)},
+                           {"mesh": 1, "material": -1, "position": (0, 0, 0), "rotation": (0, 0, 0), "scale": (1, 1, 1)}],
+             "materials": [nx.Material()], "lights": [], "settings": nx.RenderSettings(), "camera": nx.Camera()}
+    scene = scenes.build(ctx, scenes.with_triangle_data(mixed), (16, 16))
+    xs = np.linspace(-0.9, 0.9, 37, dtype=np.float32)
+    gx, gy = np.meshgrid(xs, xs)
+    o = np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, 3.0, np.float32)], 1)
+    d = np.tile(np.array([[0, 0, -1]], np.float32), (len(o), 1))
+    h = scene.TraceClosest(nx.make_rays(o, d))
+    assert np.isfinite(h["t"]).all() and (h["t"] == np.float32(3.0)).all()            # every ray reaches the quad at z = 0, nothing in front of it hits
+    assert (h["instance"] == 0).all() and np.isin(h["prim"], (3, 4)).all()
+    assert (scene.TraceAny(nx.make_rays(o, d, tmax=2.5)) == 0).all() and (scene.TraceAny(nx.make_rays(o, d, tmax=3.5)) == 1).all()
+    scene.close()
