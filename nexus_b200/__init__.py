@@ -377,6 +377,7 @@ class AssetManager:
     def __init__(self, scene):
         self.scene = scene
         self._materials, self._invalid_materials = [], set()
+        self._texture_count = 0
 
     def AddMaterial(self, material):
         p = material.pod()
@@ -428,8 +429,10 @@ class AssetManager:
         pixels = np.ascontiguousarray(pixels)
         if pixels.ndim != 3 or pixels.shape[2] != 4 or pixels.dtype not in (np.uint8, np.float32):
             raise ValueError("texture pixels must be (h, w, 4) uint8 or float32")
-        return check(self.scene.ctx._h, lib().nx_scene_add_texture(self.scene._h, _ptr(pixels), C.c_uint32(pixels.shape[1]), C.c_uint32(pixels.shape[0]),
-                                                                    C.c_int(int(pixels.dtype == np.float32)), C.c_int(int(sRGB))), "AddTexture")
+        idx = check(self.scene.ctx._h, lib().nx_scene_add_texture(self.scene._h, _ptr(pixels), C.c_uint32(pixels.shape[1]), C.c_uint32(pixels.shape[0]),
+                                                                   C.c_int(int(pixels.dtype == np.float32)), C.c_int(int(sRGB))), "AddTexture")
+        self._texture_count = idx + 1
+        return idx
 
     def InvalidateMaterial(self, index, material=None):
         """AssetManager::InvalidateMaterial (AssetManager.h:36): marks GetMaterials()[index] for upload at the next Scene.Update().
@@ -486,6 +489,42 @@ class Scene:
 
     def GetMeshInstances(self):
         return self._instances
+
+    def CreateMeshInstanceFromFile(self, filePath, fileName="", decode_image=None):
+        """Scene::CreateMeshInstanceFromFile (Scene.cpp:97-100 -> OBJLoader::LoadOBJ, OBJLoader.cpp:420-446): imports an asset
+        into THIS scene - its materials and textures are appended to the asset manager, every primitive becomes a mesh and every
+        node that references it an instance.  .glb through nexus_b200.gltf, .obj through nexus_b200.obj (the reference goes
+        through Assimp).  Returns the new MeshInstance objects; the asset's camera, if any, is ignored as in the reference's
+        loader when a scene already exists."""
+        import os as _os
+        path = _os.fspath(filePath) + fileName
+        ext = _os.path.splitext(path)[1].lower()
+        if ext == ".glb":
+            from .gltf import load_glb
+            d = load_glb(path, decode_image=decode_image)
+        elif ext == ".obj":
+            from .obj import load_obj
+            d = load_obj(path)
+        else:
+            raise NexusError(f"CreateMeshInstanceFromFile: unsupported asset type '{ext}' (.glb and .obj are)")
+        am = self._assets
+        tex0 = am._texture_count
+        for pixels, srgb in d.get("textures", []):
+            am.AddTexture(pixels, srgb)
+        mat0 = len(am._materials)
+        for m in d["materials"]:
+            for attr in ("baseColorMap", "emissiveMap", "normalMap", "roughnessMap", "metalnessMap", "metallicRoughnessMap"):
+                if getattr(m, attr) >= 0:
+                    setattr(m, attr, getattr(m, attr) + tex0)
+            am.AddMaterial(m)
+        mesh_ids = [am.AddMesh(m["name"], mat0 + m["material"], m["triangles"], m.get("triangle_data")) for m in d["meshes"]]
+        created = []
+        for i in d["instances"]:
+            mat = i.get("material", -1)
+            inst = self.CreateMeshInstanceMatrix(mesh_ids[i["mesh"]], i["matrix"], mat0 + mat if mat >= 0 else -1)
+            inst.name = d["meshes"][i["mesh"]]["name"]
+            created.append(inst)
+        return created
 
     def IsEmpty(self):
         return not self._instances
@@ -555,8 +594,13 @@ class Scene:
         return bool(self._invalid_instances or self._invalid_lights or self._camera.IsInvalid() or self._assets.IsInvalid()
                     or getattr(self, "_settings_sent", None) != (rs.useMIS, rs.pathLength, tuple(rs.backgroundColor), rs.backgroundIntensity, rs.toneMapping, rs.exposure))
 
-    def AddHDRMap(self, rgba):
-        """Scene::AddHDRMap with pixels instead of a file: (h, w, 4) float32 equirect."""
+    def AddHDRMap(self, rgba, fileName=None):
+        """Scene::AddHDRMap (Scene.cpp:102-107).  Either pixels, (h, w, 4) float32 equirect, or the reference's
+        (filePath, fileName) pair naming a Radiance .hdr file (read by nexus_b200.hdr.load_hdr as stb_image would)."""
+        if isinstance(rgba, (str, bytes)) or hasattr(rgba, "__fspath__"):
+            import os as _os
+            from .hdr import load_hdr
+            rgba = load_hdr(_os.fspath(rgba) + (fileName or ""))
         rgba = np.ascontiguousarray(rgba, np.float32)
         check(self.ctx._h, lib().nx_scene_set_hdr_map(self._h, _ptr(rgba), C.c_uint32(rgba.shape[1]), C.c_uint32(rgba.shape[0])), "AddHDRMap")
 

@@ -100,3 +100,59 @@ def test_camera_settings_material_and_light_edits(ctx):
     with pytest.raises(nx.NexusError):
         scene.GetAssetManager().InvalidateMaterial(99)
     scene.close(); other.close()
+
+
+def test_assets_and_environment_from_files(ctx, tmp_path):
+    """Scene::CreateMeshInstanceFromFile and Scene::AddHDRMap(filePath, fileName) (Scene.cpp:97-107): importing a .glb and an .obj
+    into an existing scene appends their materials, meshes and instances (material indices shifted past the scene's own), and an
+    environment map read from a Radiance .hdr file equals the same pixels handed over directly."""
+    import test_gltf
+    import test_hdr
+    import test_obj
+    from nexus_b200 import gltf, hdr, obj
+    test_gltf._two_quads_glb(tmp_path / "q.glb")
+    cube = test_obj._write(tmp_path)
+    sky = np.random.RandomState(2).uniform(0.2, 1.5, (16, 32, 3)).astype(np.float32)
+    test_hdr._write(tmp_path / "sky.hdr", test_hdr._rgbe(sky), rle=True)
+    sky_px = hdr.load_hdr(tmp_path / "sky.hdr")
+
+    def base_scene():
+        scene = nx.Scene(ctx, RES)
+        am = scene.GetAssetManager()
+        am.AddMaterial(nx.Material(baseColor=(0.3, 0.7, 0.3), roughness=0.8))
+        am.AddMesh("floor", 0, np.array([[-6, -0.5, 6, 6, -0.5, 6, 6, -0.5, -6], [-6, -0.5, 6, 6, -0.5, -6, -6, -0.5, -6]], np.float32))
+        scene.CreateMeshInstance(0)
+        scene.SetCamera(nx.Camera(position=(2.0, 4.0, 12.0), forward=(0.0, -0.19611614, -0.98058068), horizontalFOV=45.0))
+        scene.SetRenderSettings(nx.RenderSettings(pathLength=3))
+        return scene
+
+    a = base_scene()
+    got_glb = a.CreateMeshInstanceFromFile(str(tmp_path) + "/", "q.glb")
+    got_obj = a.CreateMeshInstanceFromFile(cube)
+    a.AddHDRMap(str(tmp_path) + "/", "sky.hdr")
+    a.Update()
+    assert len(got_glb) == 2 and len(got_obj) == 2 and len(a.GetMeshInstances()) == 5 and len(a.GetMaterials()) == 1 + 2 + 2
+    assert got_glb[0].materialIdx == -1 and got_obj[1].meshIdx == 4 and got_glb[1].name.startswith("quads")
+    with pytest.raises(nx.NexusError):
+        a.CreateMeshInstanceFromFile(str(tmp_path / "scene.fbx"))
+
+    # the same content assembled by hand
+    b = base_scene()
+    am = b.GetAssetManager()
+    dg, do = gltf.load_glb(tmp_path / "q.glb"), obj.load_obj(cube)
+    for d in (dg, do):
+        m0 = len(am.GetMaterials())
+        for m in d["materials"]:
+            am.AddMaterial(m)
+        ids = [am.AddMesh(m["name"], m0 + m["material"], m["triangles"], m["triangle_data"]) for m in d["meshes"]]
+        for i in d["instances"]:
+            b.CreateMeshInstanceMatrix(ids[i["mesh"]], i["matrix"], -1)
+    b.AddHDRMap(sky_px)
+    b.Update()
+    o, d = scenes.camera_rays(a.GetCamera(), RES)
+    rays = nx.make_rays(o, d)
+    ha, hb = a.TraceClosest(rays), b.TraceClosest(rays)
+    assert ha.tobytes() == hb.tobytes() and len(np.unique(ha["instance"][ha["prim"] != 0xffffffff])) >= 2
+    ia, ib = _render(ctx, a), _render(ctx, b)
+    assert ia.mean() > 0.05 and np.allclose(ia, ib, rtol=1e-4, atol=1e-5)
+    a.close(); b.close()
