@@ -211,6 +211,11 @@ int nx_scene_export_instances(nx_scene* scene, void* out160 /* n*160 */, uint32_
 int nx_scene_export_camera(nx_scene* scene, void* out88);
 int nx_scene_export_lights(nx_scene* scene, void* out52 /* n*52 */, uint32_t* out_count);
 int nx_scene_tlas(nx_scene* scene, nx_bvh8* out);                                       /* borrowed handle */
+/* The same records computed without a scene or a GPU (pure host arithmetic, the code paths nx_scene_add_instance and
+ * nx_scene_export_camera use): MeshInstance::ToDevice (src/Scene/MeshInstance.h:36-66) and Camera::ToDevice (src/Scene/Camera.cpp:130-156). */
+int nx_host_instance_record(const float position[3], const float rotation_deg[3], const float scale[3], const nx_aabb* mesh_bounds,
+                            uint32_t mesh_idx, uint32_t material_idx, void* out160);
+int nx_host_camera_record(const nx_camera* cam, uint32_t width, uint32_t height, void* out88);
 
 /* Parity hook: closest hits of a ray batch through the product traversal kernel (HOST buffers). */
 int nx_trace_closest(nx_scene* scene, const nx_ray* rays, uint32_t n, nx_hit* hits, float* out_device_ms);

@@ -638,6 +638,29 @@ int nx_scene_export_camera(nx_scene* s, void* out88)
     std::memcpy(out88, &c, 88);
     return NX_OK;
 }
+// The host arithmetic behind nx_scene_add_instance / nx_scene_set_instance_transform and nx_scene_export_camera, callable without a
+// scene or a GPU: the D_MeshInstance (160 B) and D_Camera (88 B) records for the given inputs, through the very functions the scene
+// code uses (compose_trs, m4_inverse, transformed_bounds, nxi_camera_to_device).  Lets the CPU tests pin them against the
+// reference's own host code (MeshInstance::ToDevice, Camera::ToDevice).
+int nx_host_instance_record(const float pos[3], const float rotDeg[3], const float scale[3], const nx_aabb* meshBounds, uint32_t meshIdx,
+                            uint32_t materialIdx, void* out160)
+{
+    if (!pos || !rotDeg || !scale || !meshBounds || !out160) return NX_ERR_INVALID;
+    M4 m = compose_trs(pos, rotDeg, scale), inv; m4_inverse(m, inv);
+    const nx_aabb b = transformed_bounds(m.c, *meshBounds);
+    uint8_t* o = (uint8_t*)out160;
+    std::memcpy(o, &meshIdx, 4); std::memcpy(o + 4, &materialIdx, 4);
+    std::memcpy(o + 8, m.c, 64); std::memcpy(o + 72, inv.c, 64); std::memcpy(o + 136, &b, 24);
+    return NX_OK;
+}
+int nx_host_camera_record(const nx_camera* cam, uint32_t width, uint32_t height, void* out88)
+{
+    if (!cam || !out88 || !width || !height) return NX_ERR_INVALID;
+    const DCamera c = nxi_camera_to_device(*cam, width, height);
+    std::memcpy(out88, &c, 88);
+    return NX_OK;
+}
+
 int nx_scene_export_lights(nx_scene* s, void* out52, uint32_t* outCount)
 {
     if (!s || !outCount) return NX_ERR_INVALID;

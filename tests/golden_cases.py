@@ -103,3 +103,27 @@ def cpu_collapse_cases():
              ("rock9798", np.asarray(scenes.rock(11), np.float32).reshape(-1, 9), False),
              ("sphere224", np.asarray(scenes.uv_sphere(224, 224), np.float32).reshape(-1, 9), False)]
     return cases
+
+
+def host_cases():
+    """Inputs of the host-record golden (scripts/make_golden_host.py): instance transforms (position, Euler degrees, scale, mesh box,
+    ids) and cameras (position, forward, horizontal FOV, focus distance, defocus angle, resolution)."""
+    rng = np.random.default_rng(77)
+    n = 48
+    inst = {"position": rng.uniform(-20, 20, (n, 3)).astype(np.float32), "rotation": rng.uniform(-360, 720, (n, 3)).astype(np.float32),
+            "scale": rng.uniform(0.05, 4.0, (n, 3)).astype(np.float32),
+            "mesh_bounds": np.concatenate([rng.uniform(-3, 0, (n, 3)), rng.uniform(0, 3, (n, 3))], 1).astype(np.float32),
+            "mesh_idx": rng.integers(0, 1000, n).astype(np.uint32), "material_idx": rng.integers(0, 50, n).astype(np.uint32)}
+    inst["position"][0] = 0; inst["rotation"][0] = 0; inst["scale"][0] = 1                      # identity
+    inst["rotation"][1] = (90, 0, 0); inst["rotation"][2] = (0, 90, 0); inst["rotation"][3] = (0, 0, 90)   # one axis at a time
+    inst["scale"][4] = (-1, 2, 0.5)                                                             # mirrored
+    inst["scale"][5] = (1.5, 1.5, 1.5); inst["rotation"][5] = (10, 200, 35)
+    m = 12
+    fwd = rng.normal(size=(m, 3)); fwd[:, 1] *= 0.3
+    fwd /= np.linalg.norm(fwd, axis=1, keepdims=True)
+    cams = {"position": rng.uniform(-10, 10, (m, 3)).astype(np.float32), "forward": fwd.astype(np.float32),
+            "hfov": rng.uniform(20, 100, m).astype(np.float32), "focus": rng.uniform(0.5, 20, m).astype(np.float32),
+            "defocus": rng.uniform(0, 5, m).astype(np.float32),
+            "res": np.array([(1920, 1080), (3840, 2160), (640, 480), (96, 64)] * 3, np.uint32)}
+    cams["position"][0] = (0, 4, 14); cams["forward"][0] = (0, 0, -1); cams["hfov"][0] = 45; cams["focus"][0] = 5; cams["defocus"][0] = 0   # Scene.cpp:9-10
+    return inst, cams
