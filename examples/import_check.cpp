@@ -1,0 +1,35 @@
+// Host-only check of include/nexus_b200_import.hpp (no GPU, nothing of the library is called): parses an .obj (+ .mtl) and a .hdr and
+// prints what it read as JSON, for tests/test_cpp_import.py to compare with the Python readers.
+//   g++ -std=c++17 -Iinclude examples/import_check.cpp -Lnexus_b200 -lnexus_b200 -o import_check && ./import_check cube.obj sky.hdr
+#include <cstdio>
+#include "nexus_b200_import.hpp"
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { std::fprintf(stderr, "usage: import_check file.obj file.hdr\n"); return 2; }
+    try {
+        const nexus::ImportedAsset a = nexus::LoadOBJ(argv[1]);
+        std::printf("{\"materials\": [");
+        for (size_t i = 0; i < a.materials.size(); i++) {
+            const nexus::Material& m = a.materials[i];
+            std::printf("%s{\"baseColor\": [%.9g, %.9g, %.9g], \"emissionColor\": [%.9g, %.9g, %.9g], \"intensity\": %.9g, \"ior\": %.9g, \"opacity\": %.9g, \"roughness\": %.9g, \"metalness\": %.9g}",
+                        i ? ", " : "", m.baseColor.x, m.baseColor.y, m.baseColor.z, m.emissionColor.x, m.emissionColor.y, m.emissionColor.z, m.intensity, m.ior, m.opacity, m.roughness, m.metalness);
+        }
+        std::printf("], \"meshes\": [");
+        for (size_t i = 0; i < a.meshes.size(); i++) {
+            const nexus::ImportedMesh& m = a.meshes[i];
+            std::printf("%s{\"name\": \"%s\", \"material\": %u, \"triangles\": [", i ? ", " : "", m.name.c_str(), m.material);
+            const float* t = reinterpret_cast<const float*>(m.triangles.data());
+            for (size_t k = 0; k < 9 * m.triangles.size(); k++) std::printf("%s%.9g", k ? ", " : "", t[k]);
+            std::printf("], \"triangle_data\": [");
+            const float* d = reinterpret_cast<const float*>(m.triangleData.data());
+            for (size_t k = 0; k < 24 * m.triangleData.size(); k++) std::printf("%s%.9g", k ? ", " : "", d[k]);
+            std::printf("]}");
+        }
+        const nexus::HdrImage img = nexus::LoadHDR(argv[2]);
+        std::printf("], \"hdr\": {\"width\": %u, \"height\": %u, \"rgba\": [", img.width, img.height);
+        for (size_t k = 0; k < img.rgba.size(); k++) std::printf("%s%.9g", k ? ", " : "", img.rgba[k]);
+        std::printf("]}}\n");
+    } catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 1; }
+    return 0;
+}
