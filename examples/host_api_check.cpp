@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <string>
-#include "nexus_b200.hpp"
+#include "nexus_b200_import.hpp"
 
 using namespace nexus;
 
@@ -18,7 +18,7 @@ static std::vector<NXB::Triangle> quadXZ(float half, float y)
 }
 static double meanOf(const std::vector<float>& v) { double m = 0; for (float x : v) m += x; return m / (double)v.size(); }
 
-int main()
+int main(int argc, char** argv)
 {
     try {
         const uint2 res{64, 48};
@@ -99,6 +99,25 @@ int main()
         CHECK(a == b && st.frames == 16 && st.extension_rays >= 16ull * res.x * res.y);
 
         std::vector<nx_bvh2_node> hostNodes(4); NXB::FreeHostBVH(hostNodes); CHECK(hostNodes.empty());
+        // optional: assets named on the command line (.obj / .glb) imported into a fresh scene through Scene::CreateMeshInstanceFromFile
+        for (int a = 1; a < argc; a++) {
+            Scene imported(ctx, res);
+            imported.GetRenderSettings().backgroundColor = {0.6f, 0.7f, 0.8f};
+            imported.GetRenderSettings().pathLength = 2;
+            const size_t before = imported.GetMaterials().size();
+            const std::vector<uint32_t> ids = CreateMeshInstanceFromFile(imported, "", argv[a]);
+            CHECK(!ids.empty() && imported.GetMeshInstances().size() == ids.size() && imported.GetMaterials().size() > before);
+            const NXB::AABB box = imported.GetMeshInstances()[0].GetBounds();
+            std::shared_ptr<Camera> c = imported.GetCamera();
+            c->SetPosition({0.5f * (box.bmin[0] + box.bmax[0]), 0.5f * (box.bmin[1] + box.bmax[1]), box.bmax[2] + 6.0f}); c->SetForwardDirection({0.0f, 0.0f, -1.0f}); c->Invalidate();
+            imported.Update();
+            PathTracer ip(ctx, res);
+            ip.SetPixelQuery(res.x / 2, res.y / 2);
+            ip.Render(imported, 4);
+            const int32_t picked = ip.SynchronizePixelQuery();
+            CHECK(meanOf(ip.ReadAccumulation()) > 0.0 && picked >= -1 && picked < (int32_t)ids.size());
+            std::printf("imported %s: %zu instance(s), centre pixel sees instance %d\n", argv[a], ids.size(), picked);
+        }
         std::printf("host api ok\n");
     } catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 1; }
     return 0;

@@ -26,6 +26,34 @@ int main(int argc, char** argv)
             for (size_t k = 0; k < 24 * m.triangleData.size(); k++) std::printf("%s%.9g", k ? ", " : "", d[k]);
             std::printf("]}");
         }
+        if (argc > 3) {      // optional .glb: appended as "glb": {...} below
+            const nexus::ImportedScene g = nexus::LoadGLB(argv[3]);
+            std::printf("], \"glb\": {\"camera\": %s, \"camera_position\": [%.9g, %.9g, %.9g], \"camera_forward\": [%.9g, %.9g, %.9g], \"camera_hfov\": %.9g, \"materials\": [", g.hasCamera ? "true" : "false",
+                        g.camera.position.x, g.camera.position.y, g.camera.position.z, g.camera.forward.x, g.camera.forward.y, g.camera.forward.z, g.camera.horizontalFOV);
+            for (size_t i = 0; i < g.materials.size(); i++) {
+                const nexus::Material& m = g.materials[i];
+                std::printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g]", i ? ", " : "", m.baseColor.x, m.baseColor.y, m.baseColor.z, m.opacity, m.metalness,
+                            m.roughness, m.emissionColor.x, m.emissionColor.y, m.emissionColor.z, m.intensity, m.specularWeight, m.specularColor.x, m.ior, m.transmission, m.specularColor.z);
+            }
+            std::printf("], \"instances\": [");
+            for (size_t i = 0; i < g.instances.size(); i++) {
+                std::printf("%s{\"mesh\": %u, \"matrix\": [", i ? ", " : "", g.instances[i].mesh);
+                for (int k = 0; k < 16; k++) std::printf("%s%.9g", k ? ", " : "", g.instances[i].matrix[k]);
+                std::printf("]}");
+            }
+            std::printf("], \"meshes\": [");
+            for (size_t i = 0; i < g.meshes.size(); i++) {
+                const nexus::ImportedMesh& m = g.meshes[i];
+                std::printf("%s{\"name\": \"%s\", \"material\": %u, \"triangles\": [", i ? ", " : "", m.name.c_str(), m.material);
+                const float* t = reinterpret_cast<const float*>(m.triangles.data());
+                for (size_t k = 0; k < 9 * m.triangles.size(); k++) std::printf("%s%.9g", k ? ", " : "", t[k]);
+                std::printf("], \"triangle_data\": [");
+                const float* d = reinterpret_cast<const float*>(m.triangleData.data());
+                for (size_t k = 0; k < 24 * m.triangleData.size(); k++) std::printf("%s%.9g", k ? ", " : "", d[k]);
+                std::printf("]}");
+            }
+            std::printf("]}, \"end_of_glb\": [");
+        }
         const nexus::HdrImage img = nexus::LoadHDR(argv[2]);
         std::printf("], \"hdr\": {\"width\": %u, \"height\": %u, \"rgba\": [", img.width, img.height);
         for (size_t k = 0; k < img.rgba.size(); k++) std::printf("%s%.9g", k ? ", " : "", img.rgba[k]);

@@ -209,6 +209,13 @@ public:
         instances_.emplace_back(this, idx, meshId, materialIdx, position, rotationDeg, scale);
         return instances_.back();
     }
+    // an instance placed by an explicit row-major 4x4 (imported node transforms); position / rotation / scale stay at their defaults until set
+    MeshInstance& CreateMeshInstanceMatrix(uint32_t meshId, const float matrix[16], int materialIdx = -1)
+    {
+        const uint32_t idx = (uint32_t)ctx_.check(nx_scene_add_instance_matrix(h_, meshId, materialIdx, matrix), "CreateMeshInstance");
+        instances_.emplace_back(this, idx, meshId, materialIdx, float3{0, 0, 0}, float3{0, 0, 0}, float3{1, 1, 1});
+        return instances_.back();
+    }
     std::deque<MeshInstance>& GetMeshInstances() { return instances_; }   // a deque: references stay valid as instances are added
     void InvalidateMeshInstance(uint32_t instanceId) { invalidInstances_.insert(instanceId); }
     size_t AddLight(const Light& l)

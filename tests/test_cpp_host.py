@@ -77,3 +77,16 @@ def test_cpp_host_api_mirror():
     _build()
     r = subprocess.run([API_EXE], capture_output=True, text=True)
     assert r.returncode == 0 and "host api ok" in r.stdout, r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_imports_assets(tmp_path):
+    """Scene::CreateMeshInstanceFromFile in the C++ layer (include/nexus_b200_import.hpp): an .obj and a .glb imported into a fresh scene,
+    rendered, and picked with the pixel query."""
+    import test_gltf
+    import test_obj
+    _build()
+    cube = test_obj._write(tmp_path)
+    test_gltf._two_quads_glb(tmp_path / "q.glb")
+    r = subprocess.run([API_EXE, str(cube), str(tmp_path / "q.glb")], capture_output=True, text=True)
+    assert r.returncode == 0 and "host api ok" in r.stdout and r.stdout.count("imported ") == 2, r.stderr + r.stdout

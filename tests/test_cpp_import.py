@@ -51,3 +51,49 @@ def test_cpp_readers_equal_the_python_readers(tmp_path):
     (tmp_path / "bad.hdr").write_bytes(b"P6\n1 1\n255\n...")
     r4 = subprocess.run([EXE, str(cube), str(tmp_path / "bad.hdr")], capture_output=True, text=True)
     assert r4.returncode == 1 and "not a Radiance" in r4.stderr
+
+
+def _glb_json(path, tmp_path):
+    cube = test_obj._write(tmp_path)
+    test_hdr._write(tmp_path / "tiny.hdr", test_hdr._rgbe(np.ones((1, 8, 3), np.float32)), rle=False)
+    r = subprocess.run([EXE, str(cube), str(tmp_path / "tiny.hdr"), str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout)["glb"]
+
+
+def _compare_glb(got, want):
+    assert len(got["meshes"]) == len(want["meshes"]) and len(got["instances"]) == len(want["instances"]) and len(got["materials"]) == len(want["materials"])
+    for g, w in zip(got["meshes"], want["meshes"]):
+        assert g["name"] == w["name"] and g["material"] == w["material"]
+        assert (np.array(g["triangles"], np.float32) == w["triangles"].ravel()).all()
+        assert np.allclose(np.array(g["triangle_data"], np.float32), w["triangle_data"].ravel(), rtol=0, atol=1e-7)
+    for g, w in zip(got["instances"], want["instances"]):
+        assert g["mesh"] == w["mesh"] and np.allclose(np.array(g["matrix"], np.float32), w["matrix"].ravel(), rtol=1e-6, atol=1e-6)
+    for g, w in zip(got["materials"], want["materials"]):
+        ours = [*w.baseColor, w.opacity, w.metalness, w.roughness, *w.emissionColor, w.intensity, w.specularWeight, w.specularColor[0], w.ior, w.transmission, w.specularColor[2]]
+        assert np.allclose(g, ours, rtol=1e-6, atol=1e-7)
+
+
+def test_cpp_glb_reader_equals_the_python_reader(tmp_path):
+    import test_gltf
+    from nexus_b200 import gltf
+    _build()
+    test_gltf._two_quads_glb(tmp_path / "q.glb")
+    got = _glb_json(tmp_path / "q.glb", tmp_path)
+    _compare_glb(got, gltf.load_glb(tmp_path / "q.glb"))
+    assert got["camera"] is False
+    (tmp_path / "bad.glb").write_bytes(b"not a glb file at all....")
+    cube = test_obj._write(tmp_path)
+    r = subprocess.run([EXE, str(cube), str(tmp_path / "tiny.hdr"), str(tmp_path / "bad.glb")], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a binary glTF" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Nexus/assets/demo_scenes/cornell_box/cornell_box.glb"), reason="the reference's demo asset is only mounted in the build container")
+def test_cpp_glb_reader_loads_the_reference_cornell_box(tmp_path):
+    from nexus_b200 import gltf
+    _build()
+    ref = "/root/reference/Nexus/assets/demo_scenes/cornell_box/cornell_box.glb"
+    got = _glb_json(ref, tmp_path)
+    want = gltf.load_glb(ref)
+    _compare_glb(got, want)
+    assert len(got["meshes"]) == 8 and sum(len(m["triangles"]) // 9 for m in got["meshes"]) == 32
