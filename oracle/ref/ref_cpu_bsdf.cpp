@@ -1,0 +1,33 @@
+// TEST INFRASTRUCTURE ONLY.  The reference's BSDF code (Nexus/src/Cuda/BSDF/*.cuh: D_PrincipledBSDF and the conductor / dielectric / plastic
+// lobes, Microfacet, Fresnel) is device-only, but it is plain arithmetic: with host shims for the handful of device intrinsics it uses it
+// compiles UNMODIFIED with g++ and runs on the CPU (oracle/Makefile target `refcpu`).  That turns row a8 of SURVEY.md section 8 from
+// "pinned statistically through converged images" into a function-level pin: D_PrincipledBSDF::Eval for given (material, wi, wo).
+// Host arithmetic is IEEE; on the GPU the reference is compiled with --use_fast_math, so values agree to approximation error only.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "Utils/Utils.h"
+static inline float __uint_as_float(unsigned int u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned int __float_as_uint(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+extern "C" void __sincosf(float x, float* s, float* c) noexcept { *s = std::sin(x); *c = std::cos(x); }   // declared (not defined) for the host by the CUDA headers
+static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+static inline float __fdividef(float a, float b) { return a / b; }
+#include "Cuda/BSDF/PrincipledBSDF.cuh"
+
+static_assert(sizeof(D_Material) == 92, "D_Material layout");
+
+// mats: n x 92 B (D_Material), wi / wo: n x 3 floats in the local shading frame (z = normal).  out: bsdf n x 3, pdf n, ok n.
+extern "C" int ref_bsdf_eval(const void* mats, const float* wi, const float* wo, uint32_t n, float* outBsdf, float* outPdf, uint8_t* outOk)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        D_Material m; std::memcpy(&m, (const uint8_t*)mats + 92 * (size_t)i, 92);
+        float3 f; float pdf;
+        const bool ok = D_PrincipledBSDF::Eval(m, make_float3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), make_float3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), f, pdf);
+        outBsdf[3 * i] = f.x; outBsdf[3 * i + 1] = f.y; outBsdf[3 * i + 2] = f.z; outPdf[i] = pdf; outOk[i] = ok ? 1 : 0;
+    }
+    return 0;
+}

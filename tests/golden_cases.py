@@ -127,3 +127,27 @@ def host_cases():
             "res": np.array([(1920, 1080), (3840, 2160), (640, 480), (96, 64)] * 3, np.uint32)}
     cams["position"][0] = (0, 4, 14); cams["forward"][0] = (0, 0, -1); cams["hfov"][0] = 45; cams["focus"][0] = 5; cams["defocus"][0] = 0   # Scene.cpp:9-10
     return inst, cams
+
+
+def bsdf_cases(n=8192, seed=5):
+    """Random (material, wi, wo) triples for the BSDF golden (scripts/make_golden_bsdf.py): nx_material / D_Material records (92 B as 23
+    words) covering metal / dielectric / plastic mixes, anisotropy, specular weight and colour, ior, transmission; directions in the
+    local shading frame, wi mostly in the upper hemisphere, wo in both (reflection and refraction)."""
+    rng = np.random.default_rng(seed)
+    mat = np.zeros((n, 23), np.float32)
+    mat[:, 0:3] = rng.uniform(0.02, 1, (n, 3))
+    mat[:, 3] = rng.choice([0.0, 1.0, 0.3, 0.7], n)             # metalness
+    mat[:, 4] = rng.uniform(0.03, 1.0, n)                       # roughness
+    mat[:, 5] = rng.choice([0.0, 0.0, 0.5, 0.9], n)             # anisotropy
+    mat[:, 6] = rng.choice([1.0, 0.0, 0.5], n)                  # specular weight
+    mat[:, 7:10] = rng.uniform(0.2, 1, (n, 3))                  # specular colour
+    mat[:, 10] = rng.uniform(1.05, 2.2, n)                      # ior
+    mat[:, 11] = rng.choice([0.0, 1.0, 0.4], n)                 # transmission
+    mat[:, 12:15] = 1; mat[:, 15] = 0; mat[:, 16] = 1           # emission colour, intensity, opacity
+    mat.view(np.int32)[:, 17:23] = -1                           # no maps
+
+    def dirs(lower_frac):
+        v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v[:, 2] = np.abs(v[:, 2]); v[rng.uniform(size=n) < lower_frac, 2] *= -1
+        return v.astype(np.float32)
+    return mat, dirs(0.15), dirs(0.4)
