@@ -31,3 +31,15 @@ extern "C" int ref_bsdf_eval(const void* mats, const float* wi, const float* wo,
     }
     return 0;
 }
+
+// TangentFrame(n) (Nexus/src/Math/TangentFrame.h:11-22, Duff et al. 2017): tangent, bitangent, normal as 9 floats per input normal.
+#include "Math/TangentFrame.h"
+extern "C" int ref_tangent_frame(const float* normals, uint32_t n, float* out9)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        const TangentFrame f(make_float3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
+        const float v[9] = {f.tangent.x, f.tangent.y, f.tangent.z, f.bitangent.x, f.bitangent.y, f.bitangent.z, f.normal.x, f.normal.y, f.normal.z};
+        std::memcpy(out9 + 9 * (size_t)i, v, sizeof(v));
+    }
+    return 0;
+}

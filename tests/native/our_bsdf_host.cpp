@@ -47,3 +47,13 @@ extern "C" int our_bsdf_sample(const void* mats, const float* wi, const uint32_t
     }
     return 0;
 }
+// Frame(n) of bsdf.cuh: tangent, bitangent, normal as 9 floats per input normal.
+extern "C" int our_tangent_frame(const float* normals, uint32_t n, float* out9)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        const Frame f(f3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
+        const float v[9] = {f.t.x, f.t.y, f.t.z, f.b.x, f.b.y, f.b.z, f.n.x, f.n.y, f.n.z};
+        std::memcpy(out9 + 9 * (size_t)i, v, sizeof(v));
+    }
+    return 0;
+}

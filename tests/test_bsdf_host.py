@@ -78,3 +78,18 @@ def test_eval_and_sampler_against_the_live_reference(ours):
         rp_, rw_ = _rel(spdf[s], ep[s]), _rel(sw[s], ef[s] / ep[s, None])
         # the half vector is re-derived from the sampled direction on the reference's side: grazing configurations amplify rounding
         assert np.quantile(rp_, 0.999) <= 2e-3 and np.quantile(rw_, 0.99) <= 1e-3 and np.median(rw_) <= 1e-6, (metal, trans, rp_.max(), rw_.max())
+
+
+@pytest.mark.skipif(not O.have_refcpu(), reason="oracle/_ref/libnexus_refcpu.so (the compiled reference code) is not present")
+def test_tangent_frame_equals_the_reference_bit_for_bit(ours):
+    """The shading frame decides how anisotropic highlights are oriented: Frame(n) of bsdf.cuh against TangentFrame(n)
+    (Nexus/src/Math/TangentFrame.h:11-22) on random unit normals and the axis cases, including n.z = -1 and -0."""
+    R = C.CDLL(O.REFCPU_SO)
+    rng = np.random.default_rng(8)
+    nrm = rng.normal(size=(20000, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = np.concatenate([nrm, [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [0, -1, 0], [1, 0, -0.0], [0.6, 0.8, 0.0]]]).astype(np.float32)
+    a, b = np.zeros((len(nrm), 9), np.float32), np.zeros((len(nrm), 9), np.float32)
+    assert ours.our_tangent_frame(P(nrm), C.c_uint32(len(nrm)), P(a)) == 0 and R.ref_tangent_frame(P(nrm), C.c_uint32(len(nrm)), P(b)) == 0
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    t, bt, n = a[:20000, 0:3].astype(np.float64), a[:20000, 3:6].astype(np.float64), a[:20000, 6:9].astype(np.float64)
+    assert np.abs((t * bt).sum(1)).max() < 1e-6 and np.abs((t * n).sum(1)).max() < 1e-6 and np.allclose(np.cross(t, bt), n, atol=1e-6)
