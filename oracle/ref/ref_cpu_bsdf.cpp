@@ -16,6 +16,12 @@ static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); ret
 extern "C" void __sincosf(float x, float* s, float* c) noexcept { *s = std::sin(x); *c = std::cos(x); }   // declared (not defined) for the host by the CUDA headers
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 static inline float __fdividef(float a, float b) { return a / b; }
+// CUDA provides max / min overloads for floats in device code; on the host the reference's cuda_math.h only declares the int ones,
+// which would silently truncate (e.g. sqrt(max(1 - t1*t1 - t2*t2, 0.0f)) in Microfacet::SampleVndf_Heitz)
+static inline float max(float a, float b) { return a > b ? a : b; }
+static inline float min(float a, float b) { return a < b ? a : b; }
+static inline double max(double a, double b) { return a > b ? a : b; }
+static inline double min(double a, double b) { return a < b ? a : b; }
 #include "Cuda/BSDF/PrincipledBSDF.cuh"
 
 static_assert(sizeof(D_Material) == 92, "D_Material layout");
@@ -40,6 +46,20 @@ extern "C" int ref_tangent_frame(const float* normals, uint32_t n, float* out9)
         const TangentFrame f(make_float3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
         const float v[9] = {f.tangent.x, f.tangent.y, f.tangent.z, f.bitangent.x, f.bitangent.y, f.bitangent.z, f.normal.x, f.normal.y, f.normal.z};
         std::memcpy(out9 + 9 * (size_t)i, v, sizeof(v));
+    }
+    return 0;
+}
+
+// D_PrincipledBSDF::Sample with the reference's own RNG seeded by seeds[i]: outgoing direction, path weight ("throughput"), pdf.
+extern "C" int ref_bsdf_sample(const void* mats, const float* wi, const uint32_t* seeds, uint32_t n, float* outWo, float* outWeight, float* outPdf, uint8_t* outOk)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        D_Material m; std::memcpy(&m, (const uint8_t*)mats + 92 * (size_t)i, 92);
+        float3 wo = make_float3(0.0f), w = make_float3(0.0f); float pdf = 0.0f; unsigned int rng = seeds[i];
+        const bool ok = D_PrincipledBSDF::Sample(m, make_float3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), wo, w, pdf, rng);
+        outWo[3 * i] = wo.x; outWo[3 * i + 1] = wo.y; outWo[3 * i + 2] = wo.z;
+        outWeight[3 * i] = w.x; outWeight[3 * i + 1] = w.y; outWeight[3 * i + 2] = w.z;
+        outPdf[i] = pdf; outOk[i] = ok ? 1 : 0;
     }
     return 0;
 }
