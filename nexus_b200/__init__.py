@@ -539,6 +539,7 @@ class Scene:
         if inst._matrix is None and inst._trs_edited:        # position / rotation / scale were set: T * Rz * Ry * Rx * S, composed by the library
             p, r, s = (np.asarray(v, np.float32) for v in (inst.position, inst.rotation, inst.scale))
             check(self.ctx._h, lib().nx_scene_set_instance_transform(self._h, C.c_uint32(inst.index), _ptr(p), _ptr(r), _ptr(s)), "InvalidateMeshInstance")
+            inst._trs_edited = False
         if inst._material_edited:
             check(self.ctx._h, lib().nx_scene_set_instance_material(self._h, C.c_uint32(inst.index), C.c_int32(inst.materialIdx)), "AssignMaterial")
             inst._material_edited = False
