@@ -131,3 +131,53 @@ def test_materials_replaced_through_the_legacy_call_upload_at_once(fake):
     assert fake.names() == ["nx_scene_set_material"] and s.GetMaterials()[2].roughness == 0.77 and not s.IsInvalid()
     with pytest.raises(nx.NexusError):
         s.GetAssetManager().InvalidateMaterial(7)
+
+
+def test_importing_into_a_populated_scene_shifts_material_and_texture_indices(fake, tmp_path):
+    """Scene.CreateMeshInstanceFromFile appends: an asset's material indices are offset by the materials the scene already has and its
+    texture ids by the textures already registered (checked on the MaterialPod records handed to the library)."""
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    import test_gltf
+    px = np.random.RandomState(1).randint(0, 256, (2, 2, 4)).astype(np.uint8)
+    buf = io.BytesIO(); PIL.fromarray(px, "RGBA").save(buf, format="PNG")
+    png = buf.getvalue()
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    binary = pos.tobytes() + png
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "material": 1}]}],
+          "materials": [{}, {"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}, "normalTexture": {"index": 0}}],
+          "textures": [{"source": 0}], "images": [{"bufferView": 1, "mimeType": "image/png"}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}],
+          "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": pos.nbytes}, {"buffer": 0, "byteOffset": pos.nbytes, "byteLength": len(png)}],
+          "buffers": [{"byteLength": len(binary)}]}
+    test_gltf._write_glb(tmp_path / "t.glb", js, binary)
+
+    pods = []
+    real_getattr = FakeLib.__getattr__
+
+    def spy(self, name):
+        fn = real_getattr(self, name)
+        if name != "nx_scene_add_material":
+            return fn
+
+        def wrapped(*args):
+            pods.append(args[1]._obj)            # byref(MaterialPod)
+            return fn(*args)
+        return wrapped
+    FakeLib.__getattr__ = spy
+    try:
+        s = _scene(fake)                          # 3 materials, 2 meshes, 4 instances
+        s.GetAssetManager().AddTexture(np.zeros((2, 2, 4), np.uint8))
+        s.GetAssetManager().AddTexture(np.zeros((2, 2, 4), np.float32))
+        pods.clear(); fake.clear()
+        created = s.CreateMeshInstanceFromFile(str(tmp_path) + "/", "t.glb")
+    finally:
+        FakeLib.__getattr__ = real_getattr
+    assert len(created) == 1 and created[0].index == 4 and created[0].meshIdx == 2
+    assert fake.names() == ["nx_scene_add_texture", "nx_scene_add_texture", "nx_scene_add_material", "nx_scene_add_material", "nx_scene_add_mesh", "nx_scene_add_instance_matrix"]
+    assert len(pods) == 2 and pods[0].base_color_map == -1
+    assert pods[1].base_color_map == 2 and pods[1].normal_map == 3            # the asset's textures 0 (sRGB) and 1 (linear) behind the scene's two
+    add_mesh = [a for n, a in fake.calls if n == "nx_scene_add_mesh"][0]
+    assert add_mesh[-1] == 3 + 1                                              # material 1 of the asset = material 4 of the scene
+    assert len(s.GetMaterials()) == 5
