@@ -30,6 +30,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+DEFAULT_TRACE_MODE = "pool"      # what nx_ctx_create selects when NX_TRACE_MODE is unset (nx_common.cuh: trace_mode)
+
 WORKLOADS = {
     # BASELINE.json configs[2]: the configuration north_star's target is quoted on; fits one GPU (about 2.5 GB resident)
     "instanced10m_4k": dict(res=(3840, 2160), desc="10M-triangle instanced scene (1024 BLAS x 9798 tris, 1026 instances, TLAS), OpenPBR "
@@ -132,6 +134,80 @@ def algorithmic_bytes(work, kind):
     return per_ray * work["rays"] + 80 * work["nodes"] + 40 * work["tris"] + 144 * work["insts"]
 
 
+def kernel_source_sha():
+    """Hash of the CUDA sources: a committed ncu figure is only reported for the code it was measured on."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "nexus_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+NCU_METRICS = "smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__cycles_elapsed.max"
+
+
+def ncu_counters(workload, kernel_regex, launches_per_step, extra_env=None):
+    """Hardware counters of one step's launches of a kernel, measured NOW: a child `bench.py --count-pass` (scene set-up, one warm
+    step, one counted step) runs under ncu with five raw metrics.  Instruction and DRAM-byte counts do not depend on the replay;
+    no time is taken from this pass.  Returns per-launch averages over the last step's launches, or None (ncu missing / not permitted)."""
+    import csv
+    import shutil
+    if not shutil.which("ncu"):
+        return None
+    log = tempfile.mktemp(suffix=".csv")
+    cmd = ["ncu", "--metrics", NCU_METRICS, "--clock-control", "none", "-k", "regex:" + kernel_regex, "--csv", "--log-file", log,
+           sys.executable, os.path.abspath(__file__), "--workload", workload, "--count-pass"]
+    env = dict(os.environ); env.update(extra_env or {})
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600, check=True)
+        rows = [r for r in csv.reader(l for l in open(log) if l.startswith('"'))]
+    except (OSError, subprocess.SubprocessError):
+        return None
+    finally:
+        if os.path.exists(log):
+            os.unlink(log)
+    if not rows:
+        return None
+    hdr = rows[0]
+    iid, iname, ival = hdr.index("ID"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    per = {}
+    for r in rows[1:]:
+        try:
+            per.setdefault(int(r[iid]), {})[r[iname]] = float(r[ival].replace(",", ""))
+        except (ValueError, IndexError):
+            continue
+    ids = sorted(per)[-launches_per_step:]
+    if len(ids) < launches_per_step:
+        return None
+    out = {m: sum(per[i].get(m, 0.0) for i in ids) / len(ids) for m in NCU_METRICS.split(",")}
+    out["launches"] = len(ids)
+    return out
+
+
+def run_count_pass(args):
+    """Child of ncu_counters: the workload's scene, one warm step, one counted step; prints nothing."""
+    import nexus_b200 as nx
+    from nexus_b200 import scenes
+    ctx = nx.Context(0)
+    if args.workload.startswith("build"):
+        import torch
+        wl = WORKLOADS[args.workload]
+        dev_t = torch.from_numpy(build_mesh(wl)).cuda()
+        for _ in range(2):
+            nx.BuildBVH8Device(ctx, dev_t.data_ptr(), wl["n"], 1, True).Free()
+        ctx.synchronize()
+        return
+    desc = make_desc(args.workload)
+    res = WORKLOADS[args.workload]["res"]
+    scene = scenes.build(ctx, desc, res)
+    pt = nx.PathTracer(ctx, res)
+    pt.Render(scene, frames=1, firstFrame=1); ctx.synchronize()
+    pt.Render(scene, frames=1, firstFrame=2); ctx.synchronize()
+
+
 # ----------------------------------------------------------------------------------------------- our arm ----
 def run_ours(args):
     import torch
@@ -152,6 +228,7 @@ def run_ours(args):
     res = wl["res"]
 
     ctx = nx.Context(local)          # raises when the CUDA library or a GPU is missing: there is no fallback
+    ctx_trace_mode = os.environ.get("NX_TRACE_MODE", DEFAULT_TRACE_MODE)
     desc = make_desc(args.workload)
     t_scene = time.time()
     # N > 1: the BLAS builds are sharded (rank g builds meshes g, g + N, ...; one NCCL all-gather hands every rank every BLAS,
@@ -200,12 +277,25 @@ def run_ours(args):
     e0.record(stream)
     pt.Render(scene, frames=K, firstFrame=first)
     e1.record(stream)
+    local_sum = None
     if world > 1:
         with torch.cuda.stream(stream):
+            local_sum = acc_t.sum(dtype=torch.float64)          # checksum of this rank's contribution (100 MB read, inside the timed region)
             pt.SetAccumulatedFrames(reduce_accumulation(acc_t, K))
     e2.record(stream)
     barrier()
     wall = time.time() - wall0
+    reduce_check = None
+    if world > 1:
+        # multi-GPU correctness, in the run the driver records: the reduced buffer must be the sum of what the ranks rendered
+        with torch.cuda.stream(stream):
+            reduced_sum = acc_t.sum(dtype=torch.float64)
+            dist.all_reduce(local_sum)
+        barrier()
+        want, got = float(local_sum), float(reduced_sum)
+        rel = abs(got - want) / max(abs(want), 1e-30)
+        assert rel < 1e-5, f"reduced accumulation checksum {got} != sum of the per-rank checksums {want} (relative {rel:.2e})"
+        reduce_check = {"sum_of_rank_checksums": want, "reduced_checksum": got, "rel_err": rel}
     clocks = sampler.stop() if rank == 0 else None
     ms_total, ms_reduce = e0.elapsed_time(e2), e1.elapsed_time(e2)
     st = pt.Stats()
@@ -239,20 +329,42 @@ def run_ours(args):
     hbm, hbm_src = peaks()
     avg_launch_ms = tc["ms"] / max(tc["launches"], 1)
     achieved = bytes_closest / max(tc["launches"], 1) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get("trace_closest_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "trace_closest_kernel", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": hbm_src,
-                "avg_launch_ms": round(avg_launch_ms, 4), "launches": tc["launches"],
-                "algorithmic_bytes_per_launch": int(bytes_closest / max(tc["launches"], 1)),
+    # What bounds the kernel is instruction issue, not HBM (ncu: 0.4-0.9 GB of DRAM traffic per launch against 6.9 GB requested, L2
+    # throughput under 20 %): the roofline is thread-instructions per second against SMs x 4 schedulers x 32 lanes x SM clock.  The
+    # instruction and DRAM-byte counts come from an ncu pass over one step of THIS build, run now (ncu_counters); the time is the
+    # live CUDA-event time above.  The request-byte rate (SURVEY.md 8d's formula) is kept beside it under "hbm".
+    launches_per_step = max(tc["launches"] // K, 1)
+    counters = None
+    if rank == 0 and world == 1 and not args.no_ncu:
+        counters = ncu_counters(args.workload, "trace_closest", launches_per_step)
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    sms = ctx.sm_count
+    issue_peak = sms * 4 * 32 * sm_mhz * 1e6 / 1e9                      # G thread-instructions / s
+    hbm_part = {"achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4), "peak_source": hbm_src,
+                "what": "request bytes (44 B/ray + 80 B/node + 40 B/triangle + 144 B/instance entry, SURVEY.md 8d) / live launch time; most of it is served by L1/L2",
+                "algorithmic_bytes_per_launch": int(bytes_closest / max(tc["launches"], 1))}
+    if counters:
+        tinst, winst = counters["smsp__thread_inst_executed.sum"], counters["smsp__inst_executed.sum"]
+        a_issue = tinst / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+        traffic = int(counters["dram__bytes_read.sum"] + counters["dram__bytes_write.sum"])
+        hbm_part["dram_frac_of_peak"] = round(traffic / (avg_launch_ms * 1e-3) / 1e9 / hbm, 4) if avg_launch_ms > 0 else None
+        roofline = {"bound": "issue", "kernel": "trace_closest (%s loop)" % ctx_trace_mode, "achieved": round(a_issue, 1), "peak": round(issue_peak, 1), "unit": "Gthread-inst/s",
+                    "frac": round(a_issue / issue_peak, 4), "traffic": traffic,
+                    "peak_source": f"{sms} SMs x 4 schedulers x 32 lanes x {sm_mhz:.0f} MHz (SM clock sampled under load in the timed region)",
+                    "warp_inst_per_launch": int(winst), "thread_inst_per_launch": int(tinst), "lanes_per_inst": round(tinst / max(winst, 1.0), 2),
+                    "issue_slot_util": round(winst / (avg_launch_ms * 1e-3) / (sms * 4 * sm_mhz * 1e6), 4) if avg_launch_ms > 0 else None,
+                    "counters": "ncu pass over one step of this build, run inside this bench invocation (instruction / DRAM-byte counts only; times are live CUDA events)",
+                    "hbm": hbm_part}
+    else:
+        roofline = {"bound": "issue", "kernel": "trace_closest (%s loop)" % ctx_trace_mode, "achieved": None, "peak": round(issue_peak, 1), "unit": "Gthread-inst/s", "frac": None, "traffic": None,
+                    "counters": "unavailable: no ncu pass in this run (N > 1, --no-ncu, or ncu not permitted); see profiles/ for the round's captures", "hbm": hbm_part}
+    roofline.update({"avg_launch_ms": round(avg_launch_ms, 4), "launches": tc["launches"],
                 "per_ray": {"nodes": round(cw["nodes"] / max(cw["rays"], 1), 2), "tris": round(cw["tris"] / max(cw["rays"], 1), 2),
                             "insts": round(cw["insts"] / max(cw["rays"], 1), 3)},
                 "shadow_per_ray": {"nodes": round(aw["nodes"] / max(aw["rays"], 1), 2), "tris": round(aw["tris"] / max(aw["rays"], 1), 2),
                                    "insts": round(aw["insts"] / max(aw["rays"], 1), 3)},
                 "kernel_ms_per_step": {k: round(prof[k]["ms"] / K, 4) for k in pt.KERNELS},
-                "timed_pass": "a second pass over the same K frames with a CUDA event pair around every launch and the two trace streams serialised, so each kernel is timed alone (the headline region runs them overlapped and without per-launch events)"}
+                "timed_pass": "a second pass over the same K frames with a CUDA event pair around every launch and the two trace streams serialised, so each kernel is timed alone (the headline region runs them overlapped and without per-launch events)"})
 
     # ---- e2e: the call a host application makes per frame, HOST buffers on both sides, copies inside the timed region:
     # camera + render settings from host structs (H2D: the kernel parameter block), one frame, tone-mapped RGBA8 frame read
@@ -334,25 +446,98 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(desc, scene, res)
 
+    config5 = None
+    if world > 1 and args.workload == "instanced10m_4k" and not args.no_config5:
+        config5 = run_config5(nx, ctx, pt, world, rank, res, stream, barrier, sharded)
+
     if rank == 0:
         line = {"metric": "Mrays/s", "value": round(value, 1), "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "description": wl["desc"], "resolution": list(res), "path_length": desc["settings"].pathLength,
-                           "partition": f"sample partition: rank g renders frames [1+g*K, (g+1)*K]; NCCL all-reduce(sum) of float[3*W*H] accumulation ({'%.1f' % (12e-6 * res[0] * res[1])} MB)" if world > 1 else "single GPU",
-                           "bvh": "BLAS / TLAS: H-PLOC BVH2 + SAH-optimal CWBVH8 collapse (reference CPU BVH8Builder's C(n,i) table on the GPU, <= 2 primitives per leaf); same hits as the reference's trees, see like_for_like",
-                           "l2": "per-step working set (ray/hit/state queues %.0f MB at this resolution + BVH/triangles) exceeds the 126 MB L2; no flush needed" % (164e-6 * res[0] * res[1])},
+                "config": {"workload": args.workload, "description": wl["desc"], "resolution": list(res), "path_length": desc["settings"].pathLength},
+                "notes": {"partition": f"sample partition: rank g renders frames [1+g*K, (g+1)*K]; NCCL all-reduce(sum) of float[3*W*H] accumulation ({'%.1f' % (12e-6 * res[0] * res[1])} MB)" if world > 1 else "single GPU",
+                          "bvh": "BLAS / TLAS: H-PLOC BVH2 + SAH-optimal CWBVH8 collapse (reference CPU BVH8Builder's C(n,i) table on the GPU, <= 2 primitives per leaf); same hits as the reference's trees, see like_for_like",
+                          "l2": "per-step working set (ray/hit/state queues %.0f MB at this resolution + BVH/triangles) exceeds the 126 MB L2; no flush needed" % (212e-6 * res[0] * res[1]),
+                          "traversal": ctx_trace_mode},
                 "spp_per_s": round(world * K / (ms_total * 1e-3), 2),
                 "rays_per_step": int(rays_all / (K * world)), "extension_rays": int(cnt[1]), "shadow_rays": int(cnt[2]),
                 "primary_Mrays_per_s": round(world * K * res[0] * res[1] / (ms_total * 1e-3) / 1e6, 1),
                 "reduce_ms": round(ms_reduce, 3), "wall_s": round(wall, 3), "scene_setup_s": round(t_scene, 2),
                 "blas_builds": f"sharded round-robin over {world} ranks + NCCL all-gather" if sharded else "every rank builds every BLAS",
                 "mean_radiance": round(mean_radiance, 5),
-                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "like_for_like": like}
+                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "like_for_like": like,
+                "reduce_check": reduce_check, "config5": config5}
         print(json.dumps(line), flush=True)
     pt.close(); scene.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config5(nx, ctx, pt, world, rank, res, stream, barrier, sharded, total_spp=64):
+    """BASELINE.json configs[4] (SURVEY.md 8d "Config 5 inputs") inside an N > 1 run: configs[2]'s geometry under a procedural HDR sky,
+    64 samples per pixel in total = 64 / N frames per rank (sample partition), one NCCL all-reduce of the float accumulation sums, the
+    reduce timed separately.  In-run correctness: the float64 checksum of the reduced buffer must equal the all-reduced sum of the
+    per-rank checksums taken before the reduce."""
+    import torch
+    import torch.distributed as dist
+    from nexus_b200 import scenes
+    from nexus_b200.multigpu import accumulation_tensor, build_scene_sharded, frame_block
+    desc = make_desc("sky10m_4k")
+    t0 = time.time()
+    scene = build_scene_sharded(ctx, desc, res) if sharded else scenes.build(ctx, desc, res)
+    ctx.synchronize()
+    t_scene = time.time() - t0
+    per = max(1, total_spp // world)
+    acc = accumulation_tensor(pt, torch.device("cuda", ctx.device))
+    pt.ResetFrameNumber()
+    pt.Render(scene, frames=2, firstFrame=1)
+    with torch.cuda.stream(stream):
+        dist.all_reduce(acc)
+    barrier()
+    pt.ResetFrameNumber()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    barrier()
+    e0.record(stream)
+    pt.Render(scene, frames=per, firstFrame=frame_block(rank, world, per))
+    e1.record(stream)
+    with torch.cuda.stream(stream):
+        local_sum = acc.sum(dtype=torch.float64)                 # 100 MB read, ~20 us: inside the timed region
+        dist.all_reduce(acc)
+    e2.record(stream)
+    barrier()
+    with torch.cuda.stream(stream):
+        reduced_sum = acc.sum(dtype=torch.float64)
+        dist.all_reduce(local_sum)
+    barrier()
+    pt.SetAccumulatedFrames(per * world)
+    st = pt.Stats()
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], device="cuda", dtype=torch.float64)
+    c = torch.tensor([float(st["extension_rays"] + st["shadow_rays"])], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c)
+    want, got = float(local_sum), float(reduced_sum)
+    rel = abs(got - want) / max(abs(want), 1e-30)
+    assert rel < 1e-5, f"reduced accumulation checksum {got} != sum of the per-rank checksums {want} (relative {rel:.2e})"
+    # the collective alone, ranks aligned by a barrier first (the in-region figure above also contains the skew between ranks)
+    scratch = torch.empty_like(acc)
+    alone = []
+    for _ in range(5):
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a0.record(stream); dist.all_reduce(scratch); a1.record(stream)
+        barrier()
+        alone.append(a0.elapsed_time(a1))
+    alone_t = torch.tensor([float(np.median(alone))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(alone_t, op=dist.ReduceOp.MAX)
+    mean = float(pt.ReadAccumulation().mean()) if rank == 0 else 0.0
+    scene.close()
+    ms_total, ms_reduce = float(t[0]), float(t[1])
+    return {"workload": "sky10m_4k", "what": "BASELINE configs[4]: 8xB200 sample-partitioned 4K render, procedural HDR environment map, 64 spp total, NCCL all-reduce of the accumulation buffers",
+            "spp_total": per * world, "frames_per_rank": per, "value": round(float(c[0]) / (ms_total * 1e-3) / 1e6, 1), "unit": "Mrays/s",
+            "spp_per_s": round(per * world / (ms_total * 1e-3), 2), "ms_total": round(ms_total, 3), "ms_per_frame": round((ms_total - ms_reduce) / per, 4),
+            "reduce_ms": round(ms_reduce, 3), "reduce_alone_ms": round(float(alone_t[0]), 3), "reduce_bytes": int(acc.numel() * 4),
+            "reduce_busbw_GBs": round(2.0 * (world - 1) / world * acc.numel() * 4 / (float(alone_t[0]) * 1e-3) / 1e9, 1),
+            "reduce_check": {"sum_of_rank_checksums": want, "reduced_checksum": got, "rel_err": rel}, "mean_radiance": round(mean, 5), "scene_setup_s": round(t_scene, 2)}
 
 
 def cpu_baseline(desc, scene, res, budget_s=15.0):
@@ -524,9 +709,9 @@ def run_build_ours(args):
     if rank == 0:
         line = {"metric": "Mprims/s", "value": round(value, 1), "unit": "Mprims/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-                "config": {"workload": args.workload, "description": wl["desc"], "triangles": n, "prioritize_speed": speed,
-                           "partition": "replicas only: one global sort + one hierarchy does not shard; each rank builds the whole mesh" if world > 1 else "single GPU",
-                           "l2": "input (%.1f GB) and every intermediate array exceed the 126 MB L2; no flush needed" % (36e-9 * n)},
+                "config": {"workload": args.workload, "description": wl["desc"], "triangles": n, "prioritize_speed": speed},
+                "notes": {"partition": "replicas only: one global sort + one hierarchy does not shard; each rank builds the whole mesh" if world > 1 else "single GPU",
+                          "l2": "input (%.1f GB) and every intermediate array exceed the 126 MB L2; no flush needed" % (36e-9 * n)},
                 # the reference's own metric (BVHBuildMetrics::totalTime = the sum of the per-stage CUDA-event times, which is what
                 # the reference arm reports as its value): the same definition for this arm, beside the stricter whole-step `value`
                 "Mprims_per_s_stage_sum": round(n / m["total_ms"] / 1e3, 1),
@@ -631,12 +816,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="instanced10m_4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the ncu counter pass behind roofline.frac / roofline.traffic")
+    ap.add_argument("--count-pass", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-like-for-like", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the BASELINE configs[4] block (HDR sky, 64 spp total)")
     ap.add_argument("--replicated-build", action="store_true", help="N > 1: every rank builds every BLAS instead of sharding the builds")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     build = args.workload.startswith("build")
+    if args.count_pass:
+        return run_count_pass(args)
     if args.impl == "reference":
         (run_build_reference if build else run_reference)(args)
     else:

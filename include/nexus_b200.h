@@ -119,9 +119,10 @@ typedef struct nx_kernel_profile {
     uint64_t closest_work[4];             /* nodes visited, triangles tested, instances entered, rays (flags & 2) */
     uint64_t any_work[4];
     /* warp scheduling of the traversal loop (flags & 2), summed over warps: loop iterations, lanes that tested a node,
-     * triangle rounds, lanes in them, set-up (new ray / instance entry) rounds, lanes in them, instances culled by their sphere */
-    uint64_t closest_sched[7];
-    uint64_t any_sched[7];
+     * triangle rounds, lanes in them, set-up (new ray / instance entry) rounds, lanes in them, instances culled by their sphere;
+     * ray-pool loop only: node rounds, fetch rounds, rays fetched */
+    uint64_t closest_sched[10];
+    uint64_t any_sched[10];
 } nx_kernel_profile;
 
 /* ------------------------------------------------------------------------------------------------ context ---- */
@@ -140,6 +141,18 @@ int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes
 /* Collapse used for the BLASes / TLAS that nx_scene_* builds from now on (default NX_COLLAPSE_SAH_OPTIMAL, 2 primitives per leaf;
  * NX_COLLAPSE_REFERENCE_GPU reproduces NexusBVH's trees).  Hit ids and distances do not depend on the choice. */
 int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims);
+/* Traversal loop of the trace kernels.  NX_TRACE_POOL (default): a warp owns 64 rays whose state lives in shared memory and hands
+ * its lanes the rays that want the kind of work of the round (node test, triangle test, instance entry, fetch).  NX_TRACE_LANE:
+ * one ray per lane.  Hits are identical (same arithmetic, deterministic tie-break).  Also NX_TRACE_MODE=pool|lane. */
+enum { NX_TRACE_LANE = 0, NX_TRACE_POOL = 1, NX_TRACE_DUO = 2 };
+int nx_ctx_set_trace_mode(nx_ctx* ctx, int mode);
+/* Ray-pool round thresholds, in rays of the warp's pool: a round of that kind runs when at least this many rays want it (else the
+ * fullest kind runs).  any_hit != 0 sets the shadow-ray kernel's.  Also NX_POOL_TUNE / NX_POOL_TUNE_ANY = "node,tri,inst,fetch". */
+int nx_ctx_set_pool_tuning(nx_ctx* ctx, int any_hit, uint32_t node_rays, uint32_t tri_rays, uint32_t inst_rays, uint32_t fetch_rays);
+/* Traversal-stack entries per ray (2..40, default 40; the lane-bound loop never goes below its 8 shared-memory entries).  A push beyond the limit is refused and COUNTED; the next nx_ctx_synchronize /
+ * nx_renderer_stats / nx_trace_* returns NX_ERR_STATE with the count in nx_last_error (the reference's 32-entry stack overflows
+ * silently, BVH8Traversal.cuh:164).  Lowering the limit exists for the test of that report. */
+int nx_ctx_set_stack_limit(nx_ctx* ctx, uint32_t entries);
 /* 0 switches the per-instance bounding-sphere test off (measurement only; results are identical either way). */
 int nx_ctx_set_sphere_cull(nx_ctx* ctx, int enabled);
 
@@ -197,6 +210,8 @@ int nx_scene_add_light(nx_scene* scene, const nx_light* light);                 
 int nx_scene_set_light(nx_scene* scene, uint32_t idx, const nx_light* light);           /* GetLights()[idx] = ...; InvalidateLight(idx) */
 int nx_scene_remove_light(nx_scene* scene, uint32_t idx);                               /* Scene::RemoveLight */
 int nx_scene_light_count(nx_scene* scene);                                              /* lights added through AddLight (mesh lights are automatic) */
+/* Camera::OnResize: the output resolution of the scene's camera (must equal the renderer's at render time). */
+int nx_scene_set_resolution(nx_scene* s, uint32_t width, uint32_t height);
 int nx_scene_set_camera(nx_scene* scene, const nx_camera* cam);
 int nx_scene_set_render_settings(nx_scene* scene, const nx_render_settings* rs);
 /* AssetManager::AddTexture + Texture::ToDevice (src/Assets/Texture.cpp:12-46): HOST RGBA8 (is_hdr 0; srgb: decode in the sampler) or RGBA32F
@@ -269,7 +284,8 @@ int nx_renderer_sync_pixel_query(nx_renderer* r, int32_t* out_instance);
 /* The same display transform (exposure, tone curve NX_TONE_*, gamma 2.2, RGBA8 pack: src/Utils/ColorUtils.h:27-212) applied on
  * the device to a HOST linear float RGB image of `count` pixels; for previews of EXR/PFM output and for the parity tests. */
 int nx_display_transform(nx_ctx* ctx, const float* host_rgb, uint32_t count, int tone_mapping, float exposure, uint32_t* host_rgba);
-/* Headless output (north_star): PFM (little-endian float RGB) and EXR (uncompressed scanline, float RGB). */
+/* Headless output (north_star): PFM (little-endian float RGB) and EXR (uncompressed scanline, float RGB).  `rgb` is in the renderer's
+ * layout - row 0 = BOTTOM row, what nx_renderer_read_accum returns - and both files come out upright. */
 int nx_write_pfm(const char* path, const float* rgb, uint32_t w, uint32_t h);
 int nx_write_exr(const char* path, const float* rgb, uint32_t w, uint32_t h);
 

@@ -193,6 +193,8 @@ class Scene {                           // src/Scene/Scene.h:16-77
 public:
     Scene(Context& ctx, uint2 resolution) : ctx_(ctx), assets_(this), res_(resolution), camera_(std::make_shared<Camera>()) { ctx.check(nx_scene_create(ctx.handle(), resolution.x, resolution.y, &h_), "Scene"); }
     ~Scene() { nx_scene_destroy(h_); }
+    // Camera::OnResize (src/Scene/Camera.cpp:118-128): only the camera record depends on the resolution; pair with PathTracer::OnResize
+    void OnResize(uint2 resolution) { ctx_.check(nx_scene_set_resolution(h_, resolution.x, resolution.y), "Scene::OnResize"); res_ = resolution; }
     Scene(const Scene&) = delete; Scene& operator=(const Scene&) = delete;
     std::shared_ptr<Camera> GetCamera() { return camera_; }               // edit, Invalidate(), Update()
     AssetManager& GetAssetManager() { return assets_; }

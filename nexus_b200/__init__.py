@@ -55,6 +55,17 @@ class Context:
         leaf; COLLAPSE_REFERENCE_GPU gives trees identical to the reference's NexusBVH)."""
         check(self._h, lib().nx_ctx_set_scene_collapse(self._h, C.c_int(int(collapse)), C.c_int(int(maxLeafPrims))), "SetSceneCollapse")
 
+    def SetTraceMode(self, mode):
+        """'pool' (default: 64 rays per warp in shared memory, lanes take rays by kind of work) or 'lane' (one ray per lane)."""
+        m = {"lane": 0, "pool": 1, "duo": 2}.get(mode, mode)
+        check(self._h, lib().nx_ctx_set_trace_mode(self._h, C.c_int(int(m))), "SetTraceMode")
+
+    def SetPoolTuning(self, node, tri, inst, fetch, any_hit=False):
+        check(self._h, lib().nx_ctx_set_pool_tuning(self._h, C.c_int(int(any_hit)), C.c_uint32(node), C.c_uint32(tri), C.c_uint32(inst), C.c_uint32(fetch)), "SetPoolTuning")
+
+    def SetStackLimit(self, entries):
+        check(self._h, lib().nx_ctx_set_stack_limit(self._h, C.c_uint32(entries)), "SetStackLimit")
+
     def SetSphereCull(self, enabled):
         check(self._h, lib().nx_ctx_set_sphere_cull(self._h, C.c_int(int(enabled))), "SetSphereCull")
 
@@ -467,6 +478,12 @@ class Scene:
     def GetAssetManager(self):
         return self._assets
 
+    def OnResize(self, resolution):
+        """Camera::OnResize (src/Scene/Camera.cpp:118-128): the output resolution changed; only the camera record depends on it.
+        Call PathTracer.OnResize with the same resolution."""
+        self.resolution = (int(resolution[0]), int(resolution[1]))
+        check(self.ctx._h, lib().nx_scene_set_resolution(self._h, C.c_uint32(self.resolution[0]), C.c_uint32(self.resolution[1])), "Scene.OnResize")
+
     def AddMaterial(self, material):
         return self._assets.AddMaterial(material)
 
@@ -757,7 +774,7 @@ class PathTracer:
         for name, arr in (("closest_work", p.closest_work), ("any_work", p.any_work)):
             out[name] = {"nodes": arr[0], "tris": arr[1], "insts": arr[2], "rays": arr[3]}
         for name, arr in (("closest_sched", p.closest_sched), ("any_sched", p.any_sched)):
-            out[name] = dict(zip(("iters", "lanes_node", "tri_rounds", "tri_lanes", "setup_rounds", "setup_lanes", "sphere_culled"), list(arr)))
+            out[name] = dict(zip(("iters", "lanes_node", "tri_rounds", "tri_lanes", "setup_rounds", "setup_lanes", "sphere_culled", "node_rounds", "fetch_rounds", "fetch_lanes"), list(arr)))
         return out
 
     def ReadAccumulation(self, out=None):
@@ -831,6 +848,7 @@ def display_transform(ctx, rgb, toneMapping=TONE_AGX_DEFAULT, exposure=0.0):
 
 
 def write_pfm(path, rgb):
+    """rgb: (h, w, 3) float32 in the renderer's layout, row 0 = bottom row (what ReadAccumulation returns); the file is upright."""
     rgb = np.ascontiguousarray(rgb, np.float32)
     rc = lib().nx_write_pfm(str(path).encode(), _ptr(rgb), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]))
     if rc < 0:
@@ -838,6 +856,7 @@ def write_pfm(path, rgb):
 
 
 def write_exr(path, rgb):
+    """rgb: (h, w, 3) float32 in the renderer's layout, row 0 = bottom row (what ReadAccumulation returns); the file is upright."""
     rgb = np.ascontiguousarray(rgb, np.float32)
     rc = lib().nx_write_exr(str(path).encode(), _ptr(rgb), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]))
     if rc < 0:

@@ -65,7 +65,7 @@ class FrameStats(C.Structure):
 
 class KernelProfile(C.Structure):
     _fields_ = [("ms", C.c_float * 4), ("launches", C.c_uint32 * 4), ("closest_work", C.c_uint64 * 4), ("any_work", C.c_uint64 * 4),
-                ("closest_sched", C.c_uint64 * 7), ("any_sched", C.c_uint64 * 7)]
+                ("closest_sched", C.c_uint64 * 10), ("any_sched", C.c_uint64 * 10)]
 
 
 assert C.sizeof(MaterialPod) == 92 and C.sizeof(Aabb) == 24

@@ -14,6 +14,7 @@
 //     spin-waiting work queue.
 #include "nx_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include "radix_sort.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -24,6 +25,13 @@ constexpr uint32_t kSearchRadius = 8;     // H-PLOC search radius (BinaryBuilder
 constexpr uint32_t kMergeThreshold = 16;  // clusters kept per LBVH range (BinaryBuilder.cu:10)
 constexpr int kSetupBlock = 256;
 constexpr int kPlocBlock = 128;
+#ifndef NX_PLOC_CHUNK
+#define NX_PLOC_CHUNK 512
+#endif
+#ifndef NX_PLOC_MINB
+#define NX_PLOC_MINB 3
+#endif
+constexpr uint32_t kPlocChunk = NX_PLOC_CHUNK;   // sorted leaves per CTA in the block-local phase of hploc2_kernel
 constexpr int kCollapseBlock = 256;
 
 struct SceneKeys { uint32_t lo[3], hi[3]; };  // order-preserving uint encoding of the scene AABB
@@ -114,10 +122,15 @@ __device__ __forceinline__ uint64_t spread21(uint64_t x)
     return x;
 }
 
+// Also accumulates the digit histograms of every pass of the radix sort that follows (radix_sort.cuh), so the sort never makes
+// a histogram pass over the keys: shared-memory counters per CTA, one global atomic per non-empty bin at the end.
 template <typename KeyT>
 __global__ void __launch_bounds__(kSetupBlock) morton_kernel(const float4* __restrict__ nodes, uint32_t n, const SceneKeys* __restrict__ scene,
-                                                             KeyT* __restrict__ keys, uint32_t* __restrict__ order, float* __restrict__ sceneOut)
+                                                             KeyT* __restrict__ keys, uint32_t* __restrict__ order, float* __restrict__ sceneOut, uint32_t* __restrict__ hist)
 {
+    constexpr int PASSES = SortShape<KeyT>::kPasses;
+    __shared__ uint32_t sHist[PASSES * 256];
+    if (hist) { for (uint32_t i = threadIdx.x; i < PASSES * 256; i += blockDim.x) sHist[i] = 0u; __syncthreads(); }
     const float sx0 = ord2f(scene->lo[0]), sy0 = ord2f(scene->lo[1]), sz0 = ord2f(scene->lo[2]);
     const float sx1 = ord2f(scene->hi[0]), sy1 = ord2f(scene->hi[1]), sz1 = ord2f(scene->hi[2]);
     if (blockIdx.x == 0 && threadIdx.x == 0) { sceneOut[0] = sx0; sceneOut[1] = sy0; sceneOut[2] = sz0; sceneOut[3] = sx1; sceneOut[4] = sy1; sceneOut[5] = sz1; }
@@ -134,6 +147,15 @@ __global__ void __launch_bounds__(kSetupBlock) morton_kernel(const float4* __res
             keys[i] = (KeyT)(spread21(x) | (spread21(y) << 1) | (spread21(z) << 2));
         }
         order[i] = i;
+        if (hist) {
+            const KeyT k = keys[i];
+#pragma unroll
+            for (int p = 0; p < PASSES; p++) atomicAdd(&sHist[p * 256 + sort_digit<KeyT>(k, p)], 1u);
+        }
+    }
+    if (hist) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < PASSES * 256; i += blockDim.x) { const uint32_t c = sHist[i]; if (c) atomicAdd(hist + i, c); }
     }
 }
 
@@ -144,6 +166,7 @@ struct PlocArgs {
     uint32_t* parent;     // LBVH "other boundary" slots, 0xffffffff until the first child arrives
     uint32_t* allocated;  // number of BVH2 nodes handed out so far (starts at n)
     uint32_t n;
+    uint32_t* seedLo; uint32_t* seedHi;   // two-phase builder: ranges left at the chunk borders (two per chunk, INVALID when unused)
 };
 
 // Highest differing bit between neighbouring keys, with the position as tie-break (Apetrei 2014; the 32-bit flavour
@@ -275,6 +298,252 @@ __global__ void __launch_bounds__(kPlocBlock) hploc_kernel(PlocArgs a, const Key
     }
 }
 
+// ------------------------------------------------------------------------------- H-PLOC, two-phase version ----
+// Same algorithm and the same merges as hploc_kernel above (so the same tree, bit for bit), organised for the memory system:
+//
+//   Phase A (block local).  A CTA owns a chunk of C consecutive sorted leaves.  Every LBVH range that lies inside the chunk
+//   is climbed and PLOC-merged entirely in shared memory: leaf boxes, the nodes created, the cluster lists, the parent slots
+//   and the Morton keys are staged there, the hand-off between sibling ranges is a shared-memory atomicExch + block-scope
+//   fence, nodes get provisional chunk-local ids.  ncu on the one-phase kernel (profiles/r01_ncu_hploc_build10m.md): 38 % of
+//   the stall samples wait for global round trips (atomicExch, cluster ids, boxes, the node-index atomic inside every merge
+//   iteration) and 25 % for device-scope fences, at 41 % issue utilisation; more than nine merges in ten never leave a chunk.
+//   Flush.  One atomicAdd per CTA reserves the global node indices of everything the chunk created; nodes, remapped cluster
+//   ids and the half-arrived parent slots go to global memory with coalesced stores.
+//   Phase B (global).  Only ranges that cross a chunk border continue with the global protocol of the one-phase kernel:
+//   threads whose parent slot lies on the chunk border, and the holders of inside slots whose sibling (a range reaching in
+//   from a neighbouring chunk) has already arrived in global memory.
+//
+// The merge itself keeps each cluster's (box, id) in a per-warp shared-memory table: the nearest-neighbour search reads
+// neighbour boxes with two LDS instead of six SHFL, and compaction is a scatter by rank instead of __fns + seven SHFL.
+constexpr uint32_t kSlotDone = 0xfffffffeu;
+
+struct WarpTable { float4 a[40], b[40]; };   // per warp: a = {lo.xyz, hi.x}, b = {hi.y, hi.z, id, -}; 8 entries of slack for lane + radius
+
+template <uint32_t C> struct ChunkMem {
+    float4 node[2 * C][2];     // [0, C): leaves of the chunk in sorted order; [C, 2C): nodes created here (provisional ids)
+    uint32_t cluster[C];       // cluster ids (chunk-local node ids) by sorted position
+    uint32_t leafId[C];        // global node id (= primitive id) of the chunk's leaves
+    uint32_t parent[C];        // LBVH parent slots inside the chunk
+    unsigned long long key[C + 2];   // Morton keys of positions chunkStart - 1 .. chunkStart + C
+    WarpTable table[C / 32];
+    uint32_t created, base;
+};
+
+template <typename KeyT>
+__device__ __forceinline__ uint64_t key_delta_vals(KeyT ka, KeyT kb, uint32_t a, uint32_t b)
+{
+    if (sizeof(KeyT) == 4) return (((uint64_t)ka << 32) | a) ^ (((uint64_t)kb << 32) | b);
+    const uint64_t d = (uint64_t)ka ^ (uint64_t)kb;
+    return d ? d : (uint64_t)(a ^ b);
+}
+
+// PLOC merge of the clusters of one LBVH range.  LOCAL: positions, ids and nodes are the chunk's (shared memory);
+// otherwise global memory, exactly like ploc_merge_range.
+template <bool LOCAL, uint32_t C>
+__device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, WarpTable& tb, uint32_t lo, uint32_t mid, uint32_t hiEnd, bool isRoot)
+{
+    const uint32_t lane = lane_id();
+    uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
+    uint32_t id = NX_INVALID;
+    const uint32_t takeL = min(mid - lo, kMergeThreshold);
+    if (lane < takeL) id = LOCAL ? M.cluster[lo + lane] : __ldcg(a.cluster + lo + lane);
+    const uint32_t numL = __popc(__ballot_sync(NX_FULL, lane < takeL && id != NX_INVALID));
+    const uint32_t takeR = min(hiEnd - mid, kMergeThreshold);
+    const uint32_t offR = lane - numL;  // wraps for lanes below numL
+    if (offR < takeR) id = LOCAL ? M.cluster[mid + offR] : __ldcg(a.cluster + mid + offR);
+    const uint32_t numR = __popc(__ballot_sync(NX_FULL, offR < takeR && id != NX_INVALID));
+    const uint32_t loaded = numL + numR;
+    uint32_t num = loaded;
+
+    Box box; box.lo = v3(0.f, 0.f, 0.f); box.hi = v3(0.f, 0.f, 0.f);
+    if (lane < num) {
+        float4 p, q;
+        if (LOCAL) { p = M.node[id][0]; q = M.node[id][1]; } else { p = ld_cg4(a.nodes + 2 * (size_t)id); q = ld_cg4(a.nodes + 2 * (size_t)id + 1); }
+        box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y);
+    }
+    __syncwarp();
+    tb.a[lane] = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x);
+    tb.b[lane] = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), 0.f);
+    __syncwarp();
+
+    const uint32_t keep = isRoot ? 1u : kMergeThreshold;
+    while (num > keep)
+    {
+        // nearest neighbour within +-kSearchRadius by merged half-area, compared on the float bits; ties keep the candidate seen
+        // first (+1, -1, +2, -2, ...), BinaryBuilder.cu:127-167
+        uint32_t bestArea = NX_INVALID, bestLane = NX_INVALID;
+#pragma unroll
+        for (uint32_t r = 1; r <= kSearchRadius; r++)
+        {
+            const float4 o0 = tb.a[lane + r];
+            const float2 o1 = *reinterpret_cast<const float2*>(&tb.b[lane + r]);
+            uint32_t fwd = NX_INVALID;
+            if (lane + r < num) {
+                Box other; other.lo = v3(o0.x, o0.y, o0.z); other.hi = v3(o0.w, o1.x, o1.y);
+                box_grow(other, box);
+                fwd = __float_as_uint(half_area_ref(other));
+                if (fwd < bestArea) { bestArea = fwd; bestLane = lane + r; }
+            }
+            const uint32_t bwd = __shfl_up_sync(NX_FULL, fwd, r);   // the same pair seen from the other side
+            if (lane >= r && bwd < bestArea) { bestArea = bwd; bestLane = lane - r; }
+        }
+        const bool alive = lane < num;
+        const uint32_t theirs = __shfl_sync(NX_FULL, bestLane, bestLane);
+        const bool mutual = alive && theirs == lane;
+        const bool owner = mutual && lane < bestLane;          // the lower lane of a mutual pair creates the node
+        const uint32_t ownerMask = __ballot_sync(NX_FULL, owner);
+        const uint32_t created = __popc(ownerMask);
+        uint32_t base = 0;
+        if (lane == 0 && created) base = LOCAL ? atomicAdd(&M.created, created) : atomicAdd(a.allocated, created);
+        base = __shfl_sync(NX_FULL, base, 0);
+        if (owner) {
+            const float4 p0 = tb.a[bestLane], p1 = tb.b[bestLane];
+            Box pb; pb.lo = v3(p0.x, p0.y, p0.z); pb.hi = v3(p0.w, p1.x, p1.y);
+            box_grow(box, pb);
+            const uint32_t k = base + __popc(ownerMask & lane_lt);
+            const float4 n0 = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x), n1 = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), p1.z);
+            if (LOCAL) { M.node[C + k][0] = n0; M.node[C + k][1] = n1; id = C + k; }
+            else { st_cg4(a.nodes + 2 * (size_t)k, n0); st_cg4(a.nodes + 2 * (size_t)k + 1, n1); id = k; }
+        }
+        // compact: survivors are the pair owners and every cluster without a mutual partner, order preserved
+        const bool stays = alive && (owner || !mutual);
+        const uint32_t keepMask = __ballot_sync(NX_FULL, stays);
+        __syncwarp();                                         // every read of the table is done
+        if (stays) {
+            const uint32_t rank = __popc(keepMask & lane_lt);
+            tb.a[rank] = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x);
+            tb.b[rank] = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), 0.f);
+        }
+        __syncwarp();
+        num -= created;
+        id = NX_INVALID;
+        if (lane < num) {
+            const float4 p = tb.a[lane], q = tb.b[lane];
+            box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y); id = __float_as_uint(q.z);
+        }
+    }
+    if (lane < loaded) { if (LOCAL) M.cluster[lo + lane] = id; else __stcg(a.cluster + lo + lane, id); }
+    if (LOCAL) __threadfence_block(); else __threadfence();
+}
+
+template <typename KeyT, uint32_t C>
+__global__ void __launch_bounds__(C, NX_PLOC_MINB) hploc2_kernel(PlocArgs a, const KeyT* __restrict__ keys)
+{
+    extern __shared__ __align__(16) unsigned char chunk_raw[];
+    ChunkMem<C>& M = *reinterpret_cast<ChunkMem<C>*>(chunk_raw);
+    WarpTable& tb = M.table[threadIdx.x >> 5];
+    const uint32_t t = threadIdx.x, n = a.n;
+    const uint32_t chunkStart = blockIdx.x * C, count = min(C, n - chunkStart);
+
+    // ---- stage the chunk: leaf nodes in sorted order, identity cluster list, empty parent slots, keys with one of margin each side
+    if (t < count) {
+        const uint32_t prim = __ldg(a.cluster + chunkStart + t);
+        M.leafId[t] = prim; M.cluster[t] = t; M.parent[t] = NX_INVALID;
+        M.node[t][0] = __ldg(a.nodes + 2 * (size_t)prim); M.node[t][1] = __ldg(a.nodes + 2 * (size_t)prim + 1);
+    }
+    for (uint32_t i = t; i < count + 2; i += C) {
+        const uint64_t g = (uint64_t)chunkStart + i;            // key[i] = keys[chunkStart + i - 1]
+        M.key[i] = (g >= 1 && g - 1 < n) ? (unsigned long long)__ldg(keys + (g - 1)) : 0ull;
+    }
+    if (t == 0) M.created = 0;
+    __syncthreads();
+
+    // ---- phase A: climb and merge inside the chunk (positions are chunk-local)
+    uint32_t lo = t, hi = t, mid = 0;
+    bool climbing = t < count, blocked = false, blockedRight = false;
+    auto delta = [&](uint32_t x, uint32_t y) {      // local positions x, y = x + 1 (may be -1 / count: the margins)
+        return key_delta_vals<KeyT>((KeyT)M.key[x + 1], (KeyT)M.key[y + 1], chunkStart + x, chunkStart + y);
+    };
+    while (__ballot_sync(NX_FULL, climbing))
+    {
+        if (climbing)
+        {
+            const uint32_t gl = chunkStart + lo, gh = chunkStart + hi;
+            const bool parentAtHi = gl == 0 || (gh != n - 1 && delta(hi, hi + 1) < delta(lo - 1, lo));
+            const bool inside = parentAtHi ? (hi + 1 < count) : (lo > 0);      // the sibling range starts / ends inside this chunk
+            if (!inside) { blocked = true; blockedRight = parentAtHi; climbing = false; }
+            else {
+                uint32_t other;
+                if (parentAtHi) { other = atomicExch(&M.parent[hi], lo); if (other != NX_INVALID) { M.parent[hi] = kSlotDone; mid = hi + 1; hi = other; } }
+                else            { other = atomicExch(&M.parent[lo - 1], hi); if (other != NX_INVALID) { M.parent[lo - 1] = kSlotDone; mid = lo; lo = other; } }
+                if (other == NX_INVALID) climbing = false;   // first to arrive: the sibling's thread continues
+                else __threadfence_block();                  // second to arrive: acquire the sibling's cluster list
+            }
+        }
+        const uint32_t size = hi - lo + 1;
+        const bool isRoot = climbing && size == n;
+        uint32_t todo = __ballot_sync(NX_FULL, (climbing && size > kMergeThreshold) || isRoot);
+        while (todo)
+        {
+            const uint32_t src = __ffs(todo) - 1;
+            ploc_merge2<true, C>(a, M, tb, __shfl_sync(NX_FULL, lo, src), __shfl_sync(NX_FULL, mid, src), __shfl_sync(NX_FULL, hi, src) + 1,
+                                 __shfl_sync(NX_FULL, (int)isRoot, src) != 0);
+            todo &= todo - 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- flush: reserve global node ids, write the nodes created here, the cluster lists (global ids) of the chunk
+    const uint32_t made = M.created;
+    if (t == 0) M.base = made ? atomicAdd(a.allocated, made) : 0u;
+    __syncthreads();
+    const uint32_t base = M.base;
+    auto remap = [&](uint32_t id) { return id == NX_INVALID ? NX_INVALID : (id < C ? M.leafId[id] : base + (id - C)); };
+    for (uint32_t k = t; k < made; k += C) {
+        const float4 n0 = M.node[C + k][0]; float4 n1 = M.node[C + k][1];
+        n1.z = __uint_as_float(remap(__float_as_uint(n1.z))); n1.w = __uint_as_float(remap(__float_as_uint(n1.w)));
+        st_cg4(a.nodes + 2 * (size_t)(base + k), n0); st_cg4(a.nodes + 2 * (size_t)(base + k) + 1, n1);
+    }
+    if (t < count) __stcg(a.cluster + chunkStart + t, remap(M.cluster[t]));
+    __threadfence();
+    __syncthreads();
+
+    // ---- hand-over to the global phase (hploc_seed_kernel, launched behind this kernel): the parent slots inside the chunk where only
+    // one side arrived become ordinary first arrivals in global memory (nothing else touches them before the next kernel), and the
+    // at most two ranges that stopped at the chunk's borders become the seeds the global phase climbs on from.
+    if (t + 1 < count) {
+        const uint32_t v = M.parent[t];
+        a.parent[chunkStart + t] = (v != NX_INVALID && v != kSlotDone) ? chunkStart + v : NX_INVALID;
+    }
+    if (t < 2) { a.seedLo[2 * blockIdx.x + t] = NX_INVALID; a.seedHi[2 * blockIdx.x + t] = NX_INVALID; }
+    __syncthreads();
+    if (blocked) { const uint32_t k = blockedRight ? 1u : 0u;   // at most one range stops at each border
+        a.seedLo[2 * blockIdx.x + k] = chunkStart + lo; a.seedHi[2 * blockIdx.x + k] = chunkStart + hi; }
+}
+
+// Global phase of the two-phase builder: the one-phase protocol (hploc_kernel) started from the ranges the chunks could not finish.
+template <typename KeyT>
+__global__ void __launch_bounds__(kPlocBlock) hploc_seed_kernel(PlocArgs a, const KeyT* __restrict__ keys, uint32_t nSeeds)
+{
+    __shared__ WarpTable tables[kPlocBlock / 32];
+    WarpTable& tb = tables[threadIdx.x >> 5];
+    ChunkMem<32>* none = nullptr;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = a.n;
+    uint32_t lo = i < nSeeds ? __ldg(a.seedLo + i) : NX_INVALID, hi = i < nSeeds ? __ldg(a.seedHi + i) : NX_INVALID, mid = 0;
+    bool climbing = lo != NX_INVALID;
+    while (__ballot_sync(NX_FULL, climbing))
+    {
+        if (climbing)
+        {
+            const bool parentAtHi = lo == 0 || (hi != n - 1 && key_delta(keys, hi, hi + 1) < key_delta(keys, lo - 1, lo));
+            uint32_t other;
+            if (parentAtHi) { other = atomicExch(a.parent + hi, lo); if (other != NX_INVALID) { mid = hi + 1; hi = other; } }
+            else            { other = atomicExch(a.parent + lo - 1, hi); if (other != NX_INVALID) { mid = lo; lo = other; } }
+            if (other == NX_INVALID) climbing = false;   // first to arrive: the sibling's thread continues (cluster lists are read with ld.cg)
+        }
+        const uint32_t size = hi - lo + 1;
+        const bool isRoot = climbing && size == n;
+        uint32_t todo = __ballot_sync(NX_FULL, (climbing && size > kMergeThreshold) || isRoot);
+        while (todo)
+        {
+            const uint32_t src = __ffs(todo) - 1;
+            ploc_merge2<false, 32>(a, *none, tb, __shfl_sync(NX_FULL, lo, src), __shfl_sync(NX_FULL, mid, src), __shfl_sync(NX_FULL, hi, src) + 1,
+                                   __shfl_sync(NX_FULL, (int)isRoot, src) != 0);
+            todo &= todo - 1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- collapse ----
 __device__ __forceinline__ Box load_box2(const float4* n2, uint32_t i)
 {
@@ -288,7 +557,7 @@ struct CollapseArgs {
     float4* n8;            // CWBVH8 nodes, 5 x float4 each
     uint32_t* primIdx;     // leaf slot -> primitive id
     uint32_t* bvh2Of;      // work map: BVH8 node index -> BVH2 node it collapses
-    uint32_t* counters;    // [0] nodes allocated, [1] leaf slots allocated
+    uint32_t* counters;    // [0] nodes allocated, [1] leaf slots allocated, [2..4] nodes created per level (rotating, see collapse_kernel)
     uint32_t n;
     // SAH-optimal collapse only (NX_COLLAPSE_SAH_OPTIMAL): C(n, i) decisions of every BVH2 node, dp_eval_kernel
     const unsigned long long* dpDec;
@@ -302,7 +571,7 @@ struct CollapseArgs {
 // recursion with a memo table becomes one bottom-up pass here: a thread starts at every leaf and climbs, the second
 // thread to arrive at a node (atomic counter) evaluates it from its finished children.
 // dpDec[n]: byte i = decision (bits 0-1) | left count (bits 2-4) | right count (bits 5-7) for i = 0..6; byte 7 = primitives
-// in the subtree, saturated at 255.  dpCost[n * 7 + i] = C(n, i + 1).
+// in the subtree, saturated at 255.  dpCost[n * 8 + i] = C(n, i + 1), i = 0..6 (8 floats per node: two 16-byte accesses).
 constexpr uint32_t kDpLeaf = 0u, kDpInternal = 1u, kDpDistribute = 2u;
 constexpr float kCPrim = 0.3f, kCNode = 1.0f;      // BVH8Builder.h:7-8
 
@@ -322,30 +591,35 @@ __global__ void dp_parent_kernel(DpArgs a)
     }
 }
 
+// Cost table: 8 floats per node (C(n, 1..7) and a pad), so a child's table is two LDG.128 and a node's two STG.128.
 __global__ void __launch_bounds__(128) dp_eval_kernel(DpArgs a)
 {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= a.n) return;
+    float4* const cost4 = reinterpret_cast<float4*>(a.cost);
     {
         const float c = __fmul_rn(__fmul_rn(half_area_ref(load_box2(a.n2, leaf)), 1.0f), kCPrim);     // CLeaf(node, 1), :31-37
-        for (int i = 0; i < 7; i++) __stcg(a.cost + 7 * (size_t)leaf + i, c);
+        __stcg(cost4 + 2 * (size_t)leaf, make_float4(c, c, c, c)); __stcg(cost4 + 2 * (size_t)leaf + 1, make_float4(c, c, c, 0.f));
         __stcg(a.dec + leaf, 1ull << 56);                                                             // LEAF for every i, one primitive
     }
-    __threadfence();
     uint32_t p = __ldcg(a.parent + leaf);
     while (p != NX_INVALID)
     {
+        __threadfence();                                            // release this subtree's tables before announcing it
         if (atomicAdd(a.arrived + (p - a.n), 1u) == 0u) return;     // the sibling subtree is not finished: its thread continues
-        __threadfence();
+        // second to arrive: the sibling's tables are read with ld.cg (L2), which is where its release made them visible
         const float4 q = __ldg(a.n2 + 2 * (size_t)p + 1);
         const uint32_t L = __float_as_uint(q.z), R = __float_as_uint(q.w);
         float cl[7], cr[7], c[7];
-#pragma unroll
-        for (int i = 0; i < 7; i++) { cl[i] = __ldcg(a.cost + 7 * (size_t)L + i); cr[i] = __ldcg(a.cost + 7 * (size_t)R + i); }
+        {
+            const float4 l0 = __ldcg(cost4 + 2 * (size_t)L), l1 = __ldcg(cost4 + 2 * (size_t)L + 1), r0 = __ldcg(cost4 + 2 * (size_t)R), r1 = __ldcg(cost4 + 2 * (size_t)R + 1);
+            cl[0] = l0.x; cl[1] = l0.y; cl[2] = l0.z; cl[3] = l0.w; cl[4] = l1.x; cl[5] = l1.y; cl[6] = l1.z;
+            cr[0] = r0.x; cr[1] = r0.y; cr[2] = r0.z; cr[3] = r0.w; cr[4] = r1.x; cr[5] = r1.y; cr[6] = r1.z;
+        }
         const uint32_t tris = min(255u, (uint32_t)(__ldcg(a.dec + L) >> 56) + (uint32_t)(__ldcg(a.dec + R) >> 56));
         const float area = half_area_ref(load_box2(a.n2, p));
         unsigned long long dec = (unsigned long long)tris << 56;
-        // CDistribute(node, j) (:39-57): best split of j - 1 ... wait for it ... roots: k to the left child, j - 1 - k to the right
+        // CDistribute(node, j) (:39-57): best split of j - 1 roots: k to the left child, j - 1 - k to the right
         auto distribute = [&](int j, uint32_t& l, uint32_t& r) {
             float best = 1.0e30f;
 #pragma unroll
@@ -366,10 +640,8 @@ __global__ void __launch_bounds__(128) dp_eval_kernel(DpArgs a)
             if (d < c[i - 1]) { c[i] = d; dec |= (unsigned long long)(kDpDistribute | (l << 2) | (r << 5)) << (8 * i); }
             else { c[i] = c[i - 1]; dec |= ((dec >> (8 * (i - 1))) & 0xffull) << (8 * i); }
         }
-#pragma unroll
-        for (int i = 0; i < 7; i++) __stcg(a.cost + 7 * (size_t)p + i, c[i]);
+        __stcg(cost4 + 2 * (size_t)p, make_float4(c[0], c[1], c[2], c[3])); __stcg(cost4 + 2 * (size_t)p + 1, make_float4(c[4], c[5], c[6], 0.f));
         __stcg(a.dec + p, dec);
-        __threadfence();
         p = __ldcg(a.parent + p);
     }
 }
@@ -394,7 +666,7 @@ __device__ __forceinline__ uint32_t quant(float c, float p, float inv, bool up)
 // prescribes (GetChildrenIndices, BVH8Builder.cpp:165-199), leaf children holding up to max_leaf_prims primitives; slot
 // assignment, quantisation and node layout are the GPU converter's in both modes.
 template <bool OPT>
-__device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root2)
+__device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root2, uint32_t* levelCreated)
 {
     const uint32_t lane = lane_id();
     const uint32_t n = a.n;
@@ -523,7 +795,7 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
     const uint32_t total = __shfl_sync(NX_FULL, scan, 31);
     uint32_t baseNode = 0, baseLeaf = 0;
     if (lane == 31) {
-        if (total & 0xffffu) baseNode = atomicAdd(a.counters + 0, total & 0xffffu);
+        if (total & 0xffffu) { baseNode = atomicAdd(a.counters + 0, total & 0xffffu); atomicAdd(levelCreated, total & 0xffffu); }
         if (total >> 16) baseLeaf = atomicAdd(a.counters + 1, total >> 16);
     }
     baseNode = __shfl_sync(NX_FULL, baseNode, 31) + ((scan - packed) & 0xffffu);
@@ -595,26 +867,63 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
 }
 
 // Persistent cooperative kernel: BVH8 level L is exactly the node index range allocated while level L-1 was processed.
+// The size of the next level cannot be read from the allocation cursor after the barrier: threads released early are already
+// allocating for the level after it.  Each level therefore also counts what it creates in one of three rotating slots
+// (counters[2 + (L + 1) % 3]); the slot a level adds to was cleared one level earlier, after the barrier that guarantees every
+// thread has read its previous content, and is only read after the barrier that ends the level.
 template <bool OPT>
 __global__ void __launch_bounds__(kCollapseBlock, 4) collapse_kernel(CollapseArgs a)
 {
     cg::grid_group grid = cg::this_grid();
-    uint32_t begin = 0, end = 1;
+    uint32_t begin = 0, end = 1, level = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     while (begin < end)
     {
+        uint32_t* created = a.counters + 2 + (level + 1) % 3;
+        if (blockIdx.x == 0 && threadIdx.x == 0) __stcg(a.counters + 2 + (level + 2) % 3, 0u);
         const uint32_t span = end - begin;
         const uint32_t rounds = (span + stride - 1) / stride;
         for (uint32_t r = 0; r < rounds; r++)
         {
             const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
             const uint32_t node = begin + k;
-            collapse_one<OPT>(a, node, k < span ? __ldcg(a.bvh2Of + node) : NX_INVALID);   // whole warps call in, idle lanes pass INVALID
+            collapse_one<OPT>(a, node, k < span ? __ldcg(a.bvh2Of + node) : NX_INVALID, created);   // whole warps call in, idle lanes pass INVALID
         }
         __threadfence();
         grid.sync();
         begin = end;
-        end = __ldcg(a.counters);
+        end += __ldcg(created);
+        level++;
+    }
+}
+
+// The same level-by-level collapse inside ONE thread block, for inputs whose widest BVH8 level is a few rounds of a block: the barrier
+// between levels is __syncthreads (tens of cycles) instead of a grid-wide barrier (13 us per level measured at 25 CTAs, 18 levels for
+// the 100k-triangle sphere: profiles/r01_ncu_collapse_build100k.md shows 77 % of the stall samples at grid.sync), and the launch is an
+// ordinary one, so the BLAS builds of a many-mesh scene overlap on the context's build streams instead of queueing as cooperative
+// launches.  Two barriers per level: one to finish the level's allocations, one to read its size before the next level allocates.
+constexpr int kCollapseCtaThreads = 1024;
+constexpr uint32_t kCollapseCtaMaxPrims = 40000u;   // widest level <= ~2 rounds of the block; beyond that the grid-wide kernel has more warps to hide the per-node latency
+template <bool OPT>
+__global__ void __launch_bounds__(kCollapseCtaThreads, 1) collapse_cta_kernel(CollapseArgs a)
+{
+    __shared__ uint32_t sEnd;
+    uint32_t begin = 0, end = 1;
+    while (begin < end)
+    {
+        const uint32_t span = end - begin;
+        const uint32_t rounds = (span + kCollapseCtaThreads - 1) / kCollapseCtaThreads;
+        for (uint32_t r = 0; r < rounds; r++)
+        {
+            const uint32_t k = r * kCollapseCtaThreads + threadIdx.x;
+            collapse_one<OPT>(a, begin + k, k < span ? __ldcg(a.bvh2Of + begin + k) : NX_INVALID, a.counters + 2);
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (threadIdx.x == 0) sEnd = __ldcg(a.counters);
+        __syncthreads();
+        begin = end;
+        end = sEnd;
     }
 }
 
@@ -703,9 +1012,16 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
     NX_CUDA(ctx, cudaMemsetAsync(parent, 0xff, sizeof(uint32_t) * (size_t)n, s));
     NX_CUDA(ctx, cudaMemcpyAsync(allocated, &n, 4, cudaMemcpyHostToDevice, s));
 
+    const bool ownSort = ctx->sort_mode != 0;
+    uint32_t* sortHist = nullptr; uint32_t* sortStatus = nullptr;
+    constexpr int kHistWords = SortShape<KeyT>::kPasses * 256 + SortShape<KeyT>::kPasses;     // histograms, then one tile counter per pass
+    if (ownSort) {
+        NX_CUDA(ctx, allocAsync(&sortHist, (size_t)kHistWords, s)); NX_CUDA(ctx, allocAsync(&sortStatus, radix_sort_status_words<KeyT>(n), s));
+        NX_CUDA(ctx, cudaMemsetAsync(sortHist, 0, sizeof(uint32_t) * kHistWords, s));
+    }
     const int grid = (int)std::min<uint32_t>(div_up(n, kSetupBlock), (uint32_t)ctx->sm_count * 8u);
     timer.begin();
-    morton_kernel<KeyT><<<grid, kSetupBlock, 0, s>>>(nodes, n, dScene, keys, order, dSceneOut);
+    morton_kernel<KeyT><<<grid, kSetupBlock, 0, s>>>(nodes, n, dScene, keys, order, dSceneOut, sortHist);
     if (metrics) metrics->morton_ms = timer.end();
     if (dbgCodes) {
         dbgCodes->assign(n, 0);
@@ -717,27 +1033,46 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
 
     // stable LSD radix sort over the same bit window as the reference (Setup.cu:74-78): [2,32) or [1,64)
     cub::DoubleBuffer<KeyT> kb(keys, keysAlt); cub::DoubleBuffer<uint32_t> vb(order, orderAlt);
-    const int beginBit = sizeof(KeyT) == 4 ? 2 : 1, endBit = sizeof(KeyT) * 8;
-    size_t tempBytes = 0; void* temp = nullptr;
-    NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
-    NX_CUDA(ctx, cudaMallocAsync(&temp, tempBytes ? tempBytes : 1, s));
-    timer.begin();
-    NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(temp, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
-    if (metrics) metrics->sort_ms = timer.end();
+    void* temp = nullptr;
+    if (ownSort) {
+        timer.begin();
+        NX_CUDA(ctx, radix_sort_pairs<KeyT>(keys, order, keysAlt, orderAlt, n, sortHist, sortStatus, sortHist + SortShape<KeyT>::kPasses * 256, s));
+        if (metrics) metrics->sort_ms = timer.end();
+        cudaFreeAsync(sortHist, s); cudaFreeAsync(sortStatus, s);
+    } else {
+        const int beginBit = sizeof(KeyT) == 4 ? 2 : 1, endBit = sizeof(KeyT) * 8;
+        size_t tempBytes = 0;
+        NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
+        NX_CUDA(ctx, cudaMallocAsync(&temp, tempBytes ? tempBytes : 1, s));
+        timer.begin();
+        NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(temp, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
+        if (metrics) metrics->sort_ms = timer.end();
+    }
 
-    PlocArgs pa; pa.nodes = nodes; pa.cluster = vb.Current(); pa.parent = parent; pa.allocated = allocated; pa.n = n;
+    PlocArgs pa; pa.nodes = nodes; pa.cluster = vb.Current(); pa.parent = parent; pa.allocated = allocated; pa.n = n; pa.seedLo = pa.seedHi = nullptr;
     timer.begin();
-    hploc_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, kb.Current());
+    if (ctx->hploc_mode == 0) hploc_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, kb.Current());
+    else {
+        constexpr uint32_t C = kPlocChunk;
+        static bool attr = false;   // per function, not per context: a property of the loaded module
+        if (!attr) { cudaFuncSetAttribute((const void*)hploc2_kernel<KeyT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkMem<C>)); attr = true; }
+        const uint32_t chunks = div_up(n, C), nSeeds = 2 * chunks;
+        NX_CUDA(ctx, allocAsync(&pa.seedLo, nSeeds, s)); NX_CUDA(ctx, allocAsync(&pa.seedHi, nSeeds, s));
+        hploc2_kernel<KeyT, C><<<chunks, C, sizeof(ChunkMem<C>), s>>>(pa, kb.Current());
+        hploc_seed_kernel<KeyT><<<div_up(nSeeds, kPlocBlock), kPlocBlock, 0, s>>>(pa, kb.Current(), nSeeds);
+        cudaFreeAsync(pa.seedLo, s); cudaFreeAsync(pa.seedHi, s);
+    }
     if (metrics) metrics->bvh2_ms = timer.end();
     NX_CUDA(ctx, cudaGetLastError());
 
-    cudaFreeAsync(temp, s); cudaFreeAsync(keys, s); cudaFreeAsync(keysAlt, s); cudaFreeAsync(order, s); cudaFreeAsync(orderAlt, s);
+    if (temp) cudaFreeAsync(temp, s);
+    cudaFreeAsync(keys, s); cudaFreeAsync(keysAlt, s); cudaFreeAsync(order, s); cudaFreeAsync(orderAlt, s);
     cudaFreeAsync(parent, s); cudaFreeAsync(allocated, s);
     return NX_OK;
 }
 
 int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics,
-               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1, bool finalSync = true)
+               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1, bool finalSync = true, bool readBounds = true)
 {
     if (!dPrims || n == 0) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: empty primitive list");
     if (n > 0x7fffffffu / 2) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: primitive count %u exceeds 2^30", n);
@@ -762,7 +1097,7 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     int rc = bits64 ? build_bvh2_keys<uint64_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes)
                     : build_bvh2_keys<uint32_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes);
     if (rc) return rc;
-    NX_CUDA(ctx, cudaMemcpyAsync(&out->bounds, dSceneOut, 24, cudaMemcpyDeviceToHost, s));
+    if (readBounds) NX_CUDA(ctx, cudaMemcpyAsync(&out->bounds, dSceneOut, 24, cudaMemcpyDeviceToHost, s));
     if (metrics)
     {
         metrics->total_ms = metrics->scene_bounds_ms + metrics->morton_ms + metrics->sort_ms + metrics->bvh2_ms;
@@ -784,10 +1119,13 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     return NX_OK;
 }
 
-int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out)
+// asyncCounters != nullptr: fire and forget.  Nothing is read back and the stream is never waited for; the node / leaf-slot counts stay
+// in asyncCounters[0..1] (device memory of the caller, 5 words) and out->node_count / out->bounds are left to the caller.
+int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out,
+               uint32_t* asyncCounters = nullptr)
 {
     Bvh2Result b2;
-    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2, nullptr, -1, /*finalSync=*/false);
+    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2, nullptr, -1, /*finalSync=*/false, /*readBounds=*/asyncCounters == nullptr);
     if (rc) return rc;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = ctx->stream;
@@ -798,9 +1136,9 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     NX_CUDA(ctx, allocAsync(&ca.n8, 5 * cap, s));
     NX_CUDA(ctx, allocAsync(&ca.primIdx, n, s));
     NX_CUDA(ctx, allocAsync(&ca.bvh2Of, cap, s));
-    NX_CUDA(ctx, allocAsync(&ca.counters, 2, s));
-    const uint32_t initCounters[2] = {1u, 0u}, root2 = 2 * n - 2;
-    NX_CUDA(ctx, cudaMemcpyAsync(ca.counters, initCounters, 8, cudaMemcpyHostToDevice, s));
+    if (asyncCounters) ca.counters = asyncCounters; else NX_CUDA(ctx, allocAsync(&ca.counters, 5, s));
+    const uint32_t initCounters[5] = {1u, 0u, 0u, 0u, 0u}, root2 = 2 * n - 2;
+    NX_CUDA(ctx, cudaMemcpyAsync(ca.counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, s));
     NX_CUDA(ctx, cudaMemcpyAsync(ca.bvh2Of, &root2, 4, cudaMemcpyHostToDevice, s));
 
     const bool optimal = cfg && cfg->collapse == NX_COLLAPSE_SAH_OPTIMAL && n > 1;
@@ -814,7 +1152,7 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         dp.maxLeafPrims = cfg->max_leaf_prims >= 1 && cfg->max_leaf_prims <= 3 ? (uint32_t)cfg->max_leaf_prims : 3u;   // P_MAX, BVH8Builder.h:9
         NX_CUDA(ctx, allocAsync(&dp.parent, 2 * (size_t)n - 1, s));
         NX_CUDA(ctx, allocAsync(&dp.arrived, n, s));
-        NX_CUDA(ctx, allocAsync(&dp.cost, 7 * (2 * (size_t)n - 1), s));
+        NX_CUDA(ctx, allocAsync(&dp.cost, 8 * (2 * (size_t)n - 1), s));
         NX_CUDA(ctx, allocAsync(&dp.dec, 2 * (size_t)n - 1, s));
         NX_CUDA(ctx, cudaMemsetAsync(dp.parent, 0xff, 4 * (2 * (size_t)n - 1), s));
         dp_parent_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp);
@@ -822,6 +1160,10 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         ca.dpDec = dp.dec;
     }
     if (n == 1) single_leaf_kernel<<<1, 1, 0, s>>>(ca);
+    else if (n <= kCollapseCtaMaxPrims && ctx->collapse_cta) {
+        if (optimal) collapse_cta_kernel<true><<<1, kCollapseCtaThreads, 0, s>>>(ca);
+        else collapse_cta_kernel<false><<<1, kCollapseCtaThreads, 0, s>>>(ca);
+    }
     else {
         int perSm = 0;
         const void* fn = optimal ? (const void*)collapse_kernel<true> : (const void*)collapse_kernel<false>;
@@ -836,6 +1178,12 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     }
     if (optimal) { cudaFreeAsync(dp.parent, s); cudaFreeAsync(dp.arrived, s); cudaFreeAsync(dp.cost, s); cudaFreeAsync(dp.dec, s); }
     if (metrics) { metrics->bvh8_ms = timer.end(); metrics->total_ms += metrics->bvh8_ms; }
+    if (asyncCounters) {
+        NX_CUDA(ctx, cudaGetLastError());
+        out->nodes = (nx_bvh8_node*)ca.n8; out->node_count = 0; out->prim_idx = ca.primIdx; out->prim_count = n;
+        cudaFreeAsync(b2.nodes, s); cudaFreeAsync(ca.bvh2Of, s);
+        return NX_OK;
+    }
     uint32_t counters[2] = {0, 0};
     NX_CUDA(ctx, cudaMemcpyAsync(counters, ca.counters, 8, cudaMemcpyDeviceToHost, s));
     NX_CUDA(ctx, cudaStreamSynchronize(s));
@@ -871,6 +1219,15 @@ int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, in
     nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed; cfg.collapse = ctx->scene_collapse;
     cfg.max_leaf_prims = primType ? ctx->scene_max_leaf_prims : 1;
     return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out);
+}
+
+// The same build issued on `stream` without any host synchronisation (scene set-up pipeline, scene.cu).
+int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out)
+{
+    nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed; cfg.collapse = ctx->scene_collapse;
+    cfg.max_leaf_prims = primType ? ctx->scene_max_leaf_prims : 1;
+    StreamSwap swap(ctx, stream);
+    return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out, dCounters);
 }
 
 extern "C" {

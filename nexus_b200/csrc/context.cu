@@ -3,6 +3,19 @@
 #include <fstream>
 #include <cstdlib>
 
+int nxi_check_overflow(nx_ctx* ctx)
+{
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
+    NX_CUDA(ctx, cudaMemcpyAsync(ctx->hOverflow, ctx->dOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (const uint32_t dropped = *ctx->hOverflow) {
+        cudaMemsetAsync(ctx->dOverflow, 0, 4, ctx->stream);
+        NX_FAIL(ctx, NX_ERR_STATE, "traversal stack overflow: %u pushes beyond %u entries were refused, hits of the affected rays may be missing "
+                                   "(a BVH deeper than the traversal stack)", dropped, ctx->stack_limit);
+    }
+    return NX_OK;
+}
+
 extern "C" {
 
 int nx_abi_version(void) { return NX_ABI_VERSION; }
@@ -55,6 +68,22 @@ int nx_ctx_create(int device, nx_ctx** out)
         unsigned a = 0, b = 0;
         if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri_any = a; ctx->tune_inst_any = b; }
     }
+    if (const char* t = std::getenv("NX_COLLAPSE_CTA")) ctx->collapse_cta = std::atoi(t) != 0;
+    if (const char* t = std::getenv("NX_SORT")) ctx->sort_mode = std::atoi(t) != 0;
+    if (const char* t = std::getenv("NX_HPLOC")) ctx->hploc_mode = std::atoi(t) != 0;
+    if (const char* t = std::getenv("NX_TRACE_MODE")) ctx->trace_mode = (std::strcmp(t, "lane") == 0 || std::strcmp(t, "0") == 0) ? 0 : (std::strcmp(t, "duo") == 0 || std::strcmp(t, "2") == 0) ? 2 : 1;
+    if (const char* t = std::getenv("NX_POOL_TUNE")) {
+        unsigned a = 0, b = 0, c = 0, d = 0;
+        if (std::sscanf(t, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { ctx->pool_node = ctx->pool_node_any = a; ctx->pool_tri = ctx->pool_tri_any = b; ctx->pool_inst = ctx->pool_inst_any = c; ctx->pool_fetch = ctx->pool_fetch_any = d; }
+    }
+    if (const char* t = std::getenv("NX_POOL_TUNE_ANY")) {
+        unsigned a = 0, b = 0, c = 0, d = 0;
+        if (std::sscanf(t, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { ctx->pool_node_any = a; ctx->pool_tri_any = b; ctx->pool_inst_any = c; ctx->pool_fetch_any = d; }
+    }
+    if (cudaMalloc((void**)&ctx->dOverflow, 4) != cudaSuccess || cudaMemset(ctx->dOverflow, 0, 4) != cudaSuccess || cudaMallocHost((void**)&ctx->hOverflow, 4) != cudaSuccess) {
+        nx_ctx_destroy(ctx); return NX_ERR_CUDA;
+    }
+    *ctx->hOverflow = 0;
     *out = ctx;
     return NX_OK;
 }
@@ -65,6 +94,10 @@ void nx_ctx_destroy(nx_ctx* ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream_aux);
+    cudaFree(ctx->dOverflow); cudaFreeHost(ctx->hOverflow);
+    for (int k = 0; k < ctx->buildStreamCount; k++) { cudaStreamSynchronize(ctx->buildStreams[k]); cudaStreamDestroy(ctx->buildStreams[k]); }
+    if (ctx->stagePinned) cudaFreeHost(ctx->stagePinned);
+    cudaFree(ctx->poolSpill[0]); cudaFree(ctx->poolSpill[1]);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream_aux);
     delete ctx;
@@ -89,6 +122,28 @@ int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims)
     return NX_OK;
 }
 
+int nx_ctx_set_trace_mode(nx_ctx* ctx, int mode)
+{
+    if (!ctx || (mode != NX_TRACE_LANE && mode != NX_TRACE_POOL && mode != NX_TRACE_DUO)) return NX_ERR_INVALID;
+    ctx->trace_mode = mode;
+    return NX_OK;
+}
+
+int nx_ctx_set_pool_tuning(nx_ctx* ctx, int any_hit, uint32_t node_rays, uint32_t tri_rays, uint32_t inst_rays, uint32_t fetch_rays)
+{
+    if (!ctx || !node_rays || !tri_rays || !inst_rays || !fetch_rays) return NX_ERR_INVALID;
+    if (any_hit) { ctx->pool_node_any = node_rays; ctx->pool_tri_any = tri_rays; ctx->pool_inst_any = inst_rays; ctx->pool_fetch_any = fetch_rays; }
+    else { ctx->pool_node = node_rays; ctx->pool_tri = tri_rays; ctx->pool_inst = inst_rays; ctx->pool_fetch = fetch_rays; }
+    return NX_OK;
+}
+
+int nx_ctx_set_stack_limit(nx_ctx* ctx, uint32_t entries)
+{
+    if (!ctx || entries < 2 || entries > 40) return NX_ERR_INVALID;
+    ctx->stack_limit = entries;
+    return NX_OK;
+}
+
 int nx_ctx_set_sphere_cull(nx_ctx* ctx, int enabled)
 {
     if (!ctx) return NX_ERR_INVALID;
@@ -100,10 +155,9 @@ int nx_ctx_synchronize(nx_ctx* ctx)
 {
     if (!ctx) return NX_ERR_INVALID;
     DeviceGuard guard(ctx->device);
-    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
+    for (int k = 0; k < ctx->buildStreamCount; k++) NX_CUDA(ctx, cudaStreamSynchronize(ctx->buildStreams[k]));
     NX_CUDA(ctx, cudaGetLastError());
-    return NX_OK;
+    return nxi_check_overflow(ctx);
 }
 
 int nx_malloc(nx_ctx* ctx, size_t bytes, void** out)
@@ -139,18 +193,21 @@ int nx_memcpy_d2h(nx_ctx* ctx, void* host, const void* dev, size_t bytes)
 }
 
 // ------------------------------------------------------------------------------------------ image output ----
-// PFM: "PF\nW H\n-1.0\n" then bottom-to-top rows of little-endian float RGB.
+// Both writers take the renderer's own layout: row 0 of `rgb` is the BOTTOM row of the image (generate_kernel maps pixel row 0 to the
+// camera's lower-left corner like the reference, PathTracer.cu:74-83), i.e. exactly what nx_renderer_read_accum returns.
+// PFM: "PF\nW H\n-1.0\n" then the rows bottom to top, little-endian float RGB - the input order.
 int nx_write_pfm(const char* path, const float* rgb, uint32_t w, uint32_t h)
 {
     if (!path || !rgb) return NX_ERR_INVALID;
     std::ofstream f(path, std::ios::binary);
     if (!f) return NX_ERR_INVALID;
     f << "PF\n" << w << " " << h << "\n-1.0\n";
-    for (uint32_t y = 0; y < h; y++) f.write((const char*)(rgb + 3 * (size_t)(h - 1 - y) * w), 12 * (size_t)w);
+    f.write((const char*)rgb, 12 * (size_t)w * h);
     return f ? NX_OK : NX_ERR_INVALID;
 }
 
 // Minimal OpenEXR 2.0 writer: single-part scanline image, three FLOAT channels (B, G, R in file order), no compression.
+// EXR scanline 0 is the TOP of the image, so scanline y is input row h - 1 - y.
 int nx_write_exr(const char* path, const float* rgb, uint32_t w, uint32_t h)
 {
     if (!path || !rgb || !w || !h) return NX_ERR_INVALID;
@@ -179,7 +236,7 @@ int nx_write_exr(const char* path, const float* rgb, uint32_t w, uint32_t h)
     for (uint32_t y = 0; y < h; y++) { f.write((const char*)&off, 8); off += chunk; }
     std::vector<float> row(3 * (size_t)w);
     for (uint32_t y = 0; y < h; y++) {
-        const float* src = rgb + 3 * (size_t)y * w;
+        const float* src = rgb + 3 * (size_t)(h - 1 - y) * w;
         for (uint32_t x = 0; x < w; x++) { row[x] = src[3 * x + 2]; row[w + x] = src[3 * x + 1]; row[2 * (size_t)w + x] = src[3 * x]; }
         int32_t yy = (int32_t)y, sz = (int32_t)rowBytes;
         f.write((const char*)&yy, 4); f.write((const char*)&sz, 4); f.write((const char*)row.data(), rowBytes);

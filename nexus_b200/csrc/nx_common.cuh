@@ -30,6 +30,24 @@ struct nx_ctx {
     int scene_blas_speed = 1;   // Mesh::Mesh builds its BLAS with prioritizeSpeed = true (32-bit Morton keys), N/Assets/Mesh.h:37
     // L2 set-aside for persisting accesses (top-level nodes + instance records of the scene being rendered); 0 = hints off
     size_t l2_persist_bytes = 0, l2_window_max = 0;
+    // Traversal loop: 1 = ray pool (traverse_pool.cuh: 64 rays per warp in shared memory, lanes take rays by kind of work), 0 = one
+    // ray per lane (traverse.cuh trace_loop).  Same hits either way.  NX_TRACE_MODE / nx_ctx_set_trace_mode.
+    int trace_mode = 1;
+    uint32_t pool_node = 28, pool_tri = 24, pool_inst = 16, pool_fetch = 16;           // ray-pool round thresholds in rays (NX_POOL_TUNE="n,t,i,f")
+    uint32_t pool_node_any = 28, pool_tri_any = 24, pool_inst_any = 16, pool_fetch_any = 16;
+    uint32_t stack_limit = 40;           // NX_STACK_TOTAL; nx_ctx_set_stack_limit lowers it in the overflow test
+    uint32_t* dOverflow = nullptr;       // device counter of refused traversal-stack pushes (TraceScene::overflow)
+    uint32_t* hOverflow = nullptr;       // pinned mirror
+    void* poolSpill[2] = {nullptr, nullptr}; size_t poolSpillWarps[2] = {0, 0};       // global spill stacks of the two trace streams
+    int gridCache[16] = {0};             // persistent-grid sizes per kernel (occupancy x SM count of THIS context's device)
+    int sort_mode = 1;                   // 1 = radix_sort.cuh (own onesweep sort), 0 = cub::DeviceRadixSort (measurement only); NX_SORT=0|1
+    int collapse_cta = 1;                // 1 = single-block collapse for builds of up to 40k primitives (NX_COLLAPSE_CTA=0: always the grid-wide kernel)
+    int hploc_mode = 1;                  // 1 = two-phase H-PLOC (block-local phase in shared memory), 0 = one-phase kernel; NX_HPLOC=0|1
+    // Scene set-up pipeline (scene.cu add_mesh): BLAS builds of successive meshes are issued round-robin on these streams without any
+    // host synchronisation; host data reaches the device through a pinned staging ring.  nx_scene_update waits for all of them once.
+    cudaStream_t buildStreams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int buildStreamCount = 0;
+    char* stagePinned = nullptr; size_t stageBytes = 0, stageUsed = 0;
     // scratch reused by the builder's parity hook
     std::vector<uint64_t> dbg_codes;
 };
@@ -38,6 +56,16 @@ struct nx_ctx {
 #define NX_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     char b_[512]; std::snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     (ctx)->error = b_; return NX_ERR_CUDA; } } while (0)
+
+// context.cu: synchronises the context's streams and turns a non-zero traversal-stack overflow counter into NX_ERR_STATE
+int nxi_check_overflow(nx_ctx* ctx);
+
+// Runs builder code (which issues everything on ctx->stream) on another stream for the lifetime of the object.
+struct StreamSwap {
+    nx_ctx* c; cudaStream_t old;
+    StreamSwap(nx_ctx* ctx, cudaStream_t s) : c(ctx), old(ctx->stream) { ctx->stream = s; }
+    ~StreamSwap() { c->stream = old; }
+};
 
 struct DeviceGuard {
     int prev = 0;

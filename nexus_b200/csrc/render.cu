@@ -14,6 +14,9 @@
 //     launched over W*H threads for a nearly empty queue and the host never waits inside a frame;
 //   * rays are 32-byte records, hits 20-byte records: 16-byte vector loads in queue order.
 #include "wave.cuh"   // shared wavefront state; generation / shading / display kernels live in shade.cu (fast-math unit)
+#include "traverse_pool.cuh"
+#include "traverse_duo.cuh"
+#include <algorithm>
 namespace {
 
 // ------------------------------------------------------------------------------------------ trace kernels ----
@@ -57,6 +60,49 @@ __global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_any
     trace_loop<true, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
 }
 
+// Two rays per lane (traverse_duo.cuh).
+template <bool STATS>
+__global__ void __launch_bounds__(NX_DUO_BLOCK, NX_DUO_MIN_BLOCKS) trace_closest_duo_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+                                                                         uint32_t* cursor, nx_hit* __restrict__ hits, TraceStats* stats, TraceTuning tune)
+{
+    __shared__ __align__(16) uint32_t smem[NX_DUO_SMEM_BYTES / 4];
+    ClosestSink sink{hits};
+    trace_loop_duo<false, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
+}
+template <bool STATS>
+__global__ void __launch_bounds__(NX_DUO_BLOCK, NX_DUO_MIN_BLOCKS) trace_any_duo_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+                                                                     uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum,
+                                                                     TraceStats* stats, TraceTuning tune)
+{
+    __shared__ __align__(16) uint32_t smem[NX_DUO_SMEM_BYTES / 4];
+    AnySink sink{occluded, radiance, accum};
+    trace_loop_duo<true, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
+}
+
+// Ray-pool versions (traverse_pool.cuh): 64 rays per warp in dynamic shared memory, spill stacks of this launch's warps in `spill`.
+template <bool STATS>
+__global__ void __launch_bounds__(NX_POOL_BLOCK, NX_POOL_MIN_BLOCKS) trace_closest_pool_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+                                                                         uint32_t* cursor, nx_hit* __restrict__ hits, TraceStats* stats, PoolTuning tune, uint2* spill)
+{
+    extern __shared__ __align__(16) unsigned char pool_smem[];
+    PoolWarp& pw = reinterpret_cast<PoolWarp*>(pool_smem)[threadIdx.x >> 5];
+    ClosestSink sink{hits};
+    trace_pool_loop<false, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, pw, sink, stats,
+                                  spill + (size_t)(blockIdx.x * NX_POOL_WARPS + (threadIdx.x >> 5)) * (NX_POOL_R * NX_POOL_SPILL));
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(NX_POOL_BLOCK, NX_POOL_MIN_BLOCKS) trace_any_pool_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+                                                                     uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum,
+                                                                     TraceStats* stats, PoolTuning tune, uint2* spill)
+{
+    extern __shared__ __align__(16) unsigned char pool_smem[];
+    PoolWarp& pw = reinterpret_cast<PoolWarp*>(pool_smem)[threadIdx.x >> 5];
+    AnySink sink{occluded, radiance, accum};
+    trace_pool_loop<true, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, pw, sink, stats,
+                                 spill + (size_t)(blockIdx.x * NX_POOL_WARPS + (threadIdx.x >> 5)) * (NX_POOL_R * NX_POOL_SPILL));
+}
+
 __global__ void frame_totals_kernel(WaveBuffers wb, uint32_t pathLength)
 {
     if (threadIdx.x || blockIdx.x) return;
@@ -75,19 +121,82 @@ __global__ void pixel_query_kernel(const nx_hit* __restrict__ hits, uint32_t slo
 
 TraceTuning trace_tuning(const nx_ctx* ctx, bool any = false)
 {
-    TraceTuning t; t.triLanes = any ? ctx->tune_tri_any : ctx->tune_tri; t.instLanes = any ? ctx->tune_inst_any : ctx->tune_inst; t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u; return t;
+    TraceTuning t; t.triLanes = any ? ctx->tune_tri_any : ctx->tune_tri; t.instLanes = any ? ctx->tune_inst_any : ctx->tune_inst; t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u;
+    t.stackLimit = std::min<uint32_t>(std::max<uint32_t>(ctx->stack_limit, NX_STACK_SHARED), NX_STACK_TOTAL);
+    return t;
+}
+PoolTuning pool_tuning(const nx_ctx* ctx, bool any = false)
+{
+    PoolTuning t;
+    t.nodeLanes = any ? ctx->pool_node_any : ctx->pool_node; t.triLanes = any ? ctx->pool_tri_any : ctx->pool_tri;
+    t.instLanes = any ? ctx->pool_inst_any : ctx->pool_inst; t.fetchLanes = any ? ctx->pool_fetch_any : ctx->pool_fetch;
+    t.sphereCull = ctx->tune_sphere; t.k47 = 0x47000000u; t.stackLimit = std::min<uint32_t>(ctx->stack_limit, NX_STACK_TOTAL);
+    return t;
 }
 
-int persistent_grid(nx_ctx* ctx, const void* fn, int block, int* cache)
+// Persistent grid of a kernel on this context's device: resident CTAs per SM x SM count, cached in the context.
+int persistent_grid(nx_ctx* ctx, const void* fn, int block, size_t smem, int slot)
 {
-    if (*cache) return *cache;
+    int& cache = ctx->gridCache[slot];
+    if (cache) return cache;
+    if (smem > 48u * 1024u) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int perSm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, block, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, block, smem);
     if (perSm < 1) perSm = 1;
-    *cache = perSm * ctx->sm_count;
-    return *cache;
+    cache = perSm * ctx->sm_count;
+    return cache;
 }
-int g_gridClosest = 0, g_gridClosestStats = 0, g_gridAny = 0, g_gridAnyStats = 0;
+
+// global spill stacks of the ray-pool kernels: one region per trace stream (closest-hit and shadow traces overlap)
+int pool_spill(nx_ctx* ctx, int which, int grid, uint2** out)
+{
+    const size_t warps = (size_t)grid * NX_POOL_WARPS;
+    if (ctx->poolSpillWarps[which] < warps) {
+        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
+        cudaFree(ctx->poolSpill[which]); ctx->poolSpill[which] = nullptr; ctx->poolSpillWarps[which] = 0;
+        NX_CUDA(ctx, cudaMalloc(&ctx->poolSpill[which], warps * NX_POOL_R * NX_POOL_SPILL * sizeof(uint2)));
+        ctx->poolSpillWarps[which] = warps;
+    }
+    *out = (uint2*)ctx->poolSpill[which];
+    return NX_OK;
+}
+
+// One closest-hit launch over a ray queue (count immediate or read on the device) in the context's traversal mode.
+template <bool STATS>
+int launch_closest(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_ray* q, uint32_t nImm, const uint32_t* nPtr, uint32_t* cursor, nx_hit* hits, TraceStats* stats)
+{
+    if (ctx->trace_mode == 1) {
+        const int grid = persistent_grid(ctx, (const void*)trace_closest_pool_kernel<STATS>, NX_POOL_BLOCK, NX_POOL_SMEM_BYTES, STATS ? 5 : 4);
+        uint2* spill = nullptr; int rc = pool_spill(ctx, 0, grid, &spill); if (rc) return rc;
+        trace_closest_pool_kernel<STATS><<<grid, NX_POOL_BLOCK, NX_POOL_SMEM_BYTES, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, pool_tuning(ctx), spill);
+    } else if (ctx->trace_mode == 2) {
+        const int grid = persistent_grid(ctx, (const void*)trace_closest_duo_kernel<STATS>, NX_DUO_BLOCK, 0, STATS ? 9 : 8);
+        TraceTuning t = trace_tuning(ctx); t.stackLimit = std::min<uint32_t>(std::max<uint32_t>(ctx->stack_limit, NX_DUO_STACK), NX_STACK_TOTAL);
+        trace_closest_duo_kernel<STATS><<<grid, NX_DUO_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, t);
+    } else {
+        const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<STATS>, NX_TRACE_BLOCK, 0, STATS ? 1 : 0);
+        trace_closest_kernel<STATS><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, trace_tuning(ctx));
+    }
+    return NX_OK;
+}
+template <bool STATS>
+int launch_any(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_ray* q, uint32_t nImm, const uint32_t* nPtr, uint32_t* cursor,
+               uint8_t* occ, const float4* rad, float* accum, TraceStats* stats)
+{
+    if (ctx->trace_mode == 1) {
+        const int grid = persistent_grid(ctx, (const void*)trace_any_pool_kernel<STATS>, NX_POOL_BLOCK, NX_POOL_SMEM_BYTES, STATS ? 7 : 6);
+        uint2* spill = nullptr; int rc = pool_spill(ctx, 1, grid, &spill); if (rc) return rc;
+        trace_any_pool_kernel<STATS><<<grid, NX_POOL_BLOCK, NX_POOL_SMEM_BYTES, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, pool_tuning(ctx, true), spill);
+    } else if (ctx->trace_mode == 2) {
+        const int grid = persistent_grid(ctx, (const void*)trace_any_duo_kernel<STATS>, NX_DUO_BLOCK, 0, STATS ? 11 : 10);
+        TraceTuning t = trace_tuning(ctx, true); t.stackLimit = std::min<uint32_t>(std::max<uint32_t>(ctx->stack_limit, NX_DUO_STACK), NX_STACK_TOTAL);
+        trace_any_duo_kernel<STATS><<<grid, NX_DUO_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
+    } else {
+        const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<STATS>, NX_TRACE_BLOCK, 0, STATS ? 3 : 2);
+        trace_any_kernel<STATS><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, trace_tuning(ctx, true));
+    }
+    return NX_OK;
+}
 
 } // namespace
 
@@ -127,15 +236,13 @@ int nxi_trace_closest(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, ui
     uint32_t* cursor = nullptr;
     NX_CUDA(ctx, cudaMallocAsync((void**)&cursor, 4, ctx->stream));
     NX_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
-    const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    trace_closest_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dHits, nullptr, trace_tuning(ctx));
+    int rc = launch_closest<false>(ctx, ctx->stream, sc, dRays, n, nullptr, cursor, dHits, nullptr); if (rc) return rc;
     if (outMs) { cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1); cudaEventElapsedTime(outMs, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     cudaFreeAsync(cursor, ctx->stream);
-    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     NX_CUDA(ctx, cudaGetLastError());
-    return NX_OK;
+    return nxi_check_overflow(ctx);
 }
 
 int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32_t n, uint8_t* dOcc, float* outMs)
@@ -144,15 +251,13 @@ int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32
     uint32_t* cursor = nullptr;
     NX_CUDA(ctx, cudaMallocAsync((void**)&cursor, 4, ctx->stream));
     NX_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream));
-    const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<false>, NX_TRACE_BLOCK, &g_gridAny);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    trace_any_kernel<false><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr, trace_tuning(ctx, true));
+    int rc = launch_any<false>(ctx, ctx->stream, sc, dRays, n, nullptr, cursor, dOcc, nullptr, nullptr, nullptr); if (rc) return rc;
     if (outMs) { cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1); cudaEventElapsedTime(outMs, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1); }
     cudaFreeAsync(cursor, ctx->stream);
-    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     NX_CUDA(ctx, cudaGetLastError());
-    return NX_OK;
+    return nxi_check_overflow(ctx);
 }
 
 // Traversal work counters for the roofline's algorithmic-byte figure: nodes, triangles, instances per ray.
@@ -165,8 +270,7 @@ extern "C" int nx_trace_stats(nx_scene* s, const nx_ray* dRays, uint32_t n, nx_h
     uint32_t* cursor = nullptr; TraceStats* st = nullptr;
     NX_CUDA(ctx, cudaMallocAsync((void**)&cursor, 4, ctx->stream)); NX_CUDA(ctx, cudaMallocAsync((void**)&st, sizeof(TraceStats), ctx->stream));
     NX_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, ctx->stream)); NX_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(TraceStats), ctx->stream));
-    const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<true>, NX_TRACE_BLOCK, &g_gridClosestStats);
-    trace_closest_kernel<true><<<grid, NX_TRACE_BLOCK, 0, ctx->stream>>>(v.trace, dRays, n, nullptr, cursor, dHits, st, trace_tuning(ctx));
+    rc = launch_closest<true>(ctx, ctx->stream, v.trace, dRays, n, nullptr, cursor, dHits, st); if (rc) return rc;
     TraceStats h{};
     NX_CUDA(ctx, cudaMemcpyAsync(&h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -257,7 +361,10 @@ int nx_renderer_resize(nx_renderer* r, uint32_t width, uint32_t height)
     if (width == r->width && height == r->height) return NX_OK;
     DeviceGuard guard(r->ctx->device);
     free_buffers(r);
-    return alloc_buffers(r, width, height);
+    r->width = r->height = 0;                       // until the new buffers exist every call on this renderer fails with NX_ERR_STATE
+    const int rc = alloc_buffers(r, width, height);
+    if (rc) { free_buffers(r); r->width = r->height = 0; }
+    return rc;
 }
 
 int nx_renderer_reset_accumulation(nx_renderer* r)
@@ -275,6 +382,7 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
 {
     if (!r || !scene || scene->ctx != r->ctx) return NX_ERR_INVALID;
     nx_ctx* ctx = r->ctx;
+    if (!r->width || !r->wb.accum) NX_FAIL(ctx, NX_ERR_STATE, "the renderer has no buffers (a resize failed)");
     if (scene->width != r->width || scene->height != r->height) NX_FAIL(ctx, NX_ERR_INVALID, "scene resolution %ux%u != renderer %ux%u", scene->width, scene->height, r->width, r->height);
     DeviceGuard guard(ctx->device);
     DSceneView sv; int rc = nxi_scene_view(scene, &sv); if (rc) return rc;
@@ -283,11 +391,6 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
     cudaStream_t s = ctx->stream, sa = (r->profFlags & 1) ? ctx->stream : ctx->stream_aux;
     const uint32_t L = sv.pathLength;
     const bool work = (r->profFlags & 2) != 0;
-    const TraceTuning tune = trace_tuning(ctx), tuneAny = trace_tuning(ctx, true);
-    const int gClosest = work ? persistent_grid(ctx, (const void*)trace_closest_kernel<true>, NX_TRACE_BLOCK, &g_gridClosestStats)
-                              : persistent_grid(ctx, (const void*)trace_closest_kernel<false>, NX_TRACE_BLOCK, &g_gridClosest);
-    const int gAny = work ? persistent_grid(ctx, (const void*)trace_any_kernel<true>, NX_TRACE_BLOCK, &g_gridAnyStats)
-                          : persistent_grid(ctx, (const void*)trace_any_kernel<false>, NX_TRACE_BLOCK, &g_gridAny);
     const int gShade = nxi_shade_grid(ctx);
     const int gGen = ctx->sm_count * 8;
     WaveBuffers& wb = r->wb;
@@ -296,8 +399,8 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
 
     auto closest = [&](const nx_ray* q, uint32_t b) {
         r->prof_begin(1, s);
-        if (work) trace_closest_kernel<true><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, r->dWork, tune);
-        else trace_closest_kernel<false><<<gClosest, NX_TRACE_BLOCK, 0, s>>>(sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, nullptr, tune);
+        if (work) launch_closest<true>(ctx, s, sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, r->dWork);
+        else launch_closest<false>(ctx, s, sv.trace, q, 0, &wb.counters->extCount[b], &wb.counters->extFetch[b], wb.hits, nullptr);
         r->prof_end(s);
         r->launches++;
     };
@@ -334,8 +437,8 @@ int nx_renderer_render(nx_renderer* r, nx_scene* scene, uint32_t firstFrame, uin
             if (b < L) closest(wb.ext[b & 1u], b);
             NX_CUDA(ctx, cudaStreamWaitEvent(sa, r->evShade, 0));
             r->prof_begin(3, sa);
-            if (work) trace_any_kernel<true><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow[b & 1u], 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad[b & 1u], wb.accum, r->dWork + 1, tuneAny);
-            else trace_any_kernel<false><<<gAny, NX_TRACE_BLOCK, 0, sa>>>(sv.trace, wb.shadow[b & 1u], 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad[b & 1u], wb.accum, nullptr, tuneAny);
+            if (work) launch_any<true>(ctx, sa, sv.trace, wb.shadow[b & 1u], 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad[b & 1u], wb.accum, r->dWork + 1);
+            else launch_any<false>(ctx, sa, sv.trace, wb.shadow[b & 1u], 0, &wb.counters->shCount[b], &wb.counters->shFetch[b], nullptr, wb.shadowRad[b & 1u], wb.accum, nullptr);
             r->prof_end(sa);
             NX_CUDA(ctx, cudaEventRecord(r->evShadow[b & 1u], sa));
             r->launches++;
@@ -358,8 +461,8 @@ int nx_renderer_stats(nx_renderer* r, nx_frame_stats* out)
     nx_ctx* ctx = r->ctx;
     DeviceGuard guard(ctx->device);
     std::memset(out, 0, sizeof(*out));
-    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
     NX_CUDA(ctx, cudaGetLastError());
+    { const int rc = nxi_check_overflow(ctx); if (rc) return rc; }
     WaveTotals t{};
     NX_CUDA(ctx, cudaMemcpy(&t, r->wb.totals, sizeof(t), cudaMemcpyDeviceToHost));
     out->extension_rays = t.ext; out->shadow_rays = t.shadow; out->shaded_hits = t.shaded; out->frames = t.frames;
@@ -393,7 +496,7 @@ int nx_renderer_profile(nx_renderer* r, nx_kernel_profile* out)
         out->closest_work[0] = h[0].nodes; out->closest_work[1] = h[0].tris; out->closest_work[2] = h[0].insts; out->closest_work[3] = h[0].rays;
         out->any_work[0] = h[1].nodes; out->any_work[1] = h[1].tris; out->any_work[2] = h[1].insts; out->any_work[3] = h[1].rays;
         const unsigned long long* a = &h[0].iters; const unsigned long long* b = &h[1].iters;
-        for (int k = 0; k < 7; k++) { out->closest_sched[k] = a[k]; out->any_sched[k] = b[k]; }
+        for (int k = 0; k < 10; k++) { out->closest_sched[k] = a[k]; out->any_sched[k] = b[k]; }
     }
     return NX_OK;
 }

@@ -69,16 +69,20 @@ nx_aabb transformed_bounds(const float* m, const nx_aabb& b)
     return r;
 }
 
-// Bounding sphere of a mesh's vertices: centre of their AABB, radius = farthest vertex (double precision, padded).
-void mesh_sphere(const nx_triangle* tris, uint32_t n, double out[4])
+// Bounds of a mesh's vertices: the AABB (exact float min / max - the same values the builder's scene-bounds reduction produces) and the
+// bounding sphere around the AABB centre, radius = farthest vertex (double precision, padded).
+void mesh_bounds_sphere(const nx_triangle* tris, uint32_t n, nx_aabb* box, double out[4])
 {
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    float lo[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, hi[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
     const float* v = (const float*)tris;
-    for (size_t i = 0; i < (size_t)n * 3; i++)
-        for (int k = 0; k < 3; k++) { const double x = v[3 * i + k]; lo[k] = x < lo[k] ? x : lo[k]; hi[k] = x > hi[k] ? x : hi[k]; }
-    for (int k = 0; k < 3; k++) out[k] = 0.5 * (lo[k] + hi[k]);
+    const size_t nv = (size_t)n * 3;
+    for (size_t i = 0; i < nv; i++) {
+        lo[0] = fminf(lo[0], v[3 * i]); lo[1] = fminf(lo[1], v[3 * i + 1]); lo[2] = fminf(lo[2], v[3 * i + 2]);
+        hi[0] = fmaxf(hi[0], v[3 * i]); hi[1] = fmaxf(hi[1], v[3 * i + 1]); hi[2] = fmaxf(hi[2], v[3 * i + 2]);
+    }
+    for (int k = 0; k < 3; k++) { box->bmin[k] = lo[k]; box->bmax[k] = hi[k]; out[k] = 0.5 * ((double)lo[k] + (double)hi[k]); }
     double r2 = 0.0;
-    for (size_t i = 0; i < (size_t)n * 3; i++) {
+    for (size_t i = 0; i < nv; i++) {
         const double dx = v[3 * i] - out[0], dy = v[3 * i + 1] - out[1], dz = v[3 * i + 2] - out[2];
         const double q = dx * dx + dy * dy + dz * dz;
         r2 = q > r2 ? q : r2;
@@ -123,16 +127,31 @@ bool material_emits(const nx_material& m)   // Scene::UpdateSceneLighting's test
 
 // ------------------------------------------------------------------------------------------- device prep ----
 // Leaf-ordered triangle stream: slot k of the BLAS gets {v0, primId}, {v1 - v0, 0}, {v2 - v0, 0}.
-__global__ void leaf_triangles_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ primIdx, uint32_t n, float4* __restrict__ out)
+__global__ void leaf_triangles_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ primIdx, uint32_t n, float4* __restrict__ out, uint32_t* bad)
 {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t p = __ldg(primIdx + k);
+        if (p >= n) { if (bad) atomicAdd(bad, 1u); continue; }     // only a caller-supplied (prebuilt) BLAS can get here; reported by Scene::Update
         const float* t = tris + 9 * (size_t)p;
         const V3 a = v3(__ldg(t), __ldg(t + 1), __ldg(t + 2)), b = v3(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)), c = v3(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
         const V3 e0 = b - a, e1 = c - a;
         out[3 * (size_t)k] = make_float4(a.x, a.y, a.z, __uint_as_float(p));
         out[3 * (size_t)k + 1] = make_float4(e0.x, e0.y, e0.z, 0.f);
         out[3 * (size_t)k + 2] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    }
+}
+
+// Shading records (scene.cuh): positions from the triangle array, vertex normals from the D_TriangleData array.
+__global__ void shade_record_kernel(const float* __restrict__ tris, const float* __restrict__ tridata, uint32_t n, float4* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* t = tris + 9 * (size_t)i; const float* d = tridata + 24 * (size_t)i;
+        float4* o = out + NX_SHADE_REC_F4 * (size_t)i;
+        o[0] = make_float4(t[0], t[1], t[2], d[0]);
+        o[1] = make_float4(t[3], t[4], t[5], d[1]);
+        o[2] = make_float4(t[6], t[7], t[8], d[2]);
+        o[3] = make_float4(d[3], d[4], d[5], d[6]);
+        o[4] = make_float4(d[7], d[8], 0.f, 0.f);
     }
 }
 
@@ -213,7 +232,7 @@ int nxi_scene_view(nx_scene* s, DSceneView* v)
 {
     if (s->dirtyInstances || s->dirtyMaterials || s->dirtyLights || s->dirtyTextures) { int rc = nx_scene_update(s); if (rc) return rc; }
     std::memset(v, 0, sizeof(*v));
-    v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst;
+    v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst; v->trace.overflow = s->ctx->dOverflow;
     v->shadeInst = s->dShadeInst; v->meshes = s->dMeshes; v->materials = s->dMaterials; v->lights = s->dLights;
     v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr; v->textures = s->dTextures;
     v->camera = nxi_camera_to_device(s->camera, s->width, s->height);
@@ -243,7 +262,9 @@ void nx_scene_destroy(nx_scene* s)
     nx_ctx* ctx = s->ctx;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
-    for (auto& m : s->meshes) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); nx_bvh8_free(ctx, &m.bvh); }
+    for (int k = 0; k < ctx->buildStreamCount; k++) cudaStreamSynchronize(ctx->buildStreams[k]);
+    for (uint32_t* c : s->buildCounterChunks) cudaFree(c);
+    for (auto& m : s->meshes) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); cudaFree(m.dShadeRec); nx_bvh8_free(ctx, &m.bvh); }
     if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
     if (s->dTop && ctx->l2_persist_bytes) {   // drop the window that points at this scene's top-level block
         cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
@@ -273,35 +294,120 @@ int nx_scene_set_material(nx_scene* s, uint32_t idx, const nx_material* m)
     return NX_OK;
 }
 
-// Mesh::Mesh (N/Assets/Mesh.h:29-40).  With `pre` the BLAS is taken from the caller (device arrays, copied) instead of built here.
 struct PrebuiltBlas { const nx_bvh8_node* dNodes; uint32_t nodeCount; const uint32_t* dPrimIdx; nx_aabb bounds; };
 
+// Host data -> device through the context's pinned staging ring (no stream synchronisation unless the ring wraps).
+static int stage_upload(nx_ctx* ctx, cudaStream_t st, void* dst, const void* src, size_t bytes)
+{
+    constexpr size_t kRing = 256u << 20;
+    if (!ctx->stagePinned) {
+        if (cudaMallocHost((void**)&ctx->stagePinned, kRing) != cudaSuccess) { cudaGetLastError(); ctx->stagePinned = nullptr; ctx->stageBytes = 0; }
+        else ctx->stageBytes = kRing;
+    }
+    if (bytes > ctx->stageBytes / 2) {                        // larger than the ring is worth: plain (staged by the driver) copy
+        NX_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return NX_OK;
+    }
+    const size_t aligned = (bytes + 255) & ~(size_t)255;
+    if (ctx->stageUsed + aligned > ctx->stageBytes) {         // wrap: everything staged so far must have left the ring
+        for (int k = 0; k < ctx->buildStreamCount; k++) NX_CUDA(ctx, cudaStreamSynchronize(ctx->buildStreams[k]));
+        NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stageUsed = 0;
+    }
+    char* p = ctx->stagePinned + ctx->stageUsed;
+    ctx->stageUsed += aligned;
+    std::memcpy(p, src, bytes);
+    NX_CUDA(ctx, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, st));
+    return NX_OK;
+}
+
+static int build_stream(nx_ctx* ctx, size_t meshIdx, cudaStream_t* out)
+{
+    constexpr int kStreams = (int)(sizeof(ctx->buildStreams) / sizeof(ctx->buildStreams[0]));
+    while (ctx->buildStreamCount < kStreams) {
+        NX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->buildStreams[ctx->buildStreamCount], cudaStreamNonBlocking));
+        ctx->buildStreamCount++;
+    }
+    *out = ctx->buildStreams[meshIdx % kStreams];
+    return NX_OK;
+}
+
+// Waits for the BLAS builds in flight and collects their node counts (one synchronisation and one read-back for all of them).
+static int nxi_scene_flush_builds(nx_scene* s)
+{
+    if (!s->pendingBuilds) return NX_OK;
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    for (int k = 0; k < ctx->buildStreamCount; k++) NX_CUDA(ctx, cudaStreamSynchronize(ctx->buildStreams[k]));
+    NX_CUDA(ctx, cudaGetLastError());
+    std::vector<uint32_t> host(8 * 1024);
+    for (size_t c = 0; c < s->buildCounterChunks.size(); c++) {
+        bool any = false;
+        for (size_t k = c * 1024; k < std::min(s->meshes.size(), (c + 1) * 1024); k++) any = any || s->meshes[k].pending;
+        if (!any) continue;
+        NX_CUDA(ctx, cudaMemcpy(host.data(), s->buildCounterChunks[c], 4 * host.size(), cudaMemcpyDeviceToHost));
+        for (size_t k = c * 1024; k < std::min(s->meshes.size(), (c + 1) * 1024); k++) {
+            HostMesh& m = s->meshes[k];
+            if (!m.pending) continue;
+            const uint32_t* cnt = host.data() + 8 * (k - c * 1024);
+            m.pending = false;
+            if (m.prebuilt) {
+                if (cnt[2]) NX_FAIL(ctx, NX_ERR_INVALID, "AddMesh(prebuilt) (mesh %zu): %u leaf slots refer to primitives outside [0, %u)", k, cnt[2], m.bvh.prim_count);
+                continue;
+            }
+            if (cnt[1] != m.bvh.prim_count) NX_FAIL(ctx, NX_ERR_STATE, "BuildBVH8 (mesh %zu): collapse placed %u of %u primitives", k, cnt[1], m.bvh.prim_count);
+            m.bvh.node_count = cnt[0];
+        }
+    }
+    s->pendingBuilds = 0;
+    return NX_OK;
+}
+
+// Mesh::Mesh (N/Assets/Mesh.h:29-40).  With `pre` the BLAS is taken from the caller (device arrays, copied) instead of built here.
+// Nothing in here waits for the GPU: uploads go through the pinned ring, the BLAS build and the leaf-ordered triangle stream are
+// issued on one of the context's build streams, and Scene::Update (nx_scene_update) collects all of them at once.  A scene of 1,024
+// meshes took 4.25 s to set up with one synchronising build per mesh (BENCH_r01 scene_setup_s) for 0.36 s of GPU work.
 static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx, const PrebuiltBlas* pre)
 {
     nx_ctx* ctx = s->ctx;
     DeviceGuard guard(ctx->device);
+    const size_t meshIdx = s->meshes.size();
+    cudaStream_t st = nullptr;
+    int rc = build_stream(ctx, meshIdx, &st); if (rc) return rc;
+    if (meshIdx / 1024 >= s->buildCounterChunks.size()) {
+        uint32_t* chunk = nullptr;
+        NX_CUDA(ctx, cudaMalloc((void**)&chunk, 4 * 8 * 1024));
+        s->buildCounterChunks.push_back(chunk);
+    }
     HostMesh m; m.materialIdx = materialIdx;
-    NX_CUDA(ctx, cudaMalloc((void**)&m.dTris, 36 * (size_t)n));
-    NX_CUDA(ctx, cudaMalloc((void**)&m.dTriData, 96 * (size_t)n));
-    NX_CUDA(ctx, cudaMalloc((void**)&m.dLeafTris, 48 * (size_t)n));
-    NX_CUDA(ctx, cudaMemcpyAsync(m.dTris, tris, 36 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* counters = s->buildCounterChunks[meshIdx / 1024] + 8 * (meshIdx % 1024);
+    auto fail = [&](int code) { cudaFreeAsync(m.dTris, st); cudaFreeAsync(m.dTriData, st); cudaFreeAsync(m.dLeafTris, st); cudaFreeAsync(m.dShadeRec, st); return code; };
+    if (cudaMallocAsync((void**)&m.dTris, 36 * (size_t)n, st) != cudaSuccess || cudaMallocAsync((void**)&m.dTriData, 96 * (size_t)n, st) != cudaSuccess ||
+        cudaMallocAsync((void**)&m.dLeafTris, 48 * (size_t)n, st) != cudaSuccess || cudaMallocAsync((void**)&m.dShadeRec, 16 * NX_SHADE_REC_F4 * (size_t)n, st) != cudaSuccess) { ctx->error = "AddMesh: out of device memory"; cudaGetLastError(); return fail(NX_ERR_CUDA); }
+    rc = stage_upload(ctx, st, m.dTris, tris, 36 * (size_t)n); if (rc) return fail(rc);
     const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
-    if (data) NX_CUDA(ctx, cudaMemcpyAsync(m.dTriData, data, 96 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    else default_tridata_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, n, m.dTriData);
-    mesh_sphere(tris, n, m.sphere);
+    if (data) { rc = stage_upload(ctx, st, m.dTriData, data, 96 * (size_t)n); if (rc) return fail(rc); }
+    else default_tridata_kernel<<<grid, 256, 0, st>>>(m.dTris, n, m.dTriData);
+    shade_record_kernel<<<grid, 256, 0, st>>>(m.dTris, m.dTriData, n, m.dShadeRec);
+    nx_aabb box;
+    mesh_bounds_sphere(tris, n, &box, m.sphere);
     if (pre) {
         // same allocator as the builder's outputs, so nx_bvh8_free / scene destruction treat both kinds alike
-        NX_CUDA(ctx, cudaMallocAsync((void**)&m.bvh.nodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, ctx->stream));
-        NX_CUDA(ctx, cudaMallocAsync((void**)&m.bvh.prim_idx, 4 * (size_t)n, ctx->stream));
-        NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.nodes, pre->dNodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, cudaMemcpyDeviceToDevice, ctx->stream));
-        NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.prim_idx, pre->dPrimIdx, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (cudaMallocAsync((void**)&m.bvh.nodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, st) != cudaSuccess ||
+            cudaMallocAsync((void**)&m.bvh.prim_idx, 4 * (size_t)n, st) != cudaSuccess) { ctx->error = "AddMesh: out of device memory"; cudaGetLastError(); return fail(NX_ERR_CUDA); }
+        // the caller's arrays were produced on other streams: the caller synchronises before handing them over (nx_scene_build_blas does)
+        NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.nodes, pre->dNodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, cudaMemcpyDeviceToDevice, st));
+        NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.prim_idx, pre->dPrimIdx, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
         m.bvh.node_count = pre->nodeCount; m.bvh.prim_count = n; m.bvh.bounds = pre->bounds;
+        NX_CUDA(ctx, cudaMemsetAsync(counters, 0, 32, st));
+        m.pending = true; m.prebuilt = true; s->pendingBuilds++;   // Update waits for the copies and reads the index check's verdict
     } else {
-        int rc = nxi_build_bvh8(ctx, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, &m.bvh);
-        if (rc) return rc;
+        rc = nxi_build_bvh8_async(ctx, st, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, counters, &m.bvh);
+        if (rc) return fail(rc);
+        m.bvh.bounds = box;                                   // = the builder's scene bounds (exact min / max of the same floats)
+        m.pending = true; s->pendingBuilds++;
     }
-    leaf_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris);
-    NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    leaf_triangles_kernel<<<grid, 256, 0, st>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris, pre ? counters + 2 : nullptr);
     NX_CUDA(ctx, cudaGetLastError());
     s->meshes.push_back(m);
     return (int)s->meshes.size() - 1;
@@ -342,6 +448,7 @@ int nx_scene_mesh_bounds(nx_scene* s, uint32_t meshIdx, nx_aabb* out)
 int nx_scene_mesh_bvh(nx_scene* s, uint32_t meshIdx, nx_bvh8* out)
 {
     if (!s || !out || meshIdx >= s->meshes.size()) return NX_ERR_INVALID;
+    { const int rc = nxi_scene_flush_builds(s); if (rc) return rc; }
     *out = s->meshes[meshIdx].bvh; return NX_OK;
 }
 
@@ -443,6 +550,13 @@ int nx_scene_add_texture(nx_scene* s, const void* rgba, uint32_t w, uint32_t h, 
     return (int)s->textures.size() - 1;
 }
 
+// Camera::OnResize (src/Scene/Camera.cpp:118-128): the resolution only feeds the camera record (aspect ratio, pixel grid); nothing is rebuilt.
+int nx_scene_set_resolution(nx_scene* s, uint32_t width, uint32_t height)
+{
+    if (!s || !width || !height) return NX_ERR_INVALID;
+    s->width = width; s->height = height;
+    return NX_OK;
+}
 int nx_scene_set_camera(nx_scene* s, const nx_camera* c) { if (!s || !c) return NX_ERR_INVALID; s->camera = *c; return NX_OK; }
 int nx_scene_set_render_settings(nx_scene* s, const nx_render_settings* r)
 {
@@ -474,6 +588,7 @@ int nx_scene_update(nx_scene* s)
     if (!s) return NX_ERR_INVALID;
     nx_ctx* ctx = s->ctx;
     DeviceGuard guard(ctx->device);
+    { const int rc = nxi_scene_flush_builds(s); if (rc) return rc; }
     if (s->instances.empty()) NX_FAIL(ctx, NX_ERR_STATE, "Scene::Update: the scene has no mesh instances");
     if (s->materials.empty()) NX_FAIL(ctx, NX_ERR_STATE, "Scene::Update: the scene has no materials");
     for (const auto& i : s->instances) if (i.materialIdx >= s->materials.size()) NX_FAIL(ctx, NX_ERR_INVALID, "instance refers to material %u of %zu", i.materialIdx, s->materials.size());
@@ -481,14 +596,18 @@ int nx_scene_update(nx_scene* s)
     for (const auto& m : s->materials)
         for (int32_t id : {m.base_color_map, m.emissive_map, m.normal_map, m.roughness_map, m.metalness_map, m.metallic_roughness_map})
             if (id < -1 || id >= (int32_t)s->textures.size()) NX_FAIL(ctx, NX_ERR_INVALID, "a material refers to texture %d of %zu", id, s->textures.size());
-    if (s->dirtyMaterials) { int rc = upload_vec(ctx, &s->dMaterials, s->materials); if (rc) return rc; }
+    if (s->dirtyMaterials) {
+        std::vector<DMaterial> dmat(s->materials.size());
+        for (size_t i = 0; i < dmat.size(); i++) { dmat[i].m = s->materials[i]; dmat[i].pad = 0; }
+        int rc = upload_vec(ctx, &s->dMaterials, dmat); if (rc) return rc;
+    }
     if (s->dirtyTextures) { int rc = upload_vec(ctx, &s->dTextures, s->textures); if (rc) return rc; s->dirtyTextures = false; }
 
     if (s->dirtyInstances)
     {
         // device mesh table
         std::vector<DMesh> dm(s->meshes.size());
-        for (size_t i = 0; i < dm.size(); i++) { dm[i].tris = s->meshes[i].dTris; dm[i].tridata = s->meshes[i].dTriData; dm[i].primCount = s->meshes[i].bvh.prim_count; dm[i].pad = 0; }
+        for (size_t i = 0; i < dm.size(); i++) { dm[i].tris = s->meshes[i].dTris; dm[i].tridata = s->meshes[i].dTriData; dm[i].shade = s->meshes[i].dShadeRec; dm[i].primCount = s->meshes[i].bvh.prim_count; dm[i].pad = 0; }
         int rc = upload_vec(ctx, &s->dMeshes, dm); if (rc) return rc;
 
         // shading records in instance order
@@ -599,6 +718,8 @@ int nx_scene_update(nx_scene* s)
         // punctual lights first, then one MESH light per emissive instance (Scene::UpdateSceneLighting, Scene.cpp:157-219)
         s->lights.clear();
         for (const nx_light& l : s->userLights) {
+            if (l.type == NX_LIGHT_MESH && l.instance >= s->instances.size())
+                NX_FAIL(ctx, NX_ERR_INVALID, "a MESH light refers to instance %u of %zu", l.instance, s->instances.size());
             DLight d{}; d.type = l.type;
             d.px = l.position[0]; d.py = l.position[1]; d.pz = l.position[2];
             d.dx = l.direction[0]; d.dy = l.direction[1]; d.dz = l.direction[2];

@@ -5,10 +5,19 @@
 
 struct DMesh {                 // replaces D_Mesh (src/Cuda/Scene/Mesh.cuh:5-9)
     const float* tris;         // 36-byte NXB::Triangle AoS, original order (shading + light sampling address by primitive id)
-    const float* tridata;      // 96-byte D_TriangleData AoS
+    const float* tridata;      // 96-byte D_TriangleData AoS (tangents and texture coordinates are read from here)
+    const float4* shade;       // 80-byte shading record per primitive, 16-byte aligned: positions + vertex normals in five float4
     uint32_t primCount;
     uint32_t pad;
 };
+
+// Shading record: what every shaded hit (and every light sample) reads.  The reference fetches nine position floats at a 36-byte
+// stride and nine normal floats at a 96-byte stride with 4-byte loads (PathTracer.cu:355-371); here it is
+// five LDG.128: {v0, n0.x} {v1, n0.y} {v2, n0.z} {n1, n2.x} {n2.y, n2.z, -, -}.
+#define NX_SHADE_REC_F4 5
+
+struct __align__(16) DMaterial { nx_material m; uint32_t pad; };   // 96 B: six LDG.128 instead of 23 scalar loads
+static_assert(sizeof(DMaterial) == 96, "DMaterial layout");
 
 struct DShadeInst {            // replaces the shading half of D_MeshInstance (src/Cuda/Scene/MeshInstance.cuh:9-16), 112 B
     float4 m0, m1, m2;         // object -> world rows
@@ -34,7 +43,7 @@ struct DSceneView {            // kernel parameter block (replaces the __constan
     TraceScene trace;
     const DShadeInst* shadeInst;
     const DMesh* meshes;
-    const nx_material* materials;
+    const DMaterial* materials;
     const DLight* lights;
     uint32_t lightCount;
     uint32_t hasHdr;
@@ -48,9 +57,12 @@ struct DSceneView {            // kernel parameter block (replaces the __constan
 struct HostMesh {
     float* dTris = nullptr; float* dTriData = nullptr;
     float4* dLeafTris = nullptr;
+    float4* dShadeRec = nullptr;
     nx_bvh8 bvh{};
     uint32_t materialIdx = 0;
     double sphere[4] = {0, 0, 0, 0};   // object-space bounding sphere of the vertices (centre, radius)
+    bool prebuilt = false;             // BLAS supplied by the caller (nx_scene_add_mesh_prebuilt): indices validated on the device
+    bool pending = false;              // BLAS build in flight on a build stream: node_count not known yet (flush_builds)
 };
 
 struct HostInstance {
@@ -79,12 +91,15 @@ struct nx_scene {
     void* dTop = nullptr; size_t topBytes = 0; const float4* dTopNodes = nullptr;
     DShadeInst* dShadeInst = nullptr;
     DMesh* dMeshes = nullptr;
-    nx_material* dMaterials = nullptr;
+    DMaterial* dMaterials = nullptr;
     DLight* dLights = nullptr;
     cudaTextureObject_t hdr = 0; cudaArray_t hdrArray = nullptr; bool hasHdr = false;
     std::vector<cudaTextureObject_t> textures; std::vector<cudaArray_t> textureArrays;   // AssetManager::AddTexture
     cudaTextureObject_t* dTextures = nullptr; bool dirtyTextures = false;
     uint32_t dMeshCount = 0;
+    // scene set-up pipeline: device counters of the BLAS builds in flight (8 words per mesh, chunks of 1024 meshes)
+    std::vector<uint32_t*> buildCounterChunks;
+    uint32_t pendingBuilds = 0;
 };
 
 // scene.cu
@@ -92,6 +107,7 @@ int nxi_scene_view(nx_scene* s, DSceneView* out);
 DCamera nxi_camera_to_device(const nx_camera& c, uint32_t w, uint32_t h);
 // bvh_builder.cu
 int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out);
+int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out);
 // render.cu
 int nxi_trace_closest(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32_t n, nx_hit* dHits, float* outMs);
 int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32_t n, uint8_t* dOcc, float* outMs);

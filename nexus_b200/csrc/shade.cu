@@ -79,6 +79,18 @@ __device__ __forceinline__ F3 background(const DSceneView& sv, F3 d)   // Sample
 
 struct Surface { F3 p, n, gn; };
 
+// positions and vertex normals of one primitive: five 16-byte loads from the shading record (scene.cuh)
+struct ShadeTri { F3 v0, v1, v2, n0, n1, n2; };
+__device__ __forceinline__ ShadeTri load_shade_tri(const float4* __restrict__ rec, uint32_t prim)
+{
+    const float4* r = rec + NX_SHADE_REC_F4 * (size_t)prim;
+    const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), d = __ldg(r + 3), e = __ldg(r + 4);
+    ShadeTri t;
+    t.v0 = f3(a.x, a.y, a.z); t.v1 = f3(b.x, b.y, b.z); t.v2 = f3(c.x, c.y, c.z);
+    t.n0 = f3(a.w, b.w, c.w); t.n1 = f3(d.x, d.y, d.z); t.n2 = f3(d.w, e.x, e.y);
+    return t;
+}
+
 struct ShadeOut {
     bool ext, shadow;
     F3 extO, extD, thr; float pdf;
@@ -101,11 +113,12 @@ __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_materi
         const uint32_t ti = min((uint32_t)floorf(rng_next(rng) * (float)mesh.primCount), mesh.primCount - 1u);
         const float a = rng_next(rng), b = rng_next(rng), su = sqrtf(a);
         const float u = 1.0f - su, v = b * su;                                   // uniform triangle sample (Sampler.cuh:41-48)
-        const float* t = mesh.tris + 9 * (size_t)ti; const float* td = mesh.tridata + 24 * (size_t)ti;
-        const F3 v0 = load3(t), v1 = load3(t + 3), v2 = load3(t + 6);
+        const float* td = mesh.tridata + 24 * (size_t)ti;
+        const ShadeTri st = load_shade_tri(mesh.shade, ti);
+        const F3 v0 = st.v0, v1 = st.v1, v2 = st.v2;
         F3 lp = xf_point(I.m0, I.m1, I.m2, bary(v0, v1, v2, u, v));
         const F3 lgn = normalize(xf_normal(I.i0, I.i1, I.i2, cross(v1 - v0, v2 - v0)));
-        const F3 ln = normalize(xf_normal(I.i0, I.i1, I.i2, bary(load3(td), load3(td + 3), load3(td + 6), u, v)));
+        const F3 ln = normalize(xf_normal(I.i0, I.i1, I.i2, bary(st.n0, st.n1, st.n2, u, v)));
         toLight = lp - sf.p;
         const bool sameSide = dot(-rayDir, sf.gn) * dot(toLight, sf.gn) > 0.0f;
         if (!sameSide && mat.transmission == 0.0f) return;
@@ -119,7 +132,7 @@ __device__ __forceinline__ void next_event(const DSceneView& sv, const nx_materi
         lightPdf = 1.0f / ((float)sv.lightCount * (float)mesh.primCount * area);
         lightPdf *= dot(toLight, toLight) / cosL;                                // area measure -> solid angle
         if (!pdf_ok(lightPdf)) return;
-        const nx_material& lm = sv.materials[I.materialIdx];
+        const nx_material& lm = sv.materials[I.materialIdx].m;
         const int32_t emap = __ldg(&lm.emissive_map);
         if (emap != -1) {   // the map REPLACES the emission colour here (PathTracer.cu:263-269), unlike in the material kernel
             const float tu = u * __ldg(td + 20) + v * __ldg(td + 22) + (1.0f - u - v) * __ldg(td + 18);
@@ -171,13 +184,15 @@ __device__ __forceinline__ void material_one(const DSceneView& sv, const WaveBuf
 
     const DShadeInst I = sv.shadeInst[hit.instance];
     const DMesh mesh = sv.meshes[I.meshIdx];
-    const float* t = mesh.tris + 9 * (size_t)hit.prim; const float* td = mesh.tridata + 24 * (size_t)hit.prim;
-    const F3 v0 = load3(t), v1 = load3(t + 3), v2 = load3(t + 6);
-    nx_material mat = sv.materials[I.materialIdx];
+    const float* td = mesh.tridata + 24 * (size_t)hit.prim;
+    const ShadeTri st = load_shade_tri(mesh.shade, hit.prim);
+    const F3 v0 = st.v0, v1 = st.v1, v2 = st.v2;
+    const DMaterial dmat = sv.materials[I.materialIdx];     // 96 B, 16-byte aligned: six LDG.128
+    nx_material mat = dmat.m;
 
     Surface sf;
     sf.p = xf_point(I.m0, I.m1, I.m2, bary(v0, v1, v2, hit.u, hit.v));
-    F3 nObj = normalize(bary(load3(td), load3(td + 3), load3(td + 6), hit.u, hit.v));
+    F3 nObj = normalize(bary(st.n0, st.n1, st.n2, hit.u, hit.v));
     // material maps (PathTracer.cu:373-411): all six indices are -1 <=> their AND is -1
     if ((mat.base_color_map & mat.emissive_map & mat.normal_map & mat.roughness_map & mat.metalness_map & mat.metallic_roughness_map) != -1)
     {

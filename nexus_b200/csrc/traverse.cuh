@@ -49,6 +49,8 @@ struct TraceScene {
     const float4* tlasNodes;
     const uint32_t* tlasPrimIdx;   // TLAS leaf slot -> instance id (read once per ray, at the end)
     const DTravInst* inst;         // TLAS leaf slot -> traversal record
+    uint32_t* overflow;            // device counter of traversal-stack pushes refused (a tree deeper than NX_STACK_TOTAL entries); the
+                                   // host turns a non-zero value into an error (the reference's 32-entry stack has no check, BVH8Traversal.cuh:164)
 };
 
 struct TraceTuning {               // batching thresholds (lanes): run a phase when at least this many lanes want it
@@ -56,12 +58,14 @@ struct TraceTuning {               // batching thresholds (lanes): run a phase w
     uint32_t instLanes;            // new-ray / instance-entry phase
     uint32_t sphereCull;           // 0 disables the per-instance bounding-sphere test (measurement only)
     uint32_t k47;                  // always 0x47000000 (see trace_loop: a constant the compiler must not see)
+    uint32_t stackLimit;           // NX_STACK_TOTAL; a test lowers it (not below NX_STACK_SHARED) to exercise the overflow report
 };
 
 struct TraceStats {
     unsigned long long nodes, tris, insts, rays;
     // warp scheduling: loop iterations, lanes that tested a node, triangle rounds / lanes, set-up rounds / lanes (per warp, summed)
     unsigned long long iters, lanesN, roundsT, lanesT, roundsX, lanesX, sphereCulled;
+    unsigned long long roundsN, roundsF, lanesF;   // ray-pool loop only: node rounds, fetch rounds and the rays they fetched
 };
 
 // Shared memory per block: stack entries [NX_STACK_SHARED][block] of uint2, then the parked world-space ray, 48 B per
@@ -239,8 +243,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
     unsigned long long cN = 0, cT = 0, cI = 0, cR = 0, cS = 0;
     unsigned long long wIt = 0, wLN = 0, wRT = 0, wLT = 0, wRX = 0, wLX = 0;   // lane 0 only
 
-    // deeper than NX_STACK_TOTAL entries (never seen; the reference's 32-entry stack has no check at all): the entry is dropped
-    auto push = [&](uint2 v) { if (sp < NX_STACK_SHARED) sstack[sp * NX_TRACE_BLOCK] = v; else if (sp < NX_STACK_TOTAL) spill[sp - NX_STACK_SHARED] = v; else return; sp++; };
+    // deeper than NX_STACK_TOTAL entries (never seen on a built tree; the reference's 32-entry stack has no check at all): the entry
+    // is refused and counted, and the host reports the count as an error (nx_last_error)
+    auto push = [&](uint2 v) { if (sp < NX_STACK_SHARED) sstack[sp * NX_TRACE_BLOCK] = v; else if (sp < (int)tune.stackLimit) spill[sp - NX_STACK_SHARED] = v; else { atomicAdd(sc.overflow, 1u); return; } sp++; };
     auto pop = [&]() -> uint2 { sp--; return sp < NX_STACK_SHARED ? sstack[sp * NX_TRACE_BLOCK] : spill[sp - NX_STACK_SHARED]; };
 
     // One Moeller-Trumbore test for the highest set bit of the lane's triangle group; {v0, e0 = v1 - v0, e1 = v2 - v0},

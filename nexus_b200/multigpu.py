@@ -48,20 +48,44 @@ def accumulation_tensor(path_tracer, device):
 
 
 def render_partitioned(path_tracer, scene, frames_per_rank, first_frame=1, stream=None, group=None):
-    """Renders this rank's block and reduces.  After the call every rank's accumulation holds all world*frames_per_rank frames."""
+    """Renders this rank's block of frames and reduces.  After the call every rank's accumulation holds everything it held before
+    (which must be the same on every rank: nothing, or the result of earlier calls) plus all world * frames_per_rank new frames.
+
+    Only THIS call's contribution is all-reduced: an accumulation that already holds frames is the global sum on every rank, and
+    reducing it again would count it world times.  The contribution is taken as a device-side difference against a snapshot.
+    The reduction is ordered behind the render on the device: it runs on the context's own stream, or - when `stream` is given -
+    on that stream after an event recorded on the context's stream (nx_renderer_render leaves it ordered behind the shadow-ray
+    stream, so the accumulation is complete at that point)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    before = path_tracer.GetFrameNumber()
+    if world == 1:
+        path_tracer.Render(scene, frames=frames_per_rank, firstFrame=frame_block(rank, world, frames_per_rank, first_frame))
+        return before + frames_per_rank
+    device = torch.device("cuda", path_tracer.ctx.device)
+    from ._capi import lib
+    render_stream = torch.cuda.ExternalStream(int(lib().nx_ctx_stream(path_tracer.ctx._h)), device=device)
+    acc = accumulation_tensor(path_tracer, device)
+    snapshot = None
+    if before > 0:
+        with torch.cuda.stream(render_stream):
+            snapshot = acc.clone()
     path_tracer.Render(scene, frames=frames_per_rank, firstFrame=frame_block(rank, world, frames_per_rank, first_frame))
-    if world > 1:
-        acc = accumulation_tensor(path_tracer, torch.device("cuda", path_tracer.ctx.device))
-        if stream is None:
-            path_tracer.ctx.synchronize()
-            total = reduce_accumulation(acc, frames_per_rank, group)
+    run_on = render_stream
+    if stream is not None:
+        stream.wait_event(render_stream.record_event())
+        run_on = stream
+    with torch.cuda.stream(run_on):
+        if snapshot is None:
+            added = reduce_accumulation(acc, frames_per_rank, group)
         else:
-            with torch.cuda.stream(stream):
-                total = reduce_accumulation(acc, frames_per_rank, group)
-        path_tracer.SetAccumulatedFrames(total)
-    return frames_per_rank * world
+            acc.sub_(snapshot)
+            added = reduce_accumulation(acc, frames_per_rank, group)
+            acc.add_(snapshot)
+    if stream is not None:
+        render_stream.wait_event(stream.record_event())       # later renders and reads on the context's stream see the reduced buffer
+    path_tracer.SetAccumulatedFrames(before + added)
+    return before + added
 
 
 # ------------------------------------------------------------------------------------------ sharded BLAS builds ----

@@ -76,7 +76,9 @@ def test_product_never_touches_the_oracle():
 
 
 def test_image_writers_roundtrip(tmp_path):
-    """nx_write_pfm / nx_write_exr are host-only: check the files parse back to the same pixels."""
+    """nx_write_pfm / nx_write_exr are host-only: the files parse back to the same pixels, and both take the renderer's layout
+    (row 0 = bottom row of the image): PFM stores rows bottom to top, so the file body IS the input; EXR scanline 0 is the top
+    row, so the last scanline chunk is input row 0."""
     import numpy as np
     import nexus_b200 as nx
     rng = np.random.default_rng(0)
@@ -86,7 +88,7 @@ def test_image_writers_roundtrip(tmp_path):
     raw = open(p, "rb").read()
     head, dims, scale, body = raw.split(b"\n", 3)
     assert head == b"PF" and dims == b"7 5" and float(scale) < 0
-    back = np.frombuffer(body, "<f4").reshape(5, 7, 3)[::-1]
+    back = np.frombuffer(body, "<f4").reshape(5, 7, 3)
     assert (back == img).all()
     e = tmp_path / "a.exr"
     nx.write_exr(e, img)
@@ -94,4 +96,12 @@ def test_image_writers_roundtrip(tmp_path):
     assert raw[:4] == bytes([0x76, 0x2f, 0x31, 0x01])
     # last scanline chunk: y, size, then B, G, R planes
     row = np.frombuffer(raw[-7 * 12:], "<f4").reshape(3, 7)
-    assert (row[2] == img[4, :, 0]).all() and (row[1] == img[4, :, 1]).all() and (row[0] == img[4, :, 2]).all()
+    assert (row[2] == img[0, :, 0]).all() and (row[1] == img[0, :, 1]).all() and (row[0] == img[0, :, 2]).all()
+    # first scanline chunk (behind the header and the 5-entry offset table) = top row = input row 4
+    import struct
+    hdr_end = raw.index(b"screenWindowWidth\x00float\x00") + len(b"screenWindowWidth\x00float\x00") + 4 + 4 + 1
+    off0 = struct.unpack_from("<Q", raw, hdr_end)[0]
+    y0, size0 = struct.unpack_from("<ii", raw, off0)
+    assert y0 == 0 and size0 == 7 * 12
+    top = np.frombuffer(raw[off0 + 8: off0 + 8 + 7 * 12], "<f4").reshape(3, 7)
+    assert (top[2] == img[4, :, 0]).all()

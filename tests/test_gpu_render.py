@@ -100,12 +100,28 @@ def test_resize_and_outputs(ctx, tmp_path):
         pt.Render(scene, frames=1)                  # resolution mismatch is an error, not a crash
     pt.OnResize((80, 48))
     pt.Render(scene, frames=16)
+    # and the other way round: an existing scene follows a resize end to end (Camera::OnResize), nothing is rebuilt
+    scene.OnResize((64, 40)); pt.OnResize((64, 40))
+    pt.Render(scene, frames=2)
+    assert pt.ReadAccumulation().shape == (40, 64, 3)
+    scene.OnResize((80, 48)); pt.OnResize((80, 48))
+    pt.Render(scene, frames=16)
     img = pt.ReadAccumulation()
     assert img.shape == (48, 80, 3) and np.isfinite(img).all() and img.mean() > 0.05
     rgba = pt.ReadRGBA8(scene)
     assert rgba.shape == (48, 80) and (rgba >> 24 == 0xff).all() and (rgba & 0xffffff).any()
     nx.write_pfm(tmp_path / "c.pfm", img); nx.write_exr(tmp_path / "c.exr", img)
     assert os.path.getsize(tmp_path / "c.pfm") > 48 * 80 * 12 and os.path.getsize(tmp_path / "c.exr") > 48 * 80 * 12
+    # orientation: the Cornell box's light is on the ceiling.  The accumulation has row 0 at the bottom (the reference's pixel order),
+    # PFM stores rows bottom to top, EXR scanline 0 is the top: the emitter must be in the LAST rows of the PFM body and in the FIRST
+    # scanlines of the EXR file
+    assert img[36:].max() > 4.0 * img[:12].max()
+    body = np.frombuffer(open(tmp_path / "c.pfm", "rb").read().split(b"\n", 3)[3], "<f4").reshape(48, 80, 3)
+    assert body[36:].max() > 4.0 * body[:12].max()
+    raw = open(tmp_path / "c.exr", "rb").read()
+    chunk = 8 + 80 * 12
+    lines = np.frombuffer(raw[-48 * chunk:], np.uint8).reshape(48, chunk)[:, 8:].copy().view("<f4").reshape(48, 3, 80)   # scanline, (B, G, R), x
+    assert lines[:12].max() > 4.0 * lines[36:].max()
     pt.close(); scene.close()
 
 
