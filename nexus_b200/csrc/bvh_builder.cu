@@ -13,8 +13,10 @@
 //     of a BVH2 child are read off its index (< n), allocation is one atomic per warp and counter, and there is no
 //     spin-waiting work queue.
 #include "nx_common.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include "radix_sort.cuh"
+#ifdef NX_WITH_CUB   // measurement builds only (scripts/build_variant.sh cub -DNX_WITH_CUB): the product library contains no library kernel
+#include <cub/device/device_radix_sort.cuh>
+#endif
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -24,7 +26,14 @@ namespace {
 constexpr uint32_t kSearchRadius = 8;     // H-PLOC search radius (BinaryBuilder.cu:9)
 constexpr uint32_t kMergeThreshold = 16;  // clusters kept per LBVH range (BinaryBuilder.cu:10)
 constexpr int kSetupBlock = 256;
-constexpr int kPlocBlock = 128;
+#ifndef NX_PLOC_BLOCK
+#define NX_PLOC_BLOCK 128
+#endif
+#ifndef NX_DP_BLOCK
+#define NX_DP_BLOCK 128
+#endif
+constexpr int kPlocBlock = NX_PLOC_BLOCK;   // one-phase kernel and the global phase of the two-phase builder
+constexpr int kDpBlock = NX_DP_BLOCK;
 #ifndef NX_PLOC_CHUNK
 #define NX_PLOC_CHUNK 512
 #endif
@@ -317,7 +326,11 @@ __global__ void __launch_bounds__(kPlocBlock) hploc_kernel(PlocArgs a, const Key
 // neighbour boxes with two LDS instead of six SHFL, and compaction is a scatter by rank instead of __fns + seven SHFL.
 constexpr uint32_t kSlotDone = 0xfffffffeu;
 
-struct WarpTable { float4 a[40], b[40]; };   // per warp: a = {lo.xyz, hi.x}, b = {hi.y, hi.z, id, -}; 8 entries of slack for lane + radius
+struct WarpTable {
+    float4 a[40], b[40];   // per warp: a = {lo.xyz, hi.x}, b = {hi.y, hi.z, id, -}; 8 entries of slack for lane + radius
+    float4 pa[32], pb[32]; // global path: the nodes a merge has created so far, with provisional ids (kTempId | k), written out at its end
+};
+constexpr uint32_t kTempId = 0x80000000u;   // node ids stay below 2^31 (n <= 2^30)
 
 template <uint32_t C> struct ChunkMem {
     float4 node[2 * C][2];     // [0, C): leaves of the chunk in sorted order; [C, 2C): nodes created here (provisional ids)
@@ -367,6 +380,9 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
     __syncwarp();
 
     const uint32_t keep = isRoot ? 1u : kMergeThreshold;
+    uint32_t pending = 0;   // global path: nodes created by this merge so far.  Their indices are reserved with ONE atomic at the end
+                            // (the one-phase kernel pays a global atomic round trip inside every iteration); the root, created by the
+                            // last iteration of the last merge, still gets the last index 2n - 2.
     while (num > keep)
     {
         // nearest neighbour within +-kSearchRadius by merged half-area, compared on the float bits; ties keep the candidate seen
@@ -393,9 +409,12 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
         const bool owner = mutual && lane < bestLane;          // the lower lane of a mutual pair creates the node
         const uint32_t ownerMask = __ballot_sync(NX_FULL, owner);
         const uint32_t created = __popc(ownerMask);
-        uint32_t base = 0;
-        if (lane == 0 && created) base = LOCAL ? atomicAdd(&M.created, created) : atomicAdd(a.allocated, created);
-        base = __shfl_sync(NX_FULL, base, 0);
+        uint32_t base = pending;
+        if (LOCAL) {
+            if (lane == 0 && created) base = atomicAdd(&M.created, created);
+            base = __shfl_sync(NX_FULL, base, 0);
+        }
+        pending += created;
         if (owner) {
             const float4 p0 = tb.a[bestLane], p1 = tb.b[bestLane];
             Box pb; pb.lo = v3(p0.x, p0.y, p0.z); pb.hi = v3(p0.w, p1.x, p1.y);
@@ -403,7 +422,7 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
             const uint32_t k = base + __popc(ownerMask & lane_lt);
             const float4 n0 = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x), n1 = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), p1.z);
             if (LOCAL) { M.node[C + k][0] = n0; M.node[C + k][1] = n1; id = C + k; }
-            else { st_cg4(a.nodes + 2 * (size_t)k, n0); st_cg4(a.nodes + 2 * (size_t)k + 1, n1); id = k; }
+            else { tb.pa[k] = n0; tb.pb[k] = n1; id = kTempId | k; }
         }
         // compact: survivors are the pair owners and every cluster without a mutual partner, order preserved
         const bool stays = alive && (owner || !mutual);
@@ -421,6 +440,23 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
             const float4 p = tb.a[lane], q = tb.b[lane];
             box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y); id = __float_as_uint(q.z);
         }
+    }
+    if (!LOCAL) {
+        // reserve the indices, write the nodes with their children's provisional ids resolved, resolve the surviving cluster ids
+        uint32_t base = 0;
+        if (lane == 0 && pending) base = atomicAdd(a.allocated, pending);
+        base = __shfl_sync(NX_FULL, base, 0);
+        __syncwarp();
+        if (lane < pending) {
+            const float4 n0 = tb.pa[lane]; float4 n1 = tb.pb[lane];
+            uint32_t l = __float_as_uint(n1.z), r = __float_as_uint(n1.w);
+            if (l & kTempId) l = base + (l & ~kTempId);
+            if (r & kTempId) r = base + (r & ~kTempId);
+            n1.z = __uint_as_float(l); n1.w = __uint_as_float(r);
+            st_cg4(a.nodes + 2 * (size_t)(base + lane), n0); st_cg4(a.nodes + 2 * (size_t)(base + lane) + 1, n1);
+        }
+        if (id != NX_INVALID && (id & kTempId)) id = base + (id & ~kTempId);
+        __syncwarp();
     }
     if (lane < loaded) { if (LOCAL) M.cluster[lo + lane] = id; else __stcg(a.cluster + lo + lane, id); }
     if (LOCAL) __threadfence_block(); else __threadfence();
@@ -512,14 +548,18 @@ __global__ void __launch_bounds__(C, NX_PLOC_MINB) hploc2_kernel(PlocArgs a, con
 }
 
 // Global phase of the two-phase builder: the one-phase protocol (hploc_kernel) started from the ranges the chunks could not finish.
+#ifndef NX_SEED_MINB
+#define NX_SEED_MINB 1
+#endif
 template <typename KeyT>
-__global__ void __launch_bounds__(kPlocBlock) hploc_seed_kernel(PlocArgs a, const KeyT* __restrict__ keys, uint32_t nSeeds)
+__global__ void __launch_bounds__(kPlocBlock, NX_SEED_MINB) hploc_seed_kernel(PlocArgs a, const KeyT* __restrict__ keys, uint32_t nSeeds)
 {
     __shared__ WarpTable tables[kPlocBlock / 32];
     WarpTable& tb = tables[threadIdx.x >> 5];
     ChunkMem<32>* none = nullptr;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = a.n;
-    uint32_t lo = i < nSeeds ? __ldg(a.seedLo + i) : NX_INVALID, hi = i < nSeeds ? __ldg(a.seedHi + i) : NX_INVALID, mid = 0;
+    // without a seed list every leaf is its own seed: the one-phase protocol with the shared-memory merge table
+    uint32_t lo = i < nSeeds ? (a.seedLo ? __ldg(a.seedLo + i) : i) : NX_INVALID, hi = i < nSeeds ? (a.seedHi ? __ldg(a.seedHi + i) : i) : NX_INVALID, mid = 0;
     bool climbing = lo != NX_INVALID;
     while (__ballot_sync(NX_FULL, climbing))
     {
@@ -592,7 +632,7 @@ __global__ void dp_parent_kernel(DpArgs a)
 }
 
 // Cost table: 8 floats per node (C(n, 1..7) and a pad), so a child's table is two LDG.128 and a node's two STG.128.
-__global__ void __launch_bounds__(128) dp_eval_kernel(DpArgs a)
+__global__ void __launch_bounds__(kDpBlock) dp_eval_kernel(DpArgs a)
 {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= a.n) return;
@@ -996,7 +1036,21 @@ struct StageTimer {
     float end() { if (!on) return 0.f; cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
-template <typename T> cudaError_t allocAsync(T** p, size_t count, cudaStream_t s) { return cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), s); }
+// Temporaries of a build.  Ordinary builds take them from the stream-ordered pool; a build issued by the scene set-up pipeline
+// (nxi_build_bvh8_async) takes them from its build stream's workspace by bumping a pointer - no driver call, nothing to free - and its
+// outputs from the scene's arena.
+template <typename T> cudaError_t allocAsync(nx_ctx* ctx, T** p, size_t count, cudaStream_t s, bool output = false)
+{
+    const size_t bytes = (sizeof(T) * (count ? count : 1) + 255) & ~(size_t)255;
+    nx_bump* b = output ? ctx->outArena : ctx->buildWs;
+    if (b) {
+        if (b->used + bytes > b->cap) return cudaErrorMemoryAllocation;
+        *p = (T*)(b->base + b->used); b->used += bytes;
+        return cudaSuccess;
+    }
+    return cudaMallocAsync((void**)p, bytes, s);
+}
+inline void freeAsync(nx_ctx* ctx, void* p, cudaStream_t s) { if (!ctx->buildWs) cudaFreeAsync(p, s); }
 
 struct Bvh2Result { float4* nodes = nullptr; nx_aabb bounds{}; };
 
@@ -1006,9 +1060,9 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
 {
     cudaStream_t s = ctx->stream;
     KeyT *keys = nullptr, *keysAlt = nullptr; uint32_t *order = nullptr, *orderAlt = nullptr, *parent = nullptr, *allocated = nullptr;
-    NX_CUDA(ctx, allocAsync(&keys, n, s)); NX_CUDA(ctx, allocAsync(&keysAlt, n, s));
-    NX_CUDA(ctx, allocAsync(&order, n, s)); NX_CUDA(ctx, allocAsync(&orderAlt, n, s));
-    NX_CUDA(ctx, allocAsync(&parent, n, s)); NX_CUDA(ctx, allocAsync(&allocated, 1, s));
+    NX_CUDA(ctx, allocAsync(ctx, &keys, n, s)); NX_CUDA(ctx, allocAsync(ctx, &keysAlt, n, s));
+    NX_CUDA(ctx, allocAsync(ctx, &order, n, s)); NX_CUDA(ctx, allocAsync(ctx, &orderAlt, n, s));
+    NX_CUDA(ctx, allocAsync(ctx, &parent, n, s)); NX_CUDA(ctx, allocAsync(ctx, &allocated, 1, s));
     NX_CUDA(ctx, cudaMemsetAsync(parent, 0xff, sizeof(uint32_t) * (size_t)n, s));
     NX_CUDA(ctx, cudaMemcpyAsync(allocated, &n, 4, cudaMemcpyHostToDevice, s));
 
@@ -1016,7 +1070,7 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
     uint32_t* sortHist = nullptr; uint32_t* sortStatus = nullptr;
     constexpr int kHistWords = SortShape<KeyT>::kPasses * 256 + SortShape<KeyT>::kPasses;     // histograms, then one tile counter per pass
     if (ownSort) {
-        NX_CUDA(ctx, allocAsync(&sortHist, (size_t)kHistWords, s)); NX_CUDA(ctx, allocAsync(&sortStatus, radix_sort_status_words<KeyT>(n), s));
+        NX_CUDA(ctx, allocAsync(ctx, &sortHist, (size_t)kHistWords, s)); NX_CUDA(ctx, allocAsync(ctx, &sortStatus, radix_sort_status_words<KeyT>(n), s));
         NX_CUDA(ctx, cudaMemsetAsync(sortHist, 0, sizeof(uint32_t) * kHistWords, s));
     }
     const int grid = (int)std::min<uint32_t>(div_up(n, kSetupBlock), (uint32_t)ctx->sm_count * 8u);
@@ -1032,42 +1086,49 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
     }
 
     // stable LSD radix sort over the same bit window as the reference (Setup.cu:74-78): [2,32) or [1,64)
-    cub::DoubleBuffer<KeyT> kb(keys, keysAlt); cub::DoubleBuffer<uint32_t> vb(order, orderAlt);
+    KeyT* sortedKeys = keys; uint32_t* sortedOrder = order;
     void* temp = nullptr;
     if (ownSort) {
         timer.begin();
         NX_CUDA(ctx, radix_sort_pairs<KeyT>(keys, order, keysAlt, orderAlt, n, sortHist, sortStatus, sortHist + SortShape<KeyT>::kPasses * 256, s));
         if (metrics) metrics->sort_ms = timer.end();
-        cudaFreeAsync(sortHist, s); cudaFreeAsync(sortStatus, s);
+        freeAsync(ctx, sortHist, s); freeAsync(ctx, sortStatus, s);
     } else {
+#ifdef NX_WITH_CUB
+        cub::DoubleBuffer<KeyT> kb(keys, keysAlt); cub::DoubleBuffer<uint32_t> vb(order, orderAlt);
         const int beginBit = sizeof(KeyT) == 4 ? 2 : 1, endBit = sizeof(KeyT) * 8;
         size_t tempBytes = 0;
         NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
-        NX_CUDA(ctx, cudaMallocAsync(&temp, tempBytes ? tempBytes : 1, s));
+        NX_CUDA(ctx, cudaMallocAsync(ctx, &temp, tempBytes ? tempBytes : 1, s));
         timer.begin();
         NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(temp, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
         if (metrics) metrics->sort_ms = timer.end();
+        sortedKeys = kb.Current(); sortedOrder = vb.Current();
+#else
+        NX_FAIL(ctx, NX_ERR_INVALID, "NX_SORT=0 needs a library built with -DNX_WITH_CUB (measurement builds only)");
+#endif
     }
 
-    PlocArgs pa; pa.nodes = nodes; pa.cluster = vb.Current(); pa.parent = parent; pa.allocated = allocated; pa.n = n; pa.seedLo = pa.seedHi = nullptr;
+    PlocArgs pa; pa.nodes = nodes; pa.cluster = sortedOrder; pa.parent = parent; pa.allocated = allocated; pa.n = n; pa.seedLo = pa.seedHi = nullptr;
     timer.begin();
-    if (ctx->hploc_mode == 0) hploc_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, kb.Current());
+    if (ctx->hploc_mode == 0) hploc_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, sortedKeys);
+    else if (ctx->hploc_mode == 2) hploc_seed_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, sortedKeys, n);
     else {
         constexpr uint32_t C = kPlocChunk;
         static bool attr = false;   // per function, not per context: a property of the loaded module
         if (!attr) { cudaFuncSetAttribute((const void*)hploc2_kernel<KeyT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChunkMem<C>)); attr = true; }
         const uint32_t chunks = div_up(n, C), nSeeds = 2 * chunks;
-        NX_CUDA(ctx, allocAsync(&pa.seedLo, nSeeds, s)); NX_CUDA(ctx, allocAsync(&pa.seedHi, nSeeds, s));
-        hploc2_kernel<KeyT, C><<<chunks, C, sizeof(ChunkMem<C>), s>>>(pa, kb.Current());
-        hploc_seed_kernel<KeyT><<<div_up(nSeeds, kPlocBlock), kPlocBlock, 0, s>>>(pa, kb.Current(), nSeeds);
-        cudaFreeAsync(pa.seedLo, s); cudaFreeAsync(pa.seedHi, s);
+        NX_CUDA(ctx, allocAsync(ctx, &pa.seedLo, nSeeds, s)); NX_CUDA(ctx, allocAsync(ctx, &pa.seedHi, nSeeds, s));
+        hploc2_kernel<KeyT, C><<<chunks, C, sizeof(ChunkMem<C>), s>>>(pa, sortedKeys);
+        hploc_seed_kernel<KeyT><<<div_up(nSeeds, kPlocBlock), kPlocBlock, 0, s>>>(pa, sortedKeys, nSeeds);
+        freeAsync(ctx, pa.seedLo, s); freeAsync(ctx, pa.seedHi, s);
     }
     if (metrics) metrics->bvh2_ms = timer.end();
     NX_CUDA(ctx, cudaGetLastError());
 
     if (temp) cudaFreeAsync(temp, s);
-    cudaFreeAsync(keys, s); cudaFreeAsync(keysAlt, s); cudaFreeAsync(order, s); cudaFreeAsync(orderAlt, s);
-    cudaFreeAsync(parent, s); cudaFreeAsync(allocated, s);
+    freeAsync(ctx, keys, s); freeAsync(ctx, keysAlt, s); freeAsync(ctx, order, s); freeAsync(ctx, orderAlt, s);
+    freeAsync(ctx, parent, s); freeAsync(ctx, allocated, s);
     return NX_OK;
 }
 
@@ -1082,8 +1143,8 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     StageTimer timer(s, metrics != nullptr);
 
     float4* nodes = nullptr; SceneKeys* dScene = nullptr; float* dSceneOut = nullptr;
-    NX_CUDA(ctx, allocAsync(&nodes, 2 * (size_t)(2 * (size_t)n - 1), s));
-    NX_CUDA(ctx, allocAsync(&dScene, 1, s)); NX_CUDA(ctx, allocAsync(&dSceneOut, 6, s));
+    NX_CUDA(ctx, allocAsync(ctx, &nodes, 2 * (size_t)(2 * (size_t)n - 1), s));
+    NX_CUDA(ctx, allocAsync(ctx, &dScene, 1, s)); NX_CUDA(ctx, allocAsync(ctx, &dSceneOut, 6, s));
     SceneKeys init; for (int k = 0; k < 3; k++) { init.lo[k] = 0xffffffffu; init.hi[k] = 0u; }
     NX_CUDA(ctx, cudaMemcpyAsync(dScene, &init, sizeof(init), cudaMemcpyHostToDevice, s));
 
@@ -1102,16 +1163,16 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     {
         metrics->total_ms = metrics->scene_bounds_ms + metrics->morton_ms + metrics->sort_ms + metrics->bvh2_ms;
         NX_CUDA(ctx, cudaStreamSynchronize(s));
-        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(&dCost, 1, s));
+        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(ctx, &dCost, 1, s));
         NX_CUDA(ctx, cudaMemsetAsync(dCost, 0, 8, s));
         Box sb; sb.lo = v3(out->bounds.bmin[0], out->bounds.bmin[1], out->bounds.bmin[2]); sb.hi = v3(out->bounds.bmax[0], out->bounds.bmax[1], out->bounds.bmax[2]);
         bvh2_cost_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(nodes, 2 * n - 1, sb, dCost);
         double cost = 0; NX_CUDA(ctx, cudaMemcpyAsync(&cost, dCost, 8, cudaMemcpyDeviceToHost, s));
         NX_CUDA(ctx, cudaStreamSynchronize(s));
         metrics->bvh2_cost = (float)cost;
-        cudaFreeAsync(dCost, s);
+        freeAsync(ctx, dCost, s);
     }
-    cudaFreeAsync(dScene, s); cudaFreeAsync(dSceneOut, s);
+    freeAsync(ctx, dScene, s); freeAsync(ctx, dSceneOut, s);
     // BuildBVH8 continues on the same stream and synchronises once at its end: out->bounds is valid from then on
     if (finalSync) NX_CUDA(ctx, cudaStreamSynchronize(s));
     NX_CUDA(ctx, cudaGetLastError());
@@ -1133,10 +1194,10 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
 
     const size_t cap = ((size_t)4 * n - 1 + 6) / 7;   // worst case node count (BVHBuilder.cpp:184-186)
     CollapseArgs ca; ca.n2 = b2.nodes; ca.n = n; ca.dpDec = nullptr;
-    NX_CUDA(ctx, allocAsync(&ca.n8, 5 * cap, s));
-    NX_CUDA(ctx, allocAsync(&ca.primIdx, n, s));
-    NX_CUDA(ctx, allocAsync(&ca.bvh2Of, cap, s));
-    if (asyncCounters) ca.counters = asyncCounters; else NX_CUDA(ctx, allocAsync(&ca.counters, 5, s));
+    NX_CUDA(ctx, allocAsync(ctx, &ca.n8, 5 * cap, s, /*output=*/true));
+    NX_CUDA(ctx, allocAsync(ctx, &ca.primIdx, n, s, /*output=*/true));
+    NX_CUDA(ctx, allocAsync(ctx, &ca.bvh2Of, cap, s));
+    if (asyncCounters) ca.counters = asyncCounters; else NX_CUDA(ctx, allocAsync(ctx, &ca.counters, 5, s));
     const uint32_t initCounters[5] = {1u, 0u, 0u, 0u, 0u}, root2 = 2 * n - 2;
     NX_CUDA(ctx, cudaMemcpyAsync(ca.counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, s));
     NX_CUDA(ctx, cudaMemcpyAsync(ca.bvh2Of, &root2, 4, cudaMemcpyHostToDevice, s));
@@ -1150,13 +1211,13 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         if (2ull * n - 1 > 0x0fffffffull) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH8: the SAH-optimal collapse packs node ids into 28 bits (n = %u)", n);
         dp.n2 = b2.nodes; dp.n = n;
         dp.maxLeafPrims = cfg->max_leaf_prims >= 1 && cfg->max_leaf_prims <= 3 ? (uint32_t)cfg->max_leaf_prims : 3u;   // P_MAX, BVH8Builder.h:9
-        NX_CUDA(ctx, allocAsync(&dp.parent, 2 * (size_t)n - 1, s));
-        NX_CUDA(ctx, allocAsync(&dp.arrived, n, s));
-        NX_CUDA(ctx, allocAsync(&dp.cost, 8 * (2 * (size_t)n - 1), s));
-        NX_CUDA(ctx, allocAsync(&dp.dec, 2 * (size_t)n - 1, s));
+        NX_CUDA(ctx, allocAsync(ctx, &dp.parent, 2 * (size_t)n - 1, s));
+        NX_CUDA(ctx, allocAsync(ctx, &dp.arrived, n, s));
+        NX_CUDA(ctx, allocAsync(ctx, &dp.cost, 8 * (2 * (size_t)n - 1), s));
+        NX_CUDA(ctx, allocAsync(ctx, &dp.dec, 2 * (size_t)n - 1, s));
         NX_CUDA(ctx, cudaMemsetAsync(dp.parent, 0xff, 4 * (2 * (size_t)n - 1), s));
         dp_parent_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp);
-        dp_eval_kernel<<<div_up(n, 128u), 128, 0, s>>>(dp);
+        dp_eval_kernel<<<div_up(n, (uint32_t)kDpBlock), kDpBlock, 0, s>>>(dp);
         ca.dpDec = dp.dec;
     }
     if (n == 1) single_leaf_kernel<<<1, 1, 0, s>>>(ca);
@@ -1176,12 +1237,12 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         void* args[] = {&ca};
         NX_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCollapseBlock), args, 0, s));
     }
-    if (optimal) { cudaFreeAsync(dp.parent, s); cudaFreeAsync(dp.arrived, s); cudaFreeAsync(dp.cost, s); cudaFreeAsync(dp.dec, s); }
+    if (optimal) { freeAsync(ctx, dp.parent, s); freeAsync(ctx, dp.arrived, s); freeAsync(ctx, dp.cost, s); freeAsync(ctx, dp.dec, s); }
     if (metrics) { metrics->bvh8_ms = timer.end(); metrics->total_ms += metrics->bvh8_ms; }
     if (asyncCounters) {
         NX_CUDA(ctx, cudaGetLastError());
         out->nodes = (nx_bvh8_node*)ca.n8; out->node_count = 0; out->prim_idx = ca.primIdx; out->prim_count = n;
-        cudaFreeAsync(b2.nodes, s); cudaFreeAsync(ca.bvh2Of, s);
+        freeAsync(ctx, b2.nodes, s); freeAsync(ctx, ca.bvh2Of, s);
         return NX_OK;
     }
     uint32_t counters[2] = {0, 0};
@@ -1193,7 +1254,7 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     out->nodes = (nx_bvh8_node*)ca.n8; out->node_count = counters[0]; out->prim_idx = ca.primIdx; out->prim_count = n; out->bounds = b2.bounds;
     if (metrics)
     {
-        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(&dCost, 2, s));
+        double* dCost = nullptr; NX_CUDA(ctx, allocAsync(ctx, &dCost, 2, s));
         NX_CUDA(ctx, cudaMemsetAsync(dCost, 0, 16, s));
         Box sb; sb.lo = v3(b2.bounds.bmin[0], b2.bounds.bmin[1], b2.bounds.bmin[2]); sb.hi = v3(b2.bounds.bmax[0], b2.bounds.bmax[1], b2.bounds.bmax[2]);
         bvh8_cost_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(ca.n8, counters[0], sb, dCost);
@@ -1201,9 +1262,9 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         NX_CUDA(ctx, cudaStreamSynchronize(s));
         metrics->bvh8_cost = (float)cost[0];
         metrics->avg_children_per_node = (float)(cost[1] / (double)counters[0]);   // = (n + nodes - 1) / nodes with one primitive per leaf
-        cudaFreeAsync(dCost, s);
+        freeAsync(ctx, dCost, s);
     }
-    cudaFreeAsync(b2.nodes, s); cudaFreeAsync(ca.bvh2Of, s); cudaFreeAsync(ca.counters, s);
+    freeAsync(ctx, b2.nodes, s); freeAsync(ctx, ca.bvh2Of, s); freeAsync(ctx, ca.counters, s);
     NX_CUDA(ctx, cudaStreamSynchronize(s));
     return NX_OK;
 }
@@ -1222,13 +1283,23 @@ int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, in
 }
 
 // The same build issued on `stream` without any host synchronisation (scene set-up pipeline, scene.cu).
-int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out)
+// ws: the build stream's workspace (temporaries; reset here - builds on one stream run one after the other), outputs: where the CWBVH8
+// nodes and the leaf order go (the scene's arena).
+int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out,
+                         nx_bump* ws, nx_bump* outputs)
 {
     nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed; cfg.collapse = ctx->scene_collapse;
     cfg.max_leaf_prims = primType ? ctx->scene_max_leaf_prims : 1;
     StreamSwap swap(ctx, stream);
-    return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out, dCounters);
+    if (ws) ws->used = 0;
+    ctx->buildWs = ws; ctx->outArena = outputs;
+    const int rc = build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out, dCounters);
+    ctx->buildWs = nullptr; ctx->outArena = nullptr;
+    return rc;
 }
+// upper bound of the temporaries of one build of n primitives (bytes): BVH2 nodes 64n, keys and order 2 x 12n, parent 4n, sort status,
+// work map 2.3n, C(n, i) tables 2n x (32 + 8 + 4) + 4n, plus alignment slack per array
+size_t nxi_build_workspace_bytes(uint32_t n) { return (size_t)n * 200u + (1u << 20); }
 
 extern "C" {
 

@@ -70,8 +70,8 @@ int nx_ctx_create(int device, nx_ctx** out)
     }
     if (const char* t = std::getenv("NX_COLLAPSE_CTA")) ctx->collapse_cta = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_SORT")) ctx->sort_mode = std::atoi(t) != 0;
-    if (const char* t = std::getenv("NX_HPLOC")) ctx->hploc_mode = std::atoi(t) != 0;
-    if (const char* t = std::getenv("NX_TRACE_MODE")) ctx->trace_mode = (std::strcmp(t, "lane") == 0 || std::strcmp(t, "0") == 0) ? 0 : (std::strcmp(t, "duo") == 0 || std::strcmp(t, "2") == 0) ? 2 : 1;
+    if (const char* t = std::getenv("NX_HPLOC")) ctx->hploc_mode = std::atoi(t);
+    if (const char* t = std::getenv("NX_TRACE_MODE")) ctx->trace_mode = (std::strcmp(t, "duo") == 0 || std::strcmp(t, "2") == 0) ? 2 : (std::strcmp(t, "pool") == 0 || std::strcmp(t, "1") == 0) ? 1 : 0;
     if (const char* t = std::getenv("NX_POOL_TUNE")) {
         unsigned a = 0, b = 0, c = 0, d = 0;
         if (std::sscanf(t, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { ctx->pool_node = ctx->pool_node_any = a; ctx->pool_tri = ctx->pool_tri_any = b; ctx->pool_inst = ctx->pool_inst_any = c; ctx->pool_fetch = ctx->pool_fetch_any = d; }
@@ -97,6 +97,7 @@ void nx_ctx_destroy(nx_ctx* ctx)
     cudaFree(ctx->dOverflow); cudaFreeHost(ctx->hOverflow);
     for (int k = 0; k < ctx->buildStreamCount; k++) { cudaStreamSynchronize(ctx->buildStreams[k]); cudaStreamDestroy(ctx->buildStreams[k]); }
     if (ctx->stagePinned) cudaFreeHost(ctx->stagePinned);
+    for (nx_bump& b : ctx->buildWsStore) cudaFree(b.base);
     cudaFree(ctx->poolSpill[0]); cudaFree(ctx->poolSpill[1]);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream_aux);

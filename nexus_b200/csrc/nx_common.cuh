@@ -12,6 +12,9 @@
 #define NX_FULL 0xffffffffu
 #define NX_INVALID 0xffffffffu
 
+// bump allocator over one device allocation
+struct nx_bump { char* base = nullptr; size_t cap = 0, used = 0; };
+
 // ---------------------------------------------------------------------------------------------- context ----
 struct nx_ctx {
     int device = 0;
@@ -32,7 +35,7 @@ struct nx_ctx {
     size_t l2_persist_bytes = 0, l2_window_max = 0;
     // Traversal loop: 1 = ray pool (traverse_pool.cuh: 64 rays per warp in shared memory, lanes take rays by kind of work), 0 = one
     // ray per lane (traverse.cuh trace_loop).  Same hits either way.  NX_TRACE_MODE / nx_ctx_set_trace_mode.
-    int trace_mode = 1;
+    int trace_mode = 0;
     uint32_t pool_node = 28, pool_tri = 24, pool_inst = 16, pool_fetch = 16;           // ray-pool round thresholds in rays (NX_POOL_TUNE="n,t,i,f")
     uint32_t pool_node_any = 28, pool_tri_any = 24, pool_inst_any = 16, pool_fetch_any = 16;
     uint32_t stack_limit = 40;           // NX_STACK_TOTAL; nx_ctx_set_stack_limit lowers it in the overflow test
@@ -42,12 +45,15 @@ struct nx_ctx {
     int gridCache[16] = {0};             // persistent-grid sizes per kernel (occupancy x SM count of THIS context's device)
     int sort_mode = 1;                   // 1 = radix_sort.cuh (own onesweep sort), 0 = cub::DeviceRadixSort (measurement only); NX_SORT=0|1
     int collapse_cta = 1;                // 1 = single-block collapse for builds of up to 40k primitives (NX_COLLAPSE_CTA=0: always the grid-wide kernel)
-    int hploc_mode = 1;                  // 1 = two-phase H-PLOC (block-local phase in shared memory), 0 = one-phase kernel; NX_HPLOC=0|1
+    int hploc_mode = 2;                  // 0 = one-phase kernel, 1 = two-phase (block-local phase in shared memory + global phase), 2 = one-phase with the shared-memory merge table; NX_HPLOC
     // Scene set-up pipeline (scene.cu add_mesh): BLAS builds of successive meshes are issued round-robin on these streams without any
     // host synchronisation; host data reaches the device through a pinned staging ring.  nx_scene_update waits for all of them once.
     cudaStream_t buildStreams[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int buildStreamCount = 0;
     char* stagePinned = nullptr; size_t stageBytes = 0, stageUsed = 0;
+    nx_bump buildWsStore[8];             // one workspace per build stream (temporaries of the BLAS build running on it)
+    nx_bump* buildWs = nullptr;          // set while a workspace build is being issued (bvh_builder.cu allocAsync)
+    nx_bump* outArena = nullptr;         // where such a build puts its outputs
     // scratch reused by the builder's parity hook
     std::vector<uint64_t> dbg_codes;
 };

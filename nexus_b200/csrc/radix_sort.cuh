@@ -14,13 +14,22 @@
 #pragma once
 #include "nx_common.cuh"
 
-constexpr int kSortThreads = 256;
+#ifndef NX_SORT_THREADS
+#define NX_SORT_THREADS 256
+#endif
+#ifndef NX_SORT_MINB
+#define NX_SORT_MINB 5
+#endif
+#ifndef NX_SORT_ITEMS
+#define NX_SORT_ITEMS 16
+#endif
+constexpr int kSortThreads = NX_SORT_THREADS;      // a tile is kSortThreads x kItems pairs: the longer the tile, the longer the runs written per digit
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr uint32_t kSortFlagAgg = 1u << 30, kSortFlagPrefix = 2u << 30, kSortValueMask = (1u << 30) - 1u;
 
 template <typename KeyT> struct SortShape;
-template <> struct SortShape<uint32_t> { static constexpr int kItems = 16, kPasses = 4, kFirstBit = 2; };
-template <> struct SortShape<uint64_t> { static constexpr int kItems = 8, kPasses = 8, kFirstBit = 1; };
+template <> struct SortShape<uint32_t> { static constexpr int kItems = NX_SORT_ITEMS, kPasses = 4, kFirstBit = 2; };
+template <> struct SortShape<uint64_t> { static constexpr int kItems = NX_SORT_ITEMS / 2, kPasses = 8, kFirstBit = 1; };
 
 // digit of pass p: bits [first + 8p, first + 8p + 8) - the top pass simply sees zeros above the key's width
 template <typename KeyT> __device__ __forceinline__ uint32_t sort_digit(KeyT key, int pass)
@@ -47,19 +56,27 @@ __global__ void __launch_bounds__(256) sort_prefix_kernel(uint32_t* hist, int pa
     }
 }
 
+template <typename KeyT> struct SortSmem {
+    static constexpr int TILE = kSortThreads * SortShape<KeyT>::kItems;
+    uint32_t warpHist[kSortWarps][256];     // per warp: running digit counts while ranking, then exclusive offsets over the warps
+    uint32_t digitOffset[256];              // first position of the digit inside the sorted tile
+    uint32_t digitGlobal[256];              // global position of the digit's first element of this tile, minus digitOffset
+    uint32_t warpTotals[kSortWarps];
+    uint32_t tile;
+    KeyT keys[TILE];
+    uint32_t vals[TILE];
+};
+
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads) onesweep_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, KeyT* __restrict__ keysOut,
+__global__ void __launch_bounds__(kSortThreads, NX_SORT_MINB) onesweep_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, KeyT* __restrict__ keysOut,
                                                                 uint32_t* __restrict__ valsOut, uint32_t n, int pass, const uint32_t* __restrict__ digitBase,
                                                                 uint32_t* status, uint32_t* tileCounter)
 {
     constexpr int ITEMS = SortShape<KeyT>::kItems, TILE = kSortThreads * ITEMS;
-    __shared__ uint32_t warpHist[kSortWarps][256];     // per warp: running digit counts while ranking, then exclusive offsets over the warps
-    __shared__ uint32_t digitOffset[256];              // first position of the digit inside the sorted tile
-    __shared__ uint32_t digitGlobal[256];              // global position of the digit's first element of this tile, minus digitOffset
-    __shared__ uint32_t warpTotals[kSortWarps];
-    __shared__ KeyT sKeys[TILE];
-    __shared__ uint32_t sVals[TILE];
-    __shared__ uint32_t sTile;
+    extern __shared__ __align__(16) unsigned char sort_raw[];
+    SortSmem<KeyT>& S = *reinterpret_cast<SortSmem<KeyT>*>(sort_raw);
+    auto& warpHist = S.warpHist; auto& digitOffset = S.digitOffset; auto& digitGlobal = S.digitGlobal; auto& warpTotals = S.warpTotals;
+    KeyT* const sKeys = S.keys; uint32_t* const sVals = S.vals; uint32_t& sTile = S.tile;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
@@ -71,12 +88,11 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_kernel(const KeyT* __re
     const uint32_t valid = min((uint32_t)TILE, n - base);
 
     // ---- load, warp striped: item k of lane l in warp w is element w * 32 * ITEMS + k * 32 + l (coalesced, order preserving per round)
-    KeyT key[ITEMS]; uint32_t val[ITEMS]; uint32_t rank[ITEMS];
+    KeyT key[ITEMS]; uint32_t rank[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         const uint32_t i = warp * 32u * ITEMS + (uint32_t)k * 32u + lane;
         key[k] = i < valid ? __ldg(keysIn + base + i) : (KeyT)~(KeyT)0;      // padding sorts behind every real key of the tile
-        val[k] = i < valid ? __ldg(valsIn + base + i) : 0u;
     }
     // ---- rank inside the warp, round by round: lanes with the same digit find each other with match.any; the first of them reads
     // and advances the warp's counter of that digit
@@ -92,42 +108,49 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_kernel(const KeyT* __re
     }
     __syncthreads();
 
-    // ---- thread d owns digit d: offsets of the warps, the tile's count, and the look-back over earlier tiles
+    // ---- thread d (< 256) owns digit d: offsets of the warps, the tile's count, and the look-back over earlier tiles
+    const bool owner = tid < 256u;
     uint32_t count = 0;
+    if (owner) {
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) { const uint32_t t = warpHist[w][tid]; warpHist[w][tid] = count; count += t; }
-    uint32_t* const mine = status + (size_t)tile * 256u + tid;
-    __stcg(mine, (tile == 0u ? kSortFlagPrefix : kSortFlagAgg) | count);
+        for (int w = 0; w < kSortWarps; w++) { const uint32_t t = warpHist[w][tid]; warpHist[w][tid] = count; count += t; }
+    }
+    uint32_t* const mine = status + (size_t)tile * 256u + (tid & 255u);
+    if (owner) __stcg(mine, (tile == 0u ? kSortFlagPrefix : kSortFlagAgg) | count);
     // exclusive scan of the 256 counts -> position of each digit inside the sorted tile
     uint32_t scan = count;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NX_FULL, scan, o); if (lane >= (uint32_t)o) scan += t; }
     if (lane == 31u) warpTotals[warp] = scan;
     __syncthreads();
-    uint32_t before = 0;
-    for (uint32_t w = 0; w < warp; w++) before += warpTotals[w];
-    const uint32_t offset = before + scan - count;
-    digitOffset[tid] = offset;
-    uint32_t earlier = 0;
-    if (tile != 0u) {
-        for (int t = (int)tile - 1; t >= 0; t--) {
-            const volatile uint32_t* p = status + (size_t)t * 256u + tid;
-            uint32_t v;
-            do { v = *p; } while ((v & ~kSortValueMask) == 0u);
-            earlier += v & kSortValueMask;
-            if (v & kSortFlagPrefix) break;
+    if (owner) {
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; w++) before += warpTotals[w];
+        const uint32_t offset = before + scan - count;
+        digitOffset[tid] = offset;
+        uint32_t earlier = 0;
+        if (tile != 0u) {
+            for (int t = (int)tile - 1; t >= 0; t--) {
+                const volatile uint32_t* p = status + (size_t)t * 256u + tid;
+                uint32_t v;
+                do { v = *p; } while ((v & ~kSortValueMask) == 0u);
+                earlier += v & kSortValueMask;
+                if (v & kSortFlagPrefix) break;
+            }
+            __stcg(mine, kSortFlagPrefix | (earlier + count));
         }
-        __stcg(mine, kSortFlagPrefix | (earlier + count));
+        digitGlobal[tid] = __ldg(digitBase + pass * 256 + tid) + earlier - offset;
     }
-    digitGlobal[tid] = __ldg(digitBase + pass * 256 + tid) + earlier - offset;
     __syncthreads();
 
     // ---- scatter into the sorted tile in shared memory, then stream it out: consecutive threads write consecutive addresses
+    // the values are only read now (they were not needed for ranking, and sixteen fewer live registers is one more resident block)
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
+        const uint32_t i = warp * 32u * ITEMS + (uint32_t)k * 32u + lane;
         const uint32_t d = sort_digit<KeyT>(key[k], pass);
         const uint32_t pos = digitOffset[d] + warpHist[warp][d] + rank[k];
-        sKeys[pos] = key[k]; sVals[pos] = val[k];
+        sKeys[pos] = key[k]; sVals[pos] = i < valid ? __ldg(valsIn + base + i) : 0u;
     }
     __syncthreads();
 #pragma unroll
@@ -149,12 +172,14 @@ cudaError_t radix_sort_pairs(KeyT* keys, uint32_t* vals, KeyT* keysAlt, uint32_t
     constexpr int TILE = kSortThreads * SortShape<KeyT>::kItems, PASSES = SortShape<KeyT>::kPasses;
     static_assert(PASSES % 2 == 0, "the result must land in the primary buffers");
     const uint32_t tiles = (n + TILE - 1) / TILE;
+    static bool attr = false;   // a property of the loaded kernel, not of a context
+    if (!attr) { cudaFuncSetAttribute((const void*)onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<KeyT>)); attr = true; }
     sort_prefix_kernel<<<1, 256, 0, s>>>(hist, PASSES);
     for (int p = 0; p < PASSES; p++) {
         cudaError_t e = cudaMemsetAsync(status, 0, (size_t)tiles * 256u * sizeof(uint32_t), s);
         if (e != cudaSuccess) return e;
-        if (p & 1) onesweep_kernel<KeyT><<<tiles, kSortThreads, 0, s>>>(keysAlt, valsAlt, keys, vals, n, p, hist, status, counters + p);
-        else onesweep_kernel<KeyT><<<tiles, kSortThreads, 0, s>>>(keys, vals, keysAlt, valsAlt, n, p, hist, status, counters + p);
+        if (p & 1) onesweep_kernel<KeyT><<<tiles, kSortThreads, sizeof(SortSmem<KeyT>), s>>>(keysAlt, valsAlt, keys, vals, n, p, hist, status, counters + p);
+        else onesweep_kernel<KeyT><<<tiles, kSortThreads, sizeof(SortSmem<KeyT>), s>>>(keys, vals, keysAlt, valsAlt, n, p, hist, status, counters + p);
     }
     return cudaGetLastError();
 }

@@ -4,6 +4,8 @@
 #include "scene.cuh"
 #include <cmath>
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 namespace {
 
@@ -70,24 +72,40 @@ nx_aabb transformed_bounds(const float* m, const nx_aabb& b)
 }
 
 // Bounds of a mesh's vertices: the AABB (exact float min / max - the same values the builder's scene-bounds reduction produces) and the
-// bounding sphere around the AABB centre, radius = farthest vertex (double precision, padded).
+// bounding sphere around the AABB centre, radius = farthest vertex, padded for the float evaluation.  Written over blocks of four
+// vertices with twelve independent accumulators so that the host compiler vectorises it: the scalar double-precision version was the
+// largest single item of the scene set-up (0.46 s of 0.8 s for the 1,026 meshes of BASELINE configs[2]).
 void mesh_bounds_sphere(const nx_triangle* tris, uint32_t n, nx_aabb* box, double out[4])
 {
-    float lo[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, hi[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
     const float* v = (const float*)tris;
-    const size_t nv = (size_t)n * 3;
-    for (size_t i = 0; i < nv; i++) {
-        lo[0] = fminf(lo[0], v[3 * i]); lo[1] = fminf(lo[1], v[3 * i + 1]); lo[2] = fminf(lo[2], v[3 * i + 2]);
-        hi[0] = fmaxf(hi[0], v[3 * i]); hi[1] = fmaxf(hi[1], v[3 * i + 1]); hi[2] = fmaxf(hi[2], v[3 * i + 2]);
+    const size_t nf = (size_t)n * 9, blocks = nf / 12;
+    float lo[12], hi[12];
+    for (int k = 0; k < 12; k++) { lo[k] = 3.402823466e38f; hi[k] = -3.402823466e38f; }
+    for (size_t b = 0; b < blocks; b++) {
+        const float* p = v + 12 * b;
+        for (int k = 0; k < 12; k++) { lo[k] = p[k] < lo[k] ? p[k] : lo[k]; hi[k] = p[k] > hi[k] ? p[k] : hi[k]; }
     }
-    for (int k = 0; k < 3; k++) { box->bmin[k] = lo[k]; box->bmax[k] = hi[k]; out[k] = 0.5 * ((double)lo[k] + (double)hi[k]); }
-    double r2 = 0.0;
-    for (size_t i = 0; i < nv; i++) {
-        const double dx = v[3 * i] - out[0], dy = v[3 * i + 1] - out[1], dz = v[3 * i + 2] - out[2];
-        const double q = dx * dx + dy * dy + dz * dz;
-        r2 = q > r2 ? q : r2;
+    float l3[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, h3[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+    for (int k = 0; k < 12; k++) { l3[k % 3] = fminf(l3[k % 3], lo[k]); h3[k % 3] = fmaxf(h3[k % 3], hi[k]); }
+    for (size_t i = 12 * blocks; i < nf; i++) { l3[i % 3] = fminf(l3[i % 3], v[i]); h3[i % 3] = fmaxf(h3[i % 3], v[i]); }
+    for (int k = 0; k < 3; k++) { box->bmin[k] = l3[k]; box->bmax[k] = h3[k]; out[k] = 0.5 * ((double)l3[k] + (double)h3[k]); }
+    const float c[3] = {(float)out[0], (float)out[1], (float)out[2]};
+    float c12[12], r4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 12; k++) c12[k] = c[k % 3];
+    for (size_t b = 0; b < blocks; b++) {           // four vertices per block: twelve independent squares, four sums
+        const float* p = v + 12 * b;
+        float sq[12];
+        for (int k = 0; k < 12; k++) { const float d = p[k] - c12[k]; sq[k] = d * d; }
+        for (int j = 0; j < 4; j++) { const float d2 = sq[3 * j] + sq[3 * j + 1] + sq[3 * j + 2]; r4[j] = d2 > r4[j] ? d2 : r4[j]; }
     }
-    out[3] = std::sqrt(r2) * (1.0 + 1e-6);
+    float r2 = fmaxf(fmaxf(r4[0], r4[1]), fmaxf(r4[2], r4[3]));
+    for (size_t i = 12 * blocks; i + 2 < nf; i += 3) {
+        const float dx = v[i] - c[0], dy = v[i + 1] - c[1], dz = v[i + 2] - c[2];
+        r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+    }
+    // float evaluation: centre rounded to float (<= 2^-24 relative of the coordinates), each product and sum rounded once more
+    const double mag = std::fabs(out[0]) + std::fabs(out[1]) + std::fabs(out[2]);
+    out[3] = std::sqrt((double)r2) * (1.0 + 1e-5) + 1e-6 * mag + 1e-30;
 }
 
 // Largest singular value of the upper-left 3x3 of a row-major 4x4 (power iteration on A^T A, double): the factor by which the
@@ -264,7 +282,8 @@ void nx_scene_destroy(nx_scene* s)
     cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
     for (int k = 0; k < ctx->buildStreamCount; k++) cudaStreamSynchronize(ctx->buildStreams[k]);
     for (uint32_t* c : s->buildCounterChunks) cudaFree(c);
-    for (auto& m : s->meshes) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); cudaFree(m.dShadeRec); nx_bvh8_free(ctx, &m.bvh); }
+    for (auto& m : s->meshes) if (!m.arenaOwned) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); cudaFree(m.dShadeRec); nx_bvh8_free(ctx, &m.bvh); }
+    for (nx_bump& slab : s->arena) cudaFree(slab.base);
     if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
     if (s->dTop && ctx->l2_persist_bytes) {   // drop the window that points at this scene's top-level block
         cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
@@ -296,10 +315,31 @@ int nx_scene_set_material(nx_scene* s, uint32_t idx, const nx_material* m)
 
 struct PrebuiltBlas { const nx_bvh8_node* dNodes; uint32_t nodeCount; const uint32_t* dPrimIdx; nx_aabb bounds; };
 
+// NX_PROFILE_SETUP=1: host-side time per section of add_mesh, summed over the scene, printed when the builds are collected
+static double g_setupT[6] = {0, 0, 0, 0, 0, 0};
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Scene arena: every mesh's device arrays are carved out of large slabs (one cudaMalloc per 512 MB instead of six stream-ordered
+// allocations per mesh, whose pool has to grow by gigabytes the first time a large scene is loaded: 2.3 s against 0.8 s warm for the
+// 1,026-mesh scene).  Freed as a whole with the scene.
+static int arena_alloc(nx_scene* s, size_t bytes, void** out)
+{
+    nx_ctx* ctx = s->ctx;
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (s->arena.empty() || s->arena.back().used + bytes > s->arena.back().cap) {
+        nx_bump slab; slab.cap = std::max<size_t>((size_t)512 << 20, bytes);
+        NX_CUDA(ctx, cudaMalloc((void**)&slab.base, slab.cap));
+        s->arena.push_back(slab);
+    }
+    nx_bump& b = s->arena.back();
+    *out = b.base + b.used; b.used += bytes;
+    return NX_OK;
+}
+
 // Host data -> device through the context's pinned staging ring (no stream synchronisation unless the ring wraps).
 static int stage_upload(nx_ctx* ctx, cudaStream_t st, void* dst, const void* src, size_t bytes)
 {
-    constexpr size_t kRing = 256u << 20;
+    constexpr size_t kRing = 64u << 20;
     if (!ctx->stagePinned) {
         if (cudaMallocHost((void**)&ctx->stagePinned, kRing) != cudaSuccess) { cudaGetLastError(); ctx->stagePinned = nullptr; ctx->stageBytes = 0; }
         else ctx->stageBytes = kRing;
@@ -338,7 +378,13 @@ static int nxi_scene_flush_builds(nx_scene* s)
     if (!s->pendingBuilds) return NX_OK;
     nx_ctx* ctx = s->ctx;
     DeviceGuard guard(ctx->device);
+    const double tF = now_s();
     for (int k = 0; k < ctx->buildStreamCount; k++) NX_CUDA(ctx, cudaStreamSynchronize(ctx->buildStreams[k]));
+    if (std::getenv("NX_PROFILE_SETUP")) {
+        std::fprintf(stderr, "[nx setup] %.0f meshes: alloc %.3f s, staging %.3f s, bounds+sphere %.3f s, build issue %.3f s, final wait %.3f s\n",
+                     g_setupT[5], g_setupT[0], g_setupT[1], g_setupT[2], g_setupT[3], now_s() - tF);
+        for (double& v : g_setupT) v = 0;
+    }
     NX_CUDA(ctx, cudaGetLastError());
     std::vector<uint32_t> host(8 * 1024);
     for (size_t c = 0; c < s->buildCounterChunks.size(); c++) {
@@ -371,6 +417,7 @@ static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data
 {
     nx_ctx* ctx = s->ctx;
     DeviceGuard guard(ctx->device);
+    const double tA = now_s();
     const size_t meshIdx = s->meshes.size();
     cudaStream_t st = nullptr;
     int rc = build_stream(ctx, meshIdx, &st); if (rc) return rc;
@@ -379,22 +426,26 @@ static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data
         NX_CUDA(ctx, cudaMalloc((void**)&chunk, 4 * 8 * 1024));
         s->buildCounterChunks.push_back(chunk);
     }
-    HostMesh m; m.materialIdx = materialIdx;
+    HostMesh m; m.materialIdx = materialIdx; m.arenaOwned = true;
     uint32_t* counters = s->buildCounterChunks[meshIdx / 1024] + 8 * (meshIdx % 1024);
-    auto fail = [&](int code) { cudaFreeAsync(m.dTris, st); cudaFreeAsync(m.dTriData, st); cudaFreeAsync(m.dLeafTris, st); cudaFreeAsync(m.dShadeRec, st); return code; };
-    if (cudaMallocAsync((void**)&m.dTris, 36 * (size_t)n, st) != cudaSuccess || cudaMallocAsync((void**)&m.dTriData, 96 * (size_t)n, st) != cudaSuccess ||
-        cudaMallocAsync((void**)&m.dLeafTris, 48 * (size_t)n, st) != cudaSuccess || cudaMallocAsync((void**)&m.dShadeRec, 16 * NX_SHADE_REC_F4 * (size_t)n, st) != cudaSuccess) { ctx->error = "AddMesh: out of device memory"; cudaGetLastError(); return fail(NX_ERR_CUDA); }
+    auto fail = [&](int code) { return code; };               // arena memory goes back with the scene
+    rc = arena_alloc(s, 36 * (size_t)n, (void**)&m.dTris); if (rc) return rc;
+    rc = arena_alloc(s, 96 * (size_t)n, (void**)&m.dTriData); if (rc) return rc;
+    rc = arena_alloc(s, 48 * (size_t)n, (void**)&m.dLeafTris); if (rc) return rc;
+    rc = arena_alloc(s, 16 * NX_SHADE_REC_F4 * (size_t)n, (void**)&m.dShadeRec); if (rc) return rc;
+    const double tB = now_s();
     rc = stage_upload(ctx, st, m.dTris, tris, 36 * (size_t)n); if (rc) return fail(rc);
     const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
     if (data) { rc = stage_upload(ctx, st, m.dTriData, data, 96 * (size_t)n); if (rc) return fail(rc); }
     else default_tridata_kernel<<<grid, 256, 0, st>>>(m.dTris, n, m.dTriData);
     shade_record_kernel<<<grid, 256, 0, st>>>(m.dTris, m.dTriData, n, m.dShadeRec);
+    const double tC = now_s();
     nx_aabb box;
     mesh_bounds_sphere(tris, n, &box, m.sphere);
+    const double tD = now_s();
     if (pre) {
-        // same allocator as the builder's outputs, so nx_bvh8_free / scene destruction treat both kinds alike
-        if (cudaMallocAsync((void**)&m.bvh.nodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, st) != cudaSuccess ||
-            cudaMallocAsync((void**)&m.bvh.prim_idx, 4 * (size_t)n, st) != cudaSuccess) { ctx->error = "AddMesh: out of device memory"; cudaGetLastError(); return fail(NX_ERR_CUDA); }
+        rc = arena_alloc(s, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, (void**)&m.bvh.nodes); if (rc) return rc;
+        rc = arena_alloc(s, 4 * (size_t)n, (void**)&m.bvh.prim_idx); if (rc) return rc;
         // the caller's arrays were produced on other streams: the caller synchronises before handing them over (nx_scene_build_blas does)
         NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.nodes, pre->dNodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, cudaMemcpyDeviceToDevice, st));
         NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.prim_idx, pre->dPrimIdx, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -402,13 +453,27 @@ static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data
         NX_CUDA(ctx, cudaMemsetAsync(counters, 0, 32, st));
         m.pending = true; m.prebuilt = true; s->pendingBuilds++;   // Update waits for the copies and reads the index check's verdict
     } else {
-        rc = nxi_build_bvh8_async(ctx, st, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, counters, &m.bvh);
+        // temporaries: this build stream's workspace (grown when a larger mesh arrives; builds on one stream run one after the other);
+        // outputs: a region of the arena sized for the worst case (ceil((4n - 1) / 7) nodes, BVHBuilder.cpp:184-186)
+        nx_bump& ws = ctx->buildWsStore[meshIdx % (sizeof(ctx->buildWsStore) / sizeof(ctx->buildWsStore[0]))];
+        const size_t need = nxi_build_workspace_bytes(n);
+        if (ws.cap < need) {
+            NX_CUDA(ctx, cudaStreamSynchronize(st));
+            cudaFree(ws.base); ws.base = nullptr; ws.cap = 0;
+            NX_CUDA(ctx, cudaMalloc((void**)&ws.base, need + need / 2));
+            ws.cap = need + need / 2;
+        }
+        nx_bump outputs; outputs.cap = (((size_t)4 * n - 1 + 6) / 7) * sizeof(nx_bvh8_node) + 4 * (size_t)n + 1024;
+        rc = arena_alloc(s, outputs.cap, (void**)&outputs.base); if (rc) return rc;
+        rc = nxi_build_bvh8_async(ctx, st, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, counters, &m.bvh, &ws, &outputs);
         if (rc) return fail(rc);
         m.bvh.bounds = box;                                   // = the builder's scene bounds (exact min / max of the same floats)
         m.pending = true; s->pendingBuilds++;
     }
     leaf_triangles_kernel<<<grid, 256, 0, st>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris, pre ? counters + 2 : nullptr);
     NX_CUDA(ctx, cudaGetLastError());
+    const double tE = now_s();
+    g_setupT[0] += tB - tA; g_setupT[1] += tC - tB; g_setupT[2] += tD - tC; g_setupT[3] += tE - tD; g_setupT[5] += 1;
     s->meshes.push_back(m);
     return (int)s->meshes.size() - 1;
 }

@@ -61,6 +61,7 @@ struct HostMesh {
     nx_bvh8 bvh{};
     uint32_t materialIdx = 0;
     double sphere[4] = {0, 0, 0, 0};   // object-space bounding sphere of the vertices (centre, radius)
+    bool arenaOwned = false;           // all device arrays live in the scene's arena: nothing is freed per mesh
     bool prebuilt = false;             // BLAS supplied by the caller (nx_scene_add_mesh_prebuilt): indices validated on the device
     bool pending = false;              // BLAS build in flight on a build stream: node_count not known yet (flush_builds)
 };
@@ -99,6 +100,7 @@ struct nx_scene {
     uint32_t dMeshCount = 0;
     // scene set-up pipeline: device counters of the BLAS builds in flight (8 words per mesh, chunks of 1024 meshes)
     std::vector<uint32_t*> buildCounterChunks;
+    std::vector<nx_bump> arena;            // slabs holding every mesh's geometry, shading records and BLAS (freed with the scene)
     uint32_t pendingBuilds = 0;
 };
 
@@ -107,7 +109,9 @@ int nxi_scene_view(nx_scene* s, DSceneView* out);
 DCamera nxi_camera_to_device(const nx_camera& c, uint32_t w, uint32_t h);
 // bvh_builder.cu
 int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out);
-int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out);
+int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out,
+                         nx_bump* ws, nx_bump* outputs);
+size_t nxi_build_workspace_bytes(uint32_t n);
 // render.cu
 int nxi_trace_closest(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32_t n, nx_hit* dHits, float* outMs);
 int nxi_trace_any(nx_ctx* ctx, const TraceScene& sc, const nx_ray* dRays, uint32_t n, uint8_t* dOcc, float* outMs);

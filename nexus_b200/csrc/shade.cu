@@ -406,18 +406,17 @@ __global__ void resolve_rgba8_kernel(const float* __restrict__ accum, uint32_t c
         out[i] = display_pixel(f3(accum[3 * (size_t)i], accum[3 * (size_t)i + 1], accum[3 * (size_t)i + 2]), mode, gain);
 }
 
-int g_gridShade = 0;
-
 } // namespace
 
 int nxi_shade_grid(nx_ctx* ctx)
 {
-    if (g_gridShade) return g_gridShade;
+    int& cache = ctx->gridCache[12];     // per context: resident CTAs per SM x SM count of THIS context's device
+    if (cache) return cache;
     int perSm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void*)shade_kernel, kShadeBlock, 0);
     if (perSm < 1) perSm = 1;
-    g_gridShade = perSm * ctx->sm_count;
-    return g_gridShade;
+    cache = perSm * ctx->sm_count;
+    return cache;
 }
 void nxi_launch_generate(const DSceneView& sv, const WaveBuffers& wb, uint32_t frame, int grid, cudaStream_t s) { generate_kernel<<<grid, 256, 0, s>>>(sv, wb, frame); }
 void nxi_launch_shade(const DSceneView& sv, const WaveBuffers& wb, uint32_t bounce, uint32_t frame, int grid, cudaStream_t s)

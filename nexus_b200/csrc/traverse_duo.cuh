@@ -15,6 +15,7 @@
 // BOTH of its rays are blocked.
 #pragma once
 #include "traverse.cuh"
+#define NX_DUO_WATCHDOG 1   // debugging aid while the loop is new: a warp that iterates 2M times reports its state and leaves
 
 #ifndef NX_DUO_BLOCK
 #define NX_DUO_BLOCK 128
@@ -69,6 +70,7 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
 
     auto wantOf = [&]() -> uint32_t {            // the active ray's next step
         if (live) {
+            if (ANY_HIT && occluded) return DW_N;   // only waits to be retired: it must never count as wanting triangles (two such rays would swap for ever)
             if (ngroup.y & 0xff000000u) return DW_N;
             if (tgroup.y) return instDepth >= 0 ? DW_T : DW_X;
             return DW_N;                          // nothing pending: the pop at the top of the next iteration decides (treated as runnable)
@@ -138,8 +140,19 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
         }
     };
 
+#ifdef NX_DUO_WATCHDOG
+    unsigned long long wd = 0;
+#endif
     while (true)
     {
+#ifdef NX_DUO_WATCHDOG
+        if (++wd > (1ull << 21)) {
+            if (atomicAdd(sc.overflow, 1u << 16) == 0u || (wd & 0xffff) == 1)
+                printf("WD blk %d thr %d live %d dead %d bLive %d bWant %u cur %u sp %d inst %d ng %08x/%08x tg %08x/%08x ray %u hitT %g occ %d\n", blockIdx.x, threadIdx.x, (int)live, (int)dead, (int)bLive, bWant, cur, sp,
+                       instDepth, ngroup.x, ngroup.y, tgroup.x, tgroup.y, rayIdx, hitT, (int)occluded);
+            if (wd > (1ull << 21) + 2) break;
+        }
+#endif
         // ---------------------------------------------------------------- phase P: retire / pop (active ray) ----
         if (live && ((ANY_HIT && occluded) || (!(ngroup.y & 0xff000000u) && !tgroup.y)))
         {
@@ -248,17 +261,18 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
         }
 
         // ---------------------------------------------------------------- phase T: triangles (rounds until too few lanes) ----
+        bool swappedT = false;                                                    // at most one swap per lane and iteration in here
         while (true)
         {
             bool wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded);
             const bool nodeLeft = live && (ngroup.y & 0xff000000u) != 0u;
-            const bool parkedT = !wantT && !nodeLeft && bWant == DW_T;            // only the parked ray has triangles and the active one is blocked
+            const bool parkedT = !swappedT && !wantT && !nodeLeft && bWant == DW_T;   // only the parked ray has triangles and the active one is blocked
             const uint32_t mT = __ballot_sync(NX_FULL, wantT || parkedT);
             if (!mT) break;
             const uint32_t mN2 = __ballot_sync(NX_FULL, nodeLeft);
             if (__popc(mT) < tune.triLanes && mN2 != 0u) break;
             if (STATS) { wRT++; wLT += __popc(mT); }
-            if (parkedT) { swap(); wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded); }
+            if (parkedT) { swap(); swappedT = true; wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded); }
             if (wantT) test_triangle();
         }
     }

@@ -272,6 +272,36 @@ def compare_hits(ora, rays, got, want, rel=1e-5):
     return res
 
 
+def grazing_margin(desc, inst_records, ray, instance, prim):
+    """Float64 Moeller-Trumbore of one ray against one triangle of one instance (world space): returns (t, min(u, v, 1 - u - v)).
+    A margin within a few 1e-5 of zero means the ray passes through an edge or vertex of the triangle: whether it counts as a hit
+    is decided by the last bits of an fp32 evaluation, and two correct fp32 implementations (IEEE vs fast-math) may disagree."""
+    m = inst_records[instance, 8:72].copy().view(np.float32).reshape(4, 4).astype(np.float64)
+    mesh = int(inst_records[instance, 0:4].copy().view(np.uint32)[0])
+    tri = np.asarray(desc["meshes"][mesh]["triangles"], np.float64).reshape(-1, 3, 3)[prim]
+    w = tri @ m[:3, :3].T + m[:3, 3]
+    o = np.asarray(ray["origin"], np.float64).reshape(3); d = np.asarray(ray["direction"], np.float64).reshape(3)
+    e0, e1 = w[1] - w[0], w[2] - w[0]
+    pv = np.cross(d, e1); det = float(e0 @ pv)
+    if det == 0.0:
+        return 1e30, -1.0
+    s = o - w[0]; u = float(s @ pv) / det
+    qv = np.cross(s, e0); v = float(d @ qv) / det
+    return float(e1 @ qv) / det, min(u, v, 1.0 - u - v)
+
+
+def classify_hard(desc, scene, rays, got, want, hard_idx, margin=5e-5):
+    """Splits 'hard' id mismatches (compare_hits) into edge-grazing ones and real ones.  A mismatch is edge grazing when the NEARER of
+    the two reported hits - the one the other side did not see - grazes its triangle in float64 (|barycentric margin| <= margin)."""
+    inst = scene.ExportInstances()
+    graze, real = [], []
+    for i in hard_idx:
+        near = got if float(got["t"][i]) < float(want["t"][i]) else want
+        _, m = grazing_margin(desc, inst, rays[i], int(near["instance"][i]), int(near["prim"][i]))
+        (graze if abs(m) <= margin else real).append(int(i))
+    return graze, real
+
+
 def t_outliers(rays, got, want, rel=1e-5):
     """north_star's bar on hit distance is 1e-5 relative.  Hits whose distance is tiny compared with the coordinates involved
     (a ray starting almost on a surface) are ill-conditioned in fp32: the reference's own result is then 1e-5..1e-4 away

@@ -4,13 +4,15 @@ to the box, and against the CPU oracle otherwise.
  * configs[2]'s actual scene (1,024 BLASes, 10 M triangles, TLAS over 1,024 instances): one million primary rays plus one million
    incoherent secondary rays through the product's trace kernels and through the UNMODIFIED reference TraceKernel
    (PathTracer.cu:98-113 -> BVH8Trace, BVH8Traversal.cuh:149-324): primitive and instance ids exact except counted exact-distance
-   ties, hit distance within 1e-5 relative; a 200k subset against the CPU oracle bit for bit; both traversal loops (ray pool and
-   lane-bound) byte-identical.
+   ties and counted edge-grazing rays (a barycentric within 5e-5 of zero in float64, where IEEE and fast-math fp32 legitimately
+   disagree about the hit), hit distance within 1e-5 relative; a 200k subset against the CPU oracle bit for bit; the three traversal loops (one ray per
+   lane, two rays per lane, ray pool) byte-identical.
  * configs[3]: the 10 M and the 50 M triangle builds of the NexusBVH benchmark mesh canonical-tree-equal to the live reference's
    BuildBVH8 (BVHBuilder.cpp:173-267), compared through a hash of the canonical node array and leaf order when the arrays are large.
  * the traversal-stack overflow report (nx_ctx_set_stack_limit).
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -22,6 +24,7 @@ from nexus_b200 import scenes
 
 pytestmark = pytest.mark.gpu
 REL = 1e-5
+DEFAULT_MODE = os.environ.get("NX_TRACE_MODE", bench.DEFAULT_TRACE_MODE)     # what the session's context started with
 
 
 def secondary_rays(rays, hits, n, seed):
@@ -46,7 +49,7 @@ def config2(ctx):
 
 def test_config2_scene_hits_equal_reference_and_oracle(ctx, have_ref, config2):
     desc, res, scene = config2
-    assert len(desc["meshes"]) == 1024 and sum(len(m["triangles"]) for m in desc["meshes"]) >= 10_000_000
+    assert len(desc["meshes"]) >= 1024 and sum(len(m["triangles"]) for m in desc["meshes"]) >= 10_000_000
     o, d = scenes.camera_rays(desc["camera"], res)
     sel = np.random.default_rng(2).choice(len(o), 1_000_000, replace=False)
     primary = nx.make_rays(o[sel], d[sel])
@@ -55,27 +58,48 @@ def test_config2_scene_hits_equal_reference_and_oracle(ctx, have_ref, config2):
     assert len(secondary) >= 800_000
     ora = O.oracle_scene_from_product(desc, scene)
     for name, rays in (("primary", primary), ("secondary", secondary)):
-        ctx.SetTraceMode("pool")
-        got = scene.TraceClosest(rays)
-        ctx.SetTraceMode("lane")
-        lane = scene.TraceClosest(rays)
-        ctx.SetTraceMode("pool")
-        assert (got.view(np.uint8) == lane.view(np.uint8)).all(), name          # the two loops agree byte for byte
+        by_mode = {}
+        for mode in ("lane", "duo", "pool"):
+            ctx.SetTraceMode(mode)
+            by_mode[mode] = scene.TraceClosest(rays)
+        ctx.SetTraceMode(DEFAULT_MODE)
+        got = by_mode["lane"]
+        for mode in ("duo", "pool"):                                             # the three traversal loops agree byte for byte
+            assert (by_mode[mode].view(np.uint8) == got.view(np.uint8)).all(), (name, mode)
         sub = np.random.default_rng(4).choice(len(rays), 200_000, replace=False)
         want = ora.trace_closest(rays[sub])
         for f in ("prim", "instance"):
             assert (got[f][sub] == want[f]).all(), (name, f)
         for f in ("t", "u", "v"):
             assert (got[f][sub].view(np.uint32) == want[f].view(np.uint32)).all(), (name, f)
-        occ = scene.TraceAny(rays)
-        assert (occ.astype(bool) == (got["t"] < nx.MISS_T)).all(), name
+        for mode in ("lane", "duo", "pool"):
+            ctx.SetTraceMode(mode)
+            occ = scene.TraceAny(rays)
+            assert (occ.astype(bool) == (got["t"] < nx.MISS_T)).all(), (name, mode)
+        ctx.SetTraceMode(DEFAULT_MODE)
     if have_ref:
         O.ref_load_scene(desc, scene, res)
         for name, rays in (("primary", primary), ("secondary", secondary)):
             got = scene.TraceClosest(rays)
             live, _ = O.ref_trace(rays)
             cmp = O.compare_hits(ora, rays, got, live, rel=REL)
-            assert cmp["hard"] == 0, (name, cmp)
+            # At 10 M triangles and a million rays a handful of rays pass through a triangle EDGE within the last bits of an fp32
+            # barycentric: the IEEE evaluation here and the reference's fast-math one then disagree on whether that triangle is hit at
+            # all, and report different primitives at different distances.  Those are identified in float64 and counted; any other
+            # id mismatch is an error.
+            graze, real = O.classify_hard(desc, scene, rays, got, live, cmp["hard_idx"])
+            if real:      # diagnose the first few: both answers, their float64 margins, and the brute-force answer over every triangle
+                inst = scene.ExportInstances()
+                lines = []
+                for i in real[:6]:
+                    g, w = got[i], live[i]
+                    mg = O.grazing_margin(desc, inst, rays[i], int(g["instance"]), int(g["prim"])) if g["prim"] != 0xffffffff else None
+                    mw = O.grazing_margin(desc, inst, rays[i], int(w["instance"]), int(w["prim"])) if w["prim"] != 0xffffffff else None
+                    b = ora.trace_brute(rays[i:i + 1])[0]
+                    lines.append(f"ray {i}: ours t={g['t']:.7g} inst={g['instance']} prim={g['prim']} f64(t, margin)={mg} | ref t={w['t']:.7g} inst={w['instance']} prim={w['prim']} f64={mw}"
+                                 f" | brute t={b['t']:.7g} inst={b['instance']} prim={b['prim']}")
+                raise AssertionError(f"{name}: {len(real)} id mismatches that are neither ties nor edge grazing\n" + "\n".join(lines))
+            assert len(graze) <= 2e-4 * cmp["n"], (name, len(graze))
             assert cmp["tie"] <= 0.001 * cmp["n"], (name, cmp)
             bad, worse = O.t_outliers(rays, got, live, rel=REL)
             assert len(bad) <= 5e-3 * len(rays), (name, len(bad))
@@ -116,7 +140,7 @@ def test_stack_overflow_is_reported(ctx):
     rays = nx.make_rays(o, d)
     want = scene.TraceClosest(rays)
     try:
-        for mode in ("pool", "lane"):
+        for mode in ("pool", "lane", "duo"):
             ctx.SetTraceMode(mode)
             ctx.SetStackLimit(40)
             assert (scene.TraceClosest(rays).view(np.uint8) == want.view(np.uint8)).all()
@@ -129,14 +153,15 @@ def test_stack_overflow_is_reported(ctx):
             except nx.NexusError as e:
                 assert "stack overflow" in str(e)
     finally:
-        ctx.SetStackLimit(40); ctx.SetTraceMode("pool")
-    # a limit the scene certainly exceeds: forced through a deep chain of nested hits
+        ctx.SetStackLimit(40); ctx.SetTraceMode(DEFAULT_MODE)
+    # a limit the scene certainly exceeds: the ray-pool loop accepts limits down to 2 entries
     deep = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=512, nu=32, nv=32))
     s2 = scenes.build(ctx, deep, res)
     o, d = scenes.camera_rays(deep["camera"], res)
     rays = nx.make_rays(o, d)
     ok = s2.TraceClosest(rays)
     depth_needed = None
+    ctx.SetTraceMode("pool")
     try:
         for limit in range(39, 1, -1):        # the ray-pool loop accepts limits down to 2 entries (the lane-bound loop clamps at its 8 shared entries)
             ctx.SetStackLimit(limit)
@@ -148,7 +173,7 @@ def test_stack_overflow_is_reported(ctx):
                 depth_needed = limit + 1
                 break
     finally:
-        ctx.SetStackLimit(40)
+        ctx.SetStackLimit(40); ctx.SetTraceMode(DEFAULT_MODE)
     assert depth_needed is not None, "no stack limit down to 2 entries made this scene overflow"
     assert (s2.TraceClosest(rays).view(np.uint8) == ok.view(np.uint8)).all()    # the error state does not stick
     scene.close(); s2.close()
