@@ -233,7 +233,11 @@ def run_ours(args):
     t_scene = time.time()
     # N > 1: the BLAS builds are sharded (rank g builds meshes g, g + N, ...; one NCCL all-gather hands every rank every BLAS,
     # SURVEY.md 8(e)); the TLAS is built by every rank.  --replicated-build makes every rank build everything.
-    sharded = world > 1 and len(desc["meshes"]) > 1 and not args.replicated_build
+    # With instance merging (the default) the meshes of this scene end up in ONE world-space BLAS that every rank builds itself (a few
+    # milliseconds); --sharded-build turns merging off and shards the per-mesh BLAS builds over the ranks instead.
+    sharded = world > 1 and len(desc["meshes"]) > 1 and args.sharded_build
+    if sharded:
+        ctx.SetInstanceMerging(False)
     if world > 1:                                      # NCCL communicator set-up (lazy, ~1 s) is not a scene cost: do it before the clock starts
         dist.all_reduce(torch.zeros(1, device="cuda")); torch.cuda.synchronize()
         t_scene = time.time()
@@ -426,6 +430,21 @@ def run_ours(args):
     # ---- like for like (N = 1 only): the same frames on BLASes / TLAS collapsed by the reference GPU converter's rule, i.e. trees
     # identical to the ones the reference renders with.  The headline above uses the product default, the SAH-optimal collapse of
     # the reference's CPU BVH8Builder run on the GPU (same hits, fewer node visits); this line isolates what the trees contribute.
+    two_level = None
+    if world == 1 and not args.no_like_for_like:
+        # the product's trees WITHOUT instance merging: every mesh its own SAH-optimal BLAS under a TLAS of 1,026 instances (round 1's default)
+        ctx.SetInstanceMerging(False)
+        scene_tl = scenes.build(ctx, desc, res)
+        ctx.SetInstanceMerging(True)
+        pt.ResetFrameNumber()
+        pt.Render(scene_tl, frames=3, firstFrame=1); ctx.synchronize()
+        pt.ResetFrameNumber()
+        kk = min(K, 8)
+        pt.Render(scene_tl, frames=kk, firstFrame=first); ctx.synchronize()
+        s3 = pt.Stats()
+        two_level = {"what": "instance merging off: one SAH-optimal BLAS per mesh under a TLAS over all instances (clipped bounds, bounding-sphere cull)",
+                     "value": round((s3["extension_rays"] + s3["shadow_rays"]) / s3["device_ms"] / 1e3, 1), "unit": "Mrays/s", "ms_per_step": round(s3["device_ms"] / kk, 4), "steps": kk}
+        scene_tl.close()
     like = None
     if world == 1 and not args.no_like_for_like:
         ctx.SetSceneCollapse(nx.COLLAPSE_REFERENCE_GPU, 0)
@@ -456,16 +475,16 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "description": wl["desc"], "resolution": list(res), "path_length": desc["settings"].pathLength},
                 "notes": {"partition": f"sample partition: rank g renders frames [1+g*K, (g+1)*K]; NCCL all-reduce(sum) of float[3*W*H] accumulation ({'%.1f' % (12e-6 * res[0] * res[1])} MB)" if world > 1 else "single GPU",
-                          "bvh": "BLAS / TLAS: H-PLOC BVH2 + SAH-optimal CWBVH8 collapse (reference CPU BVH8Builder's C(n,i) table on the GPU, <= 2 primitives per leaf); same hits as the reference's trees, see like_for_like",
+                          "bvh": "H-PLOC BVH2 + SAH-optimal CWBVH8 collapse (reference CPU BVH8Builder's C(n,i) table on the GPU, <= 2 primitives per leaf); instances whose mesh is used once are transformed to world space and share one BLAS under the TLAS (instance merging); same hits as the reference's trees: two_level = merging off, like_for_like = NexusBVH-identical trees",
                           "l2": "per-step working set (ray/hit/state queues %.0f MB at this resolution + BVH/triangles) exceeds the 126 MB L2; no flush needed" % (212e-6 * res[0] * res[1]),
                           "traversal": ctx_trace_mode},
                 "spp_per_s": round(world * K / (ms_total * 1e-3), 2),
                 "rays_per_step": int(rays_all / (K * world)), "extension_rays": int(cnt[1]), "shadow_rays": int(cnt[2]),
                 "primary_Mrays_per_s": round(world * K * res[0] * res[1] / (ms_total * 1e-3) / 1e6, 1),
                 "reduce_ms": round(ms_reduce, 3), "wall_s": round(wall, 3), "scene_setup_s": round(t_scene, 2),
-                "blas_builds": f"sharded round-robin over {world} ranks + NCCL all-gather" if sharded else "every rank builds every BLAS",
+                "blas_builds": f"merging off, per-mesh BLAS builds sharded round-robin over {world} ranks + NCCL all-gather" if sharded else "every rank builds its own trees (merged world-space BLAS + the BLASes of shared / moved meshes)",
                 "mean_radiance": round(mean_radiance, 5),
-                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "like_for_like": like,
+                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "two_level": two_level, "like_for_like": like,
                 "reduce_check": reduce_check, "config5": config5}
         print(json.dumps(line), flush=True)
     pt.close(); scene.close(); ctx.close()
@@ -848,7 +867,7 @@ def main():
     ap.add_argument("--count-pass", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-like-for-like", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the BASELINE configs[4] block (HDR sky, 64 spp total)")
-    ap.add_argument("--replicated-build", action="store_true", help="N > 1: every rank builds every BLAS instead of sharding the builds")
+    ap.add_argument("--sharded-build", action="store_true", help="N > 1: instance merging off, per-mesh BLAS builds sharded over the ranks + NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

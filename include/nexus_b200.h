@@ -153,6 +153,11 @@ int nx_ctx_set_pool_tuning(nx_ctx* ctx, int any_hit, uint32_t node_rays, uint32_
  * nx_renderer_stats / nx_trace_* returns NX_ERR_STATE with the count in nx_last_error (the reference's 32-entry stack overflows
  * silently, BVH8Traversal.cuh:164).  Lowering the limit exists for the test of that report. */
 int nx_ctx_set_stack_limit(nx_ctx* ctx, uint32_t entries);
+/* Instance merging (default on; off in the NexusBVH-identical collapse mode): at Scene::Update the instances whose mesh no other instance
+ * uses, and that have not been moved since they were created, are transformed to world space and share ONE BLAS under the TLAS.  Hit
+ * records are unchanged (instance id, primitive id inside the mesh, world-space distance); an instance that is moved later gets a
+ * BLAS of its own, so moving things still only rebuilds the TLAS.  Applies to scenes updated after the call.  NX_MERGE_INSTANCES=0|1. */
+int nx_ctx_set_instance_merging(nx_ctx* ctx, int enabled);
 /* 0 switches the per-instance bounding-sphere test off (measurement only; results are identical either way). */
 int nx_ctx_set_sphere_cull(nx_ctx* ctx, int enabled);
 
@@ -225,6 +230,12 @@ int nx_scene_update(nx_scene* scene);
 int nx_scene_export_instances(nx_scene* scene, void* out160 /* n*160 */, uint32_t* out_count);
 int nx_scene_export_camera(nx_scene* scene, void* out88);
 int nx_scene_export_lights(nx_scene* scene, void* out52 /* n*52 */, uint32_t* out_count);
+/* Parity hooks for the merged BLAS (nx_ctx_set_instance_merging).  The TLAS is built over ENTRIES - the instances that keep a BLAS of
+ * their own, then the merged BLAS - and its prim_idx holds entry numbers: out_inst[e] = instance id of entry e, 0xffffffff = merged. */
+int nx_scene_export_tlas_entries(nx_scene* scene, uint32_t* out_inst, uint32_t* out_count);
+/* Handle of the merged BLAS and, per merged primitive, the world-space triangle it was built from (9 floats), its instance and its
+ * primitive id inside that instance's mesh.  out_count = 0 when the scene has no merged BLAS.  Any output pointer may be null. */
+int nx_scene_export_merged(nx_scene* scene, nx_bvh8* out_bvh, float* host_world_tris, uint32_t* host_inst, uint32_t* host_prim, uint32_t* out_count);
 int nx_scene_tlas(nx_scene* scene, nx_bvh8* out);                                       /* borrowed handle */
 /* The same records computed without a scene or a GPU (pure host arithmetic, the code paths nx_scene_add_instance and
  * nx_scene_export_camera use): MeshInstance::ToDevice (src/Scene/MeshInstance.h:36-66) and Camera::ToDevice (src/Scene/Camera.cpp:130-156). */

@@ -39,6 +39,8 @@ public:
     Context(const Context&) = delete; Context& operator=(const Context&) = delete;
     nx_ctx* handle() const { return h_; }
     void Synchronize() { check(nx_ctx_synchronize(h_), "synchronize"); }
+    // on (default): instances whose mesh no other instance uses, and that were never moved, share one world-space BLAS (same hits)
+    void SetInstanceMerging(bool enabled) { check(nx_ctx_set_instance_merging(h_, enabled ? 1 : 0), "SetInstanceMerging"); }
     int check(int rc, const char* what) const { if (rc < 0) throw Error(std::string(what) + ": " + nx_last_error(h_)); return rc; }
 private:
     nx_ctx* h_ = nullptr;

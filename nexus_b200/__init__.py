@@ -55,6 +55,11 @@ class Context:
         leaf; COLLAPSE_REFERENCE_GPU gives trees identical to the reference's NexusBVH)."""
         check(self._h, lib().nx_ctx_set_scene_collapse(self._h, C.c_int(int(collapse)), C.c_int(int(maxLeafPrims))), "SetSceneCollapse")
 
+    def SetInstanceMerging(self, enabled):
+        """On (default): instances whose mesh no other instance uses, and that were never moved, share one world-space BLAS.
+        Applies to scenes updated afterwards.  Hits are unchanged."""
+        check(self._h, lib().nx_ctx_set_instance_merging(self._h, C.c_int(int(enabled))), "SetInstanceMerging")
+
     def SetTraceMode(self, mode):
         """'pool' (default: 64 rays per warp in shared memory, lanes take rays by kind of work) or 'lane' (one ray per lane)."""
         m = {"lane": 0, "pool": 1, "duo": 2}.get(mode, mode)
@@ -658,6 +663,26 @@ class Scene:
         h = Bvh8()
         check(self.ctx._h, lib().nx_scene_tlas(self._h, C.byref(h)), "TLAS")
         return BVH8(self.ctx, h, owned=False)
+
+    def ExportTlasEntries(self):
+        """The TLAS is built over entries: the instances that keep a BLAS of their own, then the merged BLAS.  Returns the instance id
+        of every entry (0xffffffff for the merged BLAS); TLAS().ToHost()'s primitive indices are entry numbers."""
+        n = C.c_uint32(0)
+        check(self.ctx._h, lib().nx_scene_export_tlas_entries(self._h, None, C.byref(n)), "ExportTlasEntries")
+        out = np.zeros(max(n.value, 1), np.uint32)
+        check(self.ctx._h, lib().nx_scene_export_tlas_entries(self._h, _ptr(out), C.byref(n)), "ExportTlasEntries")
+        return out[:n.value]
+
+    def ExportMerged(self, triangles=True):
+        """The merged world-space BLAS (Context.SetInstanceMerging), or None: dict(bvh, triangles (n, 9), instance (n,), prim (n,))."""
+        n, h = C.c_uint32(0), Bvh8()
+        check(self.ctx._h, lib().nx_scene_export_merged(self._h, C.byref(h), None, None, None, C.byref(n)), "ExportMerged")
+        if not n.value:
+            return None
+        tris = np.empty((n.value, 9), np.float32) if triangles else None
+        inst, prim = np.empty(n.value, np.uint32), np.empty(n.value, np.uint32)
+        check(self.ctx._h, lib().nx_scene_export_merged(self._h, C.byref(h), _ptr(tris) if triangles else None, _ptr(inst), _ptr(prim), C.byref(n)), "ExportMerged")
+        return {"bvh": BVH8(self.ctx, h, owned=False), "triangles": tris, "instance": inst, "prim": prim}
 
     # reference device layouts, for the reference arm of parity tests
     def ExportInstances(self):

@@ -27,7 +27,7 @@ constexpr uint32_t kSearchRadius = 8;     // H-PLOC search radius (BinaryBuilder
 constexpr uint32_t kMergeThreshold = 16;  // clusters kept per LBVH range (BinaryBuilder.cu:10)
 constexpr int kSetupBlock = 256;
 #ifndef NX_PLOC_BLOCK
-#define NX_PLOC_BLOCK 128
+#define NX_PLOC_BLOCK 64
 #endif
 #ifndef NX_DP_BLOCK
 #define NX_DP_BLOCK 128
@@ -176,6 +176,8 @@ struct PlocArgs {
     uint32_t* allocated;  // number of BVH2 nodes handed out so far (starts at n)
     uint32_t n;
     uint32_t* seedLo; uint32_t* seedHi;   // two-phase builder: ranges left at the chunk borders (two per chunk, INVALID when unused)
+    uint8_t* height;      // optional (global merge path): height of every node above the leaves, saturated at 255 - lets the SAH-optimal
+                          // collapse evaluate its C(n, i) tables level by level instead of climbing with atomics (dp_wave_kernel)
 };
 
 // Highest differing bit between neighbouring keys, with the position as tie-break (Apetrei 2014; the 32-bit flavour
@@ -329,6 +331,7 @@ constexpr uint32_t kSlotDone = 0xfffffffeu;
 struct WarpTable {
     float4 a[40], b[40];   // per warp: a = {lo.xyz, hi.x}, b = {hi.y, hi.z, id, -}; 8 entries of slack for lane + radius
     float4 pa[32], pb[32]; // global path: the nodes a merge has created so far, with provisional ids (kTempId | k), written out at its end
+    uint32_t ph[32];       // ... and their heights
 };
 constexpr uint32_t kTempId = 0x80000000u;   // node ids stay below 2^31 (n <= 2^30)
 
@@ -369,14 +372,16 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
     uint32_t num = loaded;
 
     Box box; box.lo = v3(0.f, 0.f, 0.f); box.hi = v3(0.f, 0.f, 0.f);
+    uint32_t h = 0;                                       // height of the lane's cluster (global path with a.height only)
     if (lane < num) {
         float4 p, q;
         if (LOCAL) { p = M.node[id][0]; q = M.node[id][1]; } else { p = ld_cg4(a.nodes + 2 * (size_t)id); q = ld_cg4(a.nodes + 2 * (size_t)id + 1); }
+        if (!LOCAL && a.height) h = __ldcg(a.height + id);
         box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y);
     }
     __syncwarp();
     tb.a[lane] = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x);
-    tb.b[lane] = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), 0.f);
+    tb.b[lane] = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), __uint_as_float(h));
     __syncwarp();
 
     const uint32_t keep = isRoot ? 1u : kMergeThreshold;
@@ -422,7 +427,7 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
             const uint32_t k = base + __popc(ownerMask & lane_lt);
             const float4 n0 = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x), n1 = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), p1.z);
             if (LOCAL) { M.node[C + k][0] = n0; M.node[C + k][1] = n1; id = C + k; }
-            else { tb.pa[k] = n0; tb.pb[k] = n1; id = kTempId | k; }
+            else { h = min(255u, 1u + max(h, __float_as_uint(p1.w))); tb.pa[k] = n0; tb.pb[k] = n1; tb.ph[k] = h; id = kTempId | k; }
         }
         // compact: survivors are the pair owners and every cluster without a mutual partner, order preserved
         const bool stays = alive && (owner || !mutual);
@@ -431,14 +436,14 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
         if (stays) {
             const uint32_t rank = __popc(keepMask & lane_lt);
             tb.a[rank] = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x);
-            tb.b[rank] = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), 0.f);
+            tb.b[rank] = make_float4(box.hi.y, box.hi.z, __uint_as_float(id), __uint_as_float(h));
         }
         __syncwarp();
         num -= created;
         id = NX_INVALID;
         if (lane < num) {
             const float4 p = tb.a[lane], q = tb.b[lane];
-            box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y); id = __float_as_uint(q.z);
+            box.lo = v3(p.x, p.y, p.z); box.hi = v3(p.w, q.x, q.y); id = __float_as_uint(q.z); h = __float_as_uint(q.w);
         }
     }
     if (!LOCAL) {
@@ -454,6 +459,7 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
             if (r & kTempId) r = base + (r & ~kTempId);
             n1.z = __uint_as_float(l); n1.w = __uint_as_float(r);
             st_cg4(a.nodes + 2 * (size_t)(base + lane), n0); st_cg4(a.nodes + 2 * (size_t)(base + lane) + 1, n1);
+            if (a.height) a.height[base + lane] = (uint8_t)tb.ph[lane];
         }
         if (id != NX_INVALID && (id & kTempId)) id = base + (id & ~kTempId);
         __syncwarp();
@@ -632,58 +638,121 @@ __global__ void dp_parent_kernel(DpArgs a)
 }
 
 // Cost table: 8 floats per node (C(n, 1..7) and a pad), so a child's table is two LDG.128 and a node's two STG.128.
+// C(p, 1..7) and the decisions of inner node p from its children's finished tables.
+__device__ __forceinline__ void dp_eval_node(const DpArgs& a, uint32_t p)
+{
+    float4* const cost4 = reinterpret_cast<float4*>(a.cost);
+    const float4 q = __ldg(a.n2 + 2 * (size_t)p + 1);
+    const uint32_t L = __float_as_uint(q.z), R = __float_as_uint(q.w);
+    float cl[7], cr[7], c[7];
+    {
+        const float4 l0 = __ldcg(cost4 + 2 * (size_t)L), l1 = __ldcg(cost4 + 2 * (size_t)L + 1), r0 = __ldcg(cost4 + 2 * (size_t)R), r1 = __ldcg(cost4 + 2 * (size_t)R + 1);
+        cl[0] = l0.x; cl[1] = l0.y; cl[2] = l0.z; cl[3] = l0.w; cl[4] = l1.x; cl[5] = l1.y; cl[6] = l1.z;
+        cr[0] = r0.x; cr[1] = r0.y; cr[2] = r0.z; cr[3] = r0.w; cr[4] = r1.x; cr[5] = r1.y; cr[6] = r1.z;
+    }
+    const uint32_t tris = min(255u, (uint32_t)(__ldcg(a.dec + L) >> 56) + (uint32_t)(__ldcg(a.dec + R) >> 56));
+    const float area = half_area_ref(load_box2(a.n2, p));
+    unsigned long long dec = (unsigned long long)tris << 56;
+    // CDistribute(node, j) (:39-57): best split of j - 1 roots: k to the left child, j - 1 - k to the right
+    auto distribute = [&](int j, uint32_t& l, uint32_t& r) {
+        float best = 1.0e30f;
+#pragma unroll
+        for (int k = 0; k < 7; k++) if (k < j) { const float v = __fadd_rn(cl[k], cr[j - 1 - k]); if (v < best) { best = v; l = (uint32_t)k; r = (uint32_t)(j - 1 - k); } }
+        return best;
+    };
+    {   // i = 0: leaf or internal (:92-113)
+        uint32_t l = 0, r = 0;
+        const float internal = __fadd_rn(distribute(7, l, r), __fmul_rn(area, kCNode));
+        const float leafCost = tris > a.maxLeafPrims ? 1.0e30f : __fmul_rn(__fmul_rn(area, (float)tris), kCPrim);
+        if (leafCost < internal) { c[0] = leafCost; dec |= kDpLeaf; }
+        else { c[0] = internal; dec |= kDpInternal | (l << 2) | (r << 5); }
+    }
+#pragma unroll
+    for (int i = 1; i < 7; i++) {   // i roots + 1: distribute, or keep the solution with one root fewer (:115-131)
+        uint32_t l = 0, r = 0;
+        const float d = distribute(i, l, r);
+        if (d < c[i - 1]) { c[i] = d; dec |= (unsigned long long)(kDpDistribute | (l << 2) | (r << 5)) << (8 * i); }
+        else { c[i] = c[i - 1]; dec |= ((dec >> (8 * (i - 1))) & 0xffull) << (8 * i); }
+    }
+    __stcg(cost4 + 2 * (size_t)p, make_float4(c[0], c[1], c[2], c[3])); __stcg(cost4 + 2 * (size_t)p + 1, make_float4(c[4], c[5], c[6], 0.f));
+    __stcg(a.dec + p, dec);
+}
+__device__ __forceinline__ void dp_init_leaf(const DpArgs& a, uint32_t leaf)
+{
+    float4* const cost4 = reinterpret_cast<float4*>(a.cost);
+    const float c = __fmul_rn(__fmul_rn(half_area_ref(load_box2(a.n2, leaf)), 1.0f), kCPrim);     // CLeaf(node, 1), :31-37
+    __stcg(cost4 + 2 * (size_t)leaf, make_float4(c, c, c, c)); __stcg(cost4 + 2 * (size_t)leaf + 1, make_float4(c, c, c, 0.f));
+    __stcg(a.dec + leaf, 1ull << 56);                                                             // LEAF for every i, one primitive
+}
+
+// Bottom-up by climbing: a thread per leaf, the second thread to arrive at a node evaluates it (small inputs, and whenever the
+// builder recorded no node heights).
 __global__ void __launch_bounds__(kDpBlock) dp_eval_kernel(DpArgs a)
 {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= a.n) return;
-    float4* const cost4 = reinterpret_cast<float4*>(a.cost);
-    {
-        const float c = __fmul_rn(__fmul_rn(half_area_ref(load_box2(a.n2, leaf)), 1.0f), kCPrim);     // CLeaf(node, 1), :31-37
-        __stcg(cost4 + 2 * (size_t)leaf, make_float4(c, c, c, c)); __stcg(cost4 + 2 * (size_t)leaf + 1, make_float4(c, c, c, 0.f));
-        __stcg(a.dec + leaf, 1ull << 56);                                                             // LEAF for every i, one primitive
-    }
+    dp_init_leaf(a, leaf);
     uint32_t p = __ldcg(a.parent + leaf);
     while (p != NX_INVALID)
     {
         __threadfence();                                            // release this subtree's tables before announcing it
         if (atomicAdd(a.arrived + (p - a.n), 1u) == 0u) return;     // the sibling subtree is not finished: its thread continues
         // second to arrive: the sibling's tables are read with ld.cg (L2), which is where its release made them visible
-        const float4 q = __ldg(a.n2 + 2 * (size_t)p + 1);
-        const uint32_t L = __float_as_uint(q.z), R = __float_as_uint(q.w);
-        float cl[7], cr[7], c[7];
-        {
-            const float4 l0 = __ldcg(cost4 + 2 * (size_t)L), l1 = __ldcg(cost4 + 2 * (size_t)L + 1), r0 = __ldcg(cost4 + 2 * (size_t)R), r1 = __ldcg(cost4 + 2 * (size_t)R + 1);
-            cl[0] = l0.x; cl[1] = l0.y; cl[2] = l0.z; cl[3] = l0.w; cl[4] = l1.x; cl[5] = l1.y; cl[6] = l1.z;
-            cr[0] = r0.x; cr[1] = r0.y; cr[2] = r0.z; cr[3] = r0.w; cr[4] = r1.x; cr[5] = r1.y; cr[6] = r1.z;
-        }
-        const uint32_t tris = min(255u, (uint32_t)(__ldcg(a.dec + L) >> 56) + (uint32_t)(__ldcg(a.dec + R) >> 56));
-        const float area = half_area_ref(load_box2(a.n2, p));
-        unsigned long long dec = (unsigned long long)tris << 56;
-        // CDistribute(node, j) (:39-57): best split of j - 1 roots: k to the left child, j - 1 - k to the right
-        auto distribute = [&](int j, uint32_t& l, uint32_t& r) {
-            float best = 1.0e30f;
-#pragma unroll
-            for (int k = 0; k < 7; k++) if (k < j) { const float v = __fadd_rn(cl[k], cr[j - 1 - k]); if (v < best) { best = v; l = (uint32_t)k; r = (uint32_t)(j - 1 - k); } }
-            return best;
-        };
-        {   // i = 0: leaf or internal (:92-113)
-            uint32_t l = 0, r = 0;
-            const float internal = __fadd_rn(distribute(7, l, r), __fmul_rn(area, kCNode));
-            const float leafCost = tris > a.maxLeafPrims ? 1.0e30f : __fmul_rn(__fmul_rn(area, (float)tris), kCPrim);
-            if (leafCost < internal) { c[0] = leafCost; dec |= kDpLeaf; }
-            else { c[0] = internal; dec |= kDpInternal | (l << 2) | (r << 5); }
-        }
-#pragma unroll
-        for (int i = 1; i < 7; i++) {   // i roots + 1: distribute, or keep the solution with one root fewer (:115-131)
-            uint32_t l = 0, r = 0;
-            const float d = distribute(i, l, r);
-            if (d < c[i - 1]) { c[i] = d; dec |= (unsigned long long)(kDpDistribute | (l << 2) | (r << 5)) << (8 * i); }
-            else { c[i] = c[i - 1]; dec |= ((dec >> (8 * (i - 1))) & 0xffull) << (8 * i); }
-        }
-        __stcg(cost4 + 2 * (size_t)p, make_float4(c[0], c[1], c[2], c[3])); __stcg(cost4 + 2 * (size_t)p + 1, make_float4(c[4], c[5], c[6], 0.f));
-        __stcg(a.dec + p, dec);
+        dp_eval_node(a, p);
         p = __ldcg(a.parent + p);
     }
+}
+
+// Bottom-up by levels: H-PLOC records the height of every node it creates (PlocArgs::height); the inner nodes are counting-sorted by
+// height and one launch per height evaluates all nodes of that height at once - no atomics, no fences, no thread that climbs to the
+// root while its block idles.  The climb above takes 2.2 ms at 10 M triangles but 15 ms at 50 M.
+struct DpWaveArgs { const uint8_t* height; uint32_t* hist; uint32_t* cursor; uint32_t* order; };
+
+__global__ void dp_leaf_hist_kernel(DpArgs a, DpWaveArgs w)
+{
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * a.n - 1; i += gridDim.x * blockDim.x) {
+        if (i < a.n) dp_init_leaf(a, i);
+        else atomicAdd(&sh[w.height[i]], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(w.hist + threadIdx.x, sh[threadIdx.x]);
+}
+__global__ void dp_height_scan_kernel(DpWaveArgs w)     // one block of 256: cursor[h] = number of inner nodes lower than h
+{
+    __shared__ uint32_t warpSum[8];
+    const uint32_t v = w.hist[threadIdx.x];
+    uint32_t s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(NX_FULL, s, o); if (lane_id() >= (uint32_t)o) s += t; }
+    if (lane_id() == 31) warpSum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t k = 0; k < (threadIdx.x >> 5); k++) before += warpSum[k];
+    w.cursor[threadIdx.x] = before + s - v;
+}
+__global__ void dp_height_scatter_kernel(DpArgs a, DpWaveArgs w)
+{
+    uint32_t lane_lt; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
+    const uint32_t total = a.n - 1, stride = gridDim.x * blockDim.x;
+    for (uint32_t k0 = blockIdx.x * blockDim.x; k0 < total; k0 += stride) {      // whole warps iterate together
+        const uint32_t k = k0 + threadIdx.x;
+        const bool ok = k < total;
+        const uint32_t node = a.n + k, h = ok ? w.height[node] : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(NX_FULL, h);                     // neighbouring ids mostly share a height: one atomic per group
+        uint32_t base = 0;
+        const uint32_t leader = __ffs(peers) - 1;
+        if (ok && lane_id() == leader) base = atomicAdd(w.cursor + h, __popc(peers));
+        base = __shfl_sync(NX_FULL, base, leader);
+        if (ok) w.order[base + __popc(peers & lane_lt)] = node;
+    }
+}
+__global__ void __launch_bounds__(128) dp_wave_kernel(DpArgs a, const uint32_t* __restrict__ order, uint32_t first, uint32_t count)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) dp_eval_node(a, __ldg(order + first + k));
 }
 
 __device__ __forceinline__ uint32_t ceil_log2_biased(float x)   // biased exponent of the smallest power of two >= x
@@ -942,6 +1011,7 @@ __global__ void __launch_bounds__(kCollapseBlock, 4) collapse_kernel(CollapseArg
 // the 100k-triangle sphere: profiles/r01_ncu_collapse_build100k.md shows 77 % of the stall samples at grid.sync), and the launch is an
 // ordinary one, so the BLAS builds of a many-mesh scene overlap on the context's build streams instead of queueing as cooperative
 // launches.  Two barriers per level: one to finish the level's allocations, one to read its size before the next level allocates.
+constexpr uint32_t kDpWaveMinPrims = 200000u;   // below this the climb is as fast as ~40 launches
 constexpr int kCollapseCtaThreads = 1024;
 constexpr uint32_t kCollapseCtaMaxPrims = 40000u;   // widest level <= ~2 rounds of the block; beyond that the grid-wide kernel has more warps to hide the per-node latency
 template <bool OPT>
@@ -1052,11 +1122,11 @@ template <typename T> cudaError_t allocAsync(nx_ctx* ctx, T** p, size_t count, c
 }
 inline void freeAsync(nx_ctx* ctx, void* p, cudaStream_t s) { if (!ctx->buildWs) cudaFreeAsync(p, s); }
 
-struct Bvh2Result { float4* nodes = nullptr; nx_aabb bounds{}; };
+struct Bvh2Result { float4* nodes = nullptr; nx_aabb bounds{}; uint8_t* height = nullptr; /* optional: node heights for the level-wise C(n, i) pass */ };
 
 template <typename KeyT>
 int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, float* dSceneOut, nx_build_metrics* metrics, StageTimer& timer,
-                    std::vector<uint64_t>* dbgCodes)
+                    std::vector<uint64_t>* dbgCodes, uint8_t* heightOut)
 {
     cudaStream_t s = ctx->stream;
     KeyT *keys = nullptr, *keysAlt = nullptr; uint32_t *order = nullptr, *orderAlt = nullptr, *parent = nullptr, *allocated = nullptr;
@@ -1099,7 +1169,7 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
         const int beginBit = sizeof(KeyT) == 4 ? 2 : 1, endBit = sizeof(KeyT) * 8;
         size_t tempBytes = 0;
         NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
-        NX_CUDA(ctx, cudaMallocAsync(ctx, &temp, tempBytes ? tempBytes : 1, s));
+        NX_CUDA(ctx, cudaMallocAsync(&temp, tempBytes ? tempBytes : 1, s));
         timer.begin();
         NX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(temp, tempBytes, kb, vb, (int)n, beginBit, endBit, s));
         if (metrics) metrics->sort_ms = timer.end();
@@ -1109,7 +1179,7 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
 #endif
     }
 
-    PlocArgs pa; pa.nodes = nodes; pa.cluster = sortedOrder; pa.parent = parent; pa.allocated = allocated; pa.n = n; pa.seedLo = pa.seedHi = nullptr;
+    PlocArgs pa; pa.nodes = nodes; pa.cluster = sortedOrder; pa.parent = parent; pa.allocated = allocated; pa.n = n; pa.seedLo = pa.seedHi = nullptr; pa.height = heightOut;
     timer.begin();
     if (ctx->hploc_mode == 0) hploc_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, sortedKeys);
     else if (ctx->hploc_mode == 2) hploc_seed_kernel<KeyT><<<div_up(n, kPlocBlock), kPlocBlock, 0, s>>>(pa, sortedKeys, n);
@@ -1133,7 +1203,7 @@ int build_bvh2_keys(nx_ctx* ctx, uint32_t n, float4* nodes, SceneKeys* dScene, f
 }
 
 int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const nx_build_config* cfg, nx_build_metrics* metrics,
-               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1, bool finalSync = true, bool readBounds = true)
+               Bvh2Result* out, std::vector<uint64_t>* dbgCodes = nullptr, int forceBits64 = -1, bool finalSync = true, bool readBounds = true, bool wantHeights = false)
 {
     if (!dPrims || n == 0) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: empty primitive list");
     if (n > 0x7fffffffu / 2) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH2: primitive count %u exceeds 2^30", n);
@@ -1154,10 +1224,16 @@ int build_bvh2(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
     else leaf_bounds_kernel<6><<<grid, kSetupBlock, 0, s>>>((const float*)dPrims, n, nodes, dScene);
     if (metrics) metrics->scene_bounds_ms = timer.end();
 
+    uint8_t* height = nullptr;
+    if (wantHeights && ctx->hploc_mode == 2) {       // only the global merge path records heights
+        NX_CUDA(ctx, allocAsync(ctx, &height, 2 * (size_t)n - 1, s));
+        NX_CUDA(ctx, cudaMemsetAsync(height, 0, 2 * (size_t)n - 1, s));
+    }
     const bool bits64 = forceBits64 >= 0 ? forceBits64 != 0 : !(cfg && cfg->prioritize_speed);
-    int rc = bits64 ? build_bvh2_keys<uint64_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes)
-                    : build_bvh2_keys<uint32_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes);
+    int rc = bits64 ? build_bvh2_keys<uint64_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes, height)
+                    : build_bvh2_keys<uint32_t>(ctx, n, nodes, dScene, dSceneOut, metrics, timer, dbgCodes, height);
     if (rc) return rc;
+    out->height = height;
     if (readBounds) NX_CUDA(ctx, cudaMemcpyAsync(&out->bounds, dSceneOut, 24, cudaMemcpyDeviceToHost, s));
     if (metrics)
     {
@@ -1186,7 +1262,8 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
                uint32_t* asyncCounters = nullptr)
 {
     Bvh2Result b2;
-    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2, nullptr, -1, /*finalSync=*/false, /*readBounds=*/asyncCounters == nullptr);
+    const bool wantHeights = cfg && cfg->collapse == NX_COLLAPSE_SAH_OPTIMAL && n >= kDpWaveMinPrims && !asyncCounters && ctx->dp_waves;
+    int rc = build_bvh2(ctx, dPrims, n, primType, cfg, metrics, &b2, nullptr, -1, /*finalSync=*/false, /*readBounds=*/asyncCounters == nullptr, wantHeights);
     if (rc) return rc;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = ctx->stream;
@@ -1211,13 +1288,42 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         if (2ull * n - 1 > 0x0fffffffull) NX_FAIL(ctx, NX_ERR_INVALID, "BuildBVH8: the SAH-optimal collapse packs node ids into 28 bits (n = %u)", n);
         dp.n2 = b2.nodes; dp.n = n;
         dp.maxLeafPrims = cfg->max_leaf_prims >= 1 && cfg->max_leaf_prims <= 3 ? (uint32_t)cfg->max_leaf_prims : 3u;   // P_MAX, BVH8Builder.h:9
-        NX_CUDA(ctx, allocAsync(ctx, &dp.parent, 2 * (size_t)n - 1, s));
-        NX_CUDA(ctx, allocAsync(ctx, &dp.arrived, n, s));
         NX_CUDA(ctx, allocAsync(ctx, &dp.cost, 8 * (2 * (size_t)n - 1), s));
         NX_CUDA(ctx, allocAsync(ctx, &dp.dec, 2 * (size_t)n - 1, s));
-        NX_CUDA(ctx, cudaMemsetAsync(dp.parent, 0xff, 4 * (2 * (size_t)n - 1), s));
-        dp_parent_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp);
-        dp_eval_kernel<<<div_up(n, (uint32_t)kDpBlock), kDpBlock, 0, s>>>(dp);
+        bool waves = b2.height != nullptr;
+        if (waves)
+        {
+            // level by level (dp_wave_kernel): histogram of the heights, counting sort of the inner nodes, one launch per height.  The
+            // host needs the level sizes, so this path synchronises once; the set-up pipeline (asyncCounters) never records heights.
+            DpWaveArgs w; w.height = b2.height;
+            NX_CUDA(ctx, allocAsync(ctx, &w.hist, 512, s)); w.cursor = w.hist + 256;
+            NX_CUDA(ctx, allocAsync(ctx, &w.order, n, s));
+            NX_CUDA(ctx, cudaMemsetAsync(w.hist, 0, 4 * 512, s));
+            dp_leaf_hist_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp, w);
+            dp_height_scan_kernel<<<1, 256, 0, s>>>(w);
+            uint32_t hist[256];
+            NX_CUDA(ctx, cudaMemcpyAsync(hist, w.hist, sizeof(hist), cudaMemcpyDeviceToHost, s));
+            dp_height_scatter_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp, w);
+            NX_CUDA(ctx, cudaStreamSynchronize(s));
+            if (hist[0] != 0u) NX_FAIL(ctx, NX_ERR_STATE, "BuildBVH8: %u inner nodes without a height", hist[0]);
+            if (hist[255] != 0u) waves = false;          // a tree taller than 254 levels: the saturated heights no longer order the nodes; climb instead
+            uint32_t first = 0;
+            for (uint32_t h = 1; h < 255 && waves; h++) {
+                if (!hist[h]) continue;
+                dp_wave_kernel<<<div_up(hist[h], 128u), 128, 0, s>>>(dp, w.order, first, hist[h]);
+                first += hist[h];
+            }
+            if (waves && first != n - 1) NX_FAIL(ctx, NX_ERR_STATE, "BuildBVH8: %u of %u inner nodes have a height", first, n - 1);
+            freeAsync(ctx, w.hist, s); freeAsync(ctx, w.order, s);
+        }
+        if (!waves)
+        {
+            NX_CUDA(ctx, allocAsync(ctx, &dp.parent, 2 * (size_t)n - 1, s));
+            NX_CUDA(ctx, allocAsync(ctx, &dp.arrived, n, s));
+            NX_CUDA(ctx, cudaMemsetAsync(dp.parent, 0xff, 4 * (2 * (size_t)n - 1), s));
+            dp_parent_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(dp);
+            dp_eval_kernel<<<div_up(n, (uint32_t)kDpBlock), kDpBlock, 0, s>>>(dp);
+        }
         ca.dpDec = dp.dec;
     }
     if (n == 1) single_leaf_kernel<<<1, 1, 0, s>>>(ca);
@@ -1237,7 +1343,8 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
         void* args[] = {&ca};
         NX_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCollapseBlock), args, 0, s));
     }
-    if (optimal) { freeAsync(ctx, dp.parent, s); freeAsync(ctx, dp.arrived, s); freeAsync(ctx, dp.cost, s); freeAsync(ctx, dp.dec, s); }
+    if (optimal) { if (dp.parent) { freeAsync(ctx, dp.parent, s); freeAsync(ctx, dp.arrived, s); } freeAsync(ctx, dp.cost, s); freeAsync(ctx, dp.dec, s); }
+    if (b2.height) freeAsync(ctx, b2.height, s);
     if (metrics) { metrics->bvh8_ms = timer.end(); metrics->total_ms += metrics->bvh8_ms; }
     if (asyncCounters) {
         NX_CUDA(ctx, cudaGetLastError());

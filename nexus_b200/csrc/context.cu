@@ -6,8 +6,13 @@
 int nxi_check_overflow(nx_ctx* ctx)
 {
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream_aux));
-    NX_CUDA(ctx, cudaMemcpyAsync(ctx->hOverflow, ctx->dOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NX_CUDA(ctx, cudaMemcpyAsync(ctx->hOverflow, ctx->dOverflow, 8, cudaMemcpyDeviceToHost, ctx->stream));
     NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->hOverflow[1]) {      // rays with a non-finite origin or direction were answered as misses (traverse.cuh): counted, not an error
+        ctx->nonfinite_rays += ctx->hOverflow[1];
+        if (std::getenv("NX_DEBUG")) std::fprintf(stderr, "[nx] %u rays with non-finite origin / direction (answered as misses)\n", ctx->hOverflow[1]);
+        cudaMemsetAsync(ctx->dOverflow + 1, 0, 4, ctx->stream);
+    }
     if (const uint32_t dropped = *ctx->hOverflow) {
         cudaMemsetAsync(ctx->dOverflow, 0, 4, ctx->stream);
         NX_FAIL(ctx, NX_ERR_STATE, "traversal stack overflow: %u pushes beyond %u entries were refused, hits of the affected rays may be missing "
@@ -63,11 +68,14 @@ int nx_ctx_create(int device, nx_ctx** out)
         int a = 0, b = 0;
         if (std::sscanf(t, "%d,%d", &a, &b) >= 1) { ctx->scene_collapse = a; ctx->scene_max_leaf_prims = b; }
     }
+    if (const char* t = std::getenv("NX_MERGE_INSTANCES")) ctx->merge_instances = std::atoi(t) != 0;
+    if (const char* t = std::getenv("NX_MERGE_MIN_PRIMS")) ctx->merge_min_prims = (uint32_t)std::max(0, std::atoi(t));
     if (const char* t = std::getenv("NX_SCENE_BLAS_SPEED")) ctx->scene_blas_speed = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_TRACE_TUNE_ANY")) {
         unsigned a = 0, b = 0;
         if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri_any = a; ctx->tune_inst_any = b; }
     }
+    if (const char* t = std::getenv("NX_DP_WAVES")) ctx->dp_waves = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_COLLAPSE_CTA")) ctx->collapse_cta = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_SORT")) ctx->sort_mode = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_HPLOC")) ctx->hploc_mode = std::atoi(t);
@@ -80,10 +88,10 @@ int nx_ctx_create(int device, nx_ctx** out)
         unsigned a = 0, b = 0, c = 0, d = 0;
         if (std::sscanf(t, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { ctx->pool_node_any = a; ctx->pool_tri_any = b; ctx->pool_inst_any = c; ctx->pool_fetch_any = d; }
     }
-    if (cudaMalloc((void**)&ctx->dOverflow, 4) != cudaSuccess || cudaMemset(ctx->dOverflow, 0, 4) != cudaSuccess || cudaMallocHost((void**)&ctx->hOverflow, 4) != cudaSuccess) {
+    if (cudaMalloc((void**)&ctx->dOverflow, 8) != cudaSuccess || cudaMemset(ctx->dOverflow, 0, 8) != cudaSuccess || cudaMallocHost((void**)&ctx->hOverflow, 8) != cudaSuccess) {
         nx_ctx_destroy(ctx); return NX_ERR_CUDA;
     }
-    *ctx->hOverflow = 0;
+    ctx->hOverflow[0] = ctx->hOverflow[1] = 0;
     *out = ctx;
     return NX_OK;
 }
@@ -142,6 +150,13 @@ int nx_ctx_set_stack_limit(nx_ctx* ctx, uint32_t entries)
 {
     if (!ctx || entries < 2 || entries > 40) return NX_ERR_INVALID;
     ctx->stack_limit = entries;
+    return NX_OK;
+}
+
+int nx_ctx_set_instance_merging(nx_ctx* ctx, int enabled)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    ctx->merge_instances = enabled ? 1 : 0;
     return NX_OK;
 }
 

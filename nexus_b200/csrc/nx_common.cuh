@@ -30,6 +30,11 @@ struct nx_ctx {
     // reference GPU converter's trees on the 10M-triangle scene (25.5 -> 22.7 ms per 4K frame); nx_ctx_set_scene_collapse /
     // NX_SCENE_COLLAPSE="0,0" restore trees identical to NexusBVH's.
     int scene_collapse = NX_COLLAPSE_SAH_OPTIMAL, scene_max_leaf_prims = 2;
+    // Instances whose mesh is used once (and that have not been moved) are transformed to world space and share one BLAS: no instance
+    // entry, no per-object tree overlap.  Off in the NexusBVH-identical mode.  NX_MERGE_INSTANCES=0 / nx_ctx_set_instance_merging.
+    int merge_instances = 1;
+    uint32_t merge_min_prims = 0;        // meshes with fewer primitives stay instances of their own (0: every single-use mesh is merged; measured on BASELINE configs[2]:
+                                         // keeping the two-triangle ground and light out costs 30 %: each is then a scene-sized TLAS entry every ray enters) NX_MERGE_MIN_PRIMS
     int scene_blas_speed = 1;   // Mesh::Mesh builds its BLAS with prioritizeSpeed = true (32-bit Morton keys), N/Assets/Mesh.h:37
     // L2 set-aside for persisting accesses (top-level nodes + instance records of the scene being rendered); 0 = hints off
     size_t l2_persist_bytes = 0, l2_window_max = 0;
@@ -40,10 +45,12 @@ struct nx_ctx {
     uint32_t pool_node_any = 28, pool_tri_any = 24, pool_inst_any = 16, pool_fetch_any = 16;
     uint32_t stack_limit = 40;           // NX_STACK_TOTAL; nx_ctx_set_stack_limit lowers it in the overflow test
     uint32_t* dOverflow = nullptr;       // device counter of refused traversal-stack pushes (TraceScene::overflow)
-    uint32_t* hOverflow = nullptr;       // pinned mirror
+    uint32_t* hOverflow = nullptr;       // pinned mirror ([1]: rays with non-finite origin / direction, answered as misses)
+    unsigned long long nonfinite_rays = 0;
     void* poolSpill[2] = {nullptr, nullptr}; size_t poolSpillWarps[2] = {0, 0};       // global spill stacks of the two trace streams
     int gridCache[16] = {0};             // persistent-grid sizes per kernel (occupancy x SM count of THIS context's device)
     int sort_mode = 1;                   // 1 = radix_sort.cuh (own onesweep sort), 0 = cub::DeviceRadixSort (measurement only); NX_SORT=0|1
+    int dp_waves = 1;                    // 1 = C(n, i) tables level by level on builds of 200k+ primitives (NX_DP_WAVES=0: always the climb)
     int collapse_cta = 1;                // 1 = single-block collapse for builds of up to 40k primitives (NX_COLLAPSE_CTA=0: always the grid-wide kernel)
     int hploc_mode = 2;                  // 0 = one-phase kernel, 1 = two-phase (block-local phase in shared memory + global phase), 2 = one-phase with the shared-memory merge table; NX_HPLOC
     // Scene set-up pipeline (scene.cu add_mesh): BLAS builds of successive meshes are issued round-robin on these streams without any

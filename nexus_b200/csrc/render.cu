@@ -26,7 +26,7 @@ struct ClosestSink {
     __device__ __forceinline__ void finish(const TraceScene& sc, uint32_t rayIdx, uint32_t, float t, float u, float v, uint32_t prim, uint32_t slot, bool)
     {
         nx_hit h; h.t = t; h.u = u; h.v = v; h.prim = prim;
-        h.instance = slot != NX_INVALID ? __ldg(sc.tlasPrimIdx + slot) : NX_INVALID;
+        h.instance = hit_instance(sc, slot);
         hits[rayIdx] = h;
     }
 };

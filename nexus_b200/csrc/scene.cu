@@ -173,6 +173,47 @@ __global__ void shade_record_kernel(const float* __restrict__ tris, const float*
     }
 }
 
+// ---- merged BLAS: the triangles of every instance whose mesh nobody else uses, transformed to world space once ----
+struct BakeSrc { const float* tris; float m[12]; uint32_t first, count, inst, pad; };   // source j covers merged primitives [first, first + count)
+
+__device__ __forceinline__ uint32_t bake_source_of(const BakeSrc* __restrict__ src, uint32_t nSrc, uint32_t p)
+{
+    uint32_t lo = 0, hi = nSrc - 1;                                // the last source whose `first` is <= p
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (__ldg(&src[mid].first) <= p) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+__global__ void bake_triangles_kernel(const BakeSrc* __restrict__ src, uint32_t nSrc, uint32_t total, float* __restrict__ out, uint32_t* __restrict__ srcOf)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        const uint32_t j = bake_source_of(src, nSrc, p);
+        const BakeSrc S = src[j];
+        const float* t = S.tris + 9 * (size_t)(p - S.first);
+        float* o = out + 9 * (size_t)p;
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const float x = __ldg(t + 3 * v), y = __ldg(t + 3 * v + 1), z = __ldg(t + 3 * v + 2);
+#pragma unroll
+            for (int a = 0; a < 3; a++) o[3 * v + a] = __fmaf_rn(S.m[4 * a], x, __fmaf_rn(S.m[4 * a + 1], y, __fmaf_rn(S.m[4 * a + 2], z, S.m[4 * a + 3])));
+        }
+        srcOf[p] = j;
+    }
+}
+// leaf-ordered stream of the merged BLAS: {v0 | primitive id inside its mesh}, {v1 - v0 | instance id}, {v2 - v0 | 0}
+__global__ void merged_leaf_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ primIdx, uint32_t n, const uint32_t* __restrict__ srcOf,
+                                   const BakeSrc* __restrict__ src, float4* __restrict__ out)
+{
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(primIdx + k);
+        const uint32_t j = __ldg(srcOf + p);
+        const float* t = tris + 9 * (size_t)p;
+        const V3 a = v3(__ldg(t), __ldg(t + 1), __ldg(t + 2)), b = v3(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)), c = v3(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
+        const V3 e0 = b - a, e1 = c - a;
+        out[3 * (size_t)k] = make_float4(a.x, a.y, a.z, __uint_as_float(p - __ldg(&src[j].first)));
+        out[3 * (size_t)k + 1] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(__ldg(&src[j].inst)));
+        out[3 * (size_t)k + 2] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    }
+}
+
 // Default shading data when the caller passes none: flat geometric normal, zero tangents and texture coordinates.
 // World-space AABB of an instance's actual geometry: one block per instance transforms every vertex of its mesh with the
 // instance matrix (row-major 3x4) and reduces min / max.  out: 6 floats per instance.
@@ -250,7 +291,10 @@ int nxi_scene_view(nx_scene* s, DSceneView* v)
 {
     if (s->dirtyInstances || s->dirtyMaterials || s->dirtyLights || s->dirtyTextures) { int rc = nx_scene_update(s); if (rc) return rc; }
     std::memset(v, 0, sizeof(*v));
-    v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->tlas.prim_idx; v->trace.inst = s->dTravInst; v->trace.overflow = s->ctx->dOverflow;
+    v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->dSlotInst; v->trace.inst = s->dTravInst; v->trace.overflow = s->ctx->dOverflow;
+    v->trace.mergedSlot = s->mergedSlot;
+    v->trace.direct = (s->mergedSlot != NX_INVALID && s->tlasEntryInst.size() == 1) ? 1u : 0u;
+    v->trace.mNodes = (const float4*)s->merged.nodes; v->trace.mLtris = s->dMergedLeaf;
     v->shadeInst = s->dShadeInst; v->meshes = s->dMeshes; v->materials = s->dMaterials; v->lights = s->dLights;
     v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr; v->textures = s->dTextures;
     v->camera = nxi_camera_to_device(s->camera, s->width, s->height);
@@ -285,6 +329,8 @@ void nx_scene_destroy(nx_scene* s)
     for (auto& m : s->meshes) if (!m.arenaOwned) { cudaFree(m.dTris); cudaFree(m.dTriData); cudaFree(m.dLeafTris); cudaFree(m.dShadeRec); nx_bvh8_free(ctx, &m.bvh); }
     for (nx_bump& slab : s->arena) cudaFree(slab.base);
     if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
+    if (s->merged.nodes) nx_bvh8_free(ctx, &s->merged);
+    cudaFree(s->dMergedLeaf); cudaFree(s->dSlotInst);
     if (s->dTop && ctx->l2_persist_bytes) {   // drop the window that points at this scene's top-level block
         cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
         cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
@@ -409,10 +455,46 @@ static int nxi_scene_flush_builds(nx_scene* s)
     return NX_OK;
 }
 
-// Mesh::Mesh (N/Assets/Mesh.h:29-40).  With `pre` the BLAS is taken from the caller (device arrays, copied) instead of built here.
-// Nothing in here waits for the GPU: uploads go through the pinned ring, the BLAS build and the leaf-ordered triangle stream are
-// issued on one of the context's build streams, and Scene::Update (nx_scene_update) collects all of them at once.  A scene of 1,024
-// meshes took 4.25 s to set up with one synchronising build per mesh (BENCH_r01 scene_setup_s) for 0.36 s of GPU work.
+// Issues the BLAS build of one mesh on its build stream (no host synchronisation; nxi_scene_flush_builds collects the result).
+static int issue_blas_build(nx_scene* s, size_t meshIdx)
+{
+    nx_ctx* ctx = s->ctx;
+    HostMesh& m = s->meshes[meshIdx];
+    if (m.blasBuilt) return NX_OK;
+    const uint32_t n = m.bvh.prim_count;
+    cudaStream_t st = nullptr;
+    int rc = build_stream(ctx, meshIdx, &st); if (rc) return rc;
+    uint32_t* counters = s->buildCounterChunks[meshIdx / 1024] + 8 * (meshIdx % 1024);
+    rc = arena_alloc(s, 48 * (size_t)n, (void**)&m.dLeafTris); if (rc) return rc;
+    // temporaries: this build stream's workspace (grown when a larger mesh arrives; builds on one stream run one after the other);
+    // outputs: a region of the arena sized for the worst case (ceil((4n - 1) / 7) nodes, BVHBuilder.cpp:184-186)
+    nx_bump& ws = ctx->buildWsStore[meshIdx % (sizeof(ctx->buildWsStore) / sizeof(ctx->buildWsStore[0]))];
+    const size_t need = nxi_build_workspace_bytes(n);
+    if (ws.cap < need) {
+        NX_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaFree(ws.base); ws.base = nullptr; ws.cap = 0;
+        NX_CUDA(ctx, cudaMalloc((void**)&ws.base, need + need / 2));
+        ws.cap = need + need / 2;
+    }
+    nx_bump outputs; outputs.cap = (((size_t)4 * n - 1 + 6) / 7) * sizeof(nx_bvh8_node) + 4 * (size_t)n + 1024;
+    rc = arena_alloc(s, outputs.cap, (void**)&outputs.base); if (rc) return rc;
+    const nx_aabb box = m.bvh.bounds;                         // = the builder's scene bounds (exact min / max of the same floats)
+    rc = nxi_build_bvh8_async(ctx, st, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, counters, &m.bvh, &ws, &outputs);
+    if (rc) return rc;
+    m.bvh.bounds = box;
+    const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
+    leaf_triangles_kernel<<<grid, 256, 0, st>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris, nullptr);
+    NX_CUDA(ctx, cudaGetLastError());
+    m.blasBuilt = true; m.pending = true; s->pendingBuilds++;
+    return NX_OK;
+}
+
+// Mesh::Mesh (N/Assets/Mesh.h:29-40).  With `pre` the BLAS is taken from the caller (device arrays, copied) instead of built.
+// Nothing in here waits for the GPU: uploads go through the pinned ring on one of the context's build streams.  The BLAS itself is
+// built when it is first needed - by Scene::Update for the meshes that keep a BLAS of their own (the others end up in the scene's
+// merged world-space BLAS), or by a query (nx_scene_mesh_bvh) - again without waiting, all meshes of a scene pipelined over the build
+// streams and collected once.  A scene of 1,026 meshes took 4.25 s to set up with one synchronising build per mesh (BENCH_r01
+// scene_setup_s) for 0.36 s of GPU work.
 static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data* data, uint32_t n, uint32_t materialIdx, const PrebuiltBlas* pre)
 {
     nx_ctx* ctx = s->ctx;
@@ -428,49 +510,33 @@ static int add_mesh(nx_scene* s, const nx_triangle* tris, const nx_triangle_data
     }
     HostMesh m; m.materialIdx = materialIdx; m.arenaOwned = true;
     uint32_t* counters = s->buildCounterChunks[meshIdx / 1024] + 8 * (meshIdx % 1024);
-    auto fail = [&](int code) { return code; };               // arena memory goes back with the scene
     rc = arena_alloc(s, 36 * (size_t)n, (void**)&m.dTris); if (rc) return rc;
     rc = arena_alloc(s, 96 * (size_t)n, (void**)&m.dTriData); if (rc) return rc;
-    rc = arena_alloc(s, 48 * (size_t)n, (void**)&m.dLeafTris); if (rc) return rc;
     rc = arena_alloc(s, 16 * NX_SHADE_REC_F4 * (size_t)n, (void**)&m.dShadeRec); if (rc) return rc;
     const double tB = now_s();
-    rc = stage_upload(ctx, st, m.dTris, tris, 36 * (size_t)n); if (rc) return fail(rc);
+    rc = stage_upload(ctx, st, m.dTris, tris, 36 * (size_t)n); if (rc) return rc;
     const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
-    if (data) { rc = stage_upload(ctx, st, m.dTriData, data, 96 * (size_t)n); if (rc) return fail(rc); }
+    if (data) { rc = stage_upload(ctx, st, m.dTriData, data, 96 * (size_t)n); if (rc) return rc; }
     else default_tridata_kernel<<<grid, 256, 0, st>>>(m.dTris, n, m.dTriData);
     shade_record_kernel<<<grid, 256, 0, st>>>(m.dTris, m.dTriData, n, m.dShadeRec);
     const double tC = now_s();
     nx_aabb box;
     mesh_bounds_sphere(tris, n, &box, m.sphere);
     const double tD = now_s();
+    m.bvh.prim_count = n; m.bvh.bounds = box;
+    s->pendingBuilds++;                                        // the uploads: Update must wait for them even when it builds nothing
     if (pre) {
+        rc = arena_alloc(s, 48 * (size_t)n, (void**)&m.dLeafTris); if (rc) return rc;
         rc = arena_alloc(s, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, (void**)&m.bvh.nodes); if (rc) return rc;
         rc = arena_alloc(s, 4 * (size_t)n, (void**)&m.bvh.prim_idx); if (rc) return rc;
         // the caller's arrays were produced on other streams: the caller synchronises before handing them over (nx_scene_build_blas does)
         NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.nodes, pre->dNodes, sizeof(nx_bvh8_node) * (size_t)pre->nodeCount, cudaMemcpyDeviceToDevice, st));
         NX_CUDA(ctx, cudaMemcpyAsync(m.bvh.prim_idx, pre->dPrimIdx, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-        m.bvh.node_count = pre->nodeCount; m.bvh.prim_count = n; m.bvh.bounds = pre->bounds;
+        m.bvh.node_count = pre->nodeCount; m.bvh.bounds = pre->bounds;
         NX_CUDA(ctx, cudaMemsetAsync(counters, 0, 32, st));
-        m.pending = true; m.prebuilt = true; s->pendingBuilds++;   // Update waits for the copies and reads the index check's verdict
-    } else {
-        // temporaries: this build stream's workspace (grown when a larger mesh arrives; builds on one stream run one after the other);
-        // outputs: a region of the arena sized for the worst case (ceil((4n - 1) / 7) nodes, BVHBuilder.cpp:184-186)
-        nx_bump& ws = ctx->buildWsStore[meshIdx % (sizeof(ctx->buildWsStore) / sizeof(ctx->buildWsStore[0]))];
-        const size_t need = nxi_build_workspace_bytes(n);
-        if (ws.cap < need) {
-            NX_CUDA(ctx, cudaStreamSynchronize(st));
-            cudaFree(ws.base); ws.base = nullptr; ws.cap = 0;
-            NX_CUDA(ctx, cudaMalloc((void**)&ws.base, need + need / 2));
-            ws.cap = need + need / 2;
-        }
-        nx_bump outputs; outputs.cap = (((size_t)4 * n - 1 + 6) / 7) * sizeof(nx_bvh8_node) + 4 * (size_t)n + 1024;
-        rc = arena_alloc(s, outputs.cap, (void**)&outputs.base); if (rc) return rc;
-        rc = nxi_build_bvh8_async(ctx, st, m.dTris, n, 1, ctx->scene_blas_speed /* Mesh::Mesh: prioritizeSpeed = true */, counters, &m.bvh, &ws, &outputs);
-        if (rc) return fail(rc);
-        m.bvh.bounds = box;                                   // = the builder's scene bounds (exact min / max of the same floats)
-        m.pending = true; s->pendingBuilds++;
+        leaf_triangles_kernel<<<grid, 256, 0, st>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris, counters + 2);
+        m.blasBuilt = true; m.pending = true; m.prebuilt = true;   // Update waits for the copies and reads the index check's verdict
     }
-    leaf_triangles_kernel<<<grid, 256, 0, st>>>(m.dTris, m.bvh.prim_idx, n, m.dLeafTris, pre ? counters + 2 : nullptr);
     NX_CUDA(ctx, cudaGetLastError());
     const double tE = now_s();
     g_setupT[0] += tB - tA; g_setupT[1] += tC - tB; g_setupT[2] += tD - tC; g_setupT[3] += tE - tD; g_setupT[5] += 1;
@@ -513,7 +579,8 @@ int nx_scene_mesh_bounds(nx_scene* s, uint32_t meshIdx, nx_aabb* out)
 int nx_scene_mesh_bvh(nx_scene* s, uint32_t meshIdx, nx_bvh8* out)
 {
     if (!s || !out || meshIdx >= s->meshes.size()) return NX_ERR_INVALID;
-    { const int rc = nxi_scene_flush_builds(s); if (rc) return rc; }
+    DeviceGuard guard(s->ctx->device);
+    { int rc = issue_blas_build(s, meshIdx); if (rc) return rc; rc = nxi_scene_flush_builds(s); if (rc) return rc; }
     *out = s->meshes[meshIdx].bvh; return NX_OK;
 }
 
@@ -526,6 +593,7 @@ int nx_scene_add_instance_matrix(nx_scene* s, uint32_t meshIdx, int32_t material
     m4_inverse(m, inv);
     std::memcpy(inst.m, m.c, 64); std::memcpy(inst.inv, inv.c, 64);
     inst.bounds = transformed_bounds(inst.m, s->meshes[meshIdx].bvh.bounds);
+    s->meshes[meshIdx].useCount++;
     s->instances.push_back(inst); s->dirtyInstances = true; s->dirtyLights = true;
     return (int)s->instances.size() - 1;
 }
@@ -542,6 +610,7 @@ int nx_scene_set_instance_transform(nx_scene* s, uint32_t idx, const float pos[3
     M4 m = compose_trs(pos, rot, scale), inv; m4_inverse(m, inv);
     std::memcpy(inst.m, m.c, 64); std::memcpy(inst.inv, inv.c, 64);
     inst.bounds = transformed_bounds(inst.m, s->meshes[inst.meshIdx].bvh.bounds);
+    inst.dynamic = true;        // an instance that has been moved keeps a BLAS of its own from now on: further moves only rebuild the TLAS
     s->dirtyInstances = true;
     return NX_OK;
 }
@@ -670,10 +739,62 @@ int nx_scene_update(nx_scene* s)
 
     if (s->dirtyInstances)
     {
+        int rc;
+        // ---- which instances share the merged world-space BLAS: mesh used by this instance only, never moved, merging on, and not in
+        // the NexusBVH-identical mode (whose point is reference-identical trees)
+        std::vector<uint32_t> mergeSet;
+        if (ctx->merge_instances && ctx->scene_collapse != NX_COLLAPSE_REFERENCE_GPU)
+            for (uint32_t i = 0; i < s->instances.size(); i++)
+                if (!s->instances[i].dynamic && s->meshes[s->instances[i].meshIdx].useCount == 1 &&
+                    s->meshes[s->instances[i].meshIdx].bvh.prim_count >= ctx->merge_min_prims) mergeSet.push_back(i);
+        std::vector<uint8_t> isMerged(s->instances.size(), 0);
+        for (uint32_t i : mergeSet) isMerged[i] = 1;
+        // every other instance needs its mesh's own BLAS: issue the missing builds now, they run while the merged BLAS is prepared
+        for (uint32_t i = 0; i < s->instances.size(); i++)
+            if (!isMerged[i]) { rc = issue_blas_build(s, s->instances[i].meshIdx); if (rc) return rc; }
+
+        if (mergeSet != s->mergedInstances)
+        {
+            if (s->merged.nodes) { nx_bvh8_free(ctx, &s->merged); s->merged = nx_bvh8{}; }
+            if (s->dMergedLeaf) { cudaFreeAsync(s->dMergedLeaf, ctx->stream); s->dMergedLeaf = nullptr; }
+            s->mergedInstances = mergeSet; s->mergedFirst.clear();
+            if (!mergeSet.empty())
+            {
+                std::vector<BakeSrc> src(mergeSet.size());
+                uint64_t total = 0;
+                for (size_t j = 0; j < src.size(); j++) {
+                    const HostInstance& h = s->instances[mergeSet[j]];
+                    const HostMesh& hm = s->meshes[h.meshIdx];
+                    src[j].tris = hm.dTris; std::memcpy(src[j].m, h.m, 48);
+                    src[j].first = (uint32_t)total; src[j].count = hm.bvh.prim_count; src[j].inst = mergeSet[j]; src[j].pad = 0;
+                    s->mergedFirst.push_back((uint32_t)total);
+                    total += hm.bvh.prim_count;
+                }
+                if (total > 0x07ffffffull) NX_FAIL(ctx, NX_ERR_INVALID, "Scene::Update: %llu primitives in the merged BLAS (limit 2^27)", (unsigned long long)total);
+                const uint32_t n = (uint32_t)total;
+                BakeSrc* dSrc = nullptr; float* dWorld = nullptr; uint32_t* dSrcOf = nullptr;
+                rc = upload_vec(ctx, &dSrc, src); if (rc) return rc;
+                NX_CUDA(ctx, cudaMallocAsync((void**)&dWorld, 36 * (size_t)n, ctx->stream));
+                NX_CUDA(ctx, cudaMallocAsync((void**)&dSrcOf, 4 * (size_t)n, ctx->stream));
+                NX_CUDA(ctx, cudaMallocAsync((void**)&s->dMergedLeaf, 48 * (size_t)n, ctx->stream));
+                // the geometry uploads ran on the build streams
+                for (int k = 0; k < ctx->buildStreamCount; k++) NX_CUDA(ctx, cudaStreamSynchronize(ctx->buildStreams[k]));
+                const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
+                bake_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(dSrc, (uint32_t)src.size(), n, dWorld, dSrcOf);
+                // 64-bit Morton keys: the merged BLAS spans the whole scene, and 10 bits per axis would put many of its small triangles
+                // into the same cell
+                rc = nxi_build_bvh8(ctx, dWorld, n, 1, /*prioritizeSpeed=*/0, &s->merged); if (rc) return rc;
+                merged_leaf_kernel<<<grid, 256, 0, ctx->stream>>>(dWorld, s->merged.prim_idx, n, dSrcOf, dSrc, s->dMergedLeaf);
+                NX_CUDA(ctx, cudaGetLastError());
+                cudaFreeAsync(dWorld, ctx->stream); cudaFreeAsync(dSrcOf, ctx->stream); cudaFreeAsync(dSrc, ctx->stream);
+            }
+        }
+        rc = nxi_scene_flush_builds(s); if (rc) return rc;
+
         // device mesh table
         std::vector<DMesh> dm(s->meshes.size());
         for (size_t i = 0; i < dm.size(); i++) { dm[i].tris = s->meshes[i].dTris; dm[i].tridata = s->meshes[i].dTriData; dm[i].shade = s->meshes[i].dShadeRec; dm[i].primCount = s->meshes[i].bvh.prim_count; dm[i].pad = 0; }
-        int rc = upload_vec(ctx, &s->dMeshes, dm); if (rc) return rc;
+        rc = upload_vec(ctx, &s->dMeshes, dm); if (rc) return rc;
 
         // shading records in instance order
         std::vector<DShadeInst> si(s->instances.size());
@@ -686,27 +807,34 @@ int nx_scene_update(nx_scene* s)
         }
         rc = upload_vec(ctx, &s->dShadeInst, si); if (rc) return rc;
 
-        // world-space bounding sphere of every instance's geometry (conservative: radius and centre rounding padded)
-        std::vector<float4> spheres(s->instances.size());
-        for (size_t i = 0; i < spheres.size(); i++) {
-            const HostInstance& h = s->instances[i];
+        // TLAS entries: the instances that keep their own BLAS, then the merged BLAS as one more primitive
+        std::vector<uint32_t> entryInst;
+        for (uint32_t i = 0; i < s->instances.size(); i++) if (!isMerged[i]) entryInst.push_back(i);
+        const size_t nOwn = entryInst.size();
+
+        // world-space bounding sphere of every such instance's geometry (conservative: radius and centre rounding padded)
+        std::vector<float4> spheres(nOwn);
+        for (size_t e = 0; e < nOwn; e++) {
+            const HostInstance& h = s->instances[entryInst[e]];
             const HostMesh& hm = s->meshes[h.meshIdx];
             double c[3];
             for (int r = 0; r < 3; r++) c[r] = (double)h.m[4 * r] * hm.sphere[0] + (double)h.m[4 * r + 1] * hm.sphere[1] + (double)h.m[4 * r + 2] * hm.sphere[2] + (double)h.m[4 * r + 3];
             const double rad = hm.sphere[3] * max_stretch(h.m) * (1.0 + 1e-5) + 1e-30;
-            spheres[i] = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(rad * (1.0 + 1e-6)) + 1e-6f * (float)(std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2])));
+            spheres[e] = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(rad * (1.0 + 1e-6)) + 1e-6f * (float)(std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2])));
         }
+        std::vector<nx_aabb> ebounds(nOwn);
+        for (size_t e = 0; e < nOwn; e++) ebounds[e] = bounds[entryInst[e]];
         // The reference bounds an instance by the world AABB of the eight transformed corners of its mesh AABB
         // (MeshInstance::GetBounds, N/Scene/MeshInstance.h:42-66), which for a rotated object is up to sqrt(3) too wide.  Outside
         // the NexusBVH-identical mode the TLAS is built over that box clipped to the bounding sphere's box: still conservative,
         // and the node test then rejects what the per-instance sphere test would otherwise have to.
-        if (ctx->scene_collapse != NX_COLLAPSE_REFERENCE_GPU)
+        if (ctx->scene_collapse != NX_COLLAPSE_REFERENCE_GPU && nOwn)
         {
             // ... and to the box of the transformed vertices themselves (padded for the rounding of the transform)
-            std::vector<InstGeom> ig(s->instances.size());
-            for (size_t i = 0; i < ig.size(); i++) {
-                const HostInstance& h = s->instances[i];
-                ig[i].tris = s->meshes[h.meshIdx].dTris; ig[i].triCount = s->meshes[h.meshIdx].bvh.prim_count; std::memcpy(ig[i].m, h.m, 48);
+            std::vector<InstGeom> ig(nOwn);
+            for (size_t e = 0; e < nOwn; e++) {
+                const HostInstance& h = s->instances[entryInst[e]];
+                ig[e].tris = s->meshes[h.meshIdx].dTris; ig[e].triCount = s->meshes[h.meshIdx].bvh.prim_count; std::memcpy(ig[e].m, h.m, 48);
             }
             InstGeom* dIg = nullptr; float* dGb = nullptr;
             rc = upload_vec(ctx, &dIg, ig); if (rc) return rc;
@@ -716,43 +844,59 @@ int nx_scene_update(nx_scene* s)
             NX_CUDA(ctx, cudaMemcpyAsync(gb.data(), dGb, 24 * ig.size(), cudaMemcpyDeviceToHost, ctx->stream));
             NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFreeAsync(dIg, ctx->stream); cudaFreeAsync(dGb, ctx->stream);
-            for (size_t i = 0; i < bounds.size(); i++)
+            for (size_t i = 0; i < ebounds.size(); i++)
                 for (int a = 0; a < 3; a++) {
                     const float ext = gb[6 * i + 3 + a] - gb[6 * i + a], mag = std::max(std::fabs(gb[6 * i + a]), std::fabs(gb[6 * i + 3 + a]));
                     const float pad = 1.0e-5f * ext + 4.0e-6f * mag + 1.0e-30f;
-                    const float nlo = std::max(bounds[i].bmin[a], gb[6 * i + a] - pad), nhi = std::min(bounds[i].bmax[a], gb[6 * i + 3 + a] + pad);
-                    if (nlo <= nhi) { bounds[i].bmin[a] = nlo; bounds[i].bmax[a] = nhi; }
+                    const float nlo = std::max(ebounds[i].bmin[a], gb[6 * i + a] - pad), nhi = std::min(ebounds[i].bmax[a], gb[6 * i + 3 + a] + pad);
+                    if (nlo <= nhi) { ebounds[i].bmin[a] = nlo; ebounds[i].bmax[a] = nhi; }
                 }
-            for (size_t i = 0; i < bounds.size(); i++) {
+            for (size_t i = 0; i < ebounds.size(); i++) {
                 const float4 sp = spheres[i];
                 const float c3[3] = {sp.x, sp.y, sp.z};
                 for (int a = 0; a < 3; a++) {
                     const float lo = std::nextafterf(c3[a] - sp.w, -INFINITY), hi = std::nextafterf(c3[a] + sp.w, INFINITY);
-                    const float nlo = std::max(bounds[i].bmin[a], lo), nhi = std::min(bounds[i].bmax[a], hi);
-                    if (nlo <= nhi) { bounds[i].bmin[a] = nlo; bounds[i].bmax[a] = nhi; }
+                    const float nlo = std::max(ebounds[i].bmin[a], lo), nhi = std::min(ebounds[i].bmax[a], hi);
+                    if (nlo <= nhi) { ebounds[i].bmin[a] = nlo; ebounds[i].bmax[a] = nhi; }
                 }
             }
         }
+        const bool hasMerged = !s->mergedInstances.empty();
+        if (hasMerged) { entryInst.push_back(NX_INVALID); ebounds.push_back(s->merged.bounds); }
+        s->tlasEntryInst = entryInst;
 
-        // Scene::BuildTLAS (src/Scene/Scene.cpp:65-78): BuildBVH8<AABB> over the instance bounds, default config (64-bit keys)
+        // Scene::BuildTLAS (src/Scene/Scene.cpp:65-78): BuildBVH8<AABB> over the entry bounds, default config (64-bit keys)
         nx_aabb* dBounds = nullptr;
-        rc = upload_vec(ctx, &dBounds, bounds); if (rc) return rc;
+        rc = upload_vec(ctx, &dBounds, ebounds); if (rc) return rc;
         if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
-        rc = nxi_build_bvh8(ctx, dBounds, (uint32_t)bounds.size(), 0, 0, &s->tlas);
+        rc = nxi_build_bvh8(ctx, dBounds, (uint32_t)ebounds.size(), 0, 0, &s->tlas);
         cudaFreeAsync(dBounds, ctx->stream);
         if (rc) return rc;
 
-        // traversal records in TLAS leaf order
-        std::vector<uint32_t> order(bounds.size());
+        // traversal records and instance ids in TLAS leaf order
+        std::vector<uint32_t> order(ebounds.size());
         NX_CUDA(ctx, cudaMemcpyAsync(order.data(), s->tlas.prim_idx, 4 * order.size(), cudaMemcpyDeviceToHost, ctx->stream));
         NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::vector<DTravInst> ti(order.size());
+        std::vector<uint32_t> slotInst(order.size());
+        s->mergedSlot = NX_INVALID;
         for (size_t k = 0; k < order.size(); k++) {
-            const HostInstance& h = s->instances[order[k]];
+            const uint32_t e = order[k];
+            slotInst[k] = entryInst[e];
+            if (entryInst[e] == NX_INVALID) {
+                // the merged BLAS: identity transform, a sphere that is never culled
+                s->mergedSlot = (uint32_t)k;
+                ti[k].sphere = make_float4(0.f, 0.f, 0.f, INFINITY);
+                ti[k].r0 = make_float4(1.f, 0.f, 0.f, 0.f); ti[k].r1 = make_float4(0.f, 1.f, 0.f, 0.f); ti[k].r2 = make_float4(0.f, 0.f, 1.f, 0.f);
+                ti[k].nodes = (const float4*)s->merged.nodes; ti[k].ltris = s->dMergedLeaf;
+                continue;
+            }
+            const HostInstance& h = s->instances[entryInst[e]];
             std::memcpy(&ti[k].r0, h.inv, 48);
-            ti[k].sphere = spheres[order[k]];
+            ti[k].sphere = spheres[e];
             ti[k].nodes = (const float4*)s->meshes[h.meshIdx].bvh.nodes; ti[k].ltris = s->meshes[h.meshIdx].dLeafTris;
         }
+        rc = upload_vec(ctx, &s->dSlotInst, slotInst); if (rc) return rc;
         // top-level block: TLAS nodes + traversal records, one allocation, L2-persisting window on the two trace streams
         {
             const size_t nodeBytes = 80 * (size_t)s->tlas.node_count, recBytes = sizeof(DTravInst) * ti.size();
@@ -861,6 +1005,52 @@ int nx_scene_export_lights(nx_scene* s, void* out52, uint32_t* outCount)
         else if (l.type == NX_LIGHT_DIRECTIONAL) { float v[7] = {l.cr, l.cg, l.cb, l.dx, l.dy, l.dz, l.intensity}; std::memcpy(o, v, 28); }
         o[48] = (uint8_t)l.type;
         o += 52;
+    }
+    return NX_OK;
+}
+// The TLAS is built over ENTRIES: the instances that have a BLAS of their own and, last, the merged BLAS.  outInst[e] = instance id of
+// entry e, 0xffffffff for the merged BLAS (the TLAS's prim_idx holds entry numbers).
+int nx_scene_export_tlas_entries(nx_scene* s, uint32_t* outInst, uint32_t* outCount)
+{
+    if (!s || !outCount) return NX_ERR_INVALID;
+    if (s->dirtyInstances) { int rc = nx_scene_update(s); if (rc) return rc; }
+    *outCount = (uint32_t)s->tlasEntryInst.size();
+    if (outInst) std::memcpy(outInst, s->tlasEntryInst.data(), 4 * s->tlasEntryInst.size());
+    return NX_OK;
+}
+// The merged BLAS for the parity tests: its handle, and per merged primitive the world-space triangle (exactly the floats it was built
+// from: the same kernel again), the instance it belongs to and its primitive id inside that instance's mesh.  Any pointer may be null.
+int nx_scene_export_merged(nx_scene* s, nx_bvh8* outBvh, float* hostWorldTris, uint32_t* hostInst, uint32_t* hostPrim, uint32_t* outCount)
+{
+    if (!s || !outCount) return NX_ERR_INVALID;
+    if (s->dirtyInstances) { int rc = nx_scene_update(s); if (rc) return rc; }
+    nx_ctx* ctx = s->ctx;
+    DeviceGuard guard(ctx->device);
+    *outCount = s->mergedInstances.empty() ? 0u : s->merged.prim_count;
+    if (outBvh) *outBvh = s->merged;
+    if (!*outCount) return NX_OK;
+    const uint32_t n = s->merged.prim_count;
+    if (hostInst || hostPrim)
+        for (size_t j = 0; j < s->mergedInstances.size(); j++) {
+            const uint32_t first = s->mergedFirst[j], count = s->meshes[s->instances[s->mergedInstances[j]].meshIdx].bvh.prim_count;
+            for (uint32_t p = 0; p < count; p++) { if (hostInst) hostInst[first + p] = s->mergedInstances[j]; if (hostPrim) hostPrim[first + p] = p; }
+        }
+    if (hostWorldTris) {
+        std::vector<BakeSrc> src(s->mergedInstances.size());
+        for (size_t j = 0; j < src.size(); j++) {
+            const HostInstance& h = s->instances[s->mergedInstances[j]];
+            src[j].tris = s->meshes[h.meshIdx].dTris; std::memcpy(src[j].m, h.m, 48);
+            src[j].first = s->mergedFirst[j]; src[j].count = s->meshes[h.meshIdx].bvh.prim_count; src[j].inst = s->mergedInstances[j]; src[j].pad = 0;
+        }
+        BakeSrc* dSrc = nullptr; float* dWorld = nullptr; uint32_t* dSrcOf = nullptr;
+        int rc = upload_vec(ctx, &dSrc, src); if (rc) return rc;
+        NX_CUDA(ctx, cudaMallocAsync((void**)&dWorld, 36 * (size_t)n, ctx->stream));
+        NX_CUDA(ctx, cudaMallocAsync((void**)&dSrcOf, 4 * (size_t)n, ctx->stream));
+        const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
+        bake_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(dSrc, (uint32_t)src.size(), n, dWorld, dSrcOf);
+        NX_CUDA(ctx, cudaMemcpyAsync(hostWorldTris, dWorld, 36 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeAsync(dSrc, ctx->stream); cudaFreeAsync(dWorld, ctx->stream); cudaFreeAsync(dSrcOf, ctx->stream);
     }
     return NX_OK;
 }

@@ -61,6 +61,8 @@ struct HostMesh {
     nx_bvh8 bvh{};
     uint32_t materialIdx = 0;
     double sphere[4] = {0, 0, 0, 0};   // object-space bounding sphere of the vertices (centre, radius)
+    bool blasBuilt = false;            // the mesh has a BLAS of its own (built on demand: meshes that only live in the merged BLAS never get one)
+    uint32_t useCount = 0;             // instances referring to the mesh
     bool arenaOwned = false;           // all device arrays live in the scene's arena: nothing is freed per mesh
     bool prebuilt = false;             // BLAS supplied by the caller (nx_scene_add_mesh_prebuilt): indices validated on the device
     bool pending = false;              // BLAS build in flight on a build stream: node_count not known yet (flush_builds)
@@ -70,6 +72,7 @@ struct HostInstance {
     uint32_t meshIdx = 0, materialIdx = 0;
     float m[16]; float inv[16];
     nx_aabb bounds{};
+    bool dynamic = false;              // moved after creation (nx_scene_set_instance_transform): never merged
 };
 
 struct nx_scene {
@@ -102,6 +105,14 @@ struct nx_scene {
     std::vector<uint32_t*> buildCounterChunks;
     std::vector<nx_bump> arena;            // slabs holding every mesh's geometry, shading records and BLAS (freed with the scene)
     uint32_t pendingBuilds = 0;
+    // merged BLAS: one world-space BLAS over all instances whose mesh is used exactly once and that have not been moved
+    std::vector<uint32_t> mergedInstances;   // instance ids in it, ascending
+    std::vector<uint32_t> mergedFirst;       // first merged primitive of each of them
+    nx_bvh8 merged{};
+    float4* dMergedLeaf = nullptr;
+    uint32_t mergedSlot = 0xffffffffu;       // its TLAS leaf slot
+    std::vector<uint32_t> tlasEntryInst;     // TLAS primitive (entry) -> instance id, 0xffffffff for the merged BLAS
+    uint32_t* dSlotInst = nullptr;           // TLAS leaf slot -> instance id
 };
 
 // scene.cu

@@ -47,8 +47,13 @@ struct DTravInst {           // 80 B; TLAS-leaf order
 
 struct TraceScene {
     const float4* tlasNodes;
-    const uint32_t* tlasPrimIdx;   // TLAS leaf slot -> instance id (read once per ray, at the end)
+    const uint32_t* tlasPrimIdx;   // TLAS leaf slot -> instance id (read once per ray, at the end); unused for the merged BLAS's slot
     const DTravInst* inst;         // TLAS leaf slot -> traversal record
+    // Merged BLAS (scene.cu): the instances whose mesh nobody else uses are transformed to world space once and share ONE BLAS, entered
+    // with the identity transform.  Its leaf triangles carry the instance id ({v0 | prim}, {e0 | instance}, {e1 | -}).
+    uint32_t mergedSlot;           // TLAS leaf slot of that BLAS, NX_INVALID when the scene has none
+    uint32_t direct;               // 1: it is the ONLY TLAS entry, rays start inside it and never see the TLAS
+    const float4* mNodes; const float4* mLtris;
     uint32_t* overflow;            // device counter of traversal-stack pushes refused (a tree deeper than NX_STACK_TOTAL entries); the
                                    // host turns a non-zero value into an error (the reference's 32-entry stack has no check, BVH8Traversal.cuh:164)
 };
@@ -83,6 +88,14 @@ __device__ __forceinline__ uint32_t octant_inv4(V3 d)
 }
 __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 
+// A hit remembers WHERE it was found as one word: a TLAS leaf slot, or - inside the merged BLAS - the instance id from the triangle
+// record with the top bit set.  NX_INVALID (no hit) has that bit set too and is tested first.
+__device__ __forceinline__ uint32_t hit_instance(const TraceScene& sc, uint32_t where)
+{
+    if (where == NX_INVALID) return NX_INVALID;
+    return (where & 0x80000000u) ? (where & 0x7fffffffu) : __ldg(sc.tlasPrimIdx + where);
+}
+
 // Which of the six quantised planes per child are converted byte -> float on the ALU pipe (PRMT into the mantissa of
 // 2^15, the bias folded into the FMA addend) instead of the XU pipe (I2F.U8): bit a = near plane of axis a, bit 3 + a =
 // far plane.  ncu (profiles/r01_trace_closest.md): 48 I2F.U8 per node kept the XU pipe at 54-61 % with the I2Fs holding
@@ -93,6 +106,12 @@ __device__ __forceinline__ float rcp_ieee(float x) { return __frcp_rn(x); }
 
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // one MUFU; 2^-22 relative
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// Reciprocal of a direction component for the slab test, clamped to +-1e18.  With an infinite reciprocal (a ray exactly parallel to an
+// axis) the fused form q * (cell / d) + (p - o) / d of the slab test is inf - inf = NaN on that axis, the NaN drops out of min / max and
+// the axis is IGNORED: conservative, but a vertical ray then visits every node of the scene whose height range it crosses, whatever
+// their x and z (found in round 2: one such ray per frame took 5 s in a flat 10 M-triangle BVH).  With a huge finite reciprocal the
+// planes of that axis sit at -huge / +huge when the origin is inside the slab and at the same sign when it is outside: a miss.
+__device__ __forceinline__ float rcp_dir(float x) { return fminf(fmaxf(rcp_fast(x), -1.0e18f), 1.0e18f); }
 __device__ __forceinline__ uint32_t shl_wrap(uint32_t v, uint32_t n) { uint32_t r; asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(v), "r"(n)); return r; }
 
 // Byte j of `word` as a float.  MAGIC: the byte is spliced into 0x4700qq00 = 32768 + q (one PRMT on the ALU pipe); the
@@ -239,6 +258,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
     uint32_t octinv4 = 0, curSlot = NX_INVALID, rayIdx = 0, rayPad = 0;
     int sp = 0, instDepth = -1;
     bool live = false, dead = false, occluded = false;
+#ifdef NX_TRACE_WATCHDOG
+    uint32_t wdSteps = 0;
+#endif
     WarpFetcher fetch;
     unsigned long long cN = 0, cT = 0, cI = 0, cR = 0, cS = 0;
     unsigned long long wIt = 0, wLN = 0, wRT = 0, wLT = 0, wRX = 0, wLX = 0;   // lane 0 only
@@ -270,13 +292,14 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             const uint32_t prim = __float_as_uint(a.w);
             if (ANY_HIT) { if (t < tmax) occluded = true; }
             else {
+                const uint32_t here = curSlot == sc.mergedSlot ? (0x80000000u | __float_as_uint(b.w)) : curSlot;
                 bool take = t < fminf(tmax, hitT);
                 if (!take && t == hitT && hitPrim != NX_INVALID) {
                     // exact tie: the smaller (instance id, primitive id) wins, whatever the visiting order
-                    const uint32_t ia = __ldg(sc.tlasPrimIdx + curSlot), ib = __ldg(sc.tlasPrimIdx + hitSlot);
+                    const uint32_t ia = hit_instance(sc, here), ib = hit_instance(sc, hitSlot);
                     take = ia < ib || (ia == ib && prim < hitPrim);
                 }
-                if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = curSlot; }
+                if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = here; }
             }
         }
     };
@@ -317,16 +340,24 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             const uint32_t mR = __ballot_sync(NX_FULL, needR);
             uint32_t got = 0;
             if (mR) got = fetch.take(cursor, mR, lane_lt);
-            bool setup = false;
+            bool setup = false, bad = false;
             if (needR) {
                 if (got < n) {
                     const float4* r = reinterpret_cast<const float4*>(rays + got);
                     const float4 a = __ldg(r), b = __ldg(r + 1);
                     o = v3(a.x, a.y, a.z); d = v3(b.x, b.y, b.z); tmax = a.w;
                     rayIdx = got; rayPad = __float_as_uint(b.w);
+#ifdef NX_TRACE_WATCHDOG
+                    wdSteps = 0;
+#endif
                     hitT = NX_MISS_T; hitU = hitV = 0.f; hitPrim = NX_INVALID; hitSlot = NX_INVALID; occluded = false;
                     nodes = sc.tlasNodes; curSlot = NX_INVALID; instDepth = -1; sp = 0;
+                    if (sc.direct) { nodes = sc.mNodes; ltris = sc.mLtris; curSlot = sc.mergedSlot; instDepth = 0; }   // world space IS its object space
                     live = true; setup = true;
+                    // a ray with a non-finite origin or direction passes every conservative box test (NaNs drop out of min / max) and would
+                    // walk the whole scene: it is a miss, and it is counted
+                    bad = !(fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(b.x) + fabsf(b.y) + fabsf(b.z) < 3.0e38f);
+                    if (bad) atomicAdd(sc.overflow + 1, 1u);
                 } else dead = true;
             } else if (wantI) {
                 // first instance of the group whose bounding sphere the ray can reach before its current limit
@@ -366,9 +397,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             }
             __syncwarp();   // new rays and instance entries reconverge here: one pass through the shared set-up, not one per branch
             if (setup) {
-                inv = v3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
+                inv = v3(rcp_dir(d.x), rcp_dir(d.y), rcp_dir(d.z));
                 octinv4 = octant_inv4(inv);
-                ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
+                ngroup = make_uint2(0u, bad ? 0u : 0x80000000u); tgroup = make_uint2(0u, 0u);
             }
             if (__all_sync(NX_FULL, dead)) break;
         }
@@ -384,6 +415,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
             const uint32_t child = ngroup.x + __popc(ngroup.y & ((1u << slot) - 1u) & 0xffu);
             intersect_children(nodes, child, o, inv, octinv4, ANY_HIT ? tmax : fminf(tmax, hitT), k47, ngroup, tgroup);
             if (STATS) cN++;
+#ifdef NX_TRACE_WATCHDOG
+            if (++wdSteps == (1u << 18)) printf("WD ray %u o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %g hitT %g inv %g %g %g sp %d inst %d child %u\n", rayIdx, o.x, o.y, o.z, d.x, d.y, d.z, tmax, hitT, inv.x, inv.y, inv.z, sp, instDepth, child);
+#endif
         }
 
         // ---------------------------------------------------------------- phase T: triangles (rounds until too few lanes) ----

@@ -15,7 +15,7 @@
 // BOTH of its rays are blocked.
 #pragma once
 #include "traverse.cuh"
-#define NX_DUO_WATCHDOG 1   // debugging aid while the loop is new: a warp that iterates 2M times reports its state and leaves
+
 
 #ifndef NX_DUO_BLOCK
 #define NX_DUO_BLOCK 128
@@ -104,7 +104,7 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
                 nodes = reinterpret_cast<const float4*>(((uint64_t)ptrs.y << 32) | ptrs.x);
                 ltris = reinterpret_cast<const float4*>(((uint64_t)ptrs.w << 32) | ptrs.z);
             }
-            inv = v3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));       // the same values the set-up phase computed from the same d
+            inv = v3(rcp_dir(d.x), rcp_dir(d.y), rcp_dir(d.z));       // the same values the set-up phase computed from the same d
             octinv4 = octant_inv4(inv);
         } else { ngroup = make_uint2(0u, 0u); tgroup = make_uint2(0u, 0u); }
         if (STATS) wSw++;
@@ -130,12 +130,13 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
             const uint32_t prim = __float_as_uint(a.w);
             if (ANY_HIT) { if (t < tmax) occluded = true; }
             else {
+                const uint32_t here = curSlot == sc.mergedSlot ? (0x80000000u | __float_as_uint(b.w)) : curSlot;
                 bool take = t < fminf(tmax, hitT);
                 if (!take && t == hitT && hitPrim != NX_INVALID) {
-                    const uint32_t ia = __ldg(sc.tlasPrimIdx + curSlot), ib = __ldg(sc.tlasPrimIdx + hitSlot);
+                    const uint32_t ia = hit_instance(sc, here), ib = hit_instance(sc, hitSlot);
                     take = ia < ib || (ia == ib && prim < hitPrim);
                 }
-                if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = curSlot; }
+                if (take) { hitT = t; hitU = u; hitV = v; hitPrim = prim; hitSlot = here; }
             }
         }
     };
@@ -204,6 +205,7 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
                     rayIdx = got; rayPad = __float_as_uint(b.w);
                     hitT = NX_MISS_T; hitU = hitV = 0.f; hitPrim = NX_INVALID; hitSlot = NX_INVALID; occluded = false;
                     nodes = sc.tlasNodes; curSlot = NX_INVALID; instDepth = -1; sp = 0;
+                    if (sc.direct) { nodes = sc.mNodes; ltris = sc.mLtris; curSlot = sc.mergedSlot; instDepth = 0; }
                     live = true; setup = true;
                 } else dead = true;
             } else if (wantI2) {
@@ -241,7 +243,7 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
             }
             __syncwarp();
             if (setup) {
-                inv = v3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
+                inv = v3(rcp_dir(d.x), rcp_dir(d.y), rcp_dir(d.z));
                 octinv4 = octant_inv4(inv);
                 ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
             }

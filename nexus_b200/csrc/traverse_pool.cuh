@@ -121,13 +121,19 @@ __device__ __forceinline__ void trace_pool_loop(const TraceScene& sc, const nx_r
             {
                 const float4* r = reinterpret_cast<const float4*>(rays + idx);
                 const float4 a = __ldg(r), b = __ldg(r + 1);
-                const V3 inv = v3(rcp_fast(b.x), rcp_fast(b.y), rcp_fast(b.z));
+                const V3 inv = v3(rcp_dir(b.x), rcp_dir(b.y), rcp_dir(b.z));
                 pw.Wo[s] = a; pw.Wd[s] = b;
                 pw.Co[s] = make_float4(a.x, a.y, a.z, ANY_HIT ? a.w : fminf(a.w, NX_MISS_T)); pw.Cd[s] = b;
                 pw.Ci[s] = make_float4(inv.x, inv.y, inv.z, __uint_as_float(octant_inv4(inv)));
                 pw.G[s] = make_uint4(0u, 0x80000000u, 0u, 0u);
-                pw.P[s] = make_uint4(tlasLo, tlasHi, 0u, 0u);
-                pw.M[s] = make_uint4(0xff00u, NX_INVALID, idx, NX_INVALID);
+                if (sc.direct) {      // the merged BLAS is the whole scene: start inside it (instance depth 0, world space is its object space)
+                    const uint64_t mn = reinterpret_cast<uint64_t>(sc.mNodes), ml = reinterpret_cast<uint64_t>(sc.mLtris);
+                    pw.P[s] = make_uint4((uint32_t)mn, (uint32_t)(mn >> 32), (uint32_t)ml, (uint32_t)(ml >> 32));
+                    pw.M[s] = make_uint4(0x0000u, sc.mergedSlot, idx, NX_INVALID);
+                } else {
+                    pw.P[s] = make_uint4(tlasLo, tlasHi, 0u, 0u);
+                    pw.M[s] = make_uint4(0xff00u, NX_INVALID, idx, NX_INVALID);
+                }
                 pw.H[s] = make_float4(NX_MISS_T, 0.f, 0.f, __uint_as_float(NX_INVALID));
                 pw.st[s] = PS_NODE;
                 if (NX_POOL_PREFETCH) { prefetch_l1(sc.tlasNodes); }
@@ -192,16 +198,17 @@ __device__ __forceinline__ void trace_pool_loop(const TraceScene& sc, const nx_r
                     if (ANY_HIT) { if (t < co.w) occluded = true; }
                     else {
                         const uint32_t prim = __float_as_uint(a.w);
+                        const uint32_t here = m.y == sc.mergedSlot ? (0x80000000u | __float_as_uint(b.w)) : m.y;
                         bool take = t < co.w;                                  // co.w = min(tmax, hit t)
                         if (!take && t == co.w) {
                             // exact tie with the hit so far: the smaller (instance id, primitive id) wins, whatever the visiting order
                             const float4 h = pw.H[s];
                             if (__float_as_uint(h.w) != NX_INVALID && t == h.x) {
-                                const uint32_t ia = __ldg(sc.tlasPrimIdx + m.y), ib = __ldg(sc.tlasPrimIdx + m.w);
+                                const uint32_t ia = hit_instance(sc, here), ib = hit_instance(sc, m.w);
                                 take = ia < ib || (ia == ib && prim < __float_as_uint(h.w));
                             }
                         }
-                        if (take) { pw.H[s] = make_float4(t, u, v, a.w); m.w = m.y; co.w = t; pw.Co[s].w = t; }
+                        if (take) { pw.H[s] = make_float4(t, u, v, a.w); m.w = here; co.w = t; pw.Co[s].w = t; }
                     }
                 }
             }
@@ -232,7 +239,7 @@ __device__ __forceinline__ void trace_pool_loop(const TraceScene& sc, const nx_r
                     const float4 r0 = __ldg(&I->r0), r1 = __ldg(&I->r1), r2 = __ldg(&I->r2);
                     const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&I->nodes));
                     const V3 oo = xform_point(r0, r1, r2, o), od = xform_vector(r0, r1, r2, d);   // direction is not renormalised: t stays in world units
-                    const V3 inv = v3(rcp_fast(od.x), rcp_fast(od.y), rcp_fast(od.z));
+                    const V3 inv = v3(rcp_dir(od.x), rcp_dir(od.y), rcp_dir(od.z));
                     pfOct = octant_inv4(inv); pfLo = ptrs.x; pfHi = ptrs.y;
                     pw.P[s] = ptrs;
                     pw.Co[s] = make_float4(oo.x, oo.y, oo.z, limit);
@@ -253,7 +260,7 @@ __device__ __forceinline__ void trace_pool_loop(const TraceScene& sc, const nx_r
             else {
                 if (sp == idp) {      // leaving the instance: back to the world-space ray
                     const float4 wo = pw.Wo[s], wd = pw.Wd[s];
-                    const V3 inv = v3(rcp_fast(wd.x), rcp_fast(wd.y), rcp_fast(wd.z));
+                    const V3 inv = v3(rcp_dir(wd.x), rcp_dir(wd.y), rcp_dir(wd.z));
                     pw.Co[s] = make_float4(wo.x, wo.y, wo.z, co.w);
                     pw.Cd[s] = wd;
                     pw.Ci[s] = make_float4(inv.x, inv.y, inv.z, __uint_as_float(octant_inv4(inv)));

@@ -81,6 +81,11 @@ inline bool triangle(const float* t, f3 o, f3 d, float& best, float& bu, float& 
     return false;
 }
 
+// reciprocal of a direction component for the slab test, clamped like the product's rcp_dir (traverse.cuh): an infinite reciprocal
+// turns the fused slab formula into inf - inf and the axis is ignored, so an axis-parallel ray would visit every node it passes in
+// the other axes.  Hits do not depend on it (the box test is only conservative culling).
+inline float rcpDir(float x) { float r = 1.0f / x; return r > 1.0e18f ? 1.0e18f : (r < -1.0e18f ? -1.0e18f : r); }
+
 // ChildTrace, BVH8Traversal.cuh:56-147: 32-bit hit mask, inner children in bits 24..31 ordered by octant
 inline uint32_t childHits(const Node8& N, f3 o, f3 d, f3 inv, uint32_t oinv, float tmax)
 {
@@ -111,7 +116,7 @@ struct Stats { uint64_t nodes = 0, tris = 0, insts = 0; };
 template <bool ANY>
 bool traverseBlas(const Mesh& M, f3 o, f3 d, float& best, Hit& hit, uint32_t instId, Stats& st)
 {
-    f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    f3 inv = mk(rcpDir(d.x), rcpDir(d.y), rcpDir(d.z));
     uint32_t oinv = octantInv(d);
     struct Entry { uint32_t base, hits, imask; bool tri; };
     std::vector<Entry> stack;
@@ -162,7 +167,7 @@ bool traverse(const SceneO& S, const Ray& r, Hit& hit, Stats& st)
     hit.t = 1.0e30f; hit.u = hit.v = 0.f; hit.prim = INVALID; hit.inst = INVALID;
     float best = ANY ? r.tmax : fminf(r.tmax, 1.0e30f);
     f3 o = r.o, d = r.d;
-    f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    f3 inv = mk(rcpDir(d.x), rcpDir(d.y), rcpDir(d.z));
     uint32_t oinv = octantInv(d);
     struct Entry { uint32_t base, hits, imask; };
     std::vector<Entry> stack;

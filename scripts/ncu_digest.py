@@ -104,7 +104,9 @@ def main():
     st = {n: sum(int(r[h[n]] or 0) for r in ins) for n in stalls}
     print("\nStall samples by reason (all samples): " + ", ".join(f"{n[6:]} {100 * v / max(tot_samp, 1):.1f}%" for n, v in sorted(st.items(), key=lambda kv: -kv[1]) if v))
     if a.lib:
-        mang = re.search(r"(\w+?)(<|\()", data[0][col["Kernel Name"]].split("::")[-1]).group(1)
+        kname = data[0][col["Kernel Name"]]
+        head = re.split(r"[<(]", kname.replace("<unnamed>::", ""), 1)[0]          # "void ns::kernel" -> kernel
+        mang = head.split()[-1].split("::")[-1]
         by_source_line(ins, h, a.lib, mang + ("ILb0" if "<0>" in data[0][col["Kernel Name"]] or "(bool)0" in data[0][col["Kernel Name"]] else ""), 40, tot_inst, tot_samp)
     print(f"\n| # | address | instruction | samples % | executed | threads/instr | top stall |")
     print("|---|---|---|---|---|---|---|")

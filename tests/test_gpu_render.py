@@ -199,6 +199,7 @@ def test_dynamic_scene_updates_rebuild_the_tlas(ctx):
     its TLAS from scratch on any instance change).  An edited scene must behave exactly like one created in the final state:
     identical closest hits (bit for bit) and an identical frame (the RNG is keyed on pixel, frame and bounce)."""
     res = (160, 120)
+    ctx.SetInstanceMerging(False)     # bit-for-bit needs the same trees in both scenes; the merged-BLAS variant follows below
 
     def make(final):
         desc = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=9, nu=16, nv=16, path_length=4))
@@ -225,6 +226,26 @@ def test_dynamic_scene_updates_rebuild_the_tlas(ctx):
     ia, ib = pa.ReadAccumulation(), pb.ReadAccumulation()
     assert np.allclose(ia, ib, rtol=1e-4, atol=1e-5)                          # float atomics: summation order only
     pa.close(); pb.close(); a.close(); b.close()
+    ctx.SetInstanceMerging(True)
+
+    # With instance merging (the default) the rocks of this scene share BLASes (4 meshes, 9 instances) and keep them, but the ground and
+    # the light - one instance each - start in the merged world-space BLAS.  Moving the ground takes it out: it gets a BLAS of its own
+    # (nothing else is rebuilt but the merged BLAS, once), the hits are those of a scene created in the final state, and a second move
+    # only rebuilds the TLAS.
+    desc_c = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=9, nu=16, nv=16, path_length=4))
+    c = scenes.build(ctx, desc_c, res)
+    assert (c.ExportTlasEntries() == 0xffffffff).sum() == 1 and c.ExportMerged(triangles=False)["bvh"].primCount == 4
+    nx.MeshInstance(c, 0, desc_c["instances"][0]["mesh"]).SetTransform((0.0, -0.25, 0.0), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+    c.Update()
+    assert c.ExportMerged(triangles=False)["bvh"].primCount == 2                 # the light's two triangles are what is left in it
+    desc_d = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=9, nu=16, nv=16, path_length=4))
+    desc_d["instances"][0]["position"] = (0.0, -0.25, 0.0)
+    d = scenes.build(ctx, desc_d, res)
+    hc, hd = c.TraceClosest(rays), d.TraceClosest(rays)
+    same = (hc["prim"] == hd["prim"]) & (hc["instance"] == hd["instance"])
+    assert same.mean() >= 0.999 and np.allclose(hc["t"][same], hd["t"][same], rtol=2e-5)
+    assert (hc["instance"][hc["prim"] != 0xffffffff] == 0).any()                 # the moved ground is being hit
+    c.close(); d.close()
 
 
 # ------------------------------------------------------------------ material maps ----
