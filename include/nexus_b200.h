@@ -141,10 +141,12 @@ int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes
 /* Collapse used for the BLASes / TLAS that nx_scene_* builds from now on (default NX_COLLAPSE_SAH_OPTIMAL, 2 primitives per leaf;
  * NX_COLLAPSE_REFERENCE_GPU reproduces NexusBVH's trees).  Hit ids and distances do not depend on the choice. */
 int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims);
-/* Traversal loop of the trace kernels.  NX_TRACE_POOL (default): a warp owns 64 rays whose state lives in shared memory and hands
- * its lanes the rays that want the kind of work of the round (node test, triangle test, instance entry, fetch).  NX_TRACE_LANE:
- * one ray per lane.  Hits are identical (same arithmetic, deterministic tie-break).  Also NX_TRACE_MODE=pool|lane. */
-enum { NX_TRACE_LANE = 0, NX_TRACE_POOL = 1, NX_TRACE_DUO = 2 };
+/* Traversal loop of the trace kernels.  NX_TRACE_LANE (default, the fastest measured): one ray per lane, the loop specialised for what
+ * the scene holds (two-level only / merged BLAS only / both); NX_TRACE_LANE_GENERAL: the same loop without the specialisation.
+ * NX_TRACE_POOL: a warp owns 64 rays whose state lives in shared memory and hands its lanes the rays that want the kind of work of
+ * the round (node test, triangle test, instance entry, fetch).  NX_TRACE_DUO: two rays per lane.  Hits are identical in all of them
+ * (same arithmetic, deterministic tie-break).  Also NX_TRACE_MODE=lane|pool|duo, NX_TRACE_GENERIC=1. */
+enum { NX_TRACE_LANE = 0, NX_TRACE_POOL = 1, NX_TRACE_DUO = 2, NX_TRACE_LANE_GENERAL = 3 };
 int nx_ctx_set_trace_mode(nx_ctx* ctx, int mode);
 /* Ray-pool round thresholds, in rays of the warp's pool: a round of that kind runs when at least this many rays want it (else the
  * fullest kind runs).  any_hit != 0 sets the shadow-ray kernel's.  Also NX_POOL_TUNE / NX_POOL_TUNE_ANY = "node,tri,inst,fetch". */
@@ -233,9 +235,10 @@ int nx_scene_export_lights(nx_scene* scene, void* out52 /* n*52 */, uint32_t* ou
 /* Parity hooks for the merged BLAS (nx_ctx_set_instance_merging).  The TLAS is built over ENTRIES - the instances that keep a BLAS of
  * their own, then the merged BLAS - and its prim_idx holds entry numbers: out_inst[e] = instance id of entry e, 0xffffffff = merged. */
 int nx_scene_export_tlas_entries(nx_scene* scene, uint32_t* out_inst, uint32_t* out_count);
-/* Handle of the merged BLAS and, per merged primitive, the world-space triangle it was built from (9 floats), its instance and its
- * primitive id inside that instance's mesh.  out_count = 0 when the scene has no merged BLAS.  Any output pointer may be null. */
-int nx_scene_export_merged(nx_scene* scene, nx_bvh8* out_bvh, float* host_world_tris, uint32_t* host_inst, uint32_t* host_prim, uint32_t* out_count);
+/* Handle of the merged BLAS and, per merged primitive, the padded world-space box it was built over (6 floats: min, max), its instance
+ * and its primitive id inside that instance's mesh.  The tree's nodes are in world space; its triangles are tested in the object space
+ * of their instance, so the hits are the two-level scene's.  out_count = 0 when the scene has no merged BLAS.  Any output pointer may be null. */
+int nx_scene_export_merged(nx_scene* scene, nx_bvh8* out_bvh, float* host_bounds, uint32_t* host_inst, uint32_t* host_prim, uint32_t* out_count);
 int nx_scene_tlas(nx_scene* scene, nx_bvh8* out);                                       /* borrowed handle */
 /* The same records computed without a scene or a GPU (pure host arithmetic, the code paths nx_scene_add_instance and
  * nx_scene_export_camera use): MeshInstance::ToDevice (src/Scene/MeshInstance.h:36-66) and Camera::ToDevice (src/Scene/Camera.cpp:130-156). */

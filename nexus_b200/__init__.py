@@ -61,8 +61,9 @@ class Context:
         check(self._h, lib().nx_ctx_set_instance_merging(self._h, C.c_int(int(enabled))), "SetInstanceMerging")
 
     def SetTraceMode(self, mode):
-        """'pool' (default: 64 rays per warp in shared memory, lanes take rays by kind of work) or 'lane' (one ray per lane)."""
-        m = {"lane": 0, "pool": 1, "duo": 2}.get(mode, mode)
+        """'lane' (default: one ray per lane, loop specialised for the scene kind), 'general' (the same loop unspecialised), 'pool' (64
+        rays per warp in shared memory, lanes take rays by kind of work) or 'duo' (two rays per lane).  Same hits in all of them."""
+        m = {"lane": 0, "pool": 1, "duo": 2, "general": 3}.get(mode, mode)
         check(self._h, lib().nx_ctx_set_trace_mode(self._h, C.c_int(int(m))), "SetTraceMode")
 
     def SetPoolTuning(self, node, tri, inst, fetch, any_hit=False):
@@ -673,16 +674,17 @@ class Scene:
         check(self.ctx._h, lib().nx_scene_export_tlas_entries(self._h, _ptr(out), C.byref(n)), "ExportTlasEntries")
         return out[:n.value]
 
-    def ExportMerged(self, triangles=True):
-        """The merged world-space BLAS (Context.SetInstanceMerging), or None: dict(bvh, triangles (n, 9), instance (n,), prim (n,))."""
+    def ExportMerged(self, bounds=True):
+        """The merged BLAS (Context.SetInstanceMerging; world-space nodes, object-space triangle tests), or None:
+        dict(bvh, bounds (n, 6) padded world boxes the tree was built over, instance (n,), prim (n,))."""
         n, h = C.c_uint32(0), Bvh8()
         check(self.ctx._h, lib().nx_scene_export_merged(self._h, C.byref(h), None, None, None, C.byref(n)), "ExportMerged")
         if not n.value:
             return None
-        tris = np.empty((n.value, 9), np.float32) if triangles else None
+        box = np.empty((n.value, 6), np.float32) if bounds else None
         inst, prim = np.empty(n.value, np.uint32), np.empty(n.value, np.uint32)
-        check(self.ctx._h, lib().nx_scene_export_merged(self._h, C.byref(h), _ptr(tris) if triangles else None, _ptr(inst), _ptr(prim), C.byref(n)), "ExportMerged")
-        return {"bvh": BVH8(self.ctx, h, owned=False), "triangles": tris, "instance": inst, "prim": prim}
+        check(self.ctx._h, lib().nx_scene_export_merged(self._h, C.byref(h), _ptr(box) if bounds else None, _ptr(inst), _ptr(prim), C.byref(n)), "ExportMerged")
+        return {"bvh": BVH8(self.ctx, h, owned=False), "bounds": box, "instance": inst, "prim": prim}
 
     # reference device layouts, for the reference arm of parity tests
     def ExportInstances(self):

@@ -1379,13 +1379,13 @@ int build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, const 
 } // namespace
 
 // Internal entry used by the scene code (same translation-unit-free interface as the public C ABI).
-int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out)
+int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out, uint32_t maxLeafPrims)
 {
     // TLAS (AABB primitives = instances): one instance per leaf child.  Entering an instance costs a ray transform and a BLAS
     // root visit, far more than the C_PRIM = 0.3 the cost model charges a primitive, so sharing a leaf box between two
     // instances (3.8 -> 5.3 instance candidates per ray on the CPU oracle) is a loss; BLAS leaves hold up to max_leaf_prims.
     nx_build_config cfg; cfg.prioritize_speed = prioritizeSpeed; cfg.collapse = ctx->scene_collapse;
-    cfg.max_leaf_prims = primType ? ctx->scene_max_leaf_prims : 1;
+    cfg.max_leaf_prims = maxLeafPrims ? maxLeafPrims : (primType ? ctx->scene_max_leaf_prims : 1);   // the merged BLAS is built over boxes of triangles
     return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out);
 }
 

@@ -69,6 +69,7 @@ int nx_ctx_create(int device, nx_ctx** out)
         if (std::sscanf(t, "%d,%d", &a, &b) >= 1) { ctx->scene_collapse = a; ctx->scene_max_leaf_prims = b; }
     }
     if (const char* t = std::getenv("NX_MERGE_INSTANCES")) ctx->merge_instances = std::atoi(t) != 0;
+    if (const char* t = std::getenv("NX_TRACE_GENERIC")) ctx->trace_generic = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_MERGE_MIN_PRIMS")) ctx->merge_min_prims = (uint32_t)std::max(0, std::atoi(t));
     if (const char* t = std::getenv("NX_SCENE_BLAS_SPEED")) ctx->scene_blas_speed = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_TRACE_TUNE_ANY")) {
@@ -133,8 +134,9 @@ int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims)
 
 int nx_ctx_set_trace_mode(nx_ctx* ctx, int mode)
 {
-    if (!ctx || (mode != NX_TRACE_LANE && mode != NX_TRACE_POOL && mode != NX_TRACE_DUO)) return NX_ERR_INVALID;
-    ctx->trace_mode = mode;
+    if (!ctx || (mode != NX_TRACE_LANE && mode != NX_TRACE_POOL && mode != NX_TRACE_DUO && mode != NX_TRACE_LANE_GENERAL)) return NX_ERR_INVALID;
+    ctx->trace_mode = mode == NX_TRACE_LANE_GENERAL ? NX_TRACE_LANE : mode;
+    ctx->trace_generic = mode == NX_TRACE_LANE_GENERAL ? 1 : 0;
     return NX_OK;
 }
 

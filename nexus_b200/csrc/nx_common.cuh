@@ -48,7 +48,8 @@ struct nx_ctx {
     uint32_t* hOverflow = nullptr;       // pinned mirror ([1]: rays with non-finite origin / direction, answered as misses)
     unsigned long long nonfinite_rays = 0;
     void* poolSpill[2] = {nullptr, nullptr}; size_t poolSpillWarps[2] = {0, 0};       // global spill stacks of the two trace streams
-    int gridCache[16] = {0};             // persistent-grid sizes per kernel (occupancy x SM count of THIS context's device)
+    int trace_generic = 0;               // 1: always the general traversal loop, never the scene-kind specialisations (NX_TRACE_GENERIC; tests)
+    int gridCache[24] = {0};             // persistent-grid sizes per kernel (occupancy x SM count of THIS context's device)
     int sort_mode = 1;                   // 1 = radix_sort.cuh (own onesweep sort), 0 = cub::DeviceRadixSort (measurement only); NX_SORT=0|1
     int dp_waves = 1;                    // 1 = C(n, i) tables level by level on builds of 200k+ primitives (NX_DP_WAVES=0: always the climb)
     int collapse_cta = 1;                // 1 = single-block collapse for builds of up to 40k primitives (NX_COLLAPSE_CTA=0: always the grid-wide kernel)

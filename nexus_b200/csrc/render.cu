@@ -41,23 +41,23 @@ struct AnySink {
     }
 };
 
-template <bool STATS>
+template <bool STATS, int KIND>
 __global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_closest_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
                                                                          uint32_t* cursor, nx_hit* __restrict__ hits, TraceStats* stats, TraceTuning tune)
 {
-    __shared__ __align__(16) uint32_t smem[NX_TRACE_SMEM_BYTES / 4];
+    __shared__ __align__(16) uint32_t smem[(KIND == NX_SCENE_DIRECT ? NX_TRACE_SMEM_BYTES_DIRECT : NX_TRACE_SMEM_BYTES) / 4];
     ClosestSink sink{hits};
-    trace_loop<false, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
+    trace_loop<false, STATS, KIND>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
 }
 
-template <bool STATS>
+template <bool STATS, int KIND>
 __global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_any_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
                                                                      uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum,
                                                                      TraceStats* stats, TraceTuning tune)
 {
-    __shared__ __align__(16) uint32_t smem[NX_TRACE_SMEM_BYTES / 4];
+    __shared__ __align__(16) uint32_t smem[(KIND == NX_SCENE_DIRECT ? NX_TRACE_SMEM_BYTES_DIRECT : NX_TRACE_SMEM_BYTES) / 4];
     AnySink sink{occluded, radiance, accum};
-    trace_loop<true, STATS>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
+    trace_loop<true, STATS, KIND>(sc, rays, nPtr ? __ldg(nPtr) : nImm, cursor, tune, smem, sink, stats);
 }
 
 // Two rays per lane (traverse_duo.cuh).
@@ -161,6 +161,8 @@ int pool_spill(nx_ctx* ctx, int which, int grid, uint2** out)
     return NX_OK;
 }
 
+inline int scene_kind(const TraceScene& sc) { return sc.mergedSlot == NX_INVALID ? NX_SCENE_TWO_LEVEL : (sc.direct ? NX_SCENE_DIRECT : NX_SCENE_MIXED); }
+
 // One closest-hit launch over a ray queue (count immediate or read on the device) in the context's traversal mode.
 template <bool STATS>
 int launch_closest(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_ray* q, uint32_t nImm, const uint32_t* nPtr, uint32_t* cursor, nx_hit* hits, TraceStats* stats)
@@ -174,8 +176,19 @@ int launch_closest(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_
         TraceTuning t = trace_tuning(ctx); t.stackLimit = std::min<uint32_t>(std::max<uint32_t>(ctx->stack_limit, NX_DUO_STACK), NX_STACK_TOTAL);
         trace_closest_duo_kernel<STATS><<<grid, NX_DUO_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, t);
     } else {
-        const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<STATS>, NX_TRACE_BLOCK, 0, STATS ? 1 : 0);
-        trace_closest_kernel<STATS><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, trace_tuning(ctx));
+        // the loop specialised for what the scene holds (traverse.cuh); NX_TRACE_GENERIC=1 forces the general one (tests: same bytes)
+        const int kind = ctx->trace_generic ? NX_SCENE_MIXED : scene_kind(sc);
+        const TraceTuning t = trace_tuning(ctx);
+        if (kind == NX_SCENE_DIRECT) {
+            const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<STATS, NX_SCENE_DIRECT>, NX_TRACE_BLOCK, 0, STATS ? 17 : 16);
+            trace_closest_kernel<STATS, NX_SCENE_DIRECT><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, t);
+        } else if (kind == NX_SCENE_TWO_LEVEL) {
+            const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<STATS, NX_SCENE_TWO_LEVEL>, NX_TRACE_BLOCK, 0, STATS ? 19 : 18);
+            trace_closest_kernel<STATS, NX_SCENE_TWO_LEVEL><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, t);
+        } else {
+            const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<STATS, NX_SCENE_MIXED>, NX_TRACE_BLOCK, 0, STATS ? 1 : 0);
+            trace_closest_kernel<STATS, NX_SCENE_MIXED><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, t);
+        }
     }
     return NX_OK;
 }
@@ -192,8 +205,18 @@ int launch_any(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_ray*
         TraceTuning t = trace_tuning(ctx, true); t.stackLimit = std::min<uint32_t>(std::max<uint32_t>(ctx->stack_limit, NX_DUO_STACK), NX_STACK_TOTAL);
         trace_any_duo_kernel<STATS><<<grid, NX_DUO_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
     } else {
-        const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<STATS>, NX_TRACE_BLOCK, 0, STATS ? 3 : 2);
-        trace_any_kernel<STATS><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, trace_tuning(ctx, true));
+        const int kind = ctx->trace_generic ? NX_SCENE_MIXED : scene_kind(sc);
+        const TraceTuning t = trace_tuning(ctx, true);
+        if (kind == NX_SCENE_DIRECT) {
+            const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<STATS, NX_SCENE_DIRECT>, NX_TRACE_BLOCK, 0, STATS ? 21 : 20);
+            trace_any_kernel<STATS, NX_SCENE_DIRECT><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
+        } else if (kind == NX_SCENE_TWO_LEVEL) {
+            const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<STATS, NX_SCENE_TWO_LEVEL>, NX_TRACE_BLOCK, 0, STATS ? 23 : 22);
+            trace_any_kernel<STATS, NX_SCENE_TWO_LEVEL><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
+        } else {
+            const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<STATS, NX_SCENE_MIXED>, NX_TRACE_BLOCK, 0, STATS ? 3 : 2);
+            trace_any_kernel<STATS, NX_SCENE_MIXED><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
+        }
     }
     return NX_OK;
 }

@@ -173,8 +173,10 @@ __global__ void shade_record_kernel(const float* __restrict__ tris, const float*
     }
 }
 
-// ---- merged BLAS: the triangles of every instance whose mesh nobody else uses, transformed to world space once ----
-struct BakeSrc { const float* tris; float m[12]; uint32_t first, count, inst, pad; };   // source j covers merged primitives [first, first + count)
+// ---- merged BLAS: every instance whose mesh nobody else uses, under ONE tree built over the world-space boxes of their triangles ----
+// The leaf records stay in object space (traverse.cuh: a triangle is tested with the ray taken into its instance's object space, so the
+// hits are the two-level scene's bit for bit); only the NODES are in world space.
+struct BakeSrc { const float* tris; float m[12]; uint32_t first, count, inst; float mag; };   // source j covers merged primitives [first, first + count)
 
 __device__ __forceinline__ uint32_t bake_source_of(const BakeSrc* __restrict__ src, uint32_t nSrc, uint32_t p)
 {
@@ -182,33 +184,47 @@ __device__ __forceinline__ uint32_t bake_source_of(const BakeSrc* __restrict__ s
     while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (__ldg(&src[mid].first) <= p) lo = mid; else hi = mid - 1; }
     return lo;
 }
-__global__ void bake_triangles_kernel(const BakeSrc* __restrict__ src, uint32_t nSrc, uint32_t total, float* __restrict__ out, uint32_t* __restrict__ srcOf)
+// World-space AABB of every merged primitive (nx_aabb: min, max), padded.  The box is that of the fp32-transformed vertices; the
+// triangle test, however, runs in object space on the fp32-transformed RAY, so the surface the ray can hit sits where the exact
+// transform would put it, give or take the rounding of both transforms: a few ulps of the largest magnitude involved (world
+// coordinates and translation).  pad = 2^-21 of that magnitude (4 ulps) per side.
+__global__ void bake_bounds_kernel(const BakeSrc* __restrict__ src, uint32_t nSrc, uint32_t total, float* __restrict__ out, uint32_t* __restrict__ srcOf)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
         const uint32_t j = bake_source_of(src, nSrc, p);
         const BakeSrc S = src[j];
         const float* t = S.tris + 9 * (size_t)(p - S.first);
-        float* o = out + 9 * (size_t)p;
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        float mag = S.mag;
 #pragma unroll
         for (int v = 0; v < 3; v++) {
             const float x = __ldg(t + 3 * v), y = __ldg(t + 3 * v + 1), z = __ldg(t + 3 * v + 2);
 #pragma unroll
-            for (int a = 0; a < 3; a++) o[3 * v + a] = __fmaf_rn(S.m[4 * a], x, __fmaf_rn(S.m[4 * a + 1], y, __fmaf_rn(S.m[4 * a + 2], z, S.m[4 * a + 3])));
+            for (int a = 0; a < 3; a++) {
+                const float w = __fmaf_rn(S.m[4 * a], x, __fmaf_rn(S.m[4 * a + 1], y, __fmaf_rn(S.m[4 * a + 2], z, S.m[4 * a + 3])));
+                lo[a] = fminf(lo[a], w); hi[a] = fmaxf(hi[a], w); mag = fmaxf(mag, fabsf(w));
+            }
         }
+        const float pad = __fmul_rn(mag, 0x1p-21f);
+        float* o = out + 6 * (size_t)p;
+#pragma unroll
+        for (int a = 0; a < 3; a++) { o[a] = __fsub_rd(lo[a], pad); o[3 + a] = __fadd_ru(hi[a], pad); }
         srcOf[p] = j;
     }
 }
-// leaf-ordered stream of the merged BLAS: {v0 | primitive id inside its mesh}, {v1 - v0 | instance id}, {v2 - v0 | 0}
-__global__ void merged_leaf_kernel(const float* __restrict__ tris, const uint32_t* __restrict__ primIdx, uint32_t n, const uint32_t* __restrict__ srcOf,
+// leaf-ordered stream of the merged BLAS, OBJECT space: {v0 | primitive id inside its mesh}, {v1 - v0 | instance id}, {v2 - v0 | 0}:
+// the floats leaf_triangles_kernel writes for the mesh's own BLAS
+__global__ void merged_leaf_kernel(const uint32_t* __restrict__ primIdx, uint32_t n, const uint32_t* __restrict__ srcOf,
                                    const BakeSrc* __restrict__ src, float4* __restrict__ out)
 {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t p = __ldg(primIdx + k);
         const uint32_t j = __ldg(srcOf + p);
-        const float* t = tris + 9 * (size_t)p;
+        const uint32_t q = p - __ldg(&src[j].first);
+        const float* t = src[j].tris + 9 * (size_t)q;
         const V3 a = v3(__ldg(t), __ldg(t + 1), __ldg(t + 2)), b = v3(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)), c = v3(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
         const V3 e0 = b - a, e1 = c - a;
-        out[3 * (size_t)k] = make_float4(a.x, a.y, a.z, __uint_as_float(p - __ldg(&src[j].first)));
+        out[3 * (size_t)k] = make_float4(a.x, a.y, a.z, __uint_as_float(q));
         out[3 * (size_t)k + 1] = make_float4(e0.x, e0.y, e0.z, __uint_as_float(__ldg(&src[j].inst)));
         out[3 * (size_t)k + 2] = make_float4(e1.x, e1.y, e1.z, 0.f);
     }
@@ -294,7 +310,7 @@ int nxi_scene_view(nx_scene* s, DSceneView* v)
     v->trace.tlasNodes = s->dTopNodes; v->trace.tlasPrimIdx = s->dSlotInst; v->trace.inst = s->dTravInst; v->trace.overflow = s->ctx->dOverflow;
     v->trace.mergedSlot = s->mergedSlot;
     v->trace.direct = (s->mergedSlot != NX_INVALID && s->tlasEntryInst.size() == 1) ? 1u : 0u;
-    v->trace.mNodes = (const float4*)s->merged.nodes; v->trace.mLtris = s->dMergedLeaf;
+    v->trace.mNodes = (const float4*)s->merged.nodes; v->trace.mLtris = s->dMergedLeaf; v->trace.instInv = s->dInstInv;
     v->shadeInst = s->dShadeInst; v->meshes = s->dMeshes; v->materials = s->dMaterials; v->lights = s->dLights;
     v->lightCount = (uint32_t)s->lights.size(); v->hasHdr = s->hasHdr ? 1u : 0u; v->hdr = s->hdr; v->textures = s->dTextures;
     v->camera = nxi_camera_to_device(s->camera, s->width, s->height);
@@ -330,7 +346,7 @@ void nx_scene_destroy(nx_scene* s)
     for (nx_bump& slab : s->arena) cudaFree(slab.base);
     if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
     if (s->merged.nodes) nx_bvh8_free(ctx, &s->merged);
-    cudaFree(s->dMergedLeaf); cudaFree(s->dSlotInst);
+    cudaFree(s->dMergedLeaf); cudaFree(s->dSlotInst); cudaFree(s->dInstInv);
     if (s->dTop && ctx->l2_persist_bytes) {   // drop the window that points at this scene's top-level block
         cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
         cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
@@ -766,7 +782,8 @@ int nx_scene_update(nx_scene* s)
                     const HostInstance& h = s->instances[mergeSet[j]];
                     const HostMesh& hm = s->meshes[h.meshIdx];
                     src[j].tris = hm.dTris; std::memcpy(src[j].m, h.m, 48);
-                    src[j].first = (uint32_t)total; src[j].count = hm.bvh.prim_count; src[j].inst = mergeSet[j]; src[j].pad = 0;
+                    src[j].first = (uint32_t)total; src[j].count = hm.bvh.prim_count; src[j].inst = mergeSet[j];
+                    src[j].mag = std::max(std::fabs(h.m[3]), std::max(std::fabs(h.m[7]), std::fabs(h.m[11])));
                     s->mergedFirst.push_back((uint32_t)total);
                     total += hm.bvh.prim_count;
                 }
@@ -774,17 +791,17 @@ int nx_scene_update(nx_scene* s)
                 const uint32_t n = (uint32_t)total;
                 BakeSrc* dSrc = nullptr; float* dWorld = nullptr; uint32_t* dSrcOf = nullptr;
                 rc = upload_vec(ctx, &dSrc, src); if (rc) return rc;
-                NX_CUDA(ctx, cudaMallocAsync((void**)&dWorld, 36 * (size_t)n, ctx->stream));
+                NX_CUDA(ctx, cudaMallocAsync((void**)&dWorld, 24 * (size_t)n, ctx->stream));
                 NX_CUDA(ctx, cudaMallocAsync((void**)&dSrcOf, 4 * (size_t)n, ctx->stream));
                 NX_CUDA(ctx, cudaMallocAsync((void**)&s->dMergedLeaf, 48 * (size_t)n, ctx->stream));
                 // the geometry uploads ran on the build streams
                 for (int k = 0; k < ctx->buildStreamCount; k++) NX_CUDA(ctx, cudaStreamSynchronize(ctx->buildStreams[k]));
                 const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
-                bake_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(dSrc, (uint32_t)src.size(), n, dWorld, dSrcOf);
+                bake_bounds_kernel<<<grid, 256, 0, ctx->stream>>>(dSrc, (uint32_t)src.size(), n, dWorld, dSrcOf);
                 // 64-bit Morton keys: the merged BLAS spans the whole scene, and 10 bits per axis would put many of its small triangles
-                // into the same cell
-                rc = nxi_build_bvh8(ctx, dWorld, n, 1, /*prioritizeSpeed=*/0, &s->merged); if (rc) return rc;
-                merged_leaf_kernel<<<grid, 256, 0, ctx->stream>>>(dWorld, s->merged.prim_idx, n, dSrcOf, dSrc, s->dMergedLeaf);
+                // into the same cell.  Built over boxes (primType 0) with the triangle BLASes' leaf size.
+                rc = nxi_build_bvh8(ctx, dWorld, n, 0, /*prioritizeSpeed=*/0, &s->merged, ctx->scene_max_leaf_prims); if (rc) return rc;
+                merged_leaf_kernel<<<grid, 256, 0, ctx->stream>>>(s->merged.prim_idx, n, dSrcOf, dSrc, s->dMergedLeaf);
                 NX_CUDA(ctx, cudaGetLastError());
                 cudaFreeAsync(dWorld, ctx->stream); cudaFreeAsync(dSrcOf, ctx->stream); cudaFreeAsync(dSrc, ctx->stream);
             }
@@ -806,6 +823,11 @@ int nx_scene_update(nx_scene* s)
             bounds[i] = h.bounds;
         }
         rc = upload_vec(ctx, &s->dShadeInst, si); if (rc) return rc;
+        {   // instance id -> world -> object rows, for the object-space triangle tests inside the merged BLAS
+            std::vector<float4> ii(3 * s->instances.size());
+            for (size_t i = 0; i < s->instances.size(); i++) std::memcpy(&ii[3 * i], s->instances[i].inv, 48);
+            rc = upload_vec(ctx, &s->dInstInv, ii); if (rc) return rc;
+        }
 
         // TLAS entries: the instances that keep their own BLAS, then the merged BLAS as one more primitive
         std::vector<uint32_t> entryInst;
@@ -1018,9 +1040,9 @@ int nx_scene_export_tlas_entries(nx_scene* s, uint32_t* outInst, uint32_t* outCo
     if (outInst) std::memcpy(outInst, s->tlasEntryInst.data(), 4 * s->tlasEntryInst.size());
     return NX_OK;
 }
-// The merged BLAS for the parity tests: its handle, and per merged primitive the world-space triangle (exactly the floats it was built
-// from: the same kernel again), the instance it belongs to and its primitive id inside that instance's mesh.  Any pointer may be null.
-int nx_scene_export_merged(nx_scene* s, nx_bvh8* outBvh, float* hostWorldTris, uint32_t* hostInst, uint32_t* hostPrim, uint32_t* outCount)
+// The merged BLAS for the parity tests: its handle, and per merged primitive the padded world-space box it was built over (exactly
+// those floats: the same kernel again), the instance it belongs to and its primitive id inside that instance's mesh.  Any pointer may be null.
+int nx_scene_export_merged(nx_scene* s, nx_bvh8* outBvh, float* hostBounds, uint32_t* hostInst, uint32_t* hostPrim, uint32_t* outCount)
 {
     if (!s || !outCount) return NX_ERR_INVALID;
     if (s->dirtyInstances) { int rc = nx_scene_update(s); if (rc) return rc; }
@@ -1035,20 +1057,21 @@ int nx_scene_export_merged(nx_scene* s, nx_bvh8* outBvh, float* hostWorldTris, u
             const uint32_t first = s->mergedFirst[j], count = s->meshes[s->instances[s->mergedInstances[j]].meshIdx].bvh.prim_count;
             for (uint32_t p = 0; p < count; p++) { if (hostInst) hostInst[first + p] = s->mergedInstances[j]; if (hostPrim) hostPrim[first + p] = p; }
         }
-    if (hostWorldTris) {
+    if (hostBounds) {
         std::vector<BakeSrc> src(s->mergedInstances.size());
         for (size_t j = 0; j < src.size(); j++) {
             const HostInstance& h = s->instances[s->mergedInstances[j]];
             src[j].tris = s->meshes[h.meshIdx].dTris; std::memcpy(src[j].m, h.m, 48);
-            src[j].first = s->mergedFirst[j]; src[j].count = s->meshes[h.meshIdx].bvh.prim_count; src[j].inst = s->mergedInstances[j]; src[j].pad = 0;
+            src[j].first = s->mergedFirst[j]; src[j].count = s->meshes[h.meshIdx].bvh.prim_count; src[j].inst = s->mergedInstances[j];
+            src[j].mag = std::max(std::fabs(h.m[3]), std::max(std::fabs(h.m[7]), std::fabs(h.m[11])));
         }
         BakeSrc* dSrc = nullptr; float* dWorld = nullptr; uint32_t* dSrcOf = nullptr;
         int rc = upload_vec(ctx, &dSrc, src); if (rc) return rc;
-        NX_CUDA(ctx, cudaMallocAsync((void**)&dWorld, 36 * (size_t)n, ctx->stream));
+        NX_CUDA(ctx, cudaMallocAsync((void**)&dWorld, 24 * (size_t)n, ctx->stream));
         NX_CUDA(ctx, cudaMallocAsync((void**)&dSrcOf, 4 * (size_t)n, ctx->stream));
         const int grid = (int)std::min<uint32_t>(div_up(n, 256), (uint32_t)ctx->sm_count * 8u);
-        bake_triangles_kernel<<<grid, 256, 0, ctx->stream>>>(dSrc, (uint32_t)src.size(), n, dWorld, dSrcOf);
-        NX_CUDA(ctx, cudaMemcpyAsync(hostWorldTris, dWorld, 36 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        bake_bounds_kernel<<<grid, 256, 0, ctx->stream>>>(dSrc, (uint32_t)src.size(), n, dWorld, dSrcOf);
+        NX_CUDA(ctx, cudaMemcpyAsync(hostBounds, dWorld, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFreeAsync(dSrc, ctx->stream); cudaFreeAsync(dWorld, ctx->stream); cudaFreeAsync(dSrcOf, ctx->stream);
     }

@@ -49,11 +49,16 @@ struct TraceScene {
     const float4* tlasNodes;
     const uint32_t* tlasPrimIdx;   // TLAS leaf slot -> instance id (read once per ray, at the end); unused for the merged BLAS's slot
     const DTravInst* inst;         // TLAS leaf slot -> traversal record
-    // Merged BLAS (scene.cu): the instances whose mesh nobody else uses are transformed to world space once and share ONE BLAS, entered
-    // with the identity transform.  Its leaf triangles carry the instance id ({v0 | prim}, {e0 | instance}, {e1 | -}).
+    // Merged BLAS (scene.cu): the instances whose mesh nobody else uses share ONE BLAS whose NODES are in world space (built over the
+    // world-space boxes of their triangles), entered with the identity transform.  Its leaf records stay in OBJECT space and carry the
+    // instance id ({v0 | prim}, {e0 | instance}, {e1 | -}): a triangle is tested with the ray taken into its instance's object space by
+    // the same arithmetic an instance entry uses, so t, u, v and the accept / reject decision are bit for bit those of the two-level
+    // scene (a world-space triangle test rounds differently: at coordinates of ~1000 units it moved hits by 1e-4..1e-3 of a unit and
+    // flipped near-origin hits of secondary rays, 2e-4 of the rays of the 10 M-triangle scene).
     uint32_t mergedSlot;           // TLAS leaf slot of that BLAS, NX_INVALID when the scene has none
     uint32_t direct;               // 1: it is the ONLY TLAS entry, rays start inside it and never see the TLAS
     const float4* mNodes; const float4* mLtris;
+    const float4* instInv;         // instance id -> rows of its world -> object 3x4 (3 x float4), for the triangles of the merged BLAS
     uint32_t* overflow;            // device counter of traversal-stack pushes refused (a tree deeper than NX_STACK_TOTAL entries); the
                                    // host turns a non-zero value into an error (the reference's 32-entry stack has no check, BVH8Traversal.cuh:164)
 };
@@ -77,6 +82,7 @@ struct TraceStats {
 // thread: {origin, octant word} {direction, -} {reciprocal direction, -}.  Three LDS.128 / STS.128 per instance exit /
 // entry; a 48-byte thread stride keeps the 16-byte accesses of a quarter warp on distinct banks.
 #define NX_TRACE_SMEM_BYTES ((NX_STACK_SHARED * 8 + 48) * NX_TRACE_BLOCK)
+#define NX_TRACE_SMEM_BYTES_DIRECT (NX_STACK_SHARED * 8 * NX_TRACE_BLOCK)   // NX_SCENE_DIRECT: no instance is ever entered, nothing is parked
 
 // (7 - octant) replicated into four bytes, octant = sign bits of the direction (x: 4, y: 2, z: 1).  Any value works as long
 // as the same one decodes the hit mask it encoded (it only fixes the visiting order), so the sign BITS are used: shifts
@@ -215,6 +221,16 @@ __device__ __forceinline__ V3 xform_vector(float4 r0, float4 r1, float4 r2, V3 p
               __fmaf_rn(r2.x, p.x, __fmaf_rn(r2.y, p.y, __fmul_rn(r2.z, p.z))));
 }
 
+// The ray a triangle of the merged BLAS is tested with: the world-space ray taken into the object space of the triangle's instance,
+// exactly as an instance entry does it (same operations, same order: the two-level scene's o', d').
+__device__ __forceinline__ void merged_object_ray(const TraceScene& sc, uint32_t inst, V3& o, V3& d)
+{
+    const float4* m = sc.instInv + 3 * (size_t)inst;
+    const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+    const V3 wo = o, wd = d;
+    o = xform_point(r0, r1, r2, wo); d = xform_vector(r0, r1, r2, wd);
+}
+
 // Warp-granular dynamic fetch: a warp reserves 32 queue slots with one atomic and hands them to lanes as they finish, so
 // lanes never idle while the queue still has rays (the reference fetches one ray per atomic, BVH8Traversal.cuh:179).
 struct WarpFetcher {
@@ -236,7 +252,15 @@ struct WarpFetcher {
 
 // The traversal loop, shared by the closest-hit and the any-hit kernels.
 //   Sink::finish(rayIdx, pad, t, u, v, prim, slot, occluded) is called once per ray.
-template <bool ANY_HIT, bool STATS, typename Sink>
+// KIND specialises it for what the scene holds (the host picks the kernel; results are identical, the general loop handles everything):
+//   NX_SCENE_MIXED      TLAS over instances with their own BLAS and the merged BLAS;
+//   NX_SCENE_TWO_LEVEL  no merged BLAS: the merged-triangle path is compiled out of the triangle test;
+//   NX_SCENE_DIRECT     the merged BLAS is the whole scene: rays start inside it, there is no TLAS, no instance entry or exit, no parked
+//                       ray, and the node / triangle pointers are launch constants instead of per-lane registers.
+#define NX_SCENE_MIXED 0
+#define NX_SCENE_TWO_LEVEL 1
+#define NX_SCENE_DIRECT 2
+template <bool ANY_HIT, bool STATS, int KIND, typename Sink>
 __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* __restrict__ rays, uint32_t n, uint32_t* cursor, TraceTuning tune,
                                            uint32_t* smem, Sink& sink, TraceStats* stats)
 {
@@ -254,9 +278,9 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
     float tmax = 0.f, hitT = NX_MISS_T, hitU = 0.f, hitV = 0.f;
     uint32_t hitPrim = NX_INVALID, hitSlot = NX_INVALID;
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
-    const float4* nodes = sc.tlasNodes; const float4* ltris = nullptr;
+    const float4* nodes = KIND == NX_SCENE_DIRECT ? sc.mNodes : sc.tlasNodes; const float4* ltris = KIND == NX_SCENE_DIRECT ? sc.mLtris : nullptr;
     uint32_t octinv4 = 0, curSlot = NX_INVALID, rayIdx = 0, rayPad = 0;
-    int sp = 0, instDepth = -1;
+    int sp = 0, instDepth = KIND == NX_SCENE_DIRECT ? 0 : -1;
     bool live = false, dead = false, occluded = false;
 #ifdef NX_TRACE_WATCHDOG
     uint32_t wdSteps = 0;
@@ -278,21 +302,24 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
         if (STATS) cT++;
         const float4* tri = ltris + 3 * (size_t)(tgroup.x + bit);
         const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+        V3 to = o, td = d;
+        const bool inMerged = KIND == NX_SCENE_DIRECT || (KIND == NX_SCENE_MIXED && curSlot == sc.mergedSlot);
+        if (inMerged) merged_object_ray(sc, __float_as_uint(b.w), to, td);
         const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
-        const V3 pv = xcross(d, e1);
+        const V3 pv = xcross(td, e1);
         const float det = xdot(e0, pv);
         const float invDet = rcp_ieee(det);
-        const V3 s = o - v3(a.x, a.y, a.z);
+        const V3 s = to - v3(a.x, a.y, a.z);
         const float u = __fmul_rn(invDet, xdot(s, pv));
         const V3 qv = xcross(s, e0);
-        const float v = __fmul_rn(invDet, xdot(d, qv));
+        const float v = __fmul_rn(invDet, xdot(td, qv));
         const float t = __fmul_rn(invDet, xdot(e1, qv));
         if (u >= 0.0f && u <= 1.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f && t > 0.0f)
         {
             const uint32_t prim = __float_as_uint(a.w);
             if (ANY_HIT) { if (t < tmax) occluded = true; }
             else {
-                const uint32_t here = curSlot == sc.mergedSlot ? (0x80000000u | __float_as_uint(b.w)) : curSlot;
+                const uint32_t here = inMerged ? (0x80000000u | __float_as_uint(b.w)) : curSlot;
                 bool take = t < fminf(tmax, hitT);
                 if (!take && t == hitT && hitPrim != NX_INVALID) {
                     // exact tie: the smaller (instance id, primitive id) wins, whatever the visiting order
@@ -314,7 +341,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                 if (STATS) cR++;
                 live = false; ngroup = make_uint2(0u, 0u); tgroup = make_uint2(0u, 0u);
             } else {
-                if (sp == instDepth) {      // leaving an instance: restore the parked world-space ray
+                if (KIND != NX_SCENE_DIRECT && sp == instDepth) {      // leaving an instance: restore the parked world-space ray
                     const float4 p0 = park4[0], p1 = park4[1], p2 = park4[2];
                     o = v3(p0.x, p0.y, p0.z); d = v3(p1.x, p1.y, p1.z); inv = v3(p2.x, p2.y, p2.z);
                     octinv4 = __float_as_uint(p0.w);
@@ -327,7 +354,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
         // what every lane could do next; phases other than N run when enough lanes want them or nobody has a node to test
         const bool hasN = live && (ngroup.y & 0xff000000u) != 0u;
         const bool needR = !live && !dead;
-        const bool wantI = live && instDepth < 0 && tgroup.y != 0u;
+        const bool wantI = KIND != NX_SCENE_DIRECT && live && instDepth < 0 && tgroup.y != 0u;
         const uint32_t mN = __ballot_sync(NX_FULL, hasN);
         const uint32_t mX = __ballot_sync(NX_FULL, needR || wantI);
 
@@ -351,15 +378,17 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
                     wdSteps = 0;
 #endif
                     hitT = NX_MISS_T; hitU = hitV = 0.f; hitPrim = NX_INVALID; hitSlot = NX_INVALID; occluded = false;
-                    nodes = sc.tlasNodes; curSlot = NX_INVALID; instDepth = -1; sp = 0;
-                    if (sc.direct) { nodes = sc.mNodes; ltris = sc.mLtris; curSlot = sc.mergedSlot; instDepth = 0; }   // world space IS its object space
+                    sp = 0;
+                    if (KIND != NX_SCENE_DIRECT) { nodes = sc.tlasNodes; curSlot = NX_INVALID; instDepth = -1; }
+                    // the merged BLAS is the only TLAS entry: rays start inside it (its nodes are in world space)
+                    if (KIND == NX_SCENE_MIXED && sc.direct) { nodes = sc.mNodes; ltris = sc.mLtris; curSlot = sc.mergedSlot; instDepth = 0; }
                     live = true; setup = true;
                     // a ray with a non-finite origin or direction passes every conservative box test (NaNs drop out of min / max) and would
                     // walk the whole scene: it is a miss, and it is counted
                     bad = !(fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(b.x) + fabsf(b.y) + fabsf(b.z) < 3.0e38f);
                     if (bad) atomicAdd(sc.overflow + 1, 1u);
                 } else dead = true;
-            } else if (wantI) {
+            } else if (KIND != NX_SCENE_DIRECT && wantI) {
                 // first instance of the group whose bounding sphere the ray can reach before its current limit
                 const float dd = xdot(d, d), limit = ANY_HIT ? tmax : fminf(tmax, hitT);
                 const float dlen = sqrt_fast(dd), far = limit * dd * 1.0001f;   // the 1e-4 slack also covers the approximate root
@@ -423,7 +452,7 @@ __device__ __forceinline__ void trace_loop(const TraceScene& sc, const nx_ray* _
         // ---------------------------------------------------------------- phase T: triangles (rounds until too few lanes) ----
         while (true)
         {
-            const bool wantT = live && instDepth >= 0 && tgroup.y != 0u && !(ANY_HIT && occluded);
+            const bool wantT = live && (KIND == NX_SCENE_DIRECT || instDepth >= 0) && tgroup.y != 0u && !(ANY_HIT && occluded);
             const uint32_t mT = __ballot_sync(NX_FULL, wantT);
             if (!mT) break;
             // lanes that still have a node to test after this one keep the warp busy; otherwise triangles are all there is

@@ -116,14 +116,16 @@ __device__ __forceinline__ void trace_loop_duo(const TraceScene& sc, const nx_ra
         if (STATS) cT++;
         const float4* tri = ltris + 3 * (size_t)(tgroup.x + bit);
         const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+        V3 to = o, td = d;
+        if (curSlot == sc.mergedSlot) merged_object_ray(sc, __float_as_uint(b.w), to, td);   // traverse.cuh: object-space test inside the merged BLAS
         const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
-        const V3 pv = xcross(d, e1);
+        const V3 pv = xcross(td, e1);
         const float det = xdot(e0, pv);
         const float invDet = rcp_ieee(det);
-        const V3 s = o - v3(a.x, a.y, a.z);
+        const V3 s = to - v3(a.x, a.y, a.z);
         const float u = __fmul_rn(invDet, xdot(s, pv));
         const V3 qv = xcross(s, e0);
-        const float v = __fmul_rn(invDet, xdot(d, qv));
+        const float v = __fmul_rn(invDet, xdot(td, qv));
         const float t = __fmul_rn(invDet, xdot(e1, qv));
         if (u >= 0.0f && u <= 1.0f && v >= 0.0f && __fadd_rn(u, v) <= 1.0f && t > 0.0f)
         {

@@ -183,7 +183,8 @@ __device__ __forceinline__ void trace_pool_loop(const TraceScene& sc, const nx_r
                 if (STATS) cT++;
                 const float4* tri = ptr_from(lp.x, lp.y) + 3 * (size_t)(tg.x + bit);
                 const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
-                const V3 o = v3(co.x, co.y, co.z), d = v3(cd.x, cd.y, cd.z);
+                V3 o = v3(co.x, co.y, co.z), d = v3(cd.x, cd.y, cd.z);
+                if (m.y == sc.mergedSlot) merged_object_ray(sc, __float_as_uint(b.w), o, d);   // traverse.cuh: object-space test inside the merged BLAS
                 const V3 e0 = v3(b.x, b.y, b.z), e1 = v3(c.x, c.y, c.z);
                 const V3 pv = xcross(d, e1);
                 const float det = xdot(e0, pv);

@@ -20,13 +20,19 @@ struct Mesh {
     std::vector<float> tris;          // n * 9
     std::vector<Node8> nodes;
     std::vector<uint32_t> primIdx;
+    // The product's merged BLAS (nexus_b200/csrc/scene.cu; no counterpart in the reference): nodes in world space over many instances'
+    // triangles, each triangle kept in the OBJECT space of its instance and tested with the ray transformed the way an instance entry
+    // transforms it, so that the arithmetic of every triangle test is the two-level scene's.  instOf / primOf: per primitive of this
+    // mesh, the scene instance it belongs to and its index inside that instance's own mesh (what a hit reports).
+    std::vector<uint32_t> instOf, primOf;
 };
-struct Instance { uint32_t mesh; float inv[12]; };
+struct Instance { uint32_t mesh; float inv[12]; uint32_t id; };   // id: the instance id a hit reports (the entry's own index unless set)
 struct SceneO {
     std::vector<Mesh> meshes;
     std::vector<Instance> inst;
     std::vector<Node8> tlas;
     std::vector<uint32_t> tlasPrim;
+    std::vector<float> instInv;       // merged BLAS only: scene instance id -> world -> object 3x4 rows
 };
 
 struct Ray { f3 o; float tmax; f3 d; uint32_t pad; };
@@ -114,8 +120,9 @@ struct Stats { uint64_t nodes = 0, tris = 0, insts = 0; };
 
 // BVH8Trace without the SIMT bookkeeping: depth-first, children in octant order, leaves of a node before its stacked siblings.
 template <bool ANY>
-bool traverseBlas(const Mesh& M, f3 o, f3 d, float& best, Hit& hit, uint32_t instId, Stats& st)
+bool traverseBlas(const SceneO& S, const Mesh& M, f3 o, f3 d, float& best, Hit& hit, uint32_t instId, Stats& st)
 {
+    const bool merged = !M.instOf.empty();
     f3 inv = mk(rcpDir(d.x), rcpDir(d.y), rcpDir(d.z));
     uint32_t oinv = octantInv(d);
     struct Entry { uint32_t base, hits, imask; bool tri; };
@@ -141,7 +148,10 @@ bool traverseBlas(const Mesh& M, f3 o, f3 d, float& best, Hit& hit, uint32_t ins
             uint32_t prim = M.primIdx[tgroup.base + bit];
             st.tris++;
             float u, v;
-            const float tt = triangleT(&M.tris[9 * (size_t)prim], o, d, u, v);
+            f3 to = o, td = d;
+            if (merged) { const float* inv = &S.instInv[12 * (size_t)M.instOf[prim]]; to = xpoint(inv, o); td = xvector(inv, d); }
+            const float tt = triangleT(&M.tris[9 * (size_t)prim], to, td, u, v);
+            if (merged) { instId = M.instOf[prim]; prim = M.primOf[prim]; }
             if (tt > 0.0f) {
                 // closer hit, or an exact tie resolved by (instance id, primitive id) so that the visiting order cannot matter
                 // (the reference keeps whichever it met first, which depends on its warp schedule: SURVEY.md §7)
@@ -192,11 +202,10 @@ bool traverse(const SceneO& S, const Ray& r, Hit& hit, Stats& st)
             if (tgroup.hits) stack.push_back(tgroup);
             if (ngroup.hits & 0xff000000u) stack.push_back(ngroup);
             ngroup = Entry{0, 0, 0};
-            uint32_t instId = S.tlasPrim[tgroup.base + bit];
-            const Instance& I = S.inst[instId];
+            const Instance& I = S.inst[S.tlasPrim[tgroup.base + bit]];
             st.insts++;
             f3 lo = xpoint(I.inv, o), ld = xvector(I.inv, d);   // direction not renormalised: t stays in world units
-            if (traverseBlas<ANY>(S.meshes[I.mesh], lo, ld, best, hit, instId, st) && ANY) return true;
+            if (traverseBlas<ANY>(S, S.meshes[I.mesh], lo, ld, best, hit, I.id, st) && ANY) return true;
         }
         if ((ngroup.hits & 0xff000000u) == 0) {
             if (stack.empty()) return false;
@@ -239,9 +248,30 @@ int orc_scene_set_instances(void* s, const uint32_t* meshIdx, const float* inv, 
 {
     SceneO* S = (SceneO*)s;
     S->inst.resize(n);
-    for (uint32_t i = 0; i < n; i++) { S->inst[i].mesh = meshIdx[i]; std::memcpy(S->inst[i].inv, inv + 12 * (size_t)i, 48); }
+    for (uint32_t i = 0; i < n; i++) { S->inst[i].mesh = meshIdx[i]; std::memcpy(S->inst[i].inv, inv + 12 * (size_t)i, 48); S->inst[i].id = i; }
     S->tlas.resize(tlasNodeCount); std::memcpy(S->tlas.data(), tlasNodes, 80 * (size_t)tlasNodeCount);
     S->tlasPrim.assign(tlasPrimIdx, tlasPrimIdx + n);
+    return 0;
+}
+
+// The instance id each TLAS entry reports in a hit (default: its own index).
+int orc_scene_set_instance_ids(void* s, const uint32_t* ids, uint32_t n)
+{
+    SceneO* S = (SceneO*)s;
+    if (n != S->inst.size()) return -1;
+    for (uint32_t i = 0; i < n; i++) S->inst[i].id = ids[i];
+    return 0;
+}
+
+// Marks mesh `mesh` as the product's merged BLAS: instOf / primOf per primitive (n = its triangle count; its triangles are the
+// object-space triangles in merged order), invTab = nInst * 12 floats, world -> object rows by scene instance id.
+int orc_scene_set_merged(void* s, int mesh, const uint32_t* instOf, const uint32_t* primOf, uint32_t n, const float* invTab, uint32_t nInst)
+{
+    SceneO* S = (SceneO*)s;
+    if (mesh < 0 || (size_t)mesh >= S->meshes.size() || S->meshes[mesh].tris.size() != 9 * (size_t)n) return -1;
+    for (uint32_t i = 0; i < n; i++) if (instOf[i] >= nInst) return -2;
+    S->meshes[mesh].instOf.assign(instOf, instOf + n); S->meshes[mesh].primOf.assign(primOf, primOf + n);
+    S->instInv.assign(invTab, invTab + 12 * (size_t)nInst);
     return 0;
 }
 

@@ -11,7 +11,7 @@ res = (3840, 2160)
 ctx = nx.Context(0)
 desc = bench.make_desc("instanced10m_4k")
 scene = scenes.build(ctx, desc, res)
-m = scene.ExportMerged(triangles=False)
+m = scene.ExportMerged(bounds=False)
 print("merged prims", m["bvh"].primCount if m else 0, "nodes", m["bvh"].nodeCount if m else 0, "entries", len(scene.ExportTlasEntries()), flush=True)
 o, d = scenes.camera_rays(desc["camera"], res)
 rays = nx.make_rays(o, d)

@@ -1,0 +1,5 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q -k config2 -s 2>&1 | tail -30
+timeout 600 python -m pytest tests/test_gpu_trace.py -m gpu -x -q 2>&1 | tail -12
+NX_FRAMES=4 timeout 200 python scripts/tune_pool.py instanced10m_4k lane:6,8 general:6,8 2>&1 | tail -8
+NX_MERGE_INSTANCES=0 NX_FRAMES=4 timeout 200 python scripts/tune_pool.py instanced10m_4k lane:6,8 general:6,8 2>&1 | tail -8

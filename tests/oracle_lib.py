@@ -217,6 +217,15 @@ class OracleScene:
         oracle().orc_scene_set_instances(self._h, _p(mesh_idx), _p(inv12), C.c_uint32(mesh_idx.shape[0]), _p(tlas_nodes),
                                          C.c_uint32(tlas_nodes.shape[0]), _p(tlas_prim_idx))
 
+    def set_instance_ids(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        assert oracle().orc_scene_set_instance_ids(self._h, _p(ids), C.c_uint32(ids.shape[0])) == 0
+
+    def set_merged(self, mesh, inst_of, prim_of, inv12):
+        inst_of, prim_of = np.ascontiguousarray(inst_of, np.uint32), np.ascontiguousarray(prim_of, np.uint32)
+        inv12 = np.ascontiguousarray(inv12, np.float32).reshape(-1, 12)
+        assert oracle().orc_scene_set_merged(self._h, C.c_int(mesh), _p(inst_of), _p(prim_of), C.c_uint32(inst_of.shape[0]), _p(inv12), C.c_uint32(inv12.shape[0])) == 0
+
     def trace_closest(self, rays, threads=8, stats=False):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         hits = np.empty(rays.shape[0], HIT_DTYPE)
@@ -307,16 +316,27 @@ def incidence_cos(desc, inst_records, ray, instance, prim):
 
 
 def classify_hard(desc, scene, rays, got, want, hard_idx, ulps=32.0, cap=2e-2):
-    """Splits 'hard' id mismatches (compare_hits) into edge-grazing ones and real ones.  A mismatch is edge grazing when the NEARER of
-    the two reported hits - the one the other side did not see - grazes its triangle in float64: |barycentric margin| below
-    ulps * 2^-23 * scale (see grazing_margin), and never above `cap`."""
+    """Splits 'hard' id mismatches (compare_hits) into ill-conditioned ones and real ones.  The NEARER of the two reported hits - the
+    one the other side did not see - is examined in float64 (grazing_margin).  Two ways in which two correct fp32 evaluations (IEEE
+    here, fast-math contraction in the reference) legitimately disagree on whether that triangle is hit:
+      * edge grazing: |barycentric margin| below ulps * 2^-23 * scale, never above `cap`;
+      * origin on the surface: the ray STARTS within the fp32 rounding of the triangle's plane, so the sign of t (t > 0 is a hit, t <= 0
+        is behind the origin) is decided by rounding: |t| * |d| below ulps * 2^-23 * max|origin| / cos(incidence) - the transform of the
+        origin into object space rounds at the magnitude of the world coordinates, and the distance along the ray amplifies that
+        by 1 / cos.  (Secondary rays start 1e-3 above the surface they left and meet its neighbours at such distances.)
+    Returns (edge grazing, origin on surface, real)."""
     inst = scene.ExportInstances()
-    graze, real = [], []
+    graze, origin, real = [], [], []
     for i in hard_idx:
         near = got if float(got["t"][i]) < float(want["t"][i]) else want
-        _, m, scale = grazing_margin(desc, inst, rays[i], int(near["instance"][i]), int(near["prim"][i]))
-        (graze if abs(m) <= min(cap, ulps * 2.0 ** -23 * scale) else real).append(int(i))
-    return graze, real
+        t64, m, scale = grazing_margin(desc, inst, rays[i], int(near["instance"][i]), int(near["prim"][i]))
+        if abs(m) <= min(cap, ulps * 2.0 ** -23 * scale):
+            graze.append(int(i)); continue
+        c = incidence_cos(desc, inst, rays[i], int(near["instance"][i]), int(near["prim"][i]))
+        mag = float(np.abs(np.asarray(rays["origin"][i], np.float64)).max())
+        dlen = float(np.linalg.norm(np.asarray(rays["direction"][i], np.float64)))
+        (origin if abs(t64) * dlen <= ulps * 2.0 ** -23 * mag / max(c, 1e-3) else real).append(int(i))
+    return graze, origin, real
 
 
 def t_outliers(rays, got, want, rel=1e-5):
@@ -438,9 +458,10 @@ class ProductOracle:
     """CPU oracle over the acceleration structures the PRODUCT built (so traversal, not building, is under test), answering in the
     product's terms: instance ids and primitive ids inside the instance's mesh.
 
-    The product's TLAS is over entries - instances with a BLAS of their own, then the merged world-space BLAS (nx_scene_export_merged)
-    entered with the identity transform.  `trav` mirrors exactly that (same trees, same arithmetic: bit-identical hits); `plain` is
-    the object-space scene (every instance with its own mesh, no trees needed) for brute force and single-triangle evaluation."""
+    The product's TLAS is over entries - instances with a BLAS of their own, then the merged BLAS (nx_scene_export_merged: nodes in
+    world space, entered with the identity transform, every triangle tested in the object space of its instance).  `trav` mirrors
+    exactly that (same trees, same arithmetic: bit-identical hits); `plain` is the object-space scene (every instance with its own
+    mesh, no trees needed) for brute force and single-triangle evaluation."""
 
     def __init__(self, desc, scene):
         inst = scene.ExportInstances()
@@ -448,14 +469,20 @@ class ProductOracle:
         mesh_idx = inst[:, 0:4].copy().view(np.uint32).ravel()
         inv = inst[:, 72:136].copy().view(np.float32).reshape(-1, 16)[:, :12]
         entries = scene.ExportTlasEntries()
-        merged = scene.ExportMerged() if (entries == 0xffffffff).any() else None
+        merged = scene.ExportMerged(bounds=False) if (entries == 0xffffffff).any() else None
         tn, tp = scene.TLAS().ToHost()
         T = OracleScene()
-        slot_of_mesh, e_mesh, e_inv, added = {}, [], [], 0
+        slot_of_mesh, e_mesh, e_inv, added, merged_slot = {}, [], [], 0, None
         for e in entries:
             if e == 0xffffffff:
                 nodes, pidx = merged["bvh"].ToHost()
-                T.add_mesh(merged["triangles"], nodes, pidx)
+                # object-space triangles in merged order: instance by instance, each with its mesh's triangles in order
+                tris = np.empty((len(merged["prim"]), 9), np.float32)
+                first = np.nonzero(merged["prim"] == 0)[0]
+                for f, l in zip(first, list(first[1:]) + [len(tris)]):
+                    tris[f:l] = desc["meshes"][int(mesh_idx[merged["instance"][f]])]["triangles"][:l - f]
+                T.add_mesh(tris, nodes, pidx)
+                merged_slot = added
                 e_mesh.append(added); added += 1
                 e_inv.append(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32))
                 continue
@@ -466,6 +493,9 @@ class ProductOracle:
                 slot_of_mesh[k] = added; added += 1
             e_mesh.append(slot_of_mesh[k]); e_inv.append(inv[e])
         T.set_instances(np.asarray(e_mesh, np.uint32), np.ascontiguousarray(np.stack(e_inv), np.float32), tn, tp)
+        T.set_instance_ids(entries)                       # hits report scene instance ids (the merged BLAS reports per triangle)
+        if merged_slot is not None:
+            T.set_merged(merged_slot, merged["instance"], merged["prim"], inv)
         self.trav, self.entries, self.merged = T, entries, merged
         # object-space scene for brute force: one dummy node per mesh is enough, the BVHs are never walked
         P = OracleScene()
@@ -475,21 +505,8 @@ class ProductOracle:
         P.set_instances(mesh_idx, inv, dummy, np.arange(len(mesh_idx), dtype=np.uint32))
         self.plain = P
 
-    def _map(self, hits):
-        out = hits.copy()
-        hit = hits["prim"] != 0xffffffff
-        e = self.entries[np.where(hit, hits["instance"], 0)]
-        is_m = hit & (e == 0xffffffff)
-        out["instance"] = np.where(hit, e, 0xffffffff)
-        if is_m.any():
-            p = hits["prim"][is_m]
-            out["instance"][is_m] = self.merged["instance"][p]
-            out["prim"][is_m] = self.merged["prim"][p]
-        return out
-
     def trace_closest(self, rays, threads=8, stats=False):
-        r = self.trav.trace_closest(rays, threads=threads, stats=stats)
-        return (self._map(r[0]), r[1]) if stats else self._map(r)
+        return self.trav.trace_closest(rays, threads=threads, stats=stats)
 
     def trace_any(self, rays, threads=8):
         return self.trav.trace_any(rays, threads=threads)

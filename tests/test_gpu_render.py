@@ -234,10 +234,10 @@ def test_dynamic_scene_updates_rebuild_the_tlas(ctx):
     # only rebuilds the TLAS.
     desc_c = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=9, nu=16, nv=16, path_length=4))
     c = scenes.build(ctx, desc_c, res)
-    assert (c.ExportTlasEntries() == 0xffffffff).sum() == 1 and c.ExportMerged(triangles=False)["bvh"].primCount == 4
+    assert (c.ExportTlasEntries() == 0xffffffff).sum() == 1 and c.ExportMerged(bounds=False)["bvh"].primCount == 4
     nx.MeshInstance(c, 0, desc_c["instances"][0]["mesh"]).SetTransform((0.0, -0.25, 0.0), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
     c.Update()
-    assert c.ExportMerged(triangles=False)["bvh"].primCount == 2                 # the light's two triangles are what is left in it
+    assert c.ExportMerged(bounds=False)["bvh"].primCount == 2                 # the light's two triangles are what is left in it
     desc_d = scenes.with_triangle_data(scenes.instanced_scene(n_blas=4, n_instances=9, nu=16, nv=16, path_length=4))
     desc_d["instances"][0]["position"] = (0.0, -0.25, 0.0)
     d = scenes.build(ctx, desc_d, res)

@@ -62,6 +62,33 @@ def test_closest_hit_parity(ctx, have_ref, case):
 
 
 @pytest.mark.parametrize("case", trace_scenes(), ids=lambda c: c[0])
+def test_every_loop_and_scene_kind_gives_the_same_bytes(ctx, case):
+    """The traversal loops (one ray per lane specialised for the scene kind, the same loop unspecialised, two rays per lane, ray pool)
+    and the scene organisations (instance merging on: merged BLAS only or TLAS over instances + merged BLAS; off: plain two-level)
+    answer a ray batch with identical bytes: merging moves nodes to world space, never a triangle test."""
+    name, desc, res = case
+    rays = trace_rays(name, desc, res)
+    answers, kinds = {}, set()
+    try:
+        for merging in (True, False):
+            ctx.SetInstanceMerging(merging)
+            scene = scenes.build(ctx, desc, res)
+            entries = scene.ExportTlasEntries()
+            kinds.add("two-level" if not (entries == 0xffffffff).any() else ("merged only" if len(entries) == 1 else "mixed"))
+            for mode in ("lane", "general", "duo", "pool"):
+                ctx.SetTraceMode(mode)
+                answers[(merging, mode)] = (scene.TraceClosest(rays), scene.TraceAny(nx.make_rays(rays["origin"], rays["direction"], 2.0)))
+            scene.close()
+    finally:
+        ctx.SetInstanceMerging(True); ctx.SetTraceMode(os.environ.get("NX_TRACE_MODE", "lane"))
+    assert "two-level" in kinds and len(kinds) == 2, kinds
+    h0, o0 = answers[(True, "lane")]
+    for key, (h, o) in answers.items():
+        assert (h.view(np.uint8) == h0.view(np.uint8)).all(), key
+        assert (o == o0).all(), key
+
+
+@pytest.mark.parametrize("case", trace_scenes(), ids=lambda c: c[0])
 def test_any_hit_parity(ctx, case):
     name, desc, res = case
     scene = scenes.build(ctx, desc, res)
