@@ -50,7 +50,7 @@ int nx_ctx_create(int device, nx_ctx** out)
     }
     if (const char* t = std::getenv("NX_TRACE_TUNE")) {
         unsigned a = 0, b = 0;
-        if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = ctx->tune_tri_any = a; ctx->tune_inst = ctx->tune_inst_any = b; }
+        if (std::sscanf(t, "%u,%u", &a, &b) == 2) { ctx->tune_tri = ctx->tune_tri_any = a; ctx->tune_inst = ctx->tune_inst_any = b; ctx->tune_user = true; }
     }
     // L2 persistence for the top level of the scene (north_star: "L2-persistence hints for top-level nodes"): a small set-aside,
     // the window itself is set when a scene's TLAS is built (scene.cu).  NX_L2_PERSIST_MB=0 turns the hints off.
@@ -120,7 +120,7 @@ void* nx_ctx_stream(nx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int nx_ctx_set_trace_tuning(nx_ctx* ctx, uint32_t tri_lanes, uint32_t inst_lanes)
 {
     if (!ctx || tri_lanes > 32 || inst_lanes > 32) return NX_ERR_INVALID;
-    ctx->tune_tri = tri_lanes; ctx->tune_inst = inst_lanes;
+    ctx->tune_tri = tri_lanes; ctx->tune_inst = inst_lanes; ctx->tune_user = true;
     if (!std::getenv("NX_TRACE_TUNE_ANY")) { ctx->tune_tri_any = tri_lanes; ctx->tune_inst_any = inst_lanes; }
     return NX_OK;
 }

@@ -25,6 +25,9 @@ struct nx_ctx {
     // traversal batching thresholds in lanes (traverse.cuh TraceTuning); overridable with NX_TRACE_TUNE="tri,inst"
     uint32_t tune_tri = 6, tune_inst = 8, tune_sphere = 1;
     uint32_t tune_tri_any = 6, tune_inst_any = 8;   // any-hit kernel (NX_TRACE_TUNE_ANY)
+    bool tune_user = false;              // thresholds set by the caller / environment: used for every scene kind.  Otherwise scenes that are one
+                                         // merged BLAS (no instance entries: the set-up phase is only the ray fetch) run with 8 / 4, measured 1.8 %
+                                         // faster than 6 / 8 on the 10M-triangle scene (profiles/r02_tune_direct.log)
     // BVH2 -> BVH8 collapse used for the BLASes and the TLAS the scene code builds (nx_build_config::collapse / max_leaf_prims).
     // Default: the SAH-optimal collapse with at most 2 primitives per leaf - same hits, 22 % fewer node visits per ray than the
     // reference GPU converter's trees on the 10M-triangle scene (25.5 -> 22.7 ms per 4K frame); nx_ctx_set_scene_collapse /

@@ -178,7 +178,8 @@ int launch_closest(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_
     } else {
         // the loop specialised for what the scene holds (traverse.cuh); NX_TRACE_GENERIC=1 forces the general one (tests: same bytes)
         const int kind = ctx->trace_generic ? NX_SCENE_MIXED : scene_kind(sc);
-        const TraceTuning t = trace_tuning(ctx);
+        TraceTuning t = trace_tuning(ctx);
+        if (kind == NX_SCENE_DIRECT && !ctx->tune_user) { t.triLanes = 8; t.instLanes = 4; }
         if (kind == NX_SCENE_DIRECT) {
             const int grid = persistent_grid(ctx, (const void*)trace_closest_kernel<STATS, NX_SCENE_DIRECT>, NX_TRACE_BLOCK, 0, STATS ? 17 : 16);
             trace_closest_kernel<STATS, NX_SCENE_DIRECT><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, hits, stats, t);
@@ -206,7 +207,8 @@ int launch_any(nx_ctx* ctx, cudaStream_t st, const TraceScene& sc, const nx_ray*
         trace_any_duo_kernel<STATS><<<grid, NX_DUO_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
     } else {
         const int kind = ctx->trace_generic ? NX_SCENE_MIXED : scene_kind(sc);
-        const TraceTuning t = trace_tuning(ctx, true);
+        TraceTuning t = trace_tuning(ctx, true);
+        if (kind == NX_SCENE_DIRECT && !ctx->tune_user) { t.triLanes = 8; t.instLanes = 4; }
         if (kind == NX_SCENE_DIRECT) {
             const int grid = persistent_grid(ctx, (const void*)trace_any_kernel<STATS, NX_SCENE_DIRECT>, NX_TRACE_BLOCK, 0, STATS ? 21 : 20);
             trace_any_kernel<STATS, NX_SCENE_DIRECT><<<grid, NX_TRACE_BLOCK, 0, st>>>(sc, q, nImm, nPtr, cursor, occ, rad, accum, stats, t);
