@@ -819,7 +819,7 @@ int nx_scene_update(nx_scene* s)
         for (size_t i = 0; i < si.size(); i++) {
             const HostInstance& h = s->instances[i];
             std::memcpy(&si[i].m0, h.m, 48); std::memcpy(&si[i].i0, h.inv, 48);
-            si[i].meshIdx = h.meshIdx; si[i].materialIdx = h.materialIdx; si[i].pad0 = si[i].pad1 = 0;
+            si[i].meshIdx = h.meshIdx; si[i].materialIdx = h.materialIdx; si[i].shade = s->meshes[h.meshIdx].dShadeRec;
             bounds[i] = h.bounds;
         }
         rc = upload_vec(ctx, &s->dShadeInst, si); if (rc) return rc;

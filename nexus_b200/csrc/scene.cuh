@@ -22,8 +22,11 @@ static_assert(sizeof(DMaterial) == 96, "DMaterial layout");
 struct DShadeInst {            // replaces the shading half of D_MeshInstance (src/Cuda/Scene/MeshInstance.cuh:9-16), 112 B
     float4 m0, m1, m2;         // object -> world rows
     float4 i0, i1, i2;         // world -> object rows
-    uint32_t meshIdx, materialIdx, pad0, pad1;
+    uint32_t meshIdx, materialIdx;
+    const float4* shade;       // = meshes[meshIdx].shade: a shaded hit goes instance -> shading record without the mesh table in between,
+                               // and shade_kernel's logic phase can prefetch the record of a surviving hit (shade.cu)
 };
+static_assert(sizeof(DShadeInst) == 112, "DShadeInst layout");
 
 struct DLight {                // flattened D_Light (src/Cuda/Scene/Light.cuh:4-47)
     int32_t type;

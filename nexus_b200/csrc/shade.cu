@@ -183,9 +183,7 @@ __device__ __forceinline__ void material_one(const DSceneView& sv, const WaveBuf
     thr = thr / max3(thr);
 
     const DShadeInst I = sv.shadeInst[hit.instance];
-    const DMesh mesh = sv.meshes[I.meshIdx];
-    const float* td = mesh.tridata + 24 * (size_t)hit.prim;
-    const ShadeTri st = load_shade_tri(mesh.shade, hit.prim);
+    const ShadeTri st = load_shade_tri(I.shade, hit.prim);
     const F3 v0 = st.v0, v1 = st.v1, v2 = st.v2;
     const DMaterial dmat = sv.materials[I.materialIdx];     // 96 B, 16-byte aligned: six LDG.128
     nx_material mat = dmat.m;
@@ -196,6 +194,7 @@ __device__ __forceinline__ void material_one(const DSceneView& sv, const WaveBuf
     // material maps (PathTracer.cu:373-411): all six indices are -1 <=> their AND is -1
     if ((mat.base_color_map & mat.emissive_map & mat.normal_map & mat.roughness_map & mat.metalness_map & mat.metallic_roughness_map) != -1)
     {
+        const float* td = sv.meshes[I.meshIdx].tridata + 24 * (size_t)hit.prim;
         const float w0 = 1.0f - hit.u - hit.v;
         const float tu = hit.u * __ldg(td + 20) + hit.v * __ldg(td + 22) + w0 * __ldg(td + 18);
         const float tv = hit.u * __ldg(td + 21) + hit.v * __ldg(td + 23) + w0 * __ldg(td + 19);
@@ -235,7 +234,7 @@ __device__ __forceinline__ void material_one(const DSceneView& sv, const WaveBuf
             const float cosL = fabsf(dot(sf.n, rayDir));
             const F3 w0 = xf_point(I.m0, I.m1, I.m2, v0), w1 = xf_point(I.m0, I.m1, I.m2, v1), w2 = xf_point(I.m0, I.m1, I.m2, v2);
             const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
-            float lightPdf = 1.0f / ((float)sv.lightCount * (float)mesh.primCount * area);
+            float lightPdf = 1.0f / ((float)sv.lightCount * (float)__ldg(&sv.meshes[I.meshIdx].primCount) * area);
             lightPdf *= sqr(hit.t) / cosL;
             w = pdf_ok(lightPdf) ? power_heuristic(lastPdf, lightPdf) : 0.0f;
         }
@@ -287,14 +286,19 @@ __global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel
             pixel = __float_as_uint(d4.w);
             material_one(sv, wb, bounce, frame, h, f3(d4.x, d4.y, d4.z), pixel, f3(st.x, st.y, st.z), st.w, o);
         }
-        const uint32_t e = warp_append(&wb.counters->extCount[bounce], o.ext);
+        // both queue appends of the warp with their two atomics in flight together (lane 0: extension queue, lane 1: shadow queue)
+        const uint32_t mE = __ballot_sync(NX_FULL, o.ext), mS = __ballot_sync(NX_FULL, o.shadow);
+        uint32_t qbase = 0;
+        if (lane_id() == 0 && mE) qbase = atomicAdd(&wb.counters->extCount[bounce], __popc(mE));
+        if (lane_id() == 1 && mS) qbase = atomicAdd(&wb.counters->shCount[bounce], __popc(mS));
+        const uint32_t e = __shfl_sync(NX_FULL, qbase, 0) + __popc(mE & lanemask_lt());
+        const uint32_t s = __shfl_sync(NX_FULL, qbase, 1) + __popc(mS & lanemask_lt());
         if (o.ext) {
             float4* r = reinterpret_cast<float4*>(wb.ext[outQ] + e);
             r[0] = make_float4(o.extO.x, o.extO.y, o.extO.z, NX_MISS_T);
             r[1] = make_float4(o.extD.x, o.extD.y, o.extD.z, __uint_as_float(pixel));
             wb.state[outQ][e] = make_float4(o.thr.x, o.thr.y, o.thr.z, o.pdf);
         }
-        const uint32_t s = warp_append(&wb.counters->shCount[bounce], o.shadow);
         if (o.shadow) {
             float4* r = reinterpret_cast<float4*>(wb.shadow[bounce & 1u] + s);
             r[0] = make_float4(o.shO.x, o.shO.y, o.shO.z, o.shDist);
@@ -309,6 +313,14 @@ __global__ void __launch_bounds__(kShadeBlock, NX_SHADE_MIN_BLOCKS) shade_kernel
         bool surv = false;
         if (i < n)
         {
+            // the next iteration's queue entries, requested first: the logic phase is a streaming read whose DRAM latency is otherwise
+            // exposed once per iteration (ncu: long-scoreboard waits on these three loads, 5 CTAs per SM to hide them)
+            const uint32_t nx_i = i + gridDim.x * blockDim.x;
+            if (nx_i < n && (threadIdx.x & 3u) == 0u) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(wb.ext[in] + nx_i));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(wb.state[in] + nx_i));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(wb.hits + nx_i));
+            }
             const float4 d4 = __ldg(reinterpret_cast<const float4*>(wb.ext[in] + i) + 1);
             const float4 st = __ldg(wb.state[in] + i);
             surv = logic_one(sv, wb, bounce, frame, wb.hits[i].t, f3(d4.x, d4.y, d4.z), __float_as_uint(d4.w), f3(st.x, st.y, st.z));
