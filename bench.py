@@ -772,7 +772,8 @@ def run_build_ours(args):
                 "morton64": {"what": "same build with prioritizeSpeed = false (64-bit Morton keys, sort over bits [1, 64))", "total_ms": round(m64["total_ms"], 4),
                              "Mprims_per_s": round(n / m64["total_ms"] / 1e3, 1), "stage_ms": {k: round(v, 4) for k, v in m64.items() if k.endswith("_ms")},
                              "bvh8_nodes": int(m64["node_count"]), "bvh2_sah": round(m64["bvh2_cost"], 4), "bvh8_sah": round(m64["bvh8_cost"], 4)},
-                "host_generate_s": round(t_gen, 1), "gpu_launches": int(K * 4), "library_launches": int(K * 6), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+                "host_generate_s": round(t_gen, 1), "gpu_launches": int(K * 9), "library_launches": 0,   # per build: leaf bounds, Morton keys, sort prefix, 4 onesweep passes, H-PLOC, collapse (profiles/r02_ncu_launches_build10m.csv); no library kernel
+                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize()
     del dev_t, host
