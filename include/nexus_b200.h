@@ -148,6 +148,9 @@ int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims);
  * (same arithmetic, deterministic tie-break).  Also NX_TRACE_MODE=lane|pool|duo, NX_TRACE_GENERIC=1. */
 enum { NX_TRACE_LANE = 0, NX_TRACE_POOL = 1, NX_TRACE_DUO = 2, NX_TRACE_LANE_GENERAL = 3 };
 int nx_ctx_set_trace_mode(nx_ctx* ctx, int mode);
+/* Scene::Update after instances moved: 0 (default, the reference's behaviour) rebuilds the TLAS; 1 refits it (nx_bvh8_refit_aabb) whenever
+ * the set of TLAS entries is unchanged - cheaper per edit, same hits, tree quality degrades as objects travel.  NX_TLAS_REFIT=0|1. */
+int nx_ctx_set_tlas_refit(nx_ctx* ctx, int enabled);
 /* Ray-pool round thresholds, in rays of the warp's pool: a round of that kind runs when at least this many rays want it (else the
  * fullest kind runs).  any_hit != 0 sets the shadow-ray kernel's.  Also NX_POOL_TUNE / NX_POOL_TUNE_ANY = "node,tri,inst,fetch". */
 int nx_ctx_set_pool_tuning(nx_ctx* ctx, int any_hit, uint32_t node_rays, uint32_t tri_rays, uint32_t inst_rays, uint32_t fetch_rays);
@@ -176,6 +179,10 @@ int nx_bvh2_build_tri(nx_ctx* ctx, const nx_triangle* d_prims, uint32_t n, const
 int nx_bvh2_build_aabb(nx_ctx* ctx, const nx_aabb* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh2* out);
 int nx_bvh8_build_tri(nx_ctx* ctx, const nx_triangle* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out);
 int nx_bvh8_build_aabb(nx_ctx* ctx, const nx_aabb* d_prims, uint32_t n, const nx_build_config* cfg, nx_build_metrics* metrics, nx_bvh8* out);
+/* Refit of a BVH8 that nx_bvh8_build_aabb produced, in place: same topology and leaf order, node frames and child boxes recomputed
+ * bottom-up from d_bounds (prim_count boxes in device memory, primitive order); bvh->bounds is updated.  No counterpart in the
+ * reference, which rebuilds its TLAS on every instance change (Scene::BuildTLAS, src/Scene/Scene.cpp:65-78).  Blocking. */
+int nx_bvh8_refit_aabb(nx_ctx* ctx, nx_bvh8* bvh, const nx_aabb* d_bounds);
 int nx_bvh2_to_host(nx_ctx* ctx, const nx_bvh2* bvh, nx_bvh2_node* host_nodes);                       /* NXB::ToHost */
 int nx_bvh8_to_host(nx_ctx* ctx, const nx_bvh8* bvh, nx_bvh8_node* host_nodes, uint32_t* host_prim_idx);
 int nx_bvh2_free(nx_ctx* ctx, nx_bvh2* bvh);                                                           /* FreeDeviceBVH */
@@ -240,6 +247,7 @@ int nx_scene_export_tlas_entries(nx_scene* scene, uint32_t* out_inst, uint32_t* 
  * of their instance, so the hits are the two-level scene's.  out_count = 0 when the scene has no merged BLAS.  Any output pointer may be null. */
 int nx_scene_export_merged(nx_scene* scene, nx_bvh8* out_bvh, float* host_bounds, uint32_t* host_inst, uint32_t* host_prim, uint32_t* out_count);
 int nx_scene_tlas(nx_scene* scene, nx_bvh8* out);                                       /* borrowed handle */
+int nx_scene_tlas_history(nx_scene* scene, uint32_t* out_builds, uint32_t* out_refits);  /* how often the TLAS was built / refitted */
 /* The same records computed without a scene or a GPU (pure host arithmetic, the code paths nx_scene_add_instance and
  * nx_scene_export_camera use): MeshInstance::ToDevice (src/Scene/MeshInstance.h:36-66) and Camera::ToDevice (src/Scene/Camera.cpp:130-156). */
 int nx_host_instance_record(const float position[3], const float rotation_deg[3], const float scale[3], const nx_aabb* mesh_bounds,
@@ -287,6 +295,10 @@ int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* host_rgba)
  * (0 or 1, alternating).  nx_renderer_present_wait blocks until that ticket's image and totals are in host memory.  A slot is
  * reused two presents later: wait for a ticket before presenting twice more into the same host buffer. */
 int nx_renderer_present(nx_renderer* r, nx_scene* scene, uint32_t* host_rgba, int* out_ticket);
+/* The same resolve straight into caller-supplied DEVICE memory (W * H RGBA8 words): the mapped pixel-buffer object of an OpenGL viewer
+ * (PixelBuffer::GetDevicePtr, src/OpenGL/PixelBuffer.cpp:4-40; Renderer::Render maps it, src/Renderer/Renderer.cpp:41-48).  Queued on
+ * nx_ctx_stream() behind the frame, returns at once; synchronise that stream before unmapping the buffer. */
+int nx_renderer_present_device(nx_renderer* r, nx_scene* scene, uint32_t* dev_rgba);
 int nx_renderer_present_wait(nx_renderer* r, int ticket, nx_frame_stats* out_stats /* may be NULL; device_ms is 0 */);
 /* PathTracer::SetPixelQuery / PixelQueryPending / SynchronizePixelQuery (src/Renderer/PathTracer.h:23-27, PathTracer.cpp:221-240;
  * device side PathTracer.cu:150-151, 459-460): the instance under pixel (x, y) — row 0 is the bottom row — as seen by the

@@ -41,6 +41,8 @@ public:
     void Synchronize() { check(nx_ctx_synchronize(h_), "synchronize"); }
     // on (default): instances whose mesh no other instance uses, and that were never moved, share one world-space BLAS (same hits)
     void SetInstanceMerging(bool enabled) { check(nx_ctx_set_instance_merging(h_, enabled ? 1 : 0), "SetInstanceMerging"); }
+    // Scene::Update after instances moved: rebuild the TLAS (default, as the reference does) or refit it in place when the entry set is unchanged
+    void SetTlasRefit(bool enabled) { check(nx_ctx_set_tlas_refit(h_, enabled ? 1 : 0), "SetTlasRefit"); }
     int check(int rc, const char* what) const { if (rc < 0) throw Error(std::string(what) + ": " + nx_last_error(h_)); return rc; }
 private:
     nx_ctx* h_ = nullptr;
@@ -349,6 +351,8 @@ public:
     // Pipelined display read-back (the reference's PBO path): Present queues resolve + copy into a caller-owned (pinned) image
     // and returns a ticket; PresentWait blocks until that image is on the host and returns the render call's queue totals.
     int Present(Scene& scene, uint32_t* hostRgba) { int t = 0; ctx_.check(nx_renderer_present(h_, scene.handle(), hostRgba, &t), "Present"); return t; }
+    // ... or straight into device memory: the mapped pixel buffer of an OpenGL viewer (PixelBuffer::GetDevicePtr); queued on Context::stream()
+    void PresentDevice(Scene& scene, uint32_t* devRgba) { ctx_.check(nx_renderer_present_device(h_, scene.handle(), devRgba), "PresentDevice"); }
     nx_frame_stats PresentWait(int ticket) { nx_frame_stats s{}; ctx_.check(nx_renderer_present_wait(h_, ticket, &s), "PresentWait"); return s; }
     // src/Renderer/PathTracer.h:23-27
     void SetPixelQuery(uint32_t x, uint32_t y) { ctx_.check(nx_renderer_set_pixel_query(h_, x, y), "SetPixelQuery"); }

@@ -60,6 +60,11 @@ class Context:
         Applies to scenes updated afterwards.  Hits are unchanged."""
         check(self._h, lib().nx_ctx_set_instance_merging(self._h, C.c_int(int(enabled))), "SetInstanceMerging")
 
+    def SetTlasRefit(self, enabled):
+        """Scene.Update after instances moved: False (default, the reference's behaviour) rebuilds the TLAS, True refits it whenever the
+        set of TLAS entries is unchanged.  Same hits either way."""
+        check(self._h, lib().nx_ctx_set_tlas_refit(self._h, C.c_int(int(enabled))), "SetTlasRefit")
+
     def SetTraceMode(self, mode):
         """'lane' (default: one ray per lane, loop specialised for the scene kind), 'general' (the same loop unspecialised), 'pool' (64
         rays per warp in shared memory, lanes take rays by kind of work) or 'duo' (two rays per lane).  Same hits in all of them."""
@@ -144,6 +149,17 @@ class BVH8:
         prim = np.empty(self.h.prim_count, np.uint32)
         check(self.ctx._h, lib().nx_bvh8_to_host(self.ctx._h, C.byref(self.h), _ptr(nodes), _ptr(prim)), "nx_bvh8_to_host")
         return nodes, prim
+
+    def RefitAABB(self, bounds):
+        """In-place refit of a BVH8 built over boxes: same topology and leaf order, node frames and child boxes recomputed bottom-up from
+        `bounds` ((n, 6) host array, primitive order).  No counterpart in the reference (it rebuilds its TLAS); nx_bvh8_refit_aabb."""
+        bounds = np.ascontiguousarray(bounds, np.float32).reshape(-1, 6)
+        assert bounds.shape[0] == self.h.prim_count
+        dev = self.ctx.upload(bounds)
+        try:
+            check(self.ctx._h, lib().nx_bvh8_refit_aabb(self.ctx._h, C.byref(self.h), C.c_void_p(dev)), "RefitBVH8")
+        finally:
+            self.ctx.free(dev)
 
     def Free(self):
         if self.owned:
@@ -665,6 +681,12 @@ class Scene:
         check(self.ctx._h, lib().nx_scene_tlas(self._h, C.byref(h)), "TLAS")
         return BVH8(self.ctx, h, owned=False)
 
+    def TlasHistory(self):
+        """(builds, refits): how often this scene's TLAS was built from scratch / refitted in place."""
+        b, r = C.c_uint32(0), C.c_uint32(0)
+        check(self.ctx._h, lib().nx_scene_tlas_history(self._h, C.byref(b), C.byref(r)), "TlasHistory")
+        return b.value, r.value
+
     def ExportTlasEntries(self):
         """The TLAS is built over entries: the instances that keep a BLAS of their own, then the merged BLAS.  Returns the instance id
         of every entry (0xffffffff for the merged BLAS); TLAS().ToHost()'s primitive indices are entry numbers."""
@@ -837,6 +859,11 @@ class PathTracer:
         t = C.c_int(0)
         check(self.ctx._h, lib().nx_renderer_present(self._h, scene._h, _ptr(out), C.byref(t)), "Present")
         return t.value
+
+    def PresentDevice(self, scene, dev_ptr):
+        """The display transform of the current accumulation written straight into caller-supplied device memory (W * H RGBA8 words): what
+        the reference's OpenGL viewer does with its mapped pixel buffer (PixelBuffer.cpp:4-40).  Queued on the context's stream."""
+        check(self.ctx._h, lib().nx_renderer_present_device(self._h, scene._h, C.c_void_p(int(dev_ptr))), "PresentDevice")
 
     def PresentWait(self, ticket):
         """Blocks until the image of `ticket` is in host memory; returns the queue totals of the render call it shows."""

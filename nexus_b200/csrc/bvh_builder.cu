@@ -1056,6 +1056,103 @@ __global__ void single_leaf_kernel(CollapseArgs a)
     a.counters[0] = 1; a.counters[1] = 1;
 }
 
+// ------------------------------------------------------------------------------------------------ refit ----
+// Refit of a CWBVH8 built over boxes (a TLAS): same topology, same leaf order, every node's frame and child boxes recomputed bottom-up
+// from new primitive boxes.  The reference rebuilds its TLAS from scratch on every instance change (Scene::BuildTLAS,
+// src/Scene/Scene.cpp:65-78); a refit is what an interactive edit of a few instances wants - no sort, no hierarchy, no collapse, and the
+// leaf order (hence every traversal record) stays where it is.  Hits cannot change (boxes stay conservative: each is the union of what
+// lies below it, quantised outwards exactly like the collapse does it); the tree's quality degrades as objects move far, which is the
+// caller's trade (nx_ctx_set_tlas_refit).
+// One CTA: the trees this serves have a few thousand nodes at most.  The collapse numbers nodes level by level, so level L + 1 is the
+// index range that follows level L and holds popc(imask) nodes per node of L; levels are found top-down, then processed bottom-up with a
+// block barrier in between.  box[i]: the refitted bounds of node i (6 floats), read by its parent one level later.
+constexpr int kRefitBlock = 512, kRefitMaxLevels = 64;
+__global__ void __launch_bounds__(kRefitBlock) refit_kernel(float4* __restrict__ n8, uint32_t nodeCount, const uint32_t* __restrict__ primIdx,
+                                                             const float* __restrict__ primBounds, float* __restrict__ box, uint32_t* status)
+{
+    __shared__ uint32_t levelEnd[kRefitMaxLevels + 1];
+    __shared__ uint32_t red[kRefitBlock / 32];
+    __shared__ uint32_t nLevels;
+    // ---- level boundaries
+    uint32_t begin = 0, end = 1, L = 0;
+    if (threadIdx.x == 0) levelEnd[0] = 0;
+    while (true) {
+        uint32_t cnt = 0;
+        for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) cnt += __popc(__float_as_uint(n8[5 * (size_t)i].w) >> 24);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(NX_FULL, cnt, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        uint32_t total = 0;
+        for (int w = 0; w < kRefitBlock / 32; w++) total += red[w];
+        if (threadIdx.x == 0) levelEnd[L + 1] = end;
+        __syncthreads();
+        L++;
+        if (total == 0 || L == kRefitMaxLevels) break;
+        begin = end; end += total;
+    }
+    if (threadIdx.x == 0) { nLevels = L; if (end != nodeCount) atomicExch(status, 1u); }   // not a level-ordered tree of nodeCount nodes: refused
+    __syncthreads();
+    if (end != nodeCount) return;
+    // ---- bottom-up
+    for (int lev = (int)nLevels - 1; lev >= 0; lev--)
+    {
+        for (uint32_t i = levelEnd[lev] + threadIdx.x; i < levelEnd[lev + 1]; i += blockDim.x)
+        {
+            float4* nd = n8 + 5 * (size_t)i;
+            const float4 n0 = nd[0], n1 = nd[1];
+            const uint32_t imask = __float_as_uint(n0.w) >> 24, childBase = __float_as_uint(n1.x), primBase = __float_as_uint(n1.y);
+            const uint32_t meta[2] = {__float_as_uint(n1.z), __float_as_uint(n1.w)};
+            float clo[8][3], chi[8][3];
+            float plo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, phi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+            for (uint32_t s = 0; s < 8; s++)
+            {
+                const uint32_t m = (meta[s >> 2] >> (8 * (s & 3u))) & 0xffu;
+                for (int k = 0; k < 3; k++) { clo[s][k] = 3.0e38f; chi[s][k] = -3.0e38f; }
+                if (!m) continue;
+                if ((m & 0x1fu) >= 24u) {
+                    const float* b = box + 6 * (size_t)(childBase + __popc(imask & ((1u << s) - 1u)));
+                    for (int k = 0; k < 3; k++) { clo[s][k] = b[k]; chi[s][k] = b[3 + k]; }
+                } else {
+                    const uint32_t first = primBase + (m & 0x1fu), cnt = __popc(m >> 5);
+                    for (uint32_t t = 0; t < cnt; t++) {
+                        const float* b = primBounds + 6 * (size_t)primIdx[first + t];
+                        for (int k = 0; k < 3; k++) { clo[s][k] = fminf(clo[s][k], b[k]); chi[s][k] = fmaxf(chi[s][k], b[3 + k]); }
+                    }
+                }
+                for (int k = 0; k < 3; k++) { plo[k] = fminf(plo[k], clo[s][k]); phi[k] = fmaxf(phi[k], chi[s][k]); }
+            }
+            // quantisation frame and child planes exactly as the collapse writes them (collapse_one)
+            uint32_t e[3]; float inv[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float ext, sc;
+                asm("sub.ftz.f32 %0, %1, %2;" : "=f"(ext) : "f"(phi[k]), "f"(plo[k]));
+                asm("mul.ftz.f32 %0, %1, 0f3B808081;" : "=f"(sc) : "f"(ext));
+                e[k] = ceil_log2_biased(sc) & 0xffu;
+                inv[k] = __uint_as_float((254u - e[k]) << 23);
+            }
+            uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+            for (uint32_t s = 0; s < 8; s++)
+            {
+                const uint32_t m = (meta[s >> 2] >> (8 * (s & 3u))) & 0xffu;
+                if (!m) continue;
+                const uint32_t w = s >> 2, sh = (s & 3u) * 8u;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { qlo[k][w] |= quant(clo[s][k], plo[k], inv[k], false) << sh; qhi[k][w] |= quant(chi[s][k], plo[k], inv[k], true) << sh; }
+            }
+            nd[0] = make_float4(plo[0], plo[1], plo[2], __uint_as_float(e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24)));
+            nd[2] = make_float4(__uint_as_float(qlo[0][0]), __uint_as_float(qlo[0][1]), __uint_as_float(qlo[1][0]), __uint_as_float(qlo[1][1]));
+            nd[3] = make_float4(__uint_as_float(qlo[2][0]), __uint_as_float(qlo[2][1]), __uint_as_float(qhi[0][0]), __uint_as_float(qhi[0][1]));
+            nd[4] = make_float4(__uint_as_float(qhi[1][0]), __uint_as_float(qhi[1][1]), __uint_as_float(qhi[2][0]), __uint_as_float(qhi[2][1]));
+            float* b = box + 6 * (size_t)i;
+            for (int k = 0; k < 3; k++) { b[k] = plo[k]; b[3 + k] = phi[k]; }
+        }
+        __syncthreads();
+    }
+}
+
 // -------------------------------------------------------------------------------------------------- SAH ----
 // Cost metrics as Eval.cu:12-80 defines them (BVH2: 3 per inner, 2 per leaf; BVH8: 2 per inner child, 3 per leaf child).
 __global__ void bvh2_cost_kernel(const float4* __restrict__ n2, uint32_t nodeCount, Box scene, double* out)
@@ -1389,6 +1486,27 @@ int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, in
     return build_bvh8(ctx, dPrims, n, primType, &cfg, nullptr, out);
 }
 
+// Refit of a box-primitive BVH8 in place (refit_kernel).  dBounds: prim_count x nx_aabb in device memory, primitive order.
+int nxi_refit_bvh8(nx_ctx* ctx, nx_bvh8* bvh, const void* dBounds)
+{
+    if (!bvh || !bvh->nodes || !dBounds || !bvh->node_count) return NX_ERR_INVALID;
+    cudaStream_t s = ctx->stream;
+    float* dBox = nullptr; uint32_t* dStatus = nullptr;
+    NX_CUDA(ctx, cudaMallocAsync((void**)&dBox, 24 * (size_t)bvh->node_count + 4, s));
+    dStatus = reinterpret_cast<uint32_t*>(dBox + 6 * (size_t)bvh->node_count);
+    NX_CUDA(ctx, cudaMemsetAsync(dStatus, 0, 4, s));
+    refit_kernel<<<1, kRefitBlock, 0, s>>>((float4*)bvh->nodes, bvh->node_count, bvh->prim_idx, (const float*)dBounds, dBox, dStatus);
+    NX_CUDA(ctx, cudaGetLastError());
+    float root[6]; uint32_t status = 0;
+    NX_CUDA(ctx, cudaMemcpyAsync(root, dBox, 24, cudaMemcpyDeviceToHost, s));
+    NX_CUDA(ctx, cudaMemcpyAsync(&status, dStatus, 4, cudaMemcpyDeviceToHost, s));
+    NX_CUDA(ctx, cudaStreamSynchronize(s));
+    cudaFreeAsync(dBox, s);
+    if (status) NX_FAIL(ctx, NX_ERR_INVALID, "RefitBVH8: the node array is not a level-ordered tree of %u nodes (only trees built by this library can be refitted)", bvh->node_count);
+    for (int k = 0; k < 3; k++) { bvh->bounds.bmin[k] = root[k]; bvh->bounds.bmax[k] = root[3 + k]; }
+    return NX_OK;
+}
+
 // The same build issued on `stream` without any host synchronisation (scene set-up pipeline, scene.cu).
 // ws: the build stream's workspace (temporaries; reset here - builds on one stream run one after the other), outputs: where the CWBVH8
 // nodes and the leaf order go (the scene's arena).
@@ -1431,6 +1549,13 @@ int nx_bvh8_build_aabb(nx_ctx* ctx, const nx_aabb* p, uint32_t n, const nx_build
 {
     if (!ctx || !out) return NX_ERR_INVALID;
     return build_bvh8(ctx, p, n, 0, cfg, m, out);
+}
+
+int nx_bvh8_refit_aabb(nx_ctx* ctx, nx_bvh8* bvh, const nx_aabb* dBounds)
+{
+    if (!ctx || !bvh || !dBounds) return NX_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    return nxi_refit_bvh8(ctx, bvh, dBounds);
 }
 
 int nx_bvh2_to_host(nx_ctx* ctx, const nx_bvh2* b, nx_bvh2_node* host)

@@ -70,6 +70,7 @@ int nx_ctx_create(int device, nx_ctx** out)
     }
     if (const char* t = std::getenv("NX_MERGE_INSTANCES")) ctx->merge_instances = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_TRACE_GENERIC")) ctx->trace_generic = std::atoi(t) != 0;
+    if (const char* t = std::getenv("NX_TLAS_REFIT")) ctx->tlas_refit = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_MERGE_MIN_PRIMS")) ctx->merge_min_prims = (uint32_t)std::max(0, std::atoi(t));
     if (const char* t = std::getenv("NX_SCENE_BLAS_SPEED")) ctx->scene_blas_speed = std::atoi(t) != 0;
     if (const char* t = std::getenv("NX_TRACE_TUNE_ANY")) {
@@ -129,6 +130,13 @@ int nx_ctx_set_scene_collapse(nx_ctx* ctx, int collapse, int max_leaf_prims)
 {
     if (!ctx || (collapse != NX_COLLAPSE_REFERENCE_GPU && collapse != NX_COLLAPSE_SAH_OPTIMAL) || max_leaf_prims < 0 || max_leaf_prims > 3) return NX_ERR_INVALID;
     ctx->scene_collapse = collapse; ctx->scene_max_leaf_prims = max_leaf_prims;
+    return NX_OK;
+}
+
+int nx_ctx_set_tlas_refit(nx_ctx* ctx, int enabled)
+{
+    if (!ctx) return NX_ERR_INVALID;
+    ctx->tlas_refit = enabled ? 1 : 0;
     return NX_OK;
 }
 

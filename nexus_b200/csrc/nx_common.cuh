@@ -51,6 +51,7 @@ struct nx_ctx {
     uint32_t* hOverflow = nullptr;       // pinned mirror ([1]: rays with non-finite origin / direction, answered as misses)
     unsigned long long nonfinite_rays = 0;
     void* poolSpill[2] = {nullptr, nullptr}; size_t poolSpillWarps[2] = {0, 0};       // global spill stacks of the two trace streams
+    int tlas_refit = 0;                  // Scene::Update refits the TLAS instead of rebuilding it when the entry set is unchanged (nx_ctx_set_tlas_refit)
     int trace_generic = 0;               // 1: always the general traversal loop, never the scene-kind specialisations (NX_TRACE_GENERIC; tests)
     int gridCache[24] = {0};             // persistent-grid sizes per kernel (occupancy x SM count of THIS context's device)
     int sort_mode = 1;                   // 1 = radix_sort.cuh (own onesweep sort), 0 = cub::DeviceRadixSort (measurement only); NX_SORT=0|1

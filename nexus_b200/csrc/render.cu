@@ -580,6 +580,26 @@ int nx_renderer_read_rgba8(nx_renderer* r, nx_scene* scene, uint32_t* hostRgba)
     return NX_OK;
 }
 
+// The reference's display path without the copy: PathTracer::Render hands AccumulateKernel the device pointer of a mapped OpenGL
+// pixel buffer (src/OpenGL/PixelBuffer.cpp:4-40, src/Renderer/Renderer.cpp:41-48).  Here the caller supplies that pointer (W * H RGBA8
+// words, row 0 = bottom row like a GL texture upload expects); the resolve is queued on the render stream behind the frame and the call
+// returns at once - a viewer unmaps the buffer after synchronising nx_ctx_stream(), exactly where the reference calls cudaGraphicsUnmapResources.
+int nx_renderer_present_device(nx_renderer* r, nx_scene* scene, uint32_t* devRgba)
+{
+    if (!r || !scene || !devRgba) return NX_ERR_INVALID;
+    nx_ctx* ctx = r->ctx;
+    DeviceGuard guard(ctx->device);
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, devRgba) != cudaSuccess || (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        NX_FAIL(ctx, NX_ERR_INVALID, "PresentDevice: the destination is not device memory");
+    }
+    nxi_launch_resolve(ctx->sm_count * 4, ctx->stream, r->wb.accum, r->width * r->height, r->frames ? 1.0f / (float)r->frames : 0.f, scene->settings.exposure,
+                       scene->settings.tone_mapping, devRgba);
+    NX_CUDA(ctx, cudaGetLastError());
+    return NX_OK;
+}
+
 int nx_renderer_present(nx_renderer* r, nx_scene* scene, uint32_t* hostRgba, int* outTicket)
 {
     if (!r || !scene || !hostRgba || !outTicket) return NX_ERR_INVALID;

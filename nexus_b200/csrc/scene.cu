@@ -885,13 +885,19 @@ int nx_scene_update(nx_scene* s)
         }
         const bool hasMerged = !s->mergedInstances.empty();
         if (hasMerged) { entryInst.push_back(NX_INVALID); ebounds.push_back(s->merged.bounds); }
+        // same entries in the same order as the TLAS in hand: it can be refitted (nx_ctx_set_tlas_refit) instead of rebuilt
+        const bool refit = ctx->tlas_refit && s->tlas.nodes && entryInst == s->tlasEntryInst;
         s->tlasEntryInst = entryInst;
 
         // Scene::BuildTLAS (src/Scene/Scene.cpp:65-78): BuildBVH8<AABB> over the entry bounds, default config (64-bit keys)
         nx_aabb* dBounds = nullptr;
         rc = upload_vec(ctx, &dBounds, ebounds); if (rc) return rc;
-        if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
-        rc = nxi_build_bvh8(ctx, dBounds, (uint32_t)ebounds.size(), 0, 0, &s->tlas);
+        if (refit) { rc = nxi_refit_bvh8(ctx, &s->tlas, dBounds); s->tlasRefits++; }
+        else {
+            if (s->tlas.nodes) nx_bvh8_free(ctx, &s->tlas);
+            rc = nxi_build_bvh8(ctx, dBounds, (uint32_t)ebounds.size(), 0, 0, &s->tlas);
+            s->tlasBuilds++;
+        }
         cudaFreeAsync(dBounds, ctx->stream);
         if (rc) return rc;
 
@@ -1075,6 +1081,14 @@ int nx_scene_export_merged(nx_scene* s, nx_bvh8* outBvh, float* hostBounds, uint
         NX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFreeAsync(dSrc, ctx->stream); cudaFreeAsync(dWorld, ctx->stream); cudaFreeAsync(dSrcOf, ctx->stream);
     }
+    return NX_OK;
+}
+int nx_scene_tlas_history(nx_scene* s, uint32_t* outBuilds, uint32_t* outRefits)
+{
+    if (!s) return NX_ERR_INVALID;
+    if (s->dirtyInstances) { int rc = nx_scene_update(s); if (rc) return rc; }
+    if (outBuilds) *outBuilds = s->tlasBuilds;
+    if (outRefits) *outRefits = s->tlasRefits;
     return NX_OK;
 }
 int nx_scene_tlas(nx_scene* s, nx_bvh8* out)

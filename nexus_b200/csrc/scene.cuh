@@ -116,6 +116,7 @@ struct nx_scene {
     float4* dInstInv = nullptr;              // instance id -> rows of its world -> object 3x4
     uint32_t mergedSlot = 0xffffffffu;       // its TLAS leaf slot
     std::vector<uint32_t> tlasEntryInst;     // TLAS primitive (entry) -> instance id, 0xffffffff for the merged BLAS
+    uint32_t tlasRefits = 0, tlasBuilds = 0; // how the TLAS came to its current state (parity hook: nx_scene_tlas_history)
     uint32_t* dSlotInst = nullptr;           // TLAS leaf slot -> instance id
 };
 
@@ -124,6 +125,7 @@ int nxi_scene_view(nx_scene* s, DSceneView* out);
 DCamera nxi_camera_to_device(const nx_camera& c, uint32_t w, uint32_t h);
 // bvh_builder.cu
 int nxi_build_bvh8(nx_ctx* ctx, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, nx_bvh8* out, uint32_t maxLeafPrims = 0);
+int nxi_refit_bvh8(nx_ctx* ctx, nx_bvh8* bvh, const void* dBounds);
 int nxi_build_bvh8_async(nx_ctx* ctx, cudaStream_t stream, const void* dPrims, uint32_t n, int primType, int prioritizeSpeed, uint32_t* dCounters, nx_bvh8* out,
                          nx_bump* ws, nx_bump* outputs);
 size_t nxi_build_workspace_bytes(uint32_t n);

@@ -179,3 +179,50 @@ def test_sah_optimal_collapse_large_and_fewer_nodes(ctx):
         assert c8.shape == oc8.shape and (c8 == oc8).all() and (cp8 == ocp8).all()
     with pytest.raises(nx.NexusError):
         nx.BuildBVH8(ctx, prims[:100], collapse=7)
+
+
+def test_refit_keeps_the_topology_and_reproduces_a_build_on_unchanged_boxes(ctx):
+    """nx_bvh8_refit_aabb (TLAS refit): refitting with the boxes the tree was built from reproduces the built
+    nodes bit for bit (a collapsed node's child boxes ARE the unions of what lies below them); refitting with moved boxes keeps
+    topology and leaf order, and every node's decoded child box contains the boxes of the primitives below it."""
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 9, 300, 5000):
+        c = rng.uniform(-50, 50, size=(n, 3)).astype(np.float32)
+        h = rng.uniform(0.1, 3.0, size=(n, 3)).astype(np.float32)
+        boxes = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+        bvh = nx.BuildBVH8(ctx, boxes, prioritizeSpeed=False, collapse=nx.COLLAPSE_SAH_OPTIMAL, maxLeafPrims=1)
+        built, order = bvh.ToHost()
+        bvh.RefitAABB(boxes)
+        again, order2 = bvh.ToHost()
+        assert (again == built).all() and (order2 == order).all(), n
+        moved = boxes.copy()
+        sel = rng.random(n) < 0.3
+        moved[sel] += np.tile(rng.uniform(-20, 20, size=(int(sel.sum()), 3)).astype(np.float32), 2)
+        bvh.RefitAABB(moved)
+        nodes, order3 = bvh.ToHost()
+        assert (order3 == order).all()
+        assert (nodes[:, 4:8] == built[:, 4:8]).all() and ((nodes[:, 3] >> 24) == (built[:, 3] >> 24)).all()     # childBase, primBase, meta, imask
+        assert np.allclose(bvh.bounds, np.concatenate([moved[:, :3].min(0), moved[:, 3:].max(0)]))
+        # containment, top-down: the decoded box of every leaf child holds its primitives, of every inner child the child's own frame
+        nb = nodes.view(np.uint8).reshape(-1, 80)
+        p = nodes[:, 0:3].copy().view(np.float32)
+        e = nb[:, 12:15].astype(np.int32)
+        cell = np.ldexp(1.0, e - 127)
+        for i in range(len(nodes)):
+            imask = int(nb[i, 15]); child_base = int(nodes[i, 4]); prim_base = int(nodes[i, 5])
+            for s in range(8):
+                m = int(nb[i, 24 + s])
+                if not m:
+                    continue
+                lo = p[i] + cell[i] * nb[i, [32 + s, 40 + s, 48 + s]]
+                hi = p[i] + cell[i] * nb[i, [56 + s, 64 + s, 72 + s]]
+                if (m & 31) >= 24:
+                    ch = child_base + bin(imask & ((1 << s) - 1)).count("1")
+                    assert (p[ch] >= lo - 1e-4).all() and (p[ch] + cell[ch] * 255 >= lo - 1e-4).all(), (n, i, s)
+                    # the child's frame origin is its box minimum: inside the parent's box for it
+                    assert (p[ch] <= hi + 1e-4).all()
+                else:
+                    for t in range(bin(m >> 5).count("1")):
+                        b = moved[order3[prim_base + (m & 31) + t]]
+                        assert (b[:3] >= lo - 1e-4).all() and (b[3:] <= hi + 1e-4).all(), (n, i, s)
+        bvh.Free()

@@ -305,6 +305,52 @@ def test_constant_maps_equal_scaled_materials(ctx):
         scenes.build(ctx, d, (8, 8)).TraceClosest(nx.make_rays(np.zeros((1, 3), np.float32), np.array([[0, 0, -1]], np.float32)))
 
 
+def test_tlas_refit_gives_the_hits_of_a_rebuilt_scene(ctx):
+    """with nx_ctx_set_tlas_refit the Update after moving instances refits the TLAS in place (same topology and
+    leaf order) whenever the set of TLAS entries is unchanged; the hits are those of a scene created in the final state, byte for byte
+    (the TLAS only culls: ids, t, u, v come from the triangle tests).  The default stays the reference's rebuild."""
+    res = (160, 120)
+    rs = np.random.RandomState(5)
+
+    def desc_with(moves):
+        d = scenes.with_triangle_data(scenes.instanced_scene(n_blas=5, n_instances=24, nu=14, nv=12, path_length=3))
+        for i, (pos, rot, sc) in moves.items():
+            d["instances"][i]["position"], d["instances"][i]["rotation"], d["instances"][i]["scale"] = pos, rot, sc
+        return d
+
+    def random_moves(ids):
+        return {i: (tuple(float(v) for v in rs.uniform(-6, 6, 3) + np.array([0, 3.0, 0])), tuple(float(v) for v in rs.uniform(0, 360, 3)), (float(rs.uniform(0.6, 1.4)),) * 3) for i in ids}
+
+    base = desc_with({})
+    o, d = scenes.camera_rays(base["camera"], res)
+    rays = nx.make_rays(o, d)
+    for refit in (True, False):
+        ctx.SetTlasRefit(refit)
+        try:
+            s = scenes.build(ctx, base, res)
+            assert s.TlasHistory() == (1, 0)
+            moves = {}
+            for step, ids in enumerate(([4, 9, 17], [4, 9, 17], [9, 21], [3, 4, 9, 17, 21])):
+                moves.update(random_moves(ids))
+                for i in ids:
+                    nx.MeshInstance(s, i, base["instances"][i]["mesh"]).SetTransform(*moves[i])
+                s.Update()
+                got = s.TraceClosest(rays)
+                ctx.SetTlasRefit(False)
+                fresh = scenes.build(ctx, desc_with(moves), res)
+                ctx.SetTlasRefit(refit)
+                want = fresh.TraceClosest(rays)
+                assert (got.view(np.uint8) == want.view(np.uint8)).all(), (refit, step)
+                fresh.close()
+            builds, refits = s.TlasHistory()
+            # steps 0, 2 and 3 move instances for the first time: they leave the merged BLAS or - shared meshes - stay entries; the entry
+            # set changes only when a single-use instance moves for the first time.  Step 1 moves the same instances again: a pure refit.
+            assert builds + refits == 5 and (refits >= 1 if refit else refits == 0), (refit, builds, refits)
+            s.close()
+        finally:
+            ctx.SetTlasRefit(False)
+
+
 def test_present_is_a_pipelined_read_rgba8(ctx):
     """nx_renderer_present / present_wait (the reference's PBO path: Render returns without synchronising and the display reads the
     pixel buffer a frame later, PathTracer.cpp:170-199): the image and queue totals a ticket delivers are those of the frames
@@ -337,6 +383,28 @@ def test_present_is_a_pipelined_read_rgba8(ctx):
     with pytest.raises(nx.NexusError):
         fresh.PresentWait(1)
     fresh.close(); pt.close(); scene.close()
+
+
+def test_present_device_writes_the_display_image_into_caller_memory(ctx):
+    """nx_renderer_present_device: the headless form of the reference's OpenGL display path (the mapped pixel buffer's device pointer
+    handed to AccumulateKernel, PixelBuffer.cpp:4-40 / Renderer.cpp:41-48): the RGBA8 image lands in caller-supplied device memory, queued
+    behind the frame, and equals ReadRGBA8; host memory is refused."""
+    import torch
+    desc = scenes.with_triangle_data(scenes.cornell_box(path_length=3))
+    res = (96, 64)
+    scene = scenes.build(ctx, desc, res)
+    pt = nx.PathTracer(ctx, res)
+    pbo = torch.zeros(res[0] * res[1], dtype=torch.int32, device="cuda")       # stands in for the mapped pixel buffer object
+    torch.cuda.synchronize()
+    pt.Render(scene, frames=2, firstFrame=1)
+    pt.PresentDevice(scene, pbo.data_ptr())                                      # no host synchronisation in between
+    ctx.synchronize()
+    want = pt.ReadRGBA8(scene)
+    assert (pbo.cpu().numpy().view(np.uint32).reshape(res[1], res[0]) == want).all() and want.any()
+    host = np.zeros(res[0] * res[1], np.uint32)
+    with pytest.raises(nx.NexusError):
+        pt.PresentDevice(scene, host.ctypes.data)
+    pt.close(); scene.close()
 
 
 def test_pixel_query_returns_the_primary_hit_instance(ctx):
