@@ -535,7 +535,9 @@ def run_config5(nx, ctx, pt, world, rank, res, stream, barrier, sharded, total_s
     st = pt.Stats()
     t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], device="cuda", dtype=torch.float64)
     c = torch.tensor([float(st["extension_rays"] + st["shadow_rays"])], device="cuda", dtype=torch.float64)
+    t_min = t.clone()
     dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(c)
+    dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
     want, got = float(local_sum), float(reduced_sum)
     rel = abs(got - want) / max(abs(want), 1e-30)
     assert rel < 1e-5, f"reduced accumulation checksum {got} != sum of the per-rank checksums {want} (relative {rel:.2e})"
@@ -557,7 +559,9 @@ def run_config5(nx, ctx, pt, world, rank, res, stream, barrier, sharded, total_s
     return {"workload": "sky10m_4k", "what": "BASELINE configs[4]: 8xB200 sample-partitioned 4K render, procedural HDR environment map, 64 spp total, NCCL all-reduce of the accumulation buffers",
             "spp_total": per * world, "frames_per_rank": per, "value": round(float(c[0]) / (ms_total * 1e-3) / 1e6, 1), "unit": "Mrays/s",
             "spp_per_s": round(per * world / (ms_total * 1e-3), 2), "ms_total": round(ms_total, 3), "ms_per_frame": round((ms_total - ms_reduce) / per, 4),
-            "reduce_ms": round(ms_reduce, 3), "reduce_alone_ms": round(float(alone_t[0]), 3), "reduce_bytes": int(acc.numel() * 4),
+            "reduce_ms": round(ms_reduce, 3), "reduce_ms_last_arrival": round(float(t_min[1]), 3),
+            "reduce_what": "reduce_ms: checksum + all-reduce as the rank that finished rendering FIRST sees it (max over ranks: contains its wait for the slowest rank); reduce_ms_last_arrival: the same on the rank that arrived last (min over ranks: the collective itself); reduce_alone_ms: the all-reduce with the ranks aligned by a barrier",
+            "reduce_alone_ms": round(float(alone_t[0]), 3), "reduce_bytes": int(acc.numel() * 4),
             "reduce_busbw_GBs": round(2.0 * (world - 1) / world * acc.numel() * 4 / (float(alone_t[0]) * 1e-3) / 1e9, 1),
             "reduce_check": {"sum_of_rank_checksums": want, "reduced_checksum": got, "rel_err": rel}, "mean_radiance": round(mean, 5), "scene_setup_s": round(t_scene, 2)}
 

@@ -116,7 +116,11 @@ int main(int argc, char** argv)
             ip.Render(imported, 4);
             const int32_t picked = ip.SynchronizePixelQuery();
             CHECK(meanOf(ip.ReadAccumulation()) > 0.0 && picked >= -1 && picked < (int32_t)ids.size());
-            std::printf("imported %s: %zu instance(s), centre pixel sees instance %d\n", argv[a], ids.size(), picked);
+            const std::vector<float> acc = ip.ReadAccumulation();
+            double rgb[3] = {0, 0, 0};
+            for (size_t k = 0; k + 2 < acc.size(); k += 3) { rgb[0] += acc[k]; rgb[1] += acc[k + 1]; rgb[2] += acc[k + 2]; }
+            std::printf("imported %s: %zu instance(s), centre pixel sees instance %d, %zu texture(s), mean rgb %.5f %.5f %.5f\n", argv[a], ids.size(), picked,
+                        imported.GetAssetManager().GetTextureCount(), 3.0 * rgb[0] / acc.size(), 3.0 * rgb[1] / acc.size(), 3.0 * rgb[2] / acc.size());
         }
         std::printf("host api ok\n");
     } catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 1; }

@@ -35,6 +35,18 @@ int main(int argc, char** argv)
                 std::printf("%s[%.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g, %.9g]", i ? ", " : "", m.baseColor.x, m.baseColor.y, m.baseColor.z, m.opacity, m.metalness,
                             m.roughness, m.emissionColor.x, m.emissionColor.y, m.emissionColor.z, m.intensity, m.specularWeight, m.specularColor.x, m.ior, m.transmission, m.specularColor.z);
             }
+            std::printf("], \"maps\": [");
+            for (size_t i = 0; i < g.materials.size(); i++) {
+                const nexus::Material& m = g.materials[i];
+                std::printf("%s[%d, %d, %d, %d]", i ? ", " : "", m.baseColorMapId, m.emissiveMapId, m.normalMapId, m.metallicRoughnessMapId);
+            }
+            std::printf("], \"textures\": [");
+            for (size_t i = 0; i < g.textures.size(); i++) {
+                const nexus::ImportedTexture& t = g.textures[i];
+                std::printf("%s{\"width\": %u, \"height\": %u, \"srgb\": %s, \"rgba\": [", i ? ", " : "", t.image.width, t.image.height, t.sRGB ? "true" : "false");
+                for (size_t k = 0; k < t.image.rgba.size(); k++) std::printf("%s%u", k ? ", " : "", (unsigned)t.image.rgba[k]);
+                std::printf("]}");
+            }
             std::printf("], \"instances\": [");
             for (size_t i = 0; i < g.instances.size(); i++) {
                 std::printf("%s{\"mesh\": %u, \"matrix\": [", i ? ", " : "", g.instances[i].mesh);

@@ -189,8 +189,9 @@ public:
     bool IsInvalid() const { return !invalid_.empty(); }
     // AddTexture + Texture::ToDevice (src/Assets/Texture.cpp:12-46): RGBA8 (isHDR false) or RGBA32F pixels; returns the id Material::*MapId uses
     uint32_t AddTexture(const void* rgbaPixels, uint32_t width, uint32_t height, bool isHDR = false, bool sRGB = false);
+    size_t GetTextureCount() const { return textureCount_; }
 private:
-    Scene* scene_; std::vector<Material> materials_; std::set<uint32_t> invalid_;
+    Scene* scene_; std::vector<Material> materials_; std::set<uint32_t> invalid_; size_t textureCount_ = 0;
 };
 
 class Scene {                           // src/Scene/Scene.h:16-77
@@ -324,7 +325,12 @@ inline bool AssetManager::SendDataToDevice()
     invalid_.clear();
     return any;
 }
-inline uint32_t AssetManager::AddTexture(const void* px, uint32_t w, uint32_t h, bool isHDR, bool sRGB) { return (uint32_t)scene_->context().check(nx_scene_add_texture(scene_->handle(), px, w, h, isHDR, sRGB), "AddTexture"); }
+inline uint32_t AssetManager::AddTexture(const void* px, uint32_t w, uint32_t h, bool isHDR, bool sRGB)
+{
+    const uint32_t id = (uint32_t)scene_->context().check(nx_scene_add_texture(scene_->handle(), px, w, h, isHDR, sRGB), "AddTexture");
+    textureCount_++;
+    return id;
+}
 inline uint32_t AssetManager::AddMesh(const std::string& name, uint32_t materialIdx, const std::vector<NXB::Triangle>& tris, const std::vector<nx_triangle_data>& data)
 {
     if (!data.empty() && data.size() != tris.size()) throw Error("AddMesh(" + name + "): triangleData must have one entry per triangle");

@@ -19,6 +19,7 @@
 #include <sstream>
 
 #include "nexus_b200.hpp"
+#include "nexus_b200_image.hpp"
 
 namespace nexus {
 
@@ -206,10 +207,14 @@ inline HdrImage LoadHDR(const std::string& path)
 // Minimal .glb reader with the same coverage and rules as nexus_b200/gltf.py: triangle primitives (indexed or not; POSITION, NORMAL,
 // TANGENT, TEXCOORD_0, strided views, normalised integers), node hierarchy (matrix or translation / rotation / scale) accumulated into
 // one instance matrix per node and primitive, pbrMetallicRoughness + emissive + KHR_materials_{emissive_strength, specular, ior,
-// transmission} materials (OBJLoader.cpp:96-119), the first perspective camera.  Texture images are not decoded here (no image
-// library): a material that references one is rejected unless ignoreTextures is set.
+// transmission} materials (OBJLoader.cpp:96-119), the first perspective camera.  Embedded PNG / JPEG texture images are decoded with
+// nexus_b200_image.hpp (the reference: stb_image, IMGLoader.cpp:13-43): base-colour and emissive textures are flagged sRGB, normal and
+// metallic-roughness textures linear, an image shared by several materials is decoded once per (image, colour space); the materials'
+// *MapId fields index ImportedScene::textures.  ignoreTextures drops all maps instead.
 struct ImportedInstance { uint32_t mesh = 0; float matrix[16]; };                       // row-major object -> world
-struct ImportedScene { std::vector<Material> materials; std::vector<ImportedMesh> meshes; std::vector<ImportedInstance> instances; bool hasCamera = false; Camera camera; };
+struct ImportedTexture { DecodedImage image; bool sRGB = false; };
+struct ImportedScene { std::vector<Material> materials; std::vector<ImportedMesh> meshes; std::vector<ImportedInstance> instances; std::vector<ImportedTexture> textures;
+                       bool hasCamera = false; Camera camera; };
 
 namespace detail {
 struct Json {                               // just enough JSON for glTF
@@ -311,6 +316,21 @@ inline ImportedScene LoadGLB(const std::string& path, bool ignoreTextures = fals
     };
 
     ImportedScene out;
+    std::map<std::pair<size_t, bool>, int32_t> textureOf;
+    auto textureId = [&](const Json& ref, bool srgb) -> int32_t {
+        const size_t ti = (size_t)ref.at("index").num;
+        const auto key = std::make_pair(ti, srgb);
+        auto it = textureOf.find(key); if (it != textureOf.end()) return it->second;
+        const Json& image = js.at("images").at((size_t)js.at("textures").at(ti).at("source").num);
+        if (!image.has("bufferView")) throw Error(path + ": only images embedded in the binary chunk are supported");
+        const Json& view = js.at("bufferViews").at((size_t)image.at("bufferView").num);
+        const size_t start = (size_t)view.number("byteOffset", 0), len = (size_t)view.at("byteLength").num;
+        if (start + len > binLen) throw Error(path + ": image runs past the binary chunk");
+        ImportedTexture t; t.sRGB = srgb;
+        try { t.image = DecodeImage(bin + start, len); } catch (const ImageError& e) { throw Error(path + ": texture " + std::to_string(ti) + ": " + e.what()); }
+        out.textures.push_back(std::move(t));
+        return textureOf[key] = (int32_t)out.textures.size() - 1;
+    };
     auto vec = [](const Json* j, size_t n, std::initializer_list<double> def) { std::vector<double> v(def); if (j && j->kind == Json::Array) for (size_t i = 0; i < n && i < j->size(); i++) v[i] = j->arr[i].num; return v; };
     if (const Json* mats = js.find("materials")) for (const Json& m : mats->arr) {
         static const Json empty; const Json* pj = m.find("pbrMetallicRoughness"); const Json& pbr = pj ? *pj : empty; const Json* ej = m.find("extensions"); const Json& ext = ej ? *ej : empty;
@@ -324,8 +344,12 @@ inline ImportedScene LoadGLB(const std::string& path, bool ignoreTextures = fals
         const auto sc = vec(sp ? sp->find("specularColorFactor") : nullptr, 3, {1, 1, 1}); o.specularColor = {(float)sc[0], (float)sc[1], (float)sc[2]};
         const Json* ior = ext.find("KHR_materials_ior"); o.ior = ior ? (float)ior->number("ior", 1.5) : 1.5f;
         const Json* tr = ext.find("KHR_materials_transmission"); o.transmission = tr ? (float)tr->number("transmissionFactor", 0.0) : 0.0f;
-        if (!ignoreTextures && (pbr.has("baseColorTexture") || pbr.has("metallicRoughnessTexture") || m.has("normalTexture") || m.has("emissiveTexture")))
-            throw Error(path + ": the asset uses texture images, which this reader cannot decode (pass ignoreTextures = true to drop them)");
+        if (!ignoreTextures) {
+            if (const Json* t = pbr.find("baseColorTexture")) o.baseColorMapId = textureId(*t, true);
+            if (const Json* t = pbr.find("metallicRoughnessTexture")) o.metallicRoughnessMapId = textureId(*t, false);
+            if (const Json* t = m.find("normalTexture")) o.normalMapId = textureId(*t, false);
+            if (const Json* t = m.find("emissiveTexture")) o.emissiveMapId = textureId(*t, true);
+        }
         out.materials.push_back(o);
     }
     if (out.materials.empty()) out.materials.push_back(Material());
@@ -422,7 +446,13 @@ inline std::vector<uint32_t> CreateMeshInstanceFromFile(Scene& scene, const std:
     const uint32_t mat0 = (uint32_t)am.GetMaterials().size();
     if (ext == ".glb") {      // one mesh per primitive, one instance per node and primitive with the accumulated node transform
         const ImportedScene g = LoadGLB(path, ignoreMaps);
-        for (const Material& m : g.materials) am.AddMaterial(m);
+        // textures first: their ids in this scene replace the asset-local ones in the materials
+        std::vector<int32_t> texIds;
+        for (const ImportedTexture& t : g.textures) texIds.push_back((int32_t)am.AddTexture(t.image.rgba.data(), t.image.width, t.image.height, false, t.sRGB));
+        for (Material m : g.materials) {
+            for (int32_t* id : {&m.baseColorMapId, &m.emissiveMapId, &m.normalMapId, &m.roughnessMapId, &m.metalnessMapId, &m.metallicRoughnessMapId}) if (*id >= 0) *id = texIds[(size_t)*id];
+            am.AddMaterial(m);
+        }
         std::vector<uint32_t> meshIds, created;
         for (const ImportedMesh& m : g.meshes) meshIds.push_back(am.AddMesh(m.name, mat0 + m.material, m.triangles, m.triangleData));
         for (const ImportedInstance& i : g.instances) {

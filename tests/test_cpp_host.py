@@ -88,5 +88,34 @@ def test_cpp_host_imports_assets(tmp_path):
     _build()
     cube = test_obj._write(tmp_path)
     test_gltf._two_quads_glb(tmp_path / "q.glb")
-    r = subprocess.run([API_EXE, str(cube), str(tmp_path / "q.glb")], capture_output=True, text=True)
-    assert r.returncode == 0 and "host api ok" in r.stdout and r.stdout.count("imported ") == 2, r.stderr + r.stdout
+    # and a .glb whose only material takes its base colour from an embedded PNG (pure green on a white factor): decoded by the C++ layer
+    # itself (include/nexus_b200_image.hpp), uploaded through AddTexture, and visible in the rendered image
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    green = np.zeros((8, 8, 4), np.uint8); green[..., 1] = 255; green[..., 3] = 255
+    buf = io.BytesIO(); PIL.fromarray(green, "RGBA").save(buf, format="PNG")
+    png = buf.getvalue()
+    pos = np.array([[-2, -2, 0], [2, -2, 0], [2, 2, 0], [-2, 2, 0]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    binary = pos.tobytes() + uv.tobytes() + idx.tobytes() + png
+    o1, o2, o3 = pos.nbytes, pos.nbytes + uv.nbytes, pos.nbytes + uv.nbytes + idx.nbytes
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+          "meshes": [{"name": "card", "primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0}]}],
+          "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [1, 1, 1, 1], "metallicFactor": 0.0, "roughnessFactor": 0.9, "baseColorTexture": {"index": 0}}}],
+          "textures": [{"source": 0}], "images": [{"bufferView": 3, "mimeType": "image/png"}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"}, {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC2"},
+                        {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+          "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": pos.nbytes}, {"buffer": 0, "byteOffset": o1, "byteLength": uv.nbytes},
+                          {"buffer": 0, "byteOffset": o2, "byteLength": idx.nbytes}, {"buffer": 0, "byteOffset": o3, "byteLength": len(png)}],
+          "buffers": [{"byteLength": len(binary)}]}
+    test_gltf._write_glb(tmp_path / "card.glb", js, binary)
+    r = subprocess.run([API_EXE, str(cube), str(tmp_path / "q.glb"), str(tmp_path / "card.glb")], capture_output=True, text=True)
+    assert r.returncode == 0 and "host api ok" in r.stdout and r.stdout.count("imported ") == 3, r.stderr + r.stdout
+    card = [l for l in r.stdout.splitlines() if "card.glb" in l][0]
+    assert "1 texture(s)" in card, card
+    # the card fills the middle of the view: what it reflects of the blue-grey sky is green only, the sky around it is not; with the texture
+    # dropped (white card) the image would be brighter in red than with it
+    rgb = [float(v) for v in card.split("mean rgb")[1].split()]
+    sky = (0.6, 0.7, 0.8)
+    assert rgb[1] / sky[1] > 1.15 * rgb[0] / sky[0] and rgb[1] / sky[1] > 1.15 * rgb[2] / sky[2], card

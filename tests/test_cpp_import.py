@@ -97,3 +97,42 @@ def test_cpp_glb_reader_loads_the_reference_cornell_box(tmp_path):
     want = gltf.load_glb(ref)
     _compare_glb(got, want)
     assert len(got["meshes"]) == 8 and sum(len(m["triangles"]) // 9 for m in got["meshes"]) == 32
+
+
+def test_cpp_glb_reader_decodes_embedded_textures(tmp_path):
+    """The C++ reader decodes embedded PNG / JPEG texture images itself (include/nexus_b200_image.hpp; the reference: stb_image,
+    IMGLoader.cpp:13-43) and assigns them like the Python reader: base colour and emissive sRGB, normal and metallic-roughness linear,
+    one decode per (image, colour space)."""
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    import test_gltf
+    from nexus_b200 import gltf
+    _build()
+    rs = np.random.RandomState(5)
+    px = rs.randint(0, 256, (4, 6, 4)).astype(np.uint8)
+    buf = io.BytesIO(); PIL.fromarray(px, "RGBA").save(buf, format="PNG")
+    png = buf.getvalue()
+    smooth = np.clip(np.add.outer(np.arange(16) * 9.0, np.arange(24) * 6.0)[..., None] + np.array([0.0, 30.0, 60.0]), 0, 255).astype(np.uint8)
+    buf = io.BytesIO(); PIL.fromarray(smooth, "RGB").save(buf, format="JPEG", quality=92, subsampling=0)
+    jpg = buf.getvalue()
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    pad = b"\0" * ((4 - len(png) % 4) % 4)
+    binary = pos.tobytes() + png + pad + jpg
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "material": 0}]}],
+          "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}}, "normalTexture": {"index": 0}, "emissiveTexture": {"index": 0}}],
+          "textures": [{"source": 0}, {"source": 1}], "images": [{"bufferView": 1, "mimeType": "image/png"}, {"bufferView": 2, "mimeType": "image/jpeg"}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}],
+          "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": pos.nbytes}, {"buffer": 0, "byteOffset": pos.nbytes, "byteLength": len(png)},
+                          {"buffer": 0, "byteOffset": pos.nbytes + len(png) + len(pad), "byteLength": len(jpg)}],
+          "buffers": [{"byteLength": len(binary)}]}
+    test_gltf._write_glb(tmp_path / "t.glb", js, binary)
+    got = _glb_json(tmp_path / "t.glb", tmp_path)
+    want = gltf.load_glb(tmp_path / "t.glb")
+    m = want["materials"][0]
+    assert got["maps"][0] == [m.baseColorMap, m.emissiveMap, m.normalMap, m.metallicRoughnessMap]
+    assert len(got["textures"]) == len(want["textures"]) == 3
+    for g, (w_px, w_srgb) in zip(got["textures"], want["textures"]):
+        assert (g["height"], g["width"]) == w_px.shape[:2] and g["srgb"] == w_srgb
+        d = np.abs(np.array(g["rgba"], np.int32).reshape(w_px.shape) - w_px.astype(np.int32))
+        assert d.max() <= (0 if g["width"] == 6 else 3)            # the PNG exactly, the JPEG within decoder rounding
