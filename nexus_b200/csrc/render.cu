@@ -41,8 +41,11 @@ struct AnySink {
     }
 };
 
+#ifndef NX_TRACE_MIN_BLOCKS_DIRECT
+#define NX_TRACE_MIN_BLOCKS_DIRECT NX_TRACE_MIN_BLOCKS
+#endif
 template <bool STATS, int KIND>
-__global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_closest_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+__global__ void __launch_bounds__(NX_TRACE_BLOCK, KIND == NX_SCENE_DIRECT ? NX_TRACE_MIN_BLOCKS_DIRECT : NX_TRACE_MIN_BLOCKS) trace_closest_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
                                                                          uint32_t* cursor, nx_hit* __restrict__ hits, TraceStats* stats, TraceTuning tune)
 {
     __shared__ __align__(16) uint32_t smem[(KIND == NX_SCENE_DIRECT ? NX_TRACE_SMEM_BYTES_DIRECT : NX_TRACE_SMEM_BYTES) / 4];
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_clo
 }
 
 template <bool STATS, int KIND>
-__global__ void __launch_bounds__(NX_TRACE_BLOCK, NX_TRACE_MIN_BLOCKS) trace_any_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
+__global__ void __launch_bounds__(NX_TRACE_BLOCK, KIND == NX_SCENE_DIRECT ? NX_TRACE_MIN_BLOCKS_DIRECT : NX_TRACE_MIN_BLOCKS) trace_any_kernel(TraceScene sc, const nx_ray* __restrict__ rays, uint32_t nImm, const uint32_t* nPtr,
                                                                      uint32_t* cursor, uint8_t* occluded, const float4* __restrict__ radiance, float* accum,
                                                                      TraceStats* stats, TraceTuning tune)
 {
