@@ -39,6 +39,7 @@ public:
     Context(const Context&) = delete; Context& operator=(const Context&) = delete;
     nx_ctx* handle() const { return h_; }
     void Synchronize() { check(nx_ctx_synchronize(h_), "synchronize"); }
+    void* stream() const { return nx_ctx_stream(h_); }                    // the device stream (the runtime's stream handle) the render kernels are queued on
     // on (default): instances whose mesh no other instance uses, and that were never moved, share one world-space BLAS (same hits)
     void SetInstanceMerging(bool enabled) { check(nx_ctx_set_instance_merging(h_, enabled ? 1 : 0), "SetInstanceMerging"); }
     // Scene::Update after instances moved: rebuild the TLAS (default, as the reference does) or refit it in place when the entry set is unchanged
@@ -348,6 +349,12 @@ public:
     void Render(Scene& scene) { Render(scene, 1); }
     void Render(Scene& scene, uint32_t frames) { ctx_.check(nx_renderer_render(h_, scene.handle(), frame_ + 1, frames), "Render"); frame_ += frames; }
     uint32_t GetFrameNumber() const { return frame_; }
+    // multi-GPU sample partition (include/nexus_b200_nccl.hpp): frames [firstFrame, firstFrame + frames) - frames are pure functions of
+    // (pixel, frame index, bounce), so disjoint blocks on different GPUs add up to the image one GPU would accumulate
+    void RenderFrames(Scene& scene, uint32_t firstFrame, uint32_t frames) { ctx_.check(nx_renderer_render(h_, scene.handle(), firstFrame, frames), "Render"); frame_ += frames; }
+    float* AccumulationDevice() { float* d = nullptr; uint32_t f = 0; ctx_.check(nx_renderer_accum_device(h_, &d, &f), "AccumulationDevice"); return d; }   // 3 * W * H float SUMS
+    void SetAccumulatedFrames(uint32_t frames) { ctx_.check(nx_renderer_set_accum_frames(h_, frames), "SetAccumulatedFrames"); frame_ = frames; }       // after an external reduce
+    Context& context() { return ctx_; }
     void Reset() { ResetFrameNumber(); }                                  // PathTracer::Reset (PathTracer.cpp:61-159): the queues here are sized once per resolution
     void UpdateDeviceScene(Scene& scene) { scene.Update(); }              // PathTracer.cpp:216-219: the scene view is a per-call parameter block; flush pending edits
     uint2 GetResolution() const { return res_; }

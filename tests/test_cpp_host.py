@@ -119,3 +119,37 @@ def test_cpp_host_imports_assets(tmp_path):
     rgb = [float(v) for v in card.split("mean rgb")[1].split()]
     sky = (0.6, 0.7, 0.8)
     assert rgb[1] / sky[1] > 1.15 * rgb[0] / sky[0] and rgb[1] / sky[1] > 1.15 * rgb[2] / sky[2], card
+
+
+MULTI_EXE = os.path.join(ROOT, "examples", "render_multigpu")
+
+
+def _build_multi():
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", MULTI_EXE + ".cpp",
+                           "-L" + os.path.join(ROOT, "nexus_b200"), "-lnexus_b200", "-lnccl", "-L/usr/local/cuda/lib64", "-lcudart",
+                           "-Wl,-rpath,$ORIGIN/../nexus_b200", "-o", MULTI_EXE])
+
+
+def test_cpp_multigpu_host_compiles():
+    """include/nexus_b200_nccl.hpp + examples/render_multigpu.cpp: the C++ form of the sample partition with an NCCL all-reduce of the
+    accumulation buffers (north_star); compiles against the system NCCL and, without a GPU, fails loudly."""
+    if not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("no system NCCL headers")
+    _build_multi()
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([MULTI_EXE], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_multigpu_partition_equals_single_gpu():
+    """On every GPU of the box (one is enough to exercise the code path; `gpurun --gpus 2` for the real thing): the all-reduced image of
+    G GPUs rendering K frames each equals the image one GPU accumulates over the same G * K frame indices, and every GPU ends with
+    the same buffer - checked inside the program, which prints the time including the reduce."""
+    if not os.path.exists("/usr/include/nccl.h"):
+        pytest.skip("no system NCCL headers")
+    _build_multi()
+    r = subprocess.run([MULTI_EXE, "0", "320", "240", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multi gpu ok" in r.stdout, r.stdout + r.stderr
+    print(r.stdout.strip())
