@@ -1,4 +1,4 @@
-// Image decoding for the C++ host layer (header-only, standard library only): PNG and baseline JPEG into RGBA8, the two formats glTF
+// Image decoding for the C++ host layer (header-only, standard library only): PNG and JPEG into RGBA8, the two formats glTF
 // embeds.  The reference decodes texture images with stb_image (src/Assets/IMGLoader.cpp:13-43: stbi_load(..., 4) -> RGBA8 pixels
 // handed to AssetManager::AddTexture); an application that keeps stb feeds AddTexture directly and does not need this file.  The Python
 // host layer uses Pillow for the same job (nexus_b200/gltf.py); tests/test_cpp_image.py compares the two decoders pixel for pixel.
@@ -7,9 +7,10 @@
 //   uint32_t id = scene.GetAssetManager().AddTexture(img.rgba.data(), img.width, img.height, false, /*sRGB=*/true);
 //
 // PNG: every colour type and bit depth of the specification (16-bit samples keep their high byte), palette and colour-key transparency,
-// Adam7 interlacing; its own inflate (RFC 1950 / 1951).  JPEG: baseline and extended sequential Huffman (SOF0 / SOF1), 8-bit samples,
-// greyscale or YCbCr with sampling factors up to 2 x 2, restart intervals, libjpeg-style triangle ("fancy") chroma upsampling;
-// progressive and arithmetic-coded files are rejected with an error that says so.
+// Adam7 interlacing; its own inflate (RFC 1950 / 1951).  JPEG: baseline, extended sequential and PROGRESSIVE Huffman (SOF0 / SOF1 /
+// SOF2: spectral selection and successive approximation, interleaved and per-component scans), 8-bit samples, greyscale or YCbCr
+// with sampling factors up to 2 x 2, restart intervals, libjpeg-style triangle ("fancy") chroma upsampling; arithmetic-coded, lossless
+// and CMYK files are rejected with an error that says so.  (Three of the reference's seven demo scenes embed progressive JPEGs.)
 #ifndef NEXUS_B200_IMAGE_HPP
 #define NEXUS_B200_IMAGE_HPP
 
@@ -277,13 +278,17 @@ inline void Idct8x8(const float* in, uint8_t* out, size_t stride)
         out[(size_t)y * stride + x] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
     }
 }
+// Baseline, extended-sequential and progressive Huffman JPEG (ITU T.81): every scan is decoded into per-component coefficient arrays
+// (sequential files fill them in one go, progressive files by spectral selection and successive approximation over many scans), and
+// the image is reconstructed once at the end: dequantisation, inverse DCT, chroma upsampling, YCbCr -> RGB.
 inline DecodedImage DecodeJPEG(const uint8_t* data, size_t n)
 {
     static const uint8_t zigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; uint32_t pw = 0, ph = 0; std::vector<uint8_t> plane; };
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; uint32_t bw = 0, bh = 0, cw = 0, ch = 0; std::vector<int16_t> coef; std::vector<uint8_t> plane; };
     float qt[4][64]; bool haveQ[4] = {false, false, false, false};
     JpegHuff dc[4], ac[4];
-    Comp comp[3]; int nComp = 0; uint32_t w = 0, h = 0; int restart = 0; bool haveFrame = false;
+    Comp comp[3]; int nComp = 0; uint32_t w = 0, h = 0; int restart = 0; bool haveFrame = false, progressive = false, sawScan = false;
+    int hmax = 1, vmax = 1; uint32_t mx = 0, my = 0;
     size_t off = 2;
     auto be16 = [&](size_t o) { if (o + 2 > n) throw ImageError("JPEG: truncated file"); return (int)((data[o] << 8) | data[o + 1]); };
     while (off + 4 <= n) {
@@ -314,85 +319,175 @@ inline DecodedImage DecodeJPEG(const uint8_t* data, size_t n)
                 std::memcpy(t.vals, s + i, (size_t)total); i += total;
                 t.build();
             }
-        } else if (marker == 0xc0 || marker == 0xc1) {                 // SOF0 / SOF1
+        } else if (marker == 0xc0 || marker == 0xc1 || marker == 0xc2) {   // SOF0 / SOF1 / SOF2
+            if (haveFrame) throw ImageError("JPEG: more than one frame");
             if (sl < 6 || s[0] != 8) throw ImageError("JPEG: only 8-bit samples are supported");
+            progressive = marker == 0xc2;
             h = (uint32_t)((s[1] << 8) | s[2]); w = (uint32_t)((s[3] << 8) | s[4]); nComp = s[5];
             if ((nComp != 1 && nComp != 3) || sl < 6 + 3 * nComp || !w || !h) throw ImageError("JPEG: unsupported component count or empty image");
+            if ((uint64_t)w * h > (1ull << 28)) throw ImageError("JPEG: image too large");
             for (int k = 0; k < nComp; k++) { comp[k].id = s[6 + 3 * k]; comp[k].h = s[7 + 3 * k] >> 4; comp[k].v = s[7 + 3 * k] & 15; comp[k].tq = s[8 + 3 * k];
                 if (comp[k].h < 1 || comp[k].h > 2 || comp[k].v < 1 || comp[k].v > 2 || comp[k].tq > 3) throw ImageError("JPEG: unsupported sampling factors"); }
-            haveFrame = true;
-        } else if (marker == 0xc2) throw ImageError("JPEG: progressive files are not supported by this decoder (baseline only)");
-        else if (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc) throw ImageError("JPEG: lossless / arithmetic-coded files are not supported");
-        else if (marker == 0xdd) { if (sl < 2) throw ImageError("JPEG: corrupt DRI"); restart = (s[0] << 8) | s[1]; }
-        else if (marker == 0xda) {                                     // SOS: the one scan of a baseline file
-            if (!haveFrame) throw ImageError("JPEG: scan before the frame header");
-            if (sl < 1 || s[0] != nComp || sl < 1 + 2 * nComp) throw ImageError("JPEG: non-interleaved scans are not supported");
+            if (nComp == 1) comp[0].h = comp[0].v = 1;                  // a single component is never interleaved: 8 x 8 MCUs
+            for (int k = 0; k < nComp; k++) { hmax = std::max(hmax, comp[k].h); vmax = std::max(vmax, comp[k].v); }
+            mx = (w + 8u * hmax - 1) / (8u * hmax); my = (h + 8u * vmax - 1) / (8u * vmax);
             for (int k = 0; k < nComp; k++) {
+                Comp& c = comp[k];
+                c.bw = mx * (uint32_t)c.h; c.bh = my * (uint32_t)c.v;
+                c.cw = (w * (uint32_t)c.h + hmax - 1) / hmax; c.ch = (h * (uint32_t)c.v + vmax - 1) / vmax;
+                c.coef.assign((size_t)64 * c.bw * c.bh, 0);
+            }
+            haveFrame = true;
+        } else if (marker >= 0xc3 && marker <= 0xcf && marker != 0xc4 && marker != 0xc8 && marker != 0xcc) throw ImageError("JPEG: lossless / hierarchical / arithmetic-coded files are not supported");
+        else if (marker == 0xdd) { if (sl < 2) throw ImageError("JPEG: corrupt DRI"); restart = (s[0] << 8) | s[1]; }
+        else if (marker == 0xda) {                                     // SOS: one scan
+            if (!haveFrame) throw ImageError("JPEG: scan before the frame header");
+            const int ns = sl >= 1 ? s[0] : 0;
+            if (ns < 1 || ns > nComp || sl < 4 + 2 * ns) throw ImageError("JPEG: corrupt scan header");
+            int order[3];
+            for (int k = 0; k < ns; k++) {
                 int ci = -1; for (int j = 0; j < nComp; j++) if (comp[j].id == s[1 + 2 * k]) ci = j;
                 if (ci < 0) throw ImageError("JPEG: scan names an unknown component");
                 comp[ci].td = s[2 + 2 * k] >> 4; comp[ci].ta = s[2 + 2 * k] & 15;
-                if (comp[ci].td > 3 || comp[ci].ta > 3 || !dc[comp[ci].td].present || !ac[comp[ci].ta].present || !haveQ[comp[ci].tq]) throw ImageError("JPEG: scan uses a table the file does not define");
+                if (comp[ci].td > 3 || comp[ci].ta > 3) throw ImageError("JPEG: corrupt scan header");
+                order[k] = ci;
             }
-            const int hmax = nComp == 1 ? comp[0].h : std::max(comp[0].h, std::max(comp[1].h, comp[2].h)), vmax = nComp == 1 ? comp[0].v : std::max(comp[0].v, std::max(comp[1].v, comp[2].v));
-            if (nComp == 1) { comp[0].h = comp[0].v = 1; }             // a single-component scan is never interleaved: 8 x 8 MCUs
-            const int mh = nComp == 1 ? 1 : hmax, mv = nComp == 1 ? 1 : vmax;
-            const uint32_t mcuW = 8u * mh, mcuH = 8u * mv, mx = (w + mcuW - 1) / mcuW, my = (h + mcuH - 1) / mcuH;
-            for (int k = 0; k < nComp; k++) { comp[k].pw = mx * 8u * comp[k].h; comp[k].ph = my * 8u * comp[k].v; comp[k].plane.assign((size_t)comp[k].pw * comp[k].ph, 0); comp[k].pred = 0; }
+            const int Ss = s[1 + 2 * ns], Se = s[2 + 2 * ns], Ah = s[3 + 2 * ns] >> 4, Al = s[3 + 2 * ns] & 15;
+            if (progressive) { if (Ss > Se || Se > 63 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1) || Al > 13 || Ah > 13) throw ImageError("JPEG: invalid progressive scan parameters"); }
+            else if (Ss != 0 || Se != 63 || Ah != 0 || Al != 0) throw ImageError("JPEG: invalid sequential scan parameters");
+            for (int k = 0; k < ns; k++) {
+                const Comp& c = comp[order[k]];
+                const bool needDc = !progressive || (Ss == 0 && Ah == 0), needAc = !progressive || Ss > 0;
+                if ((needDc && !dc[c.td].present) || (needAc && !ac[c.ta].present) || !haveQ[c.tq]) throw ImageError("JPEG: scan uses a table the file does not define");
+            }
+            // scan geometry: one component -> its own block grid in raster order; several -> MCUs of h x v blocks per component
+            const bool inter = ns > 1;
+            const Comp& c0 = comp[order[0]];
+            const uint32_t unitsX = inter ? mx : (c0.cw + 7) / 8, unitsY = inter ? my : (c0.ch + 7) / 8;
             JpegBits br{data + off + (size_t)len, data + n};
-            int untilRestart = restart;
-            float block[64];
-            for (uint32_t by = 0; by < my; by++) for (uint32_t bx = 0; bx < mx; bx++) {
+            int untilRestart = restart, eobrun = 0;
+            for (int k = 0; k < ns; k++) comp[order[k]].pred = 0;
+            auto refine = [&](int16_t& cf, int p1, int m1) { if (br.get(1) && (cf & p1) == 0) cf = (int16_t)(cf + (cf >= 0 ? p1 : m1)); };
+            auto block = [&](Comp& c, int16_t* b) {
+                if (!progressive) {
+                    const int t = br.decode(dc[c.td]);
+                    if (t > 11) throw ImageError("JPEG: corrupt DC coefficient");
+                    c.pred += t ? JpegBits::extend(br.get(t), t) : 0;
+                    b[0] = (int16_t)c.pred;
+                    for (int i = 1; i < 64;) {
+                        const int rs = br.decode(ac[c.ta]), r = rs >> 4, sz = rs & 15;
+                        if (!sz) { if (r == 15) { i += 16; continue; } break; }
+                        i += r;
+                        if (i > 63) throw ImageError("JPEG: corrupt AC coefficients");
+                        b[zigzag[i]] = (int16_t)JpegBits::extend(br.get(sz), sz);
+                        i++;
+                    }
+                } else if (Ss == 0) {
+                    if (Ah == 0) {                                      // DC, first pass
+                        const int t = br.decode(dc[c.td]);
+                        if (t > 11) throw ImageError("JPEG: corrupt DC coefficient");
+                        c.pred += t ? JpegBits::extend(br.get(t), t) : 0;
+                        b[0] = (int16_t)(c.pred * (1 << Al));
+                    } else if (br.get(1)) b[0] = (int16_t)(b[0] | (1 << Al));   // DC, refinement: one more bit
+                } else if (Ah == 0) {                                   // AC band, first pass
+                    if (eobrun > 0) { eobrun--; return; }
+                    for (int k = Ss; k <= Se;) {
+                        const int rs = br.decode(ac[c.ta]), r = rs >> 4, sz = rs & 15;
+                        if (!sz) {
+                            if (r < 15) { eobrun = (1 << r) - 1; if (r) eobrun += br.get(r); break; }
+                            k += 16;
+                        } else {
+                            k += r;
+                            if (k > Se) throw ImageError("JPEG: corrupt AC coefficients");
+                            b[zigzag[k]] = (int16_t)(JpegBits::extend(br.get(sz), sz) * (1 << Al));
+                            k++;
+                        }
+                    }
+                } else {                                                // AC band, refinement (T.81 G.1.2.3)
+                    const int p1 = 1 << Al, m1 = -(1 << Al);
+                    int k = Ss;
+                    if (eobrun == 0) {
+                        for (; k <= Se; k++) {
+                            const int rs = br.decode(ac[c.ta]); int r = rs >> 4; const int sz = rs & 15;
+                            int val = 0;
+                            if (sz) { if (sz != 1) throw ImageError("JPEG: corrupt AC refinement"); val = br.get(1) ? p1 : m1; }
+                            else if (r < 15) { eobrun = 1 << r; if (r) eobrun += br.get(r); break; }
+                            // advance over r zero-history coefficients, refining the nonzero ones on the way
+                            for (; k <= Se; k++) {
+                                int16_t& cf = b[zigzag[k]];
+                                if (cf != 0) refine(cf, p1, m1);
+                                else if (--r < 0) break;
+                            }
+                            if (sz && k <= Se) b[zigzag[k]] = (int16_t)val;
+                        }
+                    }
+                    if (eobrun > 0) {
+                        for (; k <= Se; k++) { int16_t& cf = b[zigzag[k]]; if (cf != 0) refine(cf, p1, m1); }
+                        eobrun--;
+                    }
+                }
+            };
+            for (uint32_t uy = 0; uy < unitsY; uy++) for (uint32_t ux = 0; ux < unitsX; ux++) {
                 if (restart && untilRestart == 0) {
                     // the restart marker: byte aligned, right where the bit reader stopped
                     br.reset();
                     while (br.p + 1 < br.end && !(br.p[0] == 0xff && br.p[1] >= 0xd0 && br.p[1] <= 0xd7)) br.p++;
                     if (br.p + 1 < br.end) br.p += 2;
-                    for (int k = 0; k < nComp; k++) comp[k].pred = 0;
+                    for (int k = 0; k < ns; k++) comp[order[k]].pred = 0;
+                    eobrun = 0;
                     untilRestart = restart;
                 }
-                for (int k = 0; k < nComp; k++) for (int v = 0; v < comp[k].v; v++) for (int hh = 0; hh < comp[k].h; hh++) {
-                    std::memset(block, 0, sizeof(block));
-                    const int t = br.decode(dc[comp[k].td]);
-                    if (t > 11) throw ImageError("JPEG: corrupt DC coefficient");
-                    comp[k].pred += t ? JpegBits::extend(br.get(t), t) : 0;
-                    block[0] = (float)comp[k].pred * qt[comp[k].tq][0];
-                    for (int i = 1; i < 64;) {
-                        const int rs = br.decode(ac[comp[k].ta]), r = rs >> 4, sz = rs & 15;
-                        if (!sz) { if (r == 15) { i += 16; continue; } break; }
-                        i += r;
-                        if (i > 63) throw ImageError("JPEG: corrupt AC coefficients");
-                        block[zigzag[i]] = (float)JpegBits::extend(br.get(sz), sz) * qt[comp[k].tq][zigzag[i]];
-                        i++;
-                    }
-                    Idct8x8(block, comp[k].plane.data() + ((size_t)(by * comp[k].v + v) * 8) * comp[k].pw + (size_t)(bx * comp[k].h + hh) * 8, comp[k].pw);
-                }
+                if (inter) {
+                    for (int k = 0; k < ns; k++) { Comp& c = comp[order[k]];
+                        for (int v = 0; v < c.v; v++) for (int hh = 0; hh < c.h; hh++)
+                            block(c, c.coef.data() + 64 * ((size_t)(uy * c.v + v) * c.bw + (size_t)(ux * c.h + hh))); }
+                } else { Comp& c = comp[order[0]]; block(c, c.coef.data() + 64 * ((size_t)uy * c.bw + ux)); }
                 if (restart) untilRestart--;
             }
-            // ---- to RGBA: chroma upsampled with the triangle filter libjpeg calls "fancy upsampling" (3/4, 1/4 per axis), replication otherwise
-            DecodedImage img; img.width = w; img.height = h; img.rgba.assign((size_t)4 * w * h, 255);
-            auto at = [&](const Comp& c, int fx, int fy, uint32_t x, uint32_t y) -> float {      // component value at full-resolution pixel (x, y)
-                auto px = [&](long cx, long cy) { cx = cx < 0 ? 0 : cx >= (long)((w * (uint32_t)c.h + hmax - 1) / hmax) ? (long)((w * (uint32_t)c.h + hmax - 1) / hmax) - 1 : cx;
-                                                   cy = cy < 0 ? 0 : cy >= (long)((h * (uint32_t)c.v + vmax - 1) / vmax) ? (long)((h * (uint32_t)c.v + vmax - 1) / vmax) - 1 : cy;
-                                                   return (float)c.plane[(size_t)cy * c.pw + (size_t)cx]; };
-                if (fx == 1 && fy == 1) return px((long)x, (long)y);
-                const long cx = (long)(x / (uint32_t)fx), cy = (long)(y / (uint32_t)fy);
-                const long nx = fx == 2 ? ((x & 1u) ? cx + 1 : cx - 1) : cx, ny = fy == 2 ? ((y & 1u) ? cy + 1 : cy - 1) : cy;
-                const float wx = fx == 2 ? 0.25f : 0.0f, wy = fy == 2 ? 0.25f : 0.0f;
-                return (1 - wy) * ((1 - wx) * px(cx, cy) + wx * px(nx, cy)) + wy * ((1 - wx) * px(cx, ny) + wx * px(nx, ny));
-            };
-            auto clamp8 = [](float v) { const int r = (int)std::lround(v); return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r); };
-            for (uint32_t y = 0; y < h; y++) for (uint32_t x = 0; x < w; x++) {
-                uint8_t* o = img.rgba.data() + 4 * ((size_t)y * w + x);
-                if (nComp == 1) { o[0] = o[1] = o[2] = comp[0].plane[(size_t)y * comp[0].pw + x]; continue; }
-                const float Y = at(comp[0], hmax / comp[0].h, vmax / comp[0].v, x, y), Cb = at(comp[1], hmax / comp[1].h, vmax / comp[1].v, x, y) - 128.0f,
-                            Cr = at(comp[2], hmax / comp[2].h, vmax / comp[2].v, x, y) - 128.0f;
-                o[0] = clamp8(Y + 1.402f * Cr); o[1] = clamp8(Y - 0.344136f * Cb - 0.714136f * Cr); o[2] = clamp8(Y + 1.772f * Cb);
-            }
-            return img;
+            sawScan = true;
+            // the entropy-coded data follows the header: skip to the next marker that is not a restart marker or a stuffed byte
+            size_t q = off + (size_t)len;
+            while (q + 1 < n && !(data[q] == 0xff && data[q + 1] != 0 && !(data[q + 1] >= 0xd0 && data[q + 1] <= 0xd7) && data[q + 1] != 0xff)) q++;
+            off = q;
+            continue;
         }
         off += (size_t)len;
     }
-    throw ImageError("JPEG: the file has no image scan");
+    if (!haveFrame || !sawScan) throw ImageError("JPEG: the file has no image scan");
+
+    // ---- reconstruction: dequantise + inverse DCT per block
+    float blockf[64];
+    for (int k = 0; k < nComp; k++) {
+        Comp& c = comp[k];
+        const uint32_t pw = c.bw * 8u, ph = c.bh * 8u;
+        c.plane.assign((size_t)pw * ph, 0);
+        for (uint32_t by = 0; by < c.bh; by++) for (uint32_t bx = 0; bx < c.bw; bx++) {
+            const int16_t* b = c.coef.data() + 64 * ((size_t)by * c.bw + bx);
+            for (int i = 0; i < 64; i++) blockf[i] = (float)b[i] * qt[c.tq][i];
+            Idct8x8(blockf, c.plane.data() + ((size_t)by * 8) * pw + (size_t)bx * 8, pw);
+        }
+    }
+    // ---- to RGBA: chroma upsampled with the triangle filter libjpeg calls "fancy upsampling" (3/4, 1/4 per axis), replication otherwise
+    DecodedImage img; img.width = w; img.height = h; img.rgba.assign((size_t)4 * w * h, 255);
+    auto at = [&](const Comp& c, int fx, int fy, uint32_t x, uint32_t y) -> float {      // component value at full-resolution pixel (x, y)
+        const uint32_t pw = c.bw * 8u;
+        auto px = [&](long cx, long cy) { cx = cx < 0 ? 0 : cx >= (long)c.cw ? (long)c.cw - 1 : cx; cy = cy < 0 ? 0 : cy >= (long)c.ch ? (long)c.ch - 1 : cy;
+                                           return (float)c.plane[(size_t)cy * pw + (size_t)cx]; };
+        if (fx == 1 && fy == 1) return px((long)x, (long)y);
+        const long cx = (long)(x / (uint32_t)fx), cy = (long)(y / (uint32_t)fy);
+        const long nx = fx == 2 ? ((x & 1u) ? cx + 1 : cx - 1) : cx, ny = fy == 2 ? ((y & 1u) ? cy + 1 : cy - 1) : cy;
+        const float wx = fx == 2 ? 0.25f : 0.0f, wy = fy == 2 ? 0.25f : 0.0f;
+        return (1 - wy) * ((1 - wx) * px(cx, cy) + wx * px(nx, cy)) + wy * ((1 - wx) * px(cx, ny) + wx * px(nx, ny));
+    };
+    auto clamp8 = [](float v) { const int r = (int)std::lround(v); return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r); };
+    for (uint32_t y = 0; y < h; y++) for (uint32_t x = 0; x < w; x++) {
+        uint8_t* o = img.rgba.data() + 4 * ((size_t)y * w + x);
+        if (nComp == 1) { o[0] = o[1] = o[2] = comp[0].plane[(size_t)y * comp[0].bw * 8u + x]; continue; }
+        const float Y = at(comp[0], hmax / comp[0].h, vmax / comp[0].v, x, y), Cb = at(comp[1], hmax / comp[1].h, vmax / comp[1].v, x, y) - 128.0f,
+                    Cr = at(comp[2], hmax / comp[2].h, vmax / comp[2].v, x, y) - 128.0f;
+        o[0] = clamp8(Y + 1.402f * Cr); o[1] = clamp8(Y - 0.344136f * Cb - 0.714136f * Cr); o[2] = clamp8(Y + 1.772f * Cb);
+    }
+    return img;
 }
 
 }  // namespace imgdetail

@@ -136,3 +136,41 @@ def test_cpp_glb_reader_decodes_embedded_textures(tmp_path):
         assert (g["height"], g["width"]) == w_px.shape[:2] and g["srgb"] == w_srgb
         d = np.abs(np.array(g["rgba"], np.int32).reshape(w_px.shape) - w_px.astype(np.int32))
         assert d.max() <= (0 if g["width"] == 6 else 3)            # the PNG exactly, the JPEG within decoder rounding
+
+
+DEMO_SCENES = "/root/reference/Nexus/assets/demo_scenes"
+
+
+@pytest.mark.skipif(not os.path.isdir(DEMO_SCENES), reason="the reference's demo assets are only mounted in the build container")
+def test_both_readers_load_every_demo_scene_of_the_reference(tmp_path):
+    """All seven .glb demo scenes the reference ships (up to 3 M triangles, 21 embedded PNG / JPEG textures, progressive JPEGs among
+    them): the Python reader (Pillow) and the C++ reader (its own decoders) produce the same counts and, for every texture, the
+    same size, colour-space flag and pixels - PNG exactly, JPEG within decoder rounding."""
+    import glob
+    from nexus_b200 import gltf
+    pytest.importorskip("PIL.Image")
+    info = os.path.join(ROOT, "examples", "glb_info")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), info + ".cpp",
+                           "-L" + os.path.join(ROOT, "nexus_b200"), "-lnexus_b200", "-Wl,-rpath,$ORIGIN/../nexus_b200", "-o", info])
+    files = sorted(glob.glob(os.path.join(DEMO_SCENES, "*", "*.glb")))
+    assert len(files) == 7
+    textures = 0
+    for path in files:
+        want = gltf.load_glb(path)
+        prefix = str(tmp_path / "tex")
+        r = subprocess.run([info, path, prefix], capture_output=True, text=True)
+        assert r.returncode == 0, (path, r.stderr)
+        got = json.loads(r.stdout)
+        assert got["meshes"] == len(want["meshes"]) and got["instances"] == len(want["instances"]) and got["materials"] == len(want["materials"]), path
+        assert got["triangles"] == sum(len(m["triangles"]) for m in want["meshes"]), path
+        assert len(got["textures"]) == len(want["textures"]), path
+        js, _ = gltf._chunks(open(path, "rb").read())
+        for k, (g, (w_px, w_srgb)) in enumerate(zip(got["textures"], want["textures"])):
+            assert (g["height"], g["width"]) == w_px.shape[:2] and g["srgb"] == w_srgb, (path, k)
+            px = np.fromfile(prefix + str(k) + ".rgba", np.uint8).reshape(w_px.shape).astype(np.int32)
+            d = np.abs(px - w_px.astype(np.int32))
+            # lossless images must be identical; JPEGs differ by decoder rounding (mostly 4:2:0 photographs: a few levels at chroma edges)
+            if d.max() > 0:
+                assert d.mean() <= 1.0 and np.percentile(d, 99.9) <= 12, (path, k, float(d.mean()), int(d.max()))
+            textures += 1
+    assert textures >= 40
