@@ -468,7 +468,11 @@ __device__ __forceinline__ void ploc_merge2(const PlocArgs& a, ChunkMem<C>& M, W
         __syncwarp();
     }
     if (lane < loaded) { if (LOCAL) M.cluster[lo + lane] = id; else __stcg(a.cluster + lo + lane, id); }
-    if (LOCAL) __threadfence_block(); else __threadfence();
+    // Global path: no fence here.  The nodes, heights and cluster ids written above are published by the RELEASE exchange the climbing
+    // lane performs next (exch_release in hploc_seed_kernel); the reader takes them with ld.cg after it has seen that exchange.
+    // __threadfence() would be MEMBAR.SC.GPU + CCTL.IVALL: a sequentially consistent barrier plus an invalidation of the SM's whole L1,
+    // once per merge, for every warp on the SM.
+    if (LOCAL) __threadfence_block(); else __syncwarp();   // every lane's stores are ordered before the owning lane's release
 }
 
 template <typename KeyT, uint32_t C>
@@ -556,6 +560,15 @@ __global__ void __launch_bounds__(C, NX_PLOC_MINB) hploc2_kernel(PlocArgs a, con
         a.seedLo[2 * blockIdx.x + k] = chunkStart + lo; a.seedHi[2 * blockIdx.x + k] = chunkStart + hi; }
 }
 
+// atomicExch with release semantics at GPU scope: everything this thread wrote before it is visible to whoever observes the exchanged
+// value (MEMBAR.ALL.GPU + ATOMG; no L1 invalidation - nothing here is read through L1 after an acquire).
+__device__ __forceinline__ uint32_t exch_release(uint32_t* p, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.release.gpu.global.exch.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 // Global phase of the two-phase builder: the one-phase protocol (hploc_kernel) started from the ranges the chunks could not finish.
 #ifndef NX_SEED_MINB
 #define NX_SEED_MINB 1
@@ -570,19 +583,25 @@ __global__ void __launch_bounds__(kPlocBlock, NX_SEED_MINB) hploc_seed_kernel(Pl
     // without a seed list every leaf is its own seed: the one-phase protocol with the shared-memory merge table
     uint32_t lo = i < nSeeds ? (a.seedLo ? __ldg(a.seedLo + i) : i) : NX_INVALID, hi = i < nSeeds ? (a.seedHi ? __ldg(a.seedHi + i) : i) : NX_INVALID, mid = 0;
     bool climbing = lo != NX_INVALID;
+    bool wrote = a.seedLo != nullptr;      // seeds of the two-phase builder arrive with data written by the previous kernel (visible already; release is harmless)
     while (__ballot_sync(NX_FULL, climbing))
     {
         if (climbing)
         {
             const bool parentAtHi = lo == 0 || (hi != n - 1 && key_delta(keys, hi, hi + 1) < key_delta(keys, lo - 1, lo));
-            uint32_t other;
-            if (parentAtHi) { other = atomicExch(a.parent + hi, lo); if (other != NX_INVALID) { mid = hi + 1; hi = other; } }
-            else            { other = atomicExch(a.parent + lo - 1, hi); if (other != NX_INVALID) { mid = lo; lo = other; } }
+            // a lane whose range was merged in the previous iteration has nodes / cluster ids to publish: its exchange is a release;
+            // a lane that only climbs (ranges of up to kMergeThreshold leaves: nothing written yet) uses the plain exchange
+            uint32_t* slot = parentAtHi ? a.parent + hi : a.parent + lo - 1;
+            const uint32_t mine = parentAtHi ? lo : hi;
+            uint32_t other = wrote ? exch_release(slot, mine) : atomicExch(slot, mine);
+            if (other != NX_INVALID) { if (parentAtHi) { mid = hi + 1; hi = other; } else { mid = lo; lo = other; } }
             if (other == NX_INVALID) climbing = false;   // first to arrive: the sibling's thread continues (cluster lists are read with ld.cg)
         }
         const uint32_t size = hi - lo + 1;
         const bool isRoot = climbing && size == n;
-        uint32_t todo = __ballot_sync(NX_FULL, (climbing && size > kMergeThreshold) || isRoot);
+        const bool merges = (climbing && size > kMergeThreshold) || isRoot;
+        wrote = merges;
+        uint32_t todo = __ballot_sync(NX_FULL, merges);
         while (todo)
         {
             const uint32_t src = __ffs(todo) - 1;
