@@ -129,6 +129,7 @@ inline std::vector<uint8_t> Inflate(const uint8_t* data, size_t n, size_t expect
             if (d > out.size()) throw ImageError("PNG: distance beyond the start of the data");
             const size_t from = out.size() - d;
             for (int i = 0; i < len; i++) out.push_back(out[from + (size_t)i]);
+            if (out.size() > expected + 65536) throw ImageError("PNG: more image data than the header announces");
         }
     }
     return out;
