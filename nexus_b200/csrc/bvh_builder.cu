@@ -667,12 +667,22 @@ __device__ __forceinline__ void dp_eval_node(const DpArgs& a, uint32_t p)
     const float4 q = __ldg(a.n2 + 2 * (size_t)p + 1);
     const uint32_t L = __float_as_uint(q.z), R = __float_as_uint(q.w);
     float cl[7], cr[7], c[7];
-    {
-        const float4 l0 = __ldcg(cost4 + 2 * (size_t)L), l1 = __ldcg(cost4 + 2 * (size_t)L + 1), r0 = __ldcg(cost4 + 2 * (size_t)R), r1 = __ldcg(cost4 + 2 * (size_t)R + 1);
-        cl[0] = l0.x; cl[1] = l0.y; cl[2] = l0.z; cl[3] = l0.w; cl[4] = l1.x; cl[5] = l1.y; cl[6] = l1.z;
-        cr[0] = r0.x; cr[1] = r0.y; cr[2] = r0.z; cr[3] = r0.w; cr[4] = r1.x; cr[5] = r1.y; cr[6] = r1.z;
-    }
-    const uint32_t tris = min(255u, (uint32_t)(__ldcg(a.dec + L) >> 56) + (uint32_t)(__ldcg(a.dec + R) >> 56));
+    // A BVH2 leaf has no table in memory: C(leaf, i) = area * C_PRIM for every i (CLeaf(node, 1), BVH8Builder.cpp:31-37), one primitive,
+    // decision LEAF - computed here from the leaf's box (one 32-byte sector) instead of gathering a 32-byte table and an 8-byte
+    // decision word that would first have to be written for every primitive.  Half of all tables are leaves'.
+    auto table = [&](uint32_t child, float (&t)[7]) -> uint32_t {
+        if (child < a.n) {
+            const float v = __fmul_rn(__fmul_rn(half_area_ref(load_box2(a.n2, child)), 1.0f), kCPrim);
+#pragma unroll
+            for (int k = 0; k < 7; k++) t[k] = v;
+            return 1u;
+        }
+        const float4 t0 = __ldcg(cost4 + 2 * (size_t)child), t1 = __ldcg(cost4 + 2 * (size_t)child + 1);
+        t[0] = t0.x; t[1] = t0.y; t[2] = t0.z; t[3] = t0.w; t[4] = t1.x; t[5] = t1.y; t[6] = t1.z;
+        return (uint32_t)(__ldcg(a.dec + child) >> 56);
+    };
+    const uint32_t trisL = table(L, cl), trisR = table(R, cr);
+    const uint32_t tris = min(255u, trisL + trisR);
     const float area = half_area_ref(load_box2(a.n2, p));
     unsigned long long dec = (unsigned long long)tris << 56;
     // CDistribute(node, j) (:39-57): best split of j - 1 roots: k to the left child, j - 1 - k to the right
@@ -699,12 +709,10 @@ __device__ __forceinline__ void dp_eval_node(const DpArgs& a, uint32_t p)
     __stcg(cost4 + 2 * (size_t)p, make_float4(c[0], c[1], c[2], c[3])); __stcg(cost4 + 2 * (size_t)p + 1, make_float4(c[4], c[5], c[6], 0.f));
     __stcg(a.dec + p, dec);
 }
-__device__ __forceinline__ void dp_init_leaf(const DpArgs& a, uint32_t leaf)
+// decision word of any BVH2 node: leaves (ids below n) have none in memory - LEAF for every i, one primitive
+__device__ __forceinline__ unsigned long long dp_dec_of(const unsigned long long* __restrict__ dec, uint32_t n, uint32_t node)
 {
-    float4* const cost4 = reinterpret_cast<float4*>(a.cost);
-    const float c = __fmul_rn(__fmul_rn(half_area_ref(load_box2(a.n2, leaf)), 1.0f), kCPrim);     // CLeaf(node, 1), :31-37
-    __stcg(cost4 + 2 * (size_t)leaf, make_float4(c, c, c, c)); __stcg(cost4 + 2 * (size_t)leaf + 1, make_float4(c, c, c, 0.f));
-    __stcg(a.dec + leaf, 1ull << 56);                                                             // LEAF for every i, one primitive
+    return node < n ? (1ull << 56) : __ldg(dec + node);
 }
 
 // Bottom-up by climbing: a thread per leaf, the second thread to arrive at a node evaluates it (small inputs, and whenever the
@@ -713,7 +721,6 @@ __global__ void __launch_bounds__(kDpBlock) dp_eval_kernel(DpArgs a)
 {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= a.n) return;
-    dp_init_leaf(a, leaf);
     uint32_t p = __ldcg(a.parent + leaf);
     while (p != NX_INVALID)
     {
@@ -735,10 +742,7 @@ __global__ void dp_leaf_hist_kernel(DpArgs a, DpWaveArgs w)
     __shared__ uint32_t sh[256];
     sh[threadIdx.x] = 0u;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * a.n - 1; i += gridDim.x * blockDim.x) {
-        if (i < a.n) dp_init_leaf(a, i);
-        else atomicAdd(&sh[w.height[i]], 1u);
-    }
+    for (uint32_t i = a.n + blockIdx.x * blockDim.x + threadIdx.x; i < 2 * a.n - 1; i += gridDim.x * blockDim.x) atomicAdd(&sh[w.height[i]], 1u);
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(w.hist + threadIdx.x, sh[threadIdx.x]);
 }
@@ -818,7 +822,7 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
             // entries: node | count << 28 | expand flag << 31; the left entry is pushed last so that it is processed first and
             // the children come out in the recursion's order
             uint32_t stack[9]; int sp = 0;
-            auto decOf = [&](uint32_t node, uint32_t i) { return (uint32_t)(__ldg(a.dpDec + node) >> (8 * i)) & 0xffu; };
+            auto decOf = [&](uint32_t node, uint32_t i) { return (uint32_t)(dp_dec_of(a.dpDec, n, node) >> (8 * i)) & 0xffu; };
             const uint32_t d0 = decOf(root2, 0);
             if ((d0 & 3u) == kDpLeaf) stack[sp++] = root2;                  // the whole tree is one leaf child
             else stack[sp++] = root2 | 0x80000000u;                          // count 0
@@ -910,7 +914,7 @@ __device__ void collapse_one(const CollapseArgs& a, uint32_t self, uint32_t root
             uint32_t id = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) if (k == (int)c) id = child[k];
-            cnt = (uint32_t)(__ldg(a.dpDec + id) >> 56);
+            cnt = (uint32_t)(dp_dec_of(a.dpDec, n, id) >> 56);
         }
         slotPrims |= cnt << (4 * s);
     }
