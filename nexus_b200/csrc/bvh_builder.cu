@@ -1024,8 +1024,8 @@ __global__ void __launch_bounds__(kCollapseBlock, 4) collapse_kernel(CollapseArg
             const uint32_t node = begin + k;
             collapse_one<OPT>(a, node, k < span ? __ldcg(a.bvh2Of + node) : NX_INVALID, created);   // whole warps call in, idle lanes pass INVALID
         }
-        __threadfence();
-        grid.sync();
+        grid.sync();          // orders this level's stores before the next level's loads by itself: no __threadfence() per thread on top of it
+                              // (that was a MEMBAR.SC.GPU + an L1 invalidation executed by every thread of the grid, every level)
         begin = end;
         end += __ldcg(created);
         level++;

@@ -95,6 +95,7 @@ struct DeviceGuard {
 // All geometry arithmetic that decides topology or hit ids is written with explicit-rounding intrinsics so the compiler
 // can neither contract nor reorder it; the CPU oracle restates the same operation sequence with fmaf().
 struct V3 { float x, y, z; };
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __host__ __device__ __forceinline__ V3 v3(float x, float y, float z) { return {x, y, z}; }
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)}; }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }

@@ -60,7 +60,6 @@ struct __align__(16) PoolWarp {            // shared memory of one warp; [slot]
 };
 #define NX_POOL_SMEM_BYTES (sizeof(PoolWarp) * NX_POOL_WARPS)
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ const float4* ptr_from(uint32_t lo, uint32_t hi) { return reinterpret_cast<const float4*>(((uint64_t)hi << 32) | lo); }
 
 template <bool ANY_HIT, bool STATS, typename Sink>
