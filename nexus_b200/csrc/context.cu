@@ -111,6 +111,10 @@ void nx_ctx_destroy(nx_ctx* ctx)
     cudaFree(ctx->poolSpill[0]); cudaFree(ctx->poolSpill[1]);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream_aux);
+    // the blocks the stream-ordered pool kept for reuse (release threshold raised in nx_ctx_create) go back to the driver; blocks another
+    // live context of this device still holds are not touched by a trim
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
     delete ctx;
 }
 

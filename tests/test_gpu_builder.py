@@ -226,3 +226,28 @@ def test_refit_keeps_the_topology_and_reproduces_a_build_on_unchanged_boxes(ctx)
                         b = moved[order3[prim_base + (m & 31) + t]]
                         assert (b[:3] >= lo - 1e-4).all() and (b[3:] <= hi + 1e-4).all(), (n, i, s)
         bvh.Free()
+
+
+def test_build_and_free_cycles_return_their_device_memory():
+    """BuildBVH2 / BuildBVH8 (both collapses) / FreeDeviceBVH, eight times on one context: free device memory after the last cycle is
+    what it was after the first, and closing the context returns the workspace pools (BVHBuilder.h:58-66 frees per handle; the
+    temporaries of a build - keys, cluster tables, C(n, i) tables - are the context's here)."""
+    import torch
+    from nexus_b200 import scenes
+    def free_mb():
+        torch.cuda.synchronize()
+        return torch.cuda.mem_get_info()[0] / 2 ** 20
+    before = free_mb()
+    ctx = nx.Context(0)
+    prims = scenes.test_triangles(300_000, seed=4)
+    marks = []
+    for k in range(8):
+        b2 = nx.BuildBVH2(ctx, prims, prioritizeSpeed=bool(k & 1))
+        b8 = nx.BuildBVH8(ctx, prims, prioritizeSpeed=bool(k & 1))
+        b8o = nx.BuildBVH8(ctx, prims, prioritizeSpeed=True, collapse=nx.COLLAPSE_SAH_OPTIMAL, maxLeafPrims=2)
+        assert b2.h.node_count == 2 * len(prims) - 1 and b8.nodeCount > b8o.nodeCount > 0
+        b2.Free(); b8.Free(); b8o.Free()
+        marks.append(free_mb())
+    assert abs(marks[-1] - marks[0]) <= 8.0, marks
+    ctx.close()
+    assert before - free_mb() <= 64.0, (before, marks)
