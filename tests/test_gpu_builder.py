@@ -251,3 +251,25 @@ def test_build_and_free_cycles_return_their_device_memory():
     assert abs(marks[-1] - marks[0]) <= 8.0, marks
     ctx.close()
     assert before - free_mb() <= 64.0, (before, marks)
+
+
+@pytest.mark.parametrize("speed", [True, False])
+def test_every_hploc_kernel_builds_the_same_tree(speed, monkeypatch):
+    """The three H-PLOC organisations in the library (NX_HPLOC=0: one phase, clusters in registers; 1: block-local phase in shared memory
+    + global phase; 2, the default: one phase with a per-warp shared-memory merge table) perform the same merges: the same BVH2 after
+    canonical renumbering, for both key widths, on a mesh-like and on a clustered input."""
+    from nexus_b200 import scenes
+    inputs = [scenes.test_triangles(150_000, seed=21), np.asarray(scenes.uv_sphere(96, 80)).reshape(-1, 9).astype(np.float32)]
+    canon = {}
+    for mode in ("2", "0", "1"):
+        monkeypatch.setenv("NX_HPLOC", mode)
+        c = nx.Context(0)
+        for k, prims in enumerate(inputs):
+            b2 = nx.BuildBVH2(c, prims, prioritizeSpeed=speed)
+            got = O.canon_bvh2(b2.ToHost(), len(prims))
+            b2.Free()
+            if mode == "2":
+                canon[k] = got
+            else:
+                assert got.shape == canon[k].shape and (got == canon[k]).all(), (mode, k)
+        c.close()
